@@ -1,0 +1,858 @@
+// capi.cu — implementation of the C ABI declared in include/lstm_b200.h.
+// Host-side orchestration only: every arithmetic statement of the reference path runs in a CUDA
+// kernel (kernels_f32.cu for LSTM_F32, tc_*.cu for LSTM_BF16).  There is no CPU fallback.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <fstream>
+#include <iomanip>
+#include <random>
+#include <sstream>
+
+#include <dlfcn.h>
+
+#include "ctx.h"
+#include "kernels.h"
+
+using namespace lstm;
+
+// NCCL is bound at run time, only when data parallelism is requested: the library then shares the
+// NCCL instance already loaded in the process (torch ships its own libnccl.so.2) instead of pulling
+// a second copy in at load time.
+namespace {
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi g_nccl;
+bool nccl_load() {
+  if (g_nccl.ok) return true;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+  if (!h) return false;
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+  g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy && g_nccl.GetErrorString;
+  return g_nccl.ok;
+}
+}  // namespace
+#undef LSTM_NCCL
+#define LSTM_NCCL(call)                                                                               \
+  do {                                                                                                \
+    ncclResult_t r_ = (call);                                                                         \
+    if (r_ != ncclSuccess)                                                                            \
+      return lstm_fail(ctx, LSTM_ERR_NCCL, std::string(#call) + ": " + g_nccl.GetErrorString(r_));    \
+  } while (0)
+
+static thread_local std::string g_create_error;
+
+int lstm_fail(lstm_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg; else g_create_error = msg;
+  return code;
+}
+
+static inline void shape_of(const lstm_ctx* c, int which, int* rows, int* cols) {
+  const int M = c->M, N = c->N;
+  switch (which) {
+    case LSTM_W: *rows = 4 * N; *cols = M; break;
+    case LSTM_U: *rows = 4 * N; *cols = N; break;
+    case LSTM_B: *rows = 4 * N; *cols = 1; break;
+    case LSTM_WHY: *rows = M; *cols = N; break;
+    default: *rows = M; *cols = 1; break;
+  }
+}
+
+// R/lstm.cc:364-380 with an explicit seed: fresh mt19937, normal_distribution<double>, (i,j) order
+static void randn_colmajor(float* m, int rows, int cols, double mean, double stddev, uint64_t seed) {
+  std::mt19937 mt((uint32_t)seed);
+  std::normal_distribution<> dist(mean, stddev);
+  for (int i = 0; i < rows; i++)
+    for (int j = 0; j < cols; j++) m[i + (size_t)rows * j] = (float)dist(mt);
+}
+
+extern "C" const char* lstm_version(void) { return "eigen_lstm_b200 0.1 (sm_100a)"; }
+
+extern "C" const char* lstm_last_error(const lstm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int lstm_create(lstm_ctx** out, int M, int N, int S, int B, int device, int dtype) {
+  lstm_ctx* ctx = nullptr;
+  if (!out) return lstm_fail(nullptr, LSTM_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (M < 1 || M > 256 || N < 1 || S < 2 || B < 1)
+    return lstm_fail(nullptr, LSTM_ERR_ARG, "need 1 <= M <= 256 (bytes), N >= 1, S >= 2, B >= 1");
+  if (dtype != LSTM_F32 && dtype != LSTM_BF16) return lstm_fail(nullptr, LSTM_ERR_ARG, "dtype must be LSTM_F32 or LSTM_BF16");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return lstm_fail(nullptr, LSTM_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) return lstm_fail(nullptr, LSTM_ERR_ARG, "device index out of range");
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return lstm_fail(nullptr, LSTM_ERR_CUDA, cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10)
+    return lstm_fail(nullptr, LSTM_ERR_UNSUPPORTED, "this library is built for sm_100a (B200) only");
+
+  ctx = new lstm_ctx();
+  ctx->M = M; ctx->N = N; ctx->S = S; ctx->B = B; ctx->T = S - 1; ctx->device = device; ctx->dtype = dtype;
+  const size_t N4 = 4 * (size_t)N;
+  ctx->sz[LSTM_W] = N4 * M; ctx->sz[LSTM_U] = N4 * N; ctx->sz[LSTM_B] = N4;
+  ctx->sz[LSTM_WHY] = (size_t)M * N; ctx->sz[LSTM_BY] = M;
+  size_t o = 0;
+  for (int i = 0; i < 5; i++) { ctx->off[i] = o; o += (ctx->sz[i] + 3) & ~(size_t)3; }  // 16-byte aligned tensors
+  ctx->P = o;
+#define CREATE_CUDA(call)                                                                    \
+  do {                                                                                       \
+    cudaError_t e2 = (call);                                                                 \
+    if (e2 != cudaSuccess) {                                                                 \
+      std::string msg = std::string(#call) + ": " + cudaGetErrorString(e2);                  \
+      lstm_destroy(ctx);                                                                     \
+      return lstm_fail(nullptr, LSTM_ERR_CUDA, msg);                                         \
+    }                                                                                        \
+  } while (0)
+  CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
+  CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->comm_st, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_bucket[i], cudaEventDisableTiming));
+    CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_comm[i], cudaEventDisableTiming));
+  }
+  for (int i = 0; i < 16; i++) CREATE_CUDA(cudaEventCreate(&ctx->pev[i]));
+  const size_t T = ctx->T, BN = (size_t)B * N;
+  CREATE_CUDA(cudaMalloc(&ctx->params, ctx->P * sizeof(float)));
+  CREATE_CUDA(cudaMalloc(&ctx->grads, ctx->P * sizeof(float)));
+  CREATE_CUDA(cudaMalloc(&ctx->mem, ctx->P * sizeof(float)));
+  CREATE_CUDA(cudaMemsetAsync(ctx->params, 0, ctx->P * sizeof(float), ctx->st));
+  CREATE_CUDA(cudaMemsetAsync(ctx->grads, 0, ctx->P * sizeof(float), ctx->st));
+  CREATE_CUDA(cudaMemsetAsync(ctx->mem, 0, ctx->P * sizeof(float), ctx->st));
+  CREATE_CUDA(cudaMalloc(&ctx->Hs, (T + 1) * BN * sizeof(float)));
+  CREATE_CUDA(cudaMalloc(&ctx->Cs, (T + 1) * BN * sizeof(float)));
+  CREATE_CUDA(cudaMemsetAsync(ctx->Hs, 0, (T + 1) * BN * sizeof(float), ctx->st));
+  CREATE_CUDA(cudaMemsetAsync(ctx->Cs, 0, (T + 1) * BN * sizeof(float), ctx->st));
+  if (dtype == LSTM_F32) {
+    CREATE_CUDA(cudaMalloc(&ctx->Gs, T * B * N4 * sizeof(float)));
+    CREATE_CUDA(cudaMalloc(&ctx->dG, T * B * N4 * sizeof(float)));
+    CREATE_CUDA(cudaMalloc(&ctx->dY, T * B * (size_t)M * sizeof(float)));
+    CREATE_CUDA(cudaMalloc(&ctx->dHy, T * BN * sizeof(float)));
+    CREATE_CUDA(cudaMalloc(&ctx->dcnext, BN * sizeof(float)));
+  }
+  CREATE_CUDA(cudaMalloc(&ctx->surp, T * B * sizeof(float)));
+  CREATE_CUDA(cudaMalloc(&ctx->xs, (size_t)S * B * sizeof(int)));
+  CREATE_CUDA(cudaMalloc(&ctx->tg, (size_t)S * B * sizeof(int)));
+  CREATE_CUDA(cudaMemsetAsync(ctx->xs, 0xff, (size_t)S * B * sizeof(int), ctx->st));
+  CREATE_CUDA(cudaMemsetAsync(ctx->tg, 0xff, (size_t)S * B * sizeof(int), ctx->st));
+  ctx->loss_cap = 1024;
+  CREATE_CUDA(cudaMalloc(&ctx->d_loss, ctx->loss_cap * sizeof(double)));
+  CREATE_CUDA(cudaMallocHost(&ctx->h_loss_pinned, sizeof(double)));
+  CREATE_CUDA(cudaMalloc(&ctx->pos0, (size_t)B * sizeof(unsigned long long)));
+  CREATE_CUDA(cudaMalloc(&ctx->vcount, sizeof(unsigned long long)));
+  CREATE_CUDA(cudaMemsetAsync(ctx->vcount, 0, sizeof(unsigned long long), ctx->st));
+  ctx->h_pos0.assign(B, (uint64_t)S);
+  CREATE_CUDA(cudaMemcpyAsync(ctx->pos0, ctx->h_pos0.data(), (size_t)B * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->st));
+  if (dtype == LSTM_BF16) {
+    int rc = tc_create(ctx);
+    if (rc != 0) {
+      std::string msg = ctx->err;
+      lstm_destroy(ctx);
+      return lstm_fail(nullptr, rc, msg);
+    }
+  }
+  CREATE_CUDA(cudaStreamSynchronize(ctx->st));
+#undef CREATE_CUDA
+  *out = ctx;
+  return LSTM_OK;
+}
+
+extern "C" int lstm_destroy(lstm_ctx* ctx) {
+  if (!ctx) return LSTM_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->st) cudaStreamSynchronize(ctx->st);
+  if (ctx->comm_st) cudaStreamSynchronize(ctx->comm_st);
+  if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
+  if (ctx->tc) tc_destroy(ctx);
+  void* bufs[] = {ctx->params, ctx->grads, ctx->mem, ctx->Hs, ctx->Cs, ctx->Gs, ctx->dY, ctx->dHy, ctx->dG,
+                  ctx->dcnext, ctx->surp, ctx->xs, ctx->tg, ctx->d_loss, ctx->text, ctx->pos0, ctx->vcount};
+  for (void* b : bufs) if (b) cudaFree(b);
+  if (ctx->h_loss_pinned) cudaFreeHost(ctx->h_loss_pinned);
+  for (int i = 0; i < 2; i++) {
+    if (ctx->ev_bucket[i]) cudaEventDestroy(ctx->ev_bucket[i]);
+    if (ctx->ev_comm[i]) cudaEventDestroy(ctx->ev_comm[i]);
+  }
+  for (int i = 0; i < 16; i++) if (ctx->pev[i]) cudaEventDestroy(ctx->pev[i]);
+  if (ctx->st) cudaStreamDestroy(ctx->st);
+  if (ctx->comm_st) cudaStreamDestroy(ctx->comm_st);
+  delete ctx;
+  return LSTM_OK;
+}
+
+extern "C" int lstm_sync(lstm_ctx* ctx) {
+  if (!ctx) return LSTM_ERR_ARG;
+  LSTM_CUDA(cudaSetDevice(ctx->device));
+  LSTM_CUDA(cudaStreamSynchronize(ctx->st));
+  LSTM_CUDA(cudaStreamSynchronize(ctx->comm_st));
+  return LSTM_OK;
+}
+
+extern "C" long lstm_tensor_size(const lstm_ctx* ctx, int which) {
+  if (!ctx || which < 0 || which > 4) return -1;
+  return (long)ctx->sz[which];
+}
+extern "C" long lstm_launch_count(const lstm_ctx* ctx) { return ctx ? ctx->launches : -1; }
+extern "C" void* lstm_stream(lstm_ctx* ctx) { return ctx ? (void*)ctx->st : nullptr; }
+
+static float* tensor_ptr(lstm_ctx* ctx, int kind, int which) {
+  if (which < 0 || which > 4) return nullptr;
+  switch (kind) {
+    case LSTM_PARAM: return ctx->p(which);
+    case LSTM_GRAD: return ctx->g(which);
+    case LSTM_ADAGRAD_MEM: return ctx->m(which);
+    default: return nullptr;
+  }
+}
+
+extern "C" int lstm_set_tensor(lstm_ctx* ctx, int kind, int which, const float* src, size_t n) {
+  if (!ctx || !src) return LSTM_ERR_ARG;
+  float* d = tensor_ptr(ctx, kind, which);
+  if (!d || n != ctx->sz[which]) return lstm_fail(ctx, LSTM_ERR_ARG, "lstm_set_tensor: bad kind/which/size");
+  LSTM_CUDA(cudaSetDevice(ctx->device));
+  LSTM_CUDA(cudaMemcpyAsync(d, src, n * sizeof(float), cudaMemcpyHostToDevice, ctx->st));
+  LSTM_CUDA(cudaStreamSynchronize(ctx->st));
+  if (kind == LSTM_PARAM && ctx->tc) return tc_params_changed(ctx);
+  return LSTM_OK;
+}
+
+extern "C" int lstm_get_tensor(lstm_ctx* ctx, int kind, int which, float* dst, size_t n) {
+  if (!ctx || !dst) return LSTM_ERR_ARG;
+  float* d = tensor_ptr(ctx, kind, which);
+  if (!d || n != ctx->sz[which]) return lstm_fail(ctx, LSTM_ERR_ARG, "lstm_get_tensor: bad kind/which/size");
+  LSTM_CUDA(cudaSetDevice(ctx->device));
+  LSTM_CUDA(cudaStreamSynchronize(ctx->comm_st));
+  LSTM_CUDA(cudaMemcpyAsync(dst, d, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->st));
+  LSTM_CUDA(cudaStreamSynchronize(ctx->st));
+  return LSTM_OK;
+}
+
+extern "C" int lstm_init_params(lstm_ctx* ctx, uint64_t seed, float std, float forget_bias) {
+  if (!ctx) return LSTM_ERR_ARG;
+  const int order[3] = {LSTM_W, LSTM_U, LSTM_WHY};  // R/lstm.cc:113-115
+  for (int k = 0; k < 3; k++) {
+    int rows, cols;
+    shape_of(ctx, order[k], &rows, &cols);
+    std::vector<float> h((size_t)rows * cols);
+    randn_colmajor(h.data(), rows, cols, 0.0, std, seed + k);
+    int rc = lstm_set_tensor(ctx, LSTM_PARAM, order[k], h.data(), h.size());
+    if (rc) return rc;
+  }
+  std::vector<float> b(4 * (size_t)ctx->N, 0.f), by(ctx->M, 0.f);
+  for (int j = 0; j < ctx->N; j++) b[2 * (size_t)ctx->N + j] = forget_bias;
+  int rc = lstm_set_tensor(ctx, LSTM_PARAM, LSTM_B, b.data(), b.size());
+  if (rc) return rc;
+  rc = lstm_set_tensor(ctx, LSTM_PARAM, LSTM_BY, by.data(), by.size());
+  if (rc) return rc;
+  LSTM_CUDA(cudaMemsetAsync(ctx->mem, 0, ctx->P * sizeof(float), ctx->st));
+  LSTM_CUDA(cudaMemsetAsync(ctx->grads, 0, ctx->P * sizeof(float), ctx->st));
+  LSTM_CUDA(cudaStreamSynchronize(ctx->st));
+  return LSTM_OK;
+}
+
+extern "C" int lstm_set_state(lstm_ctx* ctx, const float* h0, const float* c0) {
+  if (!ctx) return LSTM_ERR_ARG;
+  LSTM_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)ctx->B * ctx->N * sizeof(float);
+  if (h0) LSTM_CUDA(cudaMemcpyAsync(ctx->Hslot(0), h0, bytes, cudaMemcpyHostToDevice, ctx->st));
+  else LSTM_CUDA(cudaMemsetAsync(ctx->Hslot(0), 0, bytes, ctx->st));
+  if (c0) LSTM_CUDA(cudaMemcpyAsync(ctx->Cslot(0), c0, bytes, cudaMemcpyHostToDevice, ctx->st));
+  else LSTM_CUDA(cudaMemsetAsync(ctx->Cslot(0), 0, bytes, ctx->st));
+  LSTM_CUDA(cudaStreamSynchronize(ctx->st));
+  return LSTM_OK;
+}
+
+extern "C" int lstm_get_state(lstm_ctx* ctx, float* h0, float* c0) {
+  if (!ctx) return LSTM_ERR_ARG;
+  LSTM_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)ctx->B * ctx->N * sizeof(float);
+  if (h0) LSTM_CUDA(cudaMemcpyAsync(h0, ctx->Hslot(0), bytes, cudaMemcpyDeviceToHost, ctx->st));
+  if (c0) LSTM_CUDA(cudaMemcpyAsync(c0, ctx->Cslot(0), bytes, cudaMemcpyDeviceToHost, ctx->st));
+  LSTM_CUDA(cudaStreamSynchronize(ctx->st));
+  return LSTM_OK;
+}
+
+extern "C" int lstm_reset_state(lstm_ctx* ctx, uint64_t seed, float std) {
+  if (!ctx) return LSTM_ERR_ARG;
+  if (std == 0.f) return lstm_set_state(ctx, nullptr, nullptr);
+  // R/lstm.cc:146-147 draws the whole N x S matrix; the column that becomes h(0) after the first
+  // shift is column 1.  For B streams the batched snapshots draw N x B per timestep
+  // (OV/lstm_eigen_opt/lstm.cc:176-181); we draw the carried-in column only: N x B, (i,j) order.
+  std::vector<float> h((size_t)ctx->N * ctx->B), c((size_t)ctx->N * ctx->B);
+  randn_colmajor(h.data(), ctx->N, ctx->B, 0.0, std, seed);
+  randn_colmajor(c.data(), ctx->N, ctx->B, 0.0, std, seed + 1);
+  return lstm_set_state(ctx, h.data(), c.data());
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward / backward / adagrad
+// ------------------------------------------------------------------------------------------------
+static int ensure_loss_cap(lstm_ctx* ctx, size_t need) {
+  if (need <= ctx->loss_cap) return LSTM_OK;
+  LSTM_CUDA(cudaStreamSynchronize(ctx->st));
+  LSTM_CUDA(cudaFree(ctx->d_loss));
+  ctx->d_loss = nullptr;
+  LSTM_CUDA(cudaMalloc(&ctx->d_loss, need * sizeof(double)));
+  ctx->loss_cap = need;
+  return LSTM_OK;
+}
+
+#define PROF(i) do { if (ctx->profiling) LSTM_CUDA(cudaEventRecord(ctx->pev[i], ctx->st)); } while (0)
+
+static int forward_device(lstm_ctx* ctx, size_t loss_slot) {
+  const int B = ctx->B, N = ctx->N, M = ctx->M, T = ctx->T;
+  PROF(1);
+  if (ctx->dtype == LSTM_BF16) {
+    int rc = tc_forward(ctx);
+    if (rc) return rc;
+  } else {
+    const size_t N4 = 4 * (size_t)N;
+    for (int t = 1; t <= T; t++) {
+      launch_step_fwd_f32(ctx->p(LSTM_U), ctx->p(LSTM_W), ctx->p(LSTM_B), ctx->Hslot(t - 1), ctx->Cslot(t - 1),
+                          ctx->xs + (size_t)t * B, ctx->Gs + (size_t)(t - 1) * B * N4, ctx->Cslot(t), ctx->Hslot(t),
+                          B, N, ctx->st);
+    }
+    LSTM_LAUNCHED(T);
+    PROF(2);
+    // K3: Y[(t,b)][m] = sum_n H[(t,b)][n] * Why(m,n) + by[m]            (R/lstm.cc:195)
+    launch_gemm_f32(ctx->Hslot(1), N, 1, ctx->p(LSTM_WHY), M, 1, ctx->dY, M, 1, ctx->p(LSTM_BY), T * B, M, N, ctx->st);
+    launch_softmax_ce_f32(ctx->dY, ctx->tg + B, ctx->surp, T * B, M, ctx->st);
+    LSTM_LAUNCHED(2);
+  }
+  launch_loss_reduce(ctx->surp, T, B, ctx->d_loss + loss_slot, ctx->st);
+  LSTM_LAUNCHED(1);
+  PROF(3);
+  ctx->fwd_done = true;
+  return LSTM_OK;
+}
+
+static int allreduce_bucket(lstm_ctx* ctx, int bucket) {
+  // bucket 0 = [W,U,b], bucket 1 = [Why,by]; both contiguous in the flat gradient vector.
+  if (ctx->world <= 1) return LSTM_OK;
+  float* ptr = bucket == 0 ? ctx->g(LSTM_W) : ctx->g(LSTM_WHY);
+  const size_t cnt = bucket == 0 ? ctx->off[LSTM_WHY] : ctx->P - ctx->off[LSTM_WHY];
+  LSTM_CUDA(cudaEventRecord(ctx->ev_bucket[bucket], ctx->st));
+  LSTM_CUDA(cudaStreamWaitEvent(ctx->comm_st, ctx->ev_bucket[bucket], 0));
+  LSTM_NCCL(g_nccl.AllReduce(ptr, ptr, cnt, ncclFloat, ncclSum, ctx->comm, ctx->comm_st));
+  LSTM_CUDA(cudaEventRecord(ctx->ev_comm[bucket], ctx->comm_st));
+  return LSTM_OK;
+}
+
+static int backward_device(lstm_ctx* ctx) {
+  if (!ctx->fwd_done) return lstm_fail(ctx, LSTM_ERR_STATE, "lstm_backward before lstm_forward");
+  const int B = ctx->B, N = ctx->N, M = ctx->M, T = ctx->T;
+  if (ctx->dtype == LSTM_BF16) {
+    int rc = tc_backward(ctx);  // records its own phase events and launches the allreduce buckets
+    if (rc) return rc;
+    return LSTM_OK;
+  }
+  const size_t N4 = 4 * (size_t)N;
+  const int BT = T * B;
+  // K4: dHy[(t,b)][n] = sum_m dY[(t,b)][m] * Why(m,n)                      (R/lstm.cc:228)
+  launch_gemm_f32(ctx->dY, M, 1, ctx->p(LSTM_WHY), 1, M, ctx->dHy, N, 1, nullptr, BT, N, M, ctx->st);
+  PROF(4);
+  // K6c first (its inputs are complete), so its allreduce bucket overlaps the BPTT recurrence:
+  // dWhy(m,n) = sum_(t,b) dY[(t,b)][m] * H_t[(t,b)][n]  (:226) ; dby = sum dY (:227)
+  launch_gemm_f32(ctx->Hslot(1), 1, N, ctx->dY, M, 1, ctx->g(LSTM_WHY), M, 1, nullptr, N, M, BT, ctx->st);
+  launch_colsum_f32(ctx->dY, ctx->g(LSTM_BY), BT, M, ctx->st);
+  LSTM_LAUNCHED(3);
+  int rc = allreduce_bucket(ctx, 1);
+  if (rc) return rc;
+  // K5: BPTT recurrence t = T..1
+  for (int t = T; t >= 1; t--) {
+    launch_step_bwd_f32(ctx->p(LSTM_U), t < T ? ctx->dG + (size_t)t * B * N4 : nullptr,
+                        ctx->dHy + (size_t)(t - 1) * B * N, ctx->Gs + (size_t)(t - 1) * B * N4, ctx->Cslot(t),
+                        ctx->Cslot(t - 1), ctx->dcnext, ctx->dG + (size_t)(t - 1) * B * N4, B, N, t == T, ctx->st);
+  }
+  LSTM_LAUNCHED(T);
+  PROF(5);
+  // K6a: dU(r,k) = sum_(t,b) dG[(t,b)][r] * H_{t-1}[(t,b)][k]              (:250)
+  launch_gemm_f32(ctx->Hslot(0), 1, N, ctx->dG, (long)N4, 1, ctx->g(LSTM_U), (long)N4, 1, nullptr, N, (int)N4, BT, ctx->st);
+  // K6b: dW(:,m) = sum of dG rows whose input byte is m                    (:251)
+  launch_dw_scatter_f32(ctx->dG, ctx->xs + B, ctx->g(LSTM_W), BT, (int)N4, M, ctx->st);
+  launch_colsum_f32(ctx->dG, ctx->g(LSTM_B), BT, (int)N4, ctx->st);      // (:252)
+  LSTM_LAUNCHED(3);
+  PROF(6);
+  rc = allreduce_bucket(ctx, 0);
+  if (rc) return rc;
+  return LSTM_OK;
+}
+
+static int adagrad_device(lstm_ctx* ctx, float lr, double eps, float clip) {
+  if (ctx->world > 1) {
+    LSTM_CUDA(cudaStreamWaitEvent(ctx->st, ctx->ev_comm[0], 0));
+    LSTM_CUDA(cudaStreamWaitEvent(ctx->st, ctx->ev_comm[1], 0));
+  }
+  PROF(7);
+  launch_adagrad_f32(ctx->params, ctx->grads, ctx->mem, ctx->P, lr, eps, clip, ctx->st);
+  LSTM_LAUNCHED(1);
+  if (ctx->tc) {
+    int rc = tc_params_changed(ctx);
+    if (rc) return rc;
+  }
+  PROF(8);
+  ctx->iteration++;
+  return LSTM_OK;
+}
+
+static int finish_profile(lstm_ctx* ctx) {
+  if (!ctx->profiling) return LSTM_OK;
+  LSTM_CUDA(cudaStreamSynchronize(ctx->st));
+  // events: 0 start(window) 1 fwd-recur start 2 logits start 3 fwd end 4 dHy end 5 bwd-recur end
+  //         6 wgrad end 7 allreduce-wait end 8 adagrad end
+  const int pairs[9][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 4}, {4, 5}, {5, 6}, {6, 7}, {7, 8}, {0, 8}};
+  for (int i = 0; i < 9; i++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->pev[pairs[i][0]], ctx->pev[pairs[i][1]]) != cudaSuccess) { ms = -1.f; cudaGetLastError(); }
+    ctx->phase_ms[i] = ms;
+  }
+  return LSTM_OK;
+}
+
+static int fetch_loss(lstm_ctx* ctx, size_t slot, double* out) {
+  LSTM_CUDA(cudaMemcpyAsync(ctx->h_loss_pinned, ctx->d_loss + slot, sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+  LSTM_CUDA(cudaStreamSynchronize(ctx->st));
+  *out = *ctx->h_loss_pinned;
+  return LSTM_OK;
+}
+
+static int upload_window(lstm_ctx* ctx, const int32_t* x_idx, const int32_t* t_idx) {
+  const size_t bytes = (size_t)ctx->S * ctx->B * sizeof(int);
+  if (!x_idx || !t_idx) return lstm_fail(ctx, LSTM_ERR_ARG, "x_idx / t_idx is NULL");
+  for (size_t i = 0; i < (size_t)ctx->S * ctx->B; i++)
+    if (x_idx[i] < -1 || x_idx[i] >= ctx->M || t_idx[i] < -1 || t_idx[i] >= ctx->M)
+      return lstm_fail(ctx, LSTM_ERR_ARG, "window index outside [-1, M)");
+  LSTM_CUDA(cudaMemcpyAsync(ctx->xs, x_idx, bytes, cudaMemcpyHostToDevice, ctx->st));
+  LSTM_CUDA(cudaMemcpyAsync(ctx->tg, t_idx, bytes, cudaMemcpyHostToDevice, ctx->st));
+  return LSTM_OK;
+}
+
+extern "C" int lstm_forward(lstm_ctx* ctx, const int32_t* x_idx, const int32_t* t_idx, double* loss_out) {
+  if (!ctx) return LSTM_ERR_ARG;
+  LSTM_CUDA(cudaSetDevice(ctx->device));
+  PROF(0);
+  int rc = upload_window(ctx, x_idx, t_idx);
+  if (rc) return rc;
+  rc = forward_device(ctx, 0);
+  if (rc) return rc;
+  if (loss_out) return fetch_loss(ctx, 0, loss_out);
+  return LSTM_OK;
+}
+
+extern "C" int lstm_backward(lstm_ctx* ctx) {
+  if (!ctx) return LSTM_ERR_ARG;
+  LSTM_CUDA(cudaSetDevice(ctx->device));
+  int rc = backward_device(ctx);
+  if (rc) return rc;
+  if (ctx->world > 1) {  // standalone backward: make the summed gradients visible to the caller
+    LSTM_CUDA(cudaStreamWaitEvent(ctx->st, ctx->ev_comm[0], 0));
+    LSTM_CUDA(cudaStreamWaitEvent(ctx->st, ctx->ev_comm[1], 0));
+  }
+  return LSTM_OK;
+}
+
+extern "C" int lstm_adagrad(lstm_ctx* ctx, float lr, double eps, float clip) {
+  if (!ctx) return LSTM_ERR_ARG;
+  LSTM_CUDA(cudaSetDevice(ctx->device));
+  return adagrad_device(ctx, lr, eps, clip);
+}
+
+extern "C" int lstm_carry_state(lstm_ctx* ctx, int stride) {
+  if (!ctx) return LSTM_ERR_ARG;
+  if (stride <= 0) return LSTM_OK;
+  if (stride > ctx->T) stride = ctx->T;
+  LSTM_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)ctx->B * ctx->N * sizeof(float);
+  LSTM_CUDA(cudaMemcpyAsync(ctx->Hslot(0), ctx->Hslot(stride), bytes, cudaMemcpyDeviceToDevice, ctx->st));
+  LSTM_CUDA(cudaMemcpyAsync(ctx->Cslot(0), ctx->Cslot(stride), bytes, cudaMemcpyDeviceToDevice, ctx->st));
+  return LSTM_OK;
+}
+
+extern "C" int lstm_train_step(lstm_ctx* ctx, const int32_t* x_idx, const int32_t* t_idx, int stride, float lr,
+                               double* loss_out) {
+  if (!ctx) return LSTM_ERR_ARG;
+  LSTM_CUDA(cudaSetDevice(ctx->device));
+  PROF(0);
+  int rc = lstm_carry_state(ctx, stride);
+  if (rc) return rc;
+  rc = upload_window(ctx, x_idx, t_idx);
+  if (rc) return rc;
+  rc = forward_device(ctx, 0);
+  if (rc) return rc;
+  rc = backward_device(ctx);
+  if (rc) return rc;
+  rc = adagrad_device(ctx, lr, 1e-10, 0.f);
+  if (rc) return rc;
+  rc = finish_profile(ctx);
+  if (rc) return rc;
+  if (loss_out) return fetch_loss(ctx, 0, loss_out);
+  return LSTM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device text pipeline
+// ------------------------------------------------------------------------------------------------
+extern "C" int lstm_load_text(lstm_ctx* ctx, const uint8_t* bytes, size_t n) {
+  if (!ctx || !bytes) return LSTM_ERR_ARG;
+  if (n < (size_t)ctx->S + 2) return lstm_fail(ctx, LSTM_ERR_ARG, "text shorter than the window");
+  LSTM_CUDA(cudaSetDevice(ctx->device));
+  LSTM_CUDA(cudaStreamSynchronize(ctx->st));
+  if (ctx->text) { LSTM_CUDA(cudaFree(ctx->text)); ctx->text = nullptr; }
+  LSTM_CUDA(cudaMalloc(&ctx->text, n));
+  LSTM_CUDA(cudaMemcpyAsync(ctx->text, bytes, n, cudaMemcpyHostToDevice, ctx->st));
+  ctx->text_len = n;
+  std::vector<uint64_t> pos(ctx->B, (uint64_t)ctx->S);
+  return lstm_set_positions(ctx, pos.data());
+}
+
+extern "C" int lstm_set_positions(lstm_ctx* ctx, const uint64_t* pos) {
+  if (!ctx || !pos) return LSTM_ERR_ARG;
+  if (!ctx->text) return lstm_fail(ctx, LSTM_ERR_STATE, "lstm_set_positions before lstm_load_text");
+  for (int b = 0; b < ctx->B; b++)
+    if (pos[b] < (uint64_t)ctx->S || pos[b] >= ctx->text_len)
+      return lstm_fail(ctx, LSTM_ERR_ARG, "position outside [S, length)");
+  LSTM_CUDA(cudaSetDevice(ctx->device));
+  ctx->h_pos0.assign(pos, pos + ctx->B);
+  ctx->v_host = 0;
+  LSTM_CUDA(cudaMemcpyAsync(ctx->pos0, ctx->h_pos0.data(), (size_t)ctx->B * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->st));
+  LSTM_CUDA(cudaMemsetAsync(ctx->vcount, 0, sizeof(unsigned long long), ctx->st));
+  LSTM_CUDA(cudaMemsetAsync(ctx->xs, 0xff, (size_t)ctx->S * ctx->B * sizeof(int), ctx->st));
+  LSTM_CUDA(cudaMemsetAsync(ctx->tg, 0xff, (size_t)ctx->S * ctx->B * sizeof(int), ctx->st));
+  LSTM_CUDA(cudaStreamSynchronize(ctx->st));
+  return LSTM_OK;
+}
+
+extern "C" int lstm_get_positions(lstm_ctx* ctx, uint64_t* pos) {
+  if (!ctx || !pos) return LSTM_ERR_ARG;
+  if (!ctx->text) return lstm_fail(ctx, LSTM_ERR_STATE, "no text loaded");
+  const uint64_t span = ctx->text_len - ctx->S;
+  for (int b = 0; b < ctx->B; b++) pos[b] = ctx->S + (ctx->h_pos0[b] - ctx->S + ctx->v_host) % span;
+  return LSTM_OK;
+}
+
+extern "C" int lstm_get_window(lstm_ctx* ctx, int32_t* x_idx, int32_t* t_idx) {
+  if (!ctx || !x_idx || !t_idx) return LSTM_ERR_ARG;
+  LSTM_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)ctx->S * ctx->B * sizeof(int);
+  LSTM_CUDA(cudaMemcpyAsync(x_idx, ctx->xs, bytes, cudaMemcpyDeviceToHost, ctx->st));
+  LSTM_CUDA(cudaMemcpyAsync(t_idx, ctx->tg, bytes, cudaMemcpyDeviceToHost, ctx->st));
+  LSTM_CUDA(cudaStreamSynchronize(ctx->st));
+  return LSTM_OK;
+}
+
+extern "C" int lstm_train_text(lstm_ctx* ctx, int iters, int stride, float lr, double* losses) {
+  if (!ctx || iters < 0 || stride < 1) return LSTM_ERR_ARG;
+  if (!ctx->text) return lstm_fail(ctx, LSTM_ERR_STATE, "lstm_train_text before lstm_load_text");
+  LSTM_CUDA(cudaSetDevice(ctx->device));
+  int rc = ensure_loss_cap(ctx, (size_t)iters);
+  if (rc) return rc;
+  for (int it = 0; it < iters; it++) {
+    PROF(0);
+    rc = lstm_carry_state(ctx, stride);
+    if (rc) return rc;
+    launch_window_advance(ctx->text, ctx->text_len, ctx->pos0, ctx->vcount, stride, ctx->S, ctx->B, ctx->xs, ctx->tg, ctx->st);
+    LSTM_LAUNCHED(1);
+    ctx->v_host += stride;
+    rc = forward_device(ctx, (size_t)it);
+    if (rc) return rc;
+    rc = backward_device(ctx);
+    if (rc) return rc;
+    rc = adagrad_device(ctx, lr, 1e-10, 0.f);
+    if (rc) return rc;
+  }
+  rc = finish_profile(ctx);
+  if (rc) return rc;
+  if (losses && iters > 0) {
+    LSTM_CUDA(cudaMemcpyAsync(losses, ctx->d_loss, (size_t)iters * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+    LSTM_CUDA(cudaStreamSynchronize(ctx->st));
+  }
+  return LSTM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// evaluation / sampling
+// ------------------------------------------------------------------------------------------------
+extern "C" int lstm_eval_bpc(lstm_ctx* ctx, const uint8_t* bytes, size_t n, double* bpc_out) {
+  if (!ctx || !bytes || !bpc_out || n < 2) return LSTM_ERR_ARG;
+  LSTM_CUDA(cudaSetDevice(ctx->device));
+  uint8_t* d_text = nullptr;
+  double* d_bits = nullptr;
+  LSTM_CUDA(cudaMalloc(&d_text, n));
+  LSTM_CUDA(cudaMalloc(&d_bits, sizeof(double)));
+  LSTM_CUDA(cudaMemcpyAsync(d_text, bytes, n, cudaMemcpyHostToDevice, ctx->st));
+  launch_recur_b1_f32(ctx->p(LSTM_W), ctx->p(LSTM_U), ctx->p(LSTM_B), ctx->p(LSTM_WHY), ctx->p(LSTM_BY), ctx->M, ctx->N,
+                      0, d_text, n, nullptr, nullptr, nullptr, nullptr, d_bits, ctx->st);
+  LSTM_LAUNCHED(1);
+  double bits = 0;
+  LSTM_CUDA(cudaMemcpyAsync(&bits, d_bits, sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+  LSTM_CUDA(cudaStreamSynchronize(ctx->st));
+  cudaFree(d_text);
+  cudaFree(d_bits);
+  *bpc_out = bits / (double)(n - 1);
+  return LSTM_OK;
+}
+
+extern "C" int lstm_sample(lstm_ctx* ctx, uint64_t seed, const float* h0, const float* c0, uint8_t* out, size_t n,
+                           int greedy) {
+  if (!ctx || !out) return LSTM_ERR_ARG;
+  if (n == 0) return LSTM_OK;
+  LSTM_CUDA(cudaSetDevice(ctx->device));
+  // R/lstm.cc:309-311,326: mt19937 + uniform_real_distribution<double>(0,1), narrowed to float
+  std::vector<float> u(n);
+  {
+    std::mt19937 gen((uint32_t)seed);
+    std::uniform_real_distribution<> dis(0, 1);
+    for (size_t i = 0; i < n; i++) u[i] = (float)dis(gen);
+  }
+  float *d_u = nullptr, *d_h = nullptr, *d_c = nullptr;
+  uint8_t* d_out = nullptr;
+  LSTM_CUDA(cudaMalloc(&d_u, n * sizeof(float)));
+  LSTM_CUDA(cudaMalloc(&d_out, n));
+  LSTM_CUDA(cudaMemcpyAsync(d_u, u.data(), n * sizeof(float), cudaMemcpyHostToDevice, ctx->st));
+  if (h0) { LSTM_CUDA(cudaMalloc(&d_h, ctx->N * sizeof(float))); LSTM_CUDA(cudaMemcpyAsync(d_h, h0, ctx->N * sizeof(float), cudaMemcpyHostToDevice, ctx->st)); }
+  if (c0) { LSTM_CUDA(cudaMalloc(&d_c, ctx->N * sizeof(float))); LSTM_CUDA(cudaMemcpyAsync(d_c, c0, ctx->N * sizeof(float), cudaMemcpyHostToDevice, ctx->st)); }
+  launch_recur_b1_f32(ctx->p(LSTM_W), ctx->p(LSTM_U), ctx->p(LSTM_B), ctx->p(LSTM_WHY), ctx->p(LSTM_BY), ctx->M, ctx->N,
+                      greedy ? 2 : 1, nullptr, n, d_u, d_h, d_c, d_out, nullptr, ctx->st);
+  LSTM_LAUNCHED(1);
+  LSTM_CUDA(cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, ctx->st));
+  LSTM_CUDA(cudaStreamSynchronize(ctx->st));
+  cudaFree(d_u); cudaFree(d_out);
+  if (d_h) cudaFree(d_h);
+  if (d_c) cudaFree(d_c);
+  return LSTM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// introspection
+// ------------------------------------------------------------------------------------------------
+extern "C" int lstm_get_activation(lstm_ctx* ctx, int what, int t, float* out, size_t n) {
+  if (!ctx || !out) return LSTM_ERR_ARG;
+  LSTM_CUDA(cudaSetDevice(ctx->device));
+  const int B = ctx->B, N = ctx->N, M = ctx->M, T = ctx->T;
+  if (t < 0 || t > T) return lstm_fail(ctx, LSTM_ERR_ARG, "t outside [0, S)");
+  if (ctx->dtype == LSTM_BF16 && what != LSTM_ACT_H && what != LSTM_ACT_C) return tc_get_activation(ctx, what, t, out, n);
+  const float* src = nullptr;
+  size_t cnt = 0;
+  switch (what) {
+    case LSTM_ACT_H: src = ctx->Hslot(t); cnt = (size_t)B * N; break;
+    case LSTM_ACT_C: src = ctx->Cslot(t); cnt = (size_t)B * N; break;
+    case LSTM_ACT_G: if (t < 1) return LSTM_ERR_ARG; src = ctx->Gs + (size_t)(t - 1) * B * 4 * N; cnt = (size_t)B * 4 * N; break;
+    case LSTM_ACT_DG: if (t < 1) return LSTM_ERR_ARG; src = ctx->dG + (size_t)(t - 1) * B * 4 * N; cnt = (size_t)B * 4 * N; break;
+    case LSTM_ACT_DHY: if (t < 1) return LSTM_ERR_ARG; src = ctx->dHy + (size_t)(t - 1) * B * N; cnt = (size_t)B * N; break;
+    case LSTM_ACT_PROBS: if (t < 1) return LSTM_ERR_ARG; src = ctx->dY + (size_t)(t - 1) * B * M; cnt = (size_t)B * M; break;
+    default: return lstm_fail(ctx, LSTM_ERR_ARG, "unknown activation selector");
+  }
+  if (n != cnt) return lstm_fail(ctx, LSTM_ERR_ARG, "lstm_get_activation: wrong size");
+  LSTM_CUDA(cudaMemcpyAsync(out, src, cnt * sizeof(float), cudaMemcpyDeviceToHost, ctx->st));
+  LSTM_CUDA(cudaStreamSynchronize(ctx->st));
+  if (what == LSTM_ACT_PROBS) {  // stored as p - onehot(target): add the one-hot back
+    std::vector<int> tgt(B);
+    LSTM_CUDA(cudaMemcpy(tgt.data(), ctx->tg + (size_t)t * B, B * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int b = 0; b < B; b++)
+      if (tgt[b] >= 0) out[(size_t)b * M + tgt[b]] += 1.0f;
+  }
+  return LSTM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// checkpoints
+// ------------------------------------------------------------------------------------------------
+static const char* kNames[5] = {"W", "U", "b", "Why", "by"};
+
+// Eigen's default IOFormat (OV/lstm_eigen_class_CUDA/io.h:24 `file << m`): every coefficient printed
+// with the stream's default precision (6 significant digits), right-aligned to the widest one,
+// separated by one space, rows separated by '\n', no trailing newline.
+static bool write_eigen_text(const std::string& path, const float* colmajor, int rows, int cols) {
+  std::ofstream f(path.c_str());
+  if (!f.is_open()) return false;
+  size_t width = 0;
+  std::vector<std::string> cell((size_t)rows * cols);
+  for (int j = 0; j < cols; j++)
+    for (int i = 0; i < rows; i++) {
+      std::ostringstream s;
+      s << colmajor[i + (size_t)rows * j];
+      cell[i + (size_t)rows * j] = s.str();
+      width = std::max(width, s.str().size());
+    }
+  for (int i = 0; i < rows; i++) {
+    if (i) f << "\n";
+    for (int j = 0; j < cols; j++) {
+      if (j) f << " ";
+      f << std::setw((int)width) << cell[i + (size_t)rows * j];
+    }
+  }
+  return f.good();
+}
+
+// readMatrix (io.h:36-74): whitespace-separated numbers, one matrix row per line, into a pre-sized matrix
+static bool read_eigen_text(const std::string& path, float* colmajor, int rows, int cols) {
+  std::ifstream f(path.c_str());
+  if (!f.is_open()) return false;
+  std::string line;
+  int r = 0;
+  while (r < rows && std::getline(f, line)) {
+    std::stringstream s(line);
+    int c = 0;
+    double v;
+    while (c < cols && (s >> v)) colmajor[r + (size_t)rows * c++] = (float)v;
+    if (c == 0) continue;  // blank line
+    if (c != cols) return false;
+    r++;
+  }
+  return r == rows;
+}
+
+extern "C" int lstm_save_text_ckpt(lstm_ctx* ctx, const char* prefix) {
+  if (!ctx || !prefix) return LSTM_ERR_ARG;
+  for (int w = 0; w < 5; w++) {
+    int rows, cols;
+    shape_of(ctx, w, &rows, &cols);
+    std::vector<float> h((size_t)rows * cols);
+    int rc = lstm_get_tensor(ctx, LSTM_PARAM, w, h.data(), h.size());
+    if (rc) return rc;
+    const std::string path = std::string(prefix) + "_" + kNames[w] + ".txt";
+    if (!write_eigen_text(path, h.data(), rows, cols)) return lstm_fail(ctx, LSTM_ERR_IO, "file save error: (" + path + ")");
+  }
+  return LSTM_OK;
+}
+
+extern "C" int lstm_load_text_ckpt(lstm_ctx* ctx, const char* prefix) {
+  if (!ctx || !prefix) return LSTM_ERR_ARG;
+  std::vector<std::vector<float>> all(5);
+  for (int w = 0; w < 5; w++) {  // read everything first: a failed load leaves the parameters untouched
+    int rows, cols;
+    shape_of(ctx, w, &rows, &cols);
+    all[w].resize((size_t)rows * cols);
+    const std::string path = std::string(prefix) + "_" + kNames[w] + ".txt";
+    if (!read_eigen_text(path, all[w].data(), rows, cols)) return lstm_fail(ctx, LSTM_ERR_IO, "file read error: (" + path + ")");
+  }
+  for (int w = 0; w < 5; w++) {
+    int rc = lstm_set_tensor(ctx, LSTM_PARAM, w, all[w].data(), all[w].size());
+    if (rc) return rc;
+  }
+  return LSTM_OK;
+}
+
+struct BinHeader {
+  char magic[8];
+  int32_t M, N, S, B;
+  int64_t iteration;
+  uint64_t v;
+};
+
+extern "C" int lstm_save_bin(lstm_ctx* ctx, const char* path) {
+  if (!ctx || !path) return LSTM_ERR_ARG;
+  int rc = lstm_sync(ctx);
+  if (rc) return rc;
+  FILE* f = fopen(path, "wb");
+  if (!f) return lstm_fail(ctx, LSTM_ERR_IO, std::string("cannot open ") + path);
+  BinHeader h;
+  memcpy(h.magic, "LSTMB200", 8);
+  h.M = ctx->M; h.N = ctx->N; h.S = ctx->S; h.B = ctx->B; h.iteration = ctx->iteration; h.v = ctx->v_host;
+  bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+  std::vector<float> buf(ctx->P);
+  for (const float* src : {ctx->params, ctx->mem}) {
+    LSTM_CUDA(cudaMemcpy(buf.data(), src, ctx->P * sizeof(float), cudaMemcpyDeviceToHost));
+    ok = ok && fwrite(buf.data(), sizeof(float), ctx->P, f) == ctx->P;
+  }
+  const size_t bn = (size_t)ctx->B * ctx->N;
+  std::vector<float> st(bn);
+  for (const float* src : {ctx->Hslot(0), ctx->Cslot(0)}) {
+    LSTM_CUDA(cudaMemcpy(st.data(), src, bn * sizeof(float), cudaMemcpyDeviceToHost));
+    ok = ok && fwrite(st.data(), sizeof(float), bn, f) == bn;
+  }
+  ok = ok && fwrite(ctx->h_pos0.data(), sizeof(uint64_t), ctx->B, f) == (size_t)ctx->B;
+  fclose(f);
+  return ok ? LSTM_OK : lstm_fail(ctx, LSTM_ERR_IO, std::string("short write to ") + path);
+}
+
+extern "C" int lstm_load_bin(lstm_ctx* ctx, const char* path) {
+  if (!ctx || !path) return LSTM_ERR_ARG;
+  FILE* f = fopen(path, "rb");
+  if (!f) return lstm_fail(ctx, LSTM_ERR_IO, std::string("cannot open ") + path);
+  BinHeader h;
+  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "LSTMB200", 8) != 0) { fclose(f); return lstm_fail(ctx, LSTM_ERR_IO, "not an LSTMB200 checkpoint"); }
+  if (h.M != ctx->M || h.N != ctx->N || h.S != ctx->S || h.B != ctx->B) { fclose(f); return lstm_fail(ctx, LSTM_ERR_ARG, "checkpoint shape differs from the context"); }
+  std::vector<float> pbuf(ctx->P), mbuf(ctx->P);
+  const size_t bn = (size_t)ctx->B * ctx->N;
+  std::vector<float> hb(bn), cb(bn);
+  std::vector<uint64_t> pos(ctx->B);
+  bool ok = fread(pbuf.data(), sizeof(float), ctx->P, f) == ctx->P && fread(mbuf.data(), sizeof(float), ctx->P, f) == ctx->P &&
+            fread(hb.data(), sizeof(float), bn, f) == bn && fread(cb.data(), sizeof(float), bn, f) == bn &&
+            fread(pos.data(), sizeof(uint64_t), ctx->B, f) == (size_t)ctx->B;
+  fclose(f);
+  if (!ok) return lstm_fail(ctx, LSTM_ERR_IO, "truncated checkpoint");
+  LSTM_CUDA(cudaSetDevice(ctx->device));
+  LSTM_CUDA(cudaMemcpy(ctx->params, pbuf.data(), ctx->P * sizeof(float), cudaMemcpyHostToDevice));
+  LSTM_CUDA(cudaMemcpy(ctx->mem, mbuf.data(), ctx->P * sizeof(float), cudaMemcpyHostToDevice));
+  int rc = lstm_set_state(ctx, hb.data(), cb.data());
+  if (rc) return rc;
+  ctx->iteration = h.iteration;
+  if (ctx->text) {
+    rc = lstm_set_positions(ctx, pos.data());
+    if (rc) return rc;
+    ctx->v_host = h.v;
+    LSTM_CUDA(cudaMemcpy(ctx->vcount, &h.v, sizeof(uint64_t), cudaMemcpyHostToDevice));
+    if (h.v > 0) {  // rebuild the window the saved run was looking at
+      launch_window_advance(ctx->text, ctx->text_len, ctx->pos0, ctx->vcount, 0, ctx->S, ctx->B, ctx->xs, ctx->tg, ctx->st);
+      LSTM_LAUNCHED(1);
+    }
+  } else {
+    ctx->h_pos0 = pos;
+    ctx->v_host = h.v;
+  }
+  if (ctx->tc) return tc_params_changed(ctx);
+  return LSTM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// data parallel
+// ------------------------------------------------------------------------------------------------
+extern "C" int lstm_dp_unique_id(uint8_t id[128]) {
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId u;
+  if (!nccl_load()) return lstm_fail(nullptr, LSTM_ERR_NCCL, "libnccl.so.2 not found");
+  if (g_nccl.GetUniqueId(&u) != ncclSuccess) return LSTM_ERR_NCCL;
+  memcpy(id, &u, 128);
+  return LSTM_OK;
+}
+
+extern "C" int lstm_dp_init(lstm_ctx* ctx, int rank, int world, const uint8_t id[128]) {
+  if (!ctx || !id || world < 1 || rank < 0 || rank >= world) return LSTM_ERR_ARG;
+  if (ctx->comm) return lstm_fail(ctx, LSTM_ERR_STATE, "communicator already initialised");
+  LSTM_CUDA(cudaSetDevice(ctx->device));
+  ncclUniqueId u;
+  memcpy(&u, id, 128);
+  if (!nccl_load()) return lstm_fail(ctx, LSTM_ERR_NCCL, "libnccl.so.2 not found");
+  LSTM_NCCL(g_nccl.CommInitRank(&ctx->comm, world, u, rank));
+  ctx->rank = rank;
+  ctx->world = world;
+  return LSTM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// measurement
+// ------------------------------------------------------------------------------------------------
+extern "C" int lstm_set_profiling(lstm_ctx* ctx, int on) {
+  if (!ctx) return LSTM_ERR_ARG;
+  ctx->profiling = on != 0;
+  return LSTM_OK;
+}
+extern "C" int lstm_get_phase_ms(lstm_ctx* ctx, float ms[16]) {
+  if (!ctx || !ms) return LSTM_ERR_ARG;
+  memcpy(ms, ctx->phase_ms, sizeof(float) * 16);
+  return LSTM_OK;
+}

@@ -1,0 +1,84 @@
+// ctx.h — the context behind the C ABI (include/lstm_b200.h): owns all device memory, one compute
+// stream, one communication stream and (optionally) one NCCL communicator.
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/lstm_b200.h"
+
+struct Bf16State;  // bf16 tensor-core path state (tc_path.cu)
+
+struct lstm_ctx {
+  int M = 0, N = 0, S = 0, B = 0, T = 0, device = 0, dtype = 0;
+  cudaStream_t st = nullptr, comm_st = nullptr;
+  cudaEvent_t ev_bucket[2] = {nullptr, nullptr}, ev_comm[2] = {nullptr, nullptr};
+  // flat parameter / gradient / Adagrad-memory vectors, tensor order W,U,b,Why,by (column-major each)
+  size_t P = 0, off[5] = {0, 0, 0, 0, 0}, sz[5] = {0, 0, 0, 0, 0};
+  float *params = nullptr, *grads = nullptr, *mem = nullptr;
+  // activations (layouts in kernels.h)
+  float *Hs = nullptr, *Cs = nullptr, *Gs = nullptr, *dY = nullptr, *dHy = nullptr, *dG = nullptr;
+  float *dcnext = nullptr, *surp = nullptr;
+  int *xs = nullptr, *tg = nullptr;
+  double* d_loss = nullptr;  // [loss_cap] per-iteration losses
+  size_t loss_cap = 0;
+  double* h_loss_pinned = nullptr;
+  // device text pipeline
+  uint8_t* text = nullptr;
+  size_t text_len = 0;
+  unsigned long long *pos0 = nullptr, *vcount = nullptr;
+  std::vector<uint64_t> h_pos0;
+  uint64_t v_host = 0;
+  // data parallel
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  // bookkeeping
+  bool fwd_done = false;
+  long launches = 0;
+  long iteration = 0;
+  std::string err;
+  // profiling
+  bool profiling = false;
+  cudaEvent_t pev[16] = {};
+  float phase_ms[16] = {};
+  Bf16State* tc = nullptr;
+
+  float* p(int which) const { return params + off[which]; }
+  float* g(int which) const { return grads + off[which]; }
+  float* m(int which) const { return mem + off[which]; }
+  float* Hslot(int t) const { return Hs + (size_t)t * B * N; }
+  float* Cslot(int t) const { return Cs + (size_t)t * B * N; }
+};
+
+int lstm_fail(lstm_ctx* c, int code, const std::string& msg);
+
+#define LSTM_CUDA(call)                                                                               \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess)                                                                            \
+      return lstm_fail(ctx, LSTM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+  } while (0)
+#define LSTM_NCCL(call)                                                                               \
+  do {                                                                                                \
+    ncclResult_t r_ = (call);                                                                         \
+    if (r_ != ncclSuccess)                                                                            \
+      return lstm_fail(ctx, LSTM_ERR_NCCL, std::string(#call) + ": " + ncclGetErrorString(r_));       \
+  } while (0)
+#define LSTM_LAUNCHED(n)                                                                              \
+  do {                                                                                                \
+    ctx->launches += (n);                                                                             \
+    cudaError_t e_ = cudaGetLastError();                                                              \
+    if (e_ != cudaSuccess)                                                                            \
+      return lstm_fail(ctx, LSTM_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_));  \
+  } while (0)
+
+// bf16 tensor-core path (tc_path.cu); all return 0 or a negative LSTM_ERR_*
+int tc_create(lstm_ctx* ctx);
+void tc_destroy(lstm_ctx* ctx);
+int tc_params_changed(lstm_ctx* ctx);  // refresh bf16 operand copies from the fp32 masters
+int tc_forward(lstm_ctx* ctx);
+int tc_backward(lstm_ctx* ctx);
+int tc_get_activation(lstm_ctx* ctx, int what, int t, float* out, size_t n);

@@ -1,0 +1,50 @@
+// kernels.h — launcher prototypes of the hand-written sm_100a kernels (host-callable, C++).
+// Layouts (all device memory, T = S-1 active timesteps, "slot" = timestep index):
+//   params/grads/adagrad memory : column-major float32 like the reference's Eigen matrices:
+//        W[m*4N + r], U[k*4N + r], b[r], Why[n*M + m], by[m]   (R/lstm.cc:65-70)
+//   Hs, Cs : [(T+1)][B][N]   h_t / c_t of stream b at slot t (slot 0 = carried-in state)
+//   Gs     : [T][B][4N]      activated gates [i o f u] of timestep t at slot t-1 (R/lstm.cc:77)
+//   dY     : [T][B][M]       logits -> probs - onehot(target) (R/lstm.cc:195-201,225)
+//   dHy    : [T][B][N]       Why^T dy (R/lstm.cc:228 without dhnext)
+//   dG     : [T][B][4N]      gate pre-activation gradients (R/lstm.cc:238-247)
+//   xs, tg : [S][B] int32    input / target byte, -1 = all-zero column; row 0 unused
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lstm {
+
+// ---- K10 data pipeline (R/lstm.cc:155-170, OV/lstm_eigen_opt/lstm.cc:190-213) ----
+void launch_window_advance(const uint8_t* text, size_t len, const unsigned long long* pos0,
+                           unsigned long long* v_counter, int stride, int S, int B, int* xs, int* tg,
+                           cudaStream_t st);
+
+// ---- fp32 SIMT path ----
+void launch_step_fwd_f32(const float* U, const float* W, const float* bias, const float* hprev,
+                         const float* cprev, const int* x, float* g, float* c, float* h, int B, int N,
+                         cudaStream_t st);
+void launch_step_bwd_f32(const float* U, const float* dg_next, const float* dHy_t, const float* g_t,
+                         const float* c_t, const float* c_prev, float* dcnext, float* dg_t, int B, int N,
+                         int first, cudaStream_t st);
+// C(i,j) = sum_k A(i,k) B(k,j) (+ bias[j]); element strides given explicitly
+void launch_gemm_f32(const float* A, long a_si, long a_sk, const float* Bm, long b_sk, long b_sj, float* C,
+                     long c_si, long c_sj, const float* bias_j, int I, int J, int K, cudaStream_t st);
+// rows of `y` ([rows][M] logits) -> p - onehot(tg) in place; surp[row] = -log2 p[tg] (0 if tg < 0)
+void launch_softmax_ce_f32(float* y, const int* tg, float* surp, int rows, int M, cudaStream_t st);
+// loss = sum_t (float)(sum_b surp[t][b]) / B  -> out[0] (double)
+void launch_loss_reduce(const float* surp, int T, int B, double* out, cudaStream_t st);
+// dW[m*4N + r] = sum over (t,b) with xs[t][b] == m of dG[t][b][r]   (R/lstm.cc:251 for one-hot x)
+void launch_dw_scatter_f32(const float* dG, const int* xs, float* dW, int rows, int N4, int M, cudaStream_t st);
+// out[j] = sum_i X[i*J + j]
+void launch_colsum_f32(const float* X, float* out, int I, int J, cudaStream_t st);
+// K7 Adagrad (R/lstm.cc:259-272) over a flat parameter vector
+void launch_adagrad_f32(float* p, const float* d, float* m, size_t n, float lr, double eps, float clip,
+                        cudaStream_t st);
+// batch-1 serial recurrence: mode 0 = eval (test(), OV/lstm_eigen_class_CUDA/lstm.cc:661-720),
+// mode 1 = sample (R/lstm.cc:293-356), mode 2 = greedy sample
+void launch_recur_b1_f32(const float* W, const float* U, const float* bias, const float* Why, const float* by,
+                         int M, int N, int mode, const uint8_t* text, size_t n, const float* uniforms,
+                         const float* h0, const float* c0, uint8_t* out, double* bits_out, cudaStream_t st);
+void launch_fill_f32(float* p, float v, size_t n, cudaStream_t st);
+
+}  // namespace lstm

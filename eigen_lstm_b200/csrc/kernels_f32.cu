@@ -1,0 +1,533 @@
+// kernels_f32.cu — fp32 SIMT kernels: the parity path (per-step loss within 1e-4 relative of the
+// reference's Eigen CPU path) and the elementwise / data-pipeline kernels shared by both dtypes.
+// Every kernel cites the reference statement(s) it computes (R/ = reference root).
+#include "kernels.h"
+
+#include <math.h>
+
+namespace lstm {
+
+// ------------------------------------------------------------------------------------------------
+// scalar functions, written to round like the reference's scalar code (no FMA contraction where
+// the reference has separate multiply and add: g++ -O3 on x86-64 baseline does not fuse)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float logistic_f(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }  // R/lstm.cc:31-33
+__device__ __forceinline__ float tanh_prime_f(float x) { return __fsub_rn(1.0f, __fmul_rn(x, x)); }          // :36-38
+__device__ __forceinline__ float logistic_prime_f(float x) { return __fmul_rn(x, __fsub_rn(1.0f, x)); }      // :41-43
+
+// ------------------------------------------------------------------------------------------------
+// 64x64x16 SIMT tile engine: 256 threads, 4x4 register micro-tile per thread.
+//   thread (ty = tid/16, tx = tid%16) owns rows ty*4+v (v<4) and columns u*16+tx (u<4)
+//   (column interleave u*16+tx: the 4 columns of a thread are the 4 GATES of one hidden unit in
+//   the recurrent kernels, and consecutive tx give coalesced stores everywhere)
+// la(ii,k) / lb(k,jj) return the operand element (0 outside the matrix).
+// ------------------------------------------------------------------------------------------------
+constexpr int TM = 64, TN = 64, TK = 16, TPAD = 4;
+
+template <bool A_KCONTIG, bool B_KCONTIG, typename LA, typename LB>
+__device__ __forceinline__ void tile_mainloop(float (&acc)[4][4], int K, LA la, LB lb) {
+  __shared__ __align__(16) float As[TK][TM + TPAD];
+  __shared__ __align__(16) float Bs[TK][TN + TPAD];
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+#pragma unroll
+  for (int v = 0; v < 4; v++)
+#pragma unroll
+    for (int u = 0; u < 4; u++) acc[v][u] = 0.f;
+  float ar[4], br[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      if (A_KCONTIG) ar[r] = la((tid >> 4) + 16 * r, k0 + (tid & 15));
+      else           ar[r] = la(tid & 63, k0 + (tid >> 6) + 4 * r);
+      if (B_KCONTIG) br[r] = lb(k0 + (tid & 15), (tid >> 4) + 16 * r);
+      else           br[r] = lb(k0 + (tid >> 6) + 4 * r, tid & 63);
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += TK) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      if (A_KCONTIG) As[tid & 15][(tid >> 4) + 16 * r] = ar[r];
+      else           As[(tid >> 6) + 4 * r][tid & 63] = ar[r];
+      if (B_KCONTIG) Bs[tid & 15][(tid >> 4) + 16 * r] = br[r];
+      else           Bs[(tid >> 6) + 4 * r][tid & 63] = br[r];
+    }
+    __syncthreads();
+    if (k0 + TK < K) fetch(k0 + TK);
+#pragma unroll
+    for (int kk = 0; kk < TK; kk++) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float a[4] = {av.x, av.y, av.z, av.w};
+      float b[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) b[u] = Bs[kk][u * 16 + tx];
+#pragma unroll
+      for (int v = 0; v < 4; v++)
+#pragma unroll
+        for (int u = 0; u < 4; u++) acc[v][u] = fmaf(a[v], b[u], acc[v][u]);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 (fp32): one recurrent timestep, fused.  R/lstm.cc:176-192
+//   g = W*x + U*h(t-1) + b ; sigmoid on [i o f], tanh on u ; c = tanh(i*u + f*c(t-1)) ; h = o*c
+// grid (ceil(N/16), ceil(B/64)); tile rows = streams b, tile cols = 4 gates x 16 hidden units.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_step_fwd_f32(const float* __restrict__ U, const float* __restrict__ W,
+                                                      const float* __restrict__ bias, const float* __restrict__ hprev,
+                                                      const float* __restrict__ cprev, const int* __restrict__ x,
+                                                      float* __restrict__ g, float* __restrict__ c,
+                                                      float* __restrict__ h, int B, int N) {
+  const int j0 = blockIdx.x * 16, b0 = blockIdx.y * 64;
+  const int N4 = 4 * N;
+  float acc[4][4];
+  auto la = [&](int ii, int k) -> float {  // A(b,k) = h(t-1)[b][k]
+    const int b = b0 + ii;
+    return (b < B && k < N) ? hprev[(size_t)b * N + k] : 0.f;
+  };
+  auto lb = [&](int k, int jj) -> float {  // B(k, gate*16+unit) = U(gate*N + j, k)
+    const int j = j0 + (jj & 15);
+    return (k < N && j < N) ? U[(size_t)k * N4 + (jj >> 4) * N + j] : 0.f;
+  };
+  tile_mainloop<true, false>(acc, N, la, lb);
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const int j = j0 + tx;
+  if (j >= N) return;
+#pragma unroll
+  for (int v = 0; v < 4; v++) {
+    const int b = b0 + ty * 4 + v;
+    if (b >= B) continue;
+    const int xb = x[b];
+    float pre[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const float wx = (xb >= 0) ? W[(size_t)xb * N4 + u * N + j] : 0.f;  // W*x for one-hot x = column x
+      pre[u] = __fadd_rn(__fadd_rn(wx, acc[v][u]), bias[u * N + j]);
+    }
+    const float gi = logistic_f(pre[0]), go = logistic_f(pre[1]), gf = logistic_f(pre[2]);
+    const float gu = tanhf(pre[3]);
+    const float cp = cprev[(size_t)b * N + j];
+    const float cc = tanhf(__fadd_rn(__fmul_rn(gi, gu), __fmul_rn(gf, cp)));  // carried value is tanh'd (:189)
+    float* gb = g + (size_t)b * N4;
+    gb[j] = gi; gb[N + j] = go; gb[2 * N + j] = gf; gb[3 * N + j] = gu;
+    c[(size_t)b * N + j] = cc;
+    h[(size_t)b * N + j] = __fmul_rn(go, cc);
+  }
+}
+
+void launch_step_fwd_f32(const float* U, const float* W, const float* bias, const float* hprev,
+                         const float* cprev, const int* x, float* g, float* c, float* h, int B, int N,
+                         cudaStream_t st) {
+  dim3 grid((N + 15) / 16, (B + 63) / 64);
+  k_step_fwd_f32<<<grid, 256, 0, st>>>(U, W, bias, hprev, cprev, x, g, c, h, B, N);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5 (fp32): one BPTT timestep, fused.  R/lstm.cc:228-256
+//   dh = Why^T dy (precomputed dHy) + U^T dg(t+1) ; dc = (dh*o + dcnext) * (1 - c^2) ;
+//   do, di, df, du through sigmoid'/tanh' ; dcnext = dc * f
+// grid (ceil(N/64), ceil(B/64)); tile rows = streams, cols = hidden units; K = 4N.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_step_bwd_f32(const float* __restrict__ U, const float* __restrict__ dg_next,
+                                                      const float* __restrict__ dHy, const float* __restrict__ g,
+                                                      const float* __restrict__ c, const float* __restrict__ cprev,
+                                                      float* __restrict__ dcnext, float* __restrict__ dg, int B,
+                                                      int N, int first) {
+  const int j0 = blockIdx.x * 64, b0 = blockIdx.y * 64;
+  const int N4 = 4 * N;
+  float acc[4][4];
+  if (!first) {
+    auto la = [&](int ii, int r) -> float {  // A(b,r) = dg(t+1)[b][r]
+      const int b = b0 + ii;
+      return (b < B && r < N4) ? dg_next[(size_t)b * N4 + r] : 0.f;
+    };
+    auto lb = [&](int r, int jj) -> float {  // B(r,j) = U(r,j)
+      const int j = j0 + jj;
+      return (r < N4 && j < N) ? U[(size_t)j * N4 + r] : 0.f;
+    };
+    tile_mainloop<true, true>(acc, N4, la, lb);
+  } else {
+#pragma unroll
+    for (int v = 0; v < 4; v++)
+#pragma unroll
+      for (int u = 0; u < 4; u++) acc[v][u] = 0.f;
+  }
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+  for (int v = 0; v < 4; v++) {
+    const int b = b0 + ty * 4 + v;
+    if (b >= B) continue;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int j = j0 + u * 16 + tx;
+      if (j >= N) continue;
+      const size_t bj = (size_t)b * N + j;
+      const float* gb = g + (size_t)b * N4;
+      const float gi = gb[j], go = gb[N + j], gf = gb[2 * N + j], gu = gb[3 * N + j];
+      const float ct = c[bj], cp = cprev[bj];
+      const float dh = __fadd_rn(dHy[bj], acc[v][u]);                             // :228
+      float dc = __fadd_rn(__fmul_rn(dh, go), first ? 0.f : dcnext[bj]);          // :233
+      dc = __fmul_rn(dc, tanh_prime_f(ct));                                       // :235
+      float* dgb = dg + (size_t)b * N4;
+      dgb[N + j] = __fmul_rn(__fmul_rn(dh, ct), logistic_prime_f(go));            // do :238,244
+      dgb[j] = __fmul_rn(__fmul_rn(dc, gu), logistic_prime_f(gi));                // di :239,244
+      dgb[2 * N + j] = __fmul_rn(__fmul_rn(dc, cp), logistic_prime_f(gf));        // df :240,244
+      dgb[3 * N + j] = __fmul_rn(__fmul_rn(dc, gi), tanh_prime_f(gu));            // du :241,247
+      dcnext[bj] = __fmul_rn(dc, gf);                                             // :256
+    }
+  }
+}
+
+void launch_step_bwd_f32(const float* U, const float* dg_next, const float* dHy_t, const float* g_t,
+                         const float* c_t, const float* c_prev, float* dcnext, float* dg_t, int B, int N,
+                         int first, cudaStream_t st) {
+  dim3 grid((N + 63) / 64, (B + 63) / 64);
+  k_step_bwd_f32<<<grid, 256, 0, st>>>(U, dg_next, dHy_t, g_t, c_t, c_prev, dcnext, dg_t, B, N, first);
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic strided GEMM (K3 logits, K4 dHy, K6a dU, K6c dWhy in the fp32 path)
+// ------------------------------------------------------------------------------------------------
+template <bool AK, bool BK>
+__global__ void __launch_bounds__(256) k_gemm_f32(const float* __restrict__ A, long a_si, long a_sk,
+                                                  const float* __restrict__ Bm, long b_sk, long b_sj,
+                                                  float* __restrict__ C, long c_si, long c_sj,
+                                                  const float* __restrict__ bias_j, int I, int J, int K) {
+  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  float acc[4][4];
+  auto la = [&](int ii, int k) -> float {
+    const int i = i0 + ii;
+    return (i < I && k < K) ? A[(size_t)i * a_si + (size_t)k * a_sk] : 0.f;
+  };
+  auto lb = [&](int k, int jj) -> float {
+    const int j = j0 + jj;
+    return (j < J && k < K) ? Bm[(size_t)k * b_sk + (size_t)j * b_sj] : 0.f;
+  };
+  tile_mainloop<AK, BK>(acc, K, la, lb);
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+  for (int v = 0; v < 4; v++) {
+    const int i = i0 + ty * 4 + v;
+    if (i >= I) continue;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int j = j0 + u * 16 + tx;
+      if (j >= J) continue;
+      float r = acc[v][u];
+      if (bias_j) r = __fadd_rn(r, bias_j[j]);
+      C[(size_t)i * c_si + (size_t)j * c_sj] = r;
+    }
+  }
+}
+
+void launch_gemm_f32(const float* A, long a_si, long a_sk, const float* Bm, long b_sk, long b_sj, float* C,
+                     long c_si, long c_sj, const float* bias_j, int I, int J, int K, cudaStream_t st) {
+  dim3 grid((J + 63) / 64, (I + 63) / 64);
+  const bool ak = (a_sk == 1), bk = (b_sk == 1);
+  if (ak && bk)       k_gemm_f32<true, true><<<grid, 256, 0, st>>>(A, a_si, a_sk, Bm, b_sk, b_sj, C, c_si, c_sj, bias_j, I, J, K);
+  else if (ak && !bk) k_gemm_f32<true, false><<<grid, 256, 0, st>>>(A, a_si, a_sk, Bm, b_sk, b_sj, C, c_si, c_sj, bias_j, I, J, K);
+  else if (!ak && bk) k_gemm_f32<false, true><<<grid, 256, 0, st>>>(A, a_si, a_sk, Bm, b_sk, b_sj, C, c_si, c_sj, bias_j, I, J, K);
+  else                k_gemm_f32<false, false><<<grid, 256, 0, st>>>(A, a_si, a_sk, Bm, b_sk, b_sj, C, c_si, c_sj, bias_j, I, J, K);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 epilogue (fp32 path): softmax + loss + dy.  R/lstm.cc:199-207,225
+//   p = exp(y) / sum(exp(y))  (no max shift, like the reference) ; surp = -log2 p[target] ;
+//   dy = p - onehot(target).  One warp per (t,b) row.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_softmax_ce_f32(float* __restrict__ y, const int* __restrict__ tg,
+                                                        float* __restrict__ surp, int rows, int M) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float* yr = y + (size_t)row * M;
+  float s = 0.f;
+  for (int m = lane; m < M; m += 32) {
+    const float e = expf(yr[m]);
+    yr[m] = e;
+    s += e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const int k = tg[row];
+  for (int m = lane; m < M; m += 32) {
+    const float p = __fdiv_rn(yr[m], s);
+    if (m == k) surp[row] = -log2f(p);
+    yr[m] = (m == k) ? __fsub_rn(p, 1.0f) : p;
+  }
+  if (k < 0 && lane == 0) surp[row] = 0.f;
+}
+
+void launch_softmax_ce_f32(float* y, const int* tg, float* surp, int rows, int M, cudaStream_t st) {
+  k_softmax_ce_f32<<<(rows + 7) / 8, 256, 0, st>>>(y, tg, surp, rows, M);
+}
+
+// loss = sum_t (float)(sum_b surp[t][b]) / (float)B    (OV/lstm_eigen_opt/lstm.cc:246-249)
+__global__ void __launch_bounds__(1024) k_loss_reduce(const float* __restrict__ surp, int T, int B,
+                                                      double* __restrict__ out) {
+  extern __shared__ float st_sum[];  // [T]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = warp; t < T; t += 32) {
+    float s = 0.f;
+    for (int b = lane; b < B; b += 32) s += surp[(size_t)t * B + b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) st_sum[t] = s / (float)B;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double l = 0.0;
+    for (int t = 0; t < T; t++) l += (double)st_sum[t];
+    out[0] = l;
+  }
+}
+
+void launch_loss_reduce(const float* surp, int T, int B, double* out, cudaStream_t st) {
+  k_loss_reduce<<<1, 1024, T * sizeof(float), st>>>(surp, T, B, out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6b (fp32 path): dW += dg * x^T for one-hot x is a segmented column sum (R/lstm.cc:251).
+// One CTA per (symbol m, 256-row chunk of the 4N gate rows); deterministic (fixed (t,b) order).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dw_scatter_f32(const float* __restrict__ dG, const int* __restrict__ xs,
+                                                        float* __restrict__ dW, int rows, int N4) {
+  const int m = blockIdx.y;
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  __shared__ int sx[256];
+  float acc = 0.f;
+  for (int base = 0; base < rows; base += 256) {
+    const int i = base + threadIdx.x;
+    sx[threadIdx.x] = (i < rows) ? xs[i] : -1;
+    __syncthreads();
+    const int lim = min(256, rows - base);
+    if (r < N4)
+      for (int q = 0; q < lim; q++)
+        if (sx[q] == m) acc += dG[(size_t)(base + q) * N4 + r];
+    __syncthreads();
+  }
+  if (r < N4) dW[(size_t)m * N4 + r] = acc;
+}
+
+void launch_dw_scatter_f32(const float* dG, const int* xs, float* dW, int rows, int N4, int M, cudaStream_t st) {
+  dim3 grid((N4 + 255) / 256, M);
+  k_dw_scatter_f32<<<grid, 256, 0, st>>>(dG, xs, dW, rows, N4);
+}
+
+// db += dg (R/lstm.cc:252), dby += dy (:227): column sums of a [I][J] row-major matrix
+__global__ void __launch_bounds__(1024) k_colsum_f32(const float* __restrict__ X, float* __restrict__ out, int I, int J) {
+  __shared__ float red[32][33];
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (j < J)
+    for (int i = threadIdx.y; i < I; i += 32) s += X[(size_t)i * J + j];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < J) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 32; q++) t += red[q][threadIdx.x];
+    out[j] = t;
+  }
+}
+
+void launch_colsum_f32(const float* X, float* out, int I, int J, cudaStream_t st) {
+  k_colsum_f32<<<(J + 31) / 32, dim3(32, 32), 0, st>>>(X, out, I, J);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7 Adagrad, R/lstm.cc:259-272:  m += d*d ; p -= lr * d / sqrtf(m + eps)   (eps added in double,
+// :25,46-48).  HBM-bound: 20 B/param (read d, read+write m, read+write p); 128-bit accesses.
+// clip > 0 clamps d first (north-star addition; 0 = the reference's behaviour).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void adagrad_one(float& p, float d, float& m, float lr, double eps, float clip) {
+  if (clip > 0.f) d = fminf(fmaxf(d, -clip), clip);
+  m = __fadd_rn(m, __fmul_rn(d, d));
+  const float s = sqrtf((float)((double)m + eps));
+  p = __fsub_rn(p, __fmul_rn(lr, __fdiv_rn(d, s)));
+}
+
+__global__ void __launch_bounds__(256) k_adagrad_f32(float* __restrict__ p, const float* __restrict__ d,
+                                                     float* __restrict__ m, size_t n, float lr, double eps,
+                                                     float clip) {
+  const size_t n4 = n >> 2;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 dv = reinterpret_cast<const float4*>(d)[i];
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    adagrad_one(pv.x, dv.x, mv.x, lr, eps, clip);
+    adagrad_one(pv.y, dv.y, mv.y, lr, eps, clip);
+    adagrad_one(pv.z, dv.z, mv.z, lr, eps, clip);
+    adagrad_one(pv.w, dv.w, mv.w, lr, eps, clip);
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+  }
+  // tail
+  for (size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    adagrad_one(p[i], d[i], m[i], lr, eps, clip);
+}
+
+void launch_adagrad_f32(float* p, const float* d, float* m, size_t n, float lr, double eps, float clip,
+                        cudaStream_t st) {
+  size_t blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;  // 8 resident CTAs per SM on 148 SMs, grid-stride
+  if (blocks < 1) blocks = 1;
+  k_adagrad_f32<<<(unsigned)blocks, 256, 0, st>>>(p, d, m, n, lr, eps, clip);
+}
+
+__global__ void k_fill_f32(float* p, float v, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+void launch_fill_f32(float* p, float v, size_t n, cudaStream_t st) {
+  size_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  k_fill_f32<<<(unsigned)blocks, 256, 0, st>>>(p, v, n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K10 data pipeline: text bytes + stream positions -> window index tensors.
+// Closed form of the reference's shift loop (R/lstm.cc:155-170; OV/lstm_eigen_opt/lstm.cc:190-213):
+// stream b has consumed v events; event q of stream b is E_b[q] = text[S + (pos0_b - S + q) mod (len - S)]
+// (positions wrap to S at the end of the text); target column s holds E_b[v-1-(S-1-s)], input column
+// s holds target column s-1; not-yet-filled columns are -1 (the all-zero one-hot).
+// Single CTA: it owns the event counter (so a captured CUDA graph can replay it).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_window_advance(const uint8_t* __restrict__ text, unsigned long long len,
+                                                         const unsigned long long* __restrict__ pos0,
+                                                         unsigned long long* __restrict__ v_counter, int stride,
+                                                         int S, int B, int* __restrict__ xs, int* __restrict__ tg) {
+  __shared__ unsigned long long v_new;
+  if (threadIdx.x == 0) {
+    v_new = v_counter[0] + (unsigned long long)stride;
+    v_counter[0] = v_new;
+  }
+  __syncthreads();
+  const long long v = (long long)v_new;
+  const unsigned long long span = len - (unsigned long long)S;
+  for (int e = threadIdx.x; e < S * B; e += blockDim.x) {
+    const int s = e / B, b = e - s * B;
+    const long long qt = v - 1 - (S - 1 - s);  // event index held by target column s
+    const long long qx = qt - 1;               // input column s = target column s-1
+    const unsigned long long off = pos0[b] - (unsigned long long)S;
+    tg[e] = (qt >= 0) ? (int)text[S + (off + (unsigned long long)qt) % span] : -1;
+    xs[e] = (qx >= 0) ? (int)text[S + (off + (unsigned long long)qx) % span] : -1;
+  }
+}
+
+void launch_window_advance(const uint8_t* text, size_t len, const unsigned long long* pos0,
+                           unsigned long long* v_counter, int stride, int S, int B, int* xs, int* tg,
+                           cudaStream_t st) {
+  k_window_advance<<<1, 1024, 0, st>>>(text, (unsigned long long)len, pos0, v_counter, stride, S, B, xs, tg);
+}
+
+// ------------------------------------------------------------------------------------------------
+// batch-1 serial recurrence, single CTA (first version of K9 / test()).
+//   eval  : for ii in [0, n-1): step on text[ii], bits += -log2 p[text[ii+1]]   (class_CUDA/lstm.cc:661-720)
+//   sample: for i in [0, n): p from current h, draw, emit, step on the drawn byte (R/lstm.cc:313-350)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_recur_b1_f32(const float* __restrict__ W, const float* __restrict__ U,
+                                                       const float* __restrict__ bias, const float* __restrict__ Why,
+                                                       const float* __restrict__ by, int M, int N, int mode,
+                                                       const uint8_t* __restrict__ text, size_t n,
+                                                       const float* __restrict__ uniforms, const float* __restrict__ h0,
+                                                       const float* __restrict__ c0, uint8_t* __restrict__ out,
+                                                       double* __restrict__ bits_out) {
+  extern __shared__ float sm[];
+  float* h = sm;              // [N]
+  float* c = h + N;           // [N]
+  float* g = c + N;           // [4N]
+  float* p = g + 4 * N;       // [M]
+  float* part = p + M;        // [4][M] partial logits
+  __shared__ float s_sum;
+  __shared__ int s_index;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int N4 = 4 * N;
+  for (int j = tid; j < N; j += nt) { h[j] = h0 ? h0[j] : 0.f; c[j] = c0 ? c0[j] : 0.f; }
+  __syncthreads();
+  double bits = 0.0;
+
+  auto cell = [&](int x) {
+    for (int r = tid; r < N4; r += nt) {
+      float acc = 0.f;
+      for (int k = 0; k < N; k++) acc = fmaf(U[(size_t)k * N4 + r], h[k], acc);
+      const float wx = (x >= 0) ? W[(size_t)x * N4 + r] : 0.f;
+      const float pre = __fadd_rn(__fadd_rn(wx, acc), bias[r]);
+      g[r] = (r < 3 * N) ? logistic_f(pre) : tanhf(pre);
+    }
+    __syncthreads();
+    for (int j = tid; j < N; j += nt) {
+      const float cc = tanhf(__fadd_rn(__fmul_rn(g[j], g[3 * N + j]), __fmul_rn(g[2 * N + j], c[j])));
+      c[j] = cc;
+      h[j] = __fmul_rn(g[N + j], cc);
+    }
+    __syncthreads();
+  };
+  auto softmax = [&]() {
+    // y = Why*h + by with the N range split in 4 chunks over the 1024 threads (needs M <= 256)
+    const int chunk = tid / 256, m = tid % 256;
+    if (m < M) {
+      float acc = 0.f;
+      const int n0 = (int)((long)N * chunk / 4), n1 = (int)((long)N * (chunk + 1) / 4);
+      for (int q = n0; q < n1; q++) acc = fmaf(Why[(size_t)q * M + m], h[q], acc);
+      part[chunk * M + m] = acc;
+    }
+    __syncthreads();
+    if (tid < M) p[tid] = expf(__fadd_rn(((part[tid] + part[M + tid]) + part[2 * M + tid]) + part[3 * M + tid], by[tid]));
+    __syncthreads();
+    if (tid < 32) {
+      float s = 0.f;
+      for (int q = tid; q < M; q += 32) s += p[q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (tid == 0) s_sum = s;
+    }
+    __syncthreads();
+    if (tid < M) p[tid] = __fdiv_rn(p[tid], s_sum);
+    __syncthreads();
+  };
+
+  if (mode == 0) {
+    for (size_t ii = 0; ii + 1 < n; ii++) {
+      cell((int)text[ii]);
+      softmax();
+      if (tid == 0) bits += -log2((double)p[text[ii + 1]]);
+    }
+    if (tid == 0) bits_out[0] = bits;
+  } else {
+    for (size_t i = 0; i < n; i++) {
+      softmax();
+      if (tid == 0) {
+        int index = 0;
+        if (mode == 2) {
+          for (int q = 1; q < M; q++) if (p[q] > p[index]) index = q;
+        } else {
+          const float r = uniforms[i];
+          float cdf = 0.f;
+          for (int q = 0; q < M; q++) {  // cdf(ii) = cdf(ii-1) + probs(ii), first r < cdf (R/lstm.cc:321-338)
+            cdf = (q == 0) ? p[0] : __fadd_rn(cdf, p[q]);
+            if (r < cdf) { index = q; break; }
+          }
+        }
+        s_index = index;
+        out[i] = (uint8_t)index;
+      }
+      __syncthreads();
+      cell(s_index);
+    }
+  }
+}
+
+void launch_recur_b1_f32(const float* W, const float* U, const float* bias, const float* Why, const float* by,
+                         int M, int N, int mode, const uint8_t* text, size_t n, const float* uniforms,
+                         const float* h0, const float* c0, uint8_t* out, double* bits_out, cudaStream_t st) {
+  const size_t smem = sizeof(float) * ((size_t)6 * N + (size_t)5 * M);
+  cudaFuncSetAttribute(k_recur_b1_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k_recur_b1_f32<<<1, 1024, smem, st>>>(W, U, bias, Why, by, M, N, mode, text, n, uniforms, h0, c0, out, bits_out);
+}
+
+}  // namespace lstm

@@ -418,6 +418,8 @@ std::vector<R>* pick(Oracle<R>* o, int kind, int which) {
     memcpy(tg, o->ti.data(), sizeof(int) * o->ti.size()); }                                           \
   extern "C" void PFX##_set_positions(void* o_, const uint64_t* p) {                                  \
     auto* o = (Oracle<R>*)o_; for (int i = 0; i < o->B; i++) o->pos[i] = (size_t)p[i]; }              \
+  extern "C" void PFX##_get_positions(void* o_, uint64_t* p) {                                        \
+    auto* o = (Oracle<R>*)o_; for (int i = 0; i < o->B; i++) p[i] = (uint64_t)o->pos[i]; }            \
   extern "C" double PFX##_forward(void* o) { return ((Oracle<R>*)o)->forward(); }                     \
   extern "C" void PFX##_backward(void* o) { ((Oracle<R>*)o)->backward(); }                            \
   extern "C" void PFX##_adagrad(void* o, double lr) { ((Oracle<R>*)o)->adagrad((R)lr); }              \

@@ -115,6 +115,11 @@ class Oracle:
         assert p.size == self.B
         self._f("set_positions")(self.o, p.ctypes.data_as(C.c_void_p))
 
+    def positions(self):
+        p = np.empty(self.B, dtype=np.uint64)
+        self._f("get_positions")(self.o, p.ctypes.data_as(C.c_void_p))
+        return p
+
     def forward(self):
         return float(self._f("forward")(self.o))
 

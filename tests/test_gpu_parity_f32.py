@@ -1,0 +1,243 @@
+"""GPU (fp32 SIMT path) vs the CPU oracle, through the C ABI.  Mirrors the reference's own
+CPU<->GPU lock-step checks (OV/lstm_eigen_CUDA/lstm.cu:416-497,564-648; compare_lstm_states,
+OV/lstm_eigen_class_CUDA/cu_lstm.h:398-415) with explicit thresholds."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.util import make_pair, random_window, rel_err
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [  # (M, N, S, B)
+    (256, 64, 3, 1),     # R/lstm.cc defaults
+    (256, 32, 5, 4),     # OV/lstm_eigen_class_batch defaults
+    (256, 20, 7, 3),     # N not a multiple of the tile (OV/lstm_eigen_class: N = 20)
+    (100, 72, 4, 70),    # B beyond one 64-row tile, M < 256
+    (256, 128, 12, 16),
+]
+
+
+@pytest.mark.parametrize("M,N,S,B", SHAPES)
+def test_forward_backward_every_intermediate(M, N, S, B):
+    o, g, _ = make_pair(M, N, S, B, seed=1)
+    rng = np.random.default_rng(5)
+    x, t = random_window(rng, M, S, B)
+    o.set_window(x, t)
+    lo = o.forward()
+    lg = g.forward(x, t)
+    assert abs(lg - lo) <= 2e-6 * abs(lo), (lg, lo)
+    for tt in range(1, S):
+        for what in ("g", "c", "h", "probs"):
+            assert rel_err(g.activation(what, tt), o.state(what, tt)) < 5e-6, (what, tt)
+    o.backward()
+    g.backward()
+    for tt in range(1, S):
+        assert rel_err(g.activation("dg", tt), o.state("dg", tt)) < 2e-5, ("dg", tt)
+    for name, a, b in zip(orc.NAMES, g.grads(), o.grads()):
+        assert rel_err(a, b) < 2e-5, name
+    o.adagrad(0.1)
+    g.adagrad(0.1)
+    for name, a, b in zip(orc.NAMES, g.params(), o.params()):
+        assert rel_err(a, b) < 1e-5, name
+    for name, a, b in zip(orc.NAMES, g.adagrad_mem(), [o.get(orc.MEM, i) for i in range(5)]):
+        assert rel_err(a, b) < 4e-5, name
+
+
+def test_adagrad_kernel_bit_exact():
+    """Same gradients in, same update out: m += d*d ; p -= lr*d/sqrtf(m+eps) (R/lstm.cc:259-272)."""
+    M, N, S, B = 256, 24, 3, 2
+    o, g, params = make_pair(M, N, S, B, seed=3)
+    rng = np.random.default_rng(0)
+    for it in range(3):
+        for w in range(5):
+            d = rng.normal(0, 10.0 ** rng.integers(-6, 1), params[w].shape).astype(np.float32)
+            o.set(orc.GRAD, w, d)
+            g.set(1, w, d)
+        o.adagrad(0.1)
+        g.adagrad(0.1)
+        for a, b in zip(g.params(), o.params()):
+            assert np.array_equal(a, b)
+        for w in range(5):
+            assert np.array_equal(g.get(2, w), o.get(orc.MEM, w))
+
+
+def test_cfg1_loss_trace_1000_iterations(alice):
+    """North-star: fp32 path matches the Eigen path's per-step loss within 1e-4 relative over the
+    first 1000 iterations (R/lstm.cc defaults: N=64, M=256, S=3, B=1, lr=0.1, alice29.txt)."""
+    M, N, S, B = 256, 64, 3, 1
+    params = orc.init_params(M, N, seed=1234, sd=0.01)
+    h0 = orc.randn(N, S, 0, 0.1, 77)[:, 1:2]   # column that becomes h(0) after the first shift (R/lstm.cc:146,163)
+    c0 = orc.randn(N, S, 0, 0.1, 78)[:, 1:2]
+    import eigen_lstm_b200 as el
+    o = orc.Oracle(M, N, S, B, "f32")
+    o.set_params(params); o.set_state("h", 1, h0); o.set_state("c", 1, c0)   # carry(1) moves slot 1 -> 0
+    ref, _ = o.train(alice, 1000, stride=1, lr=0.1)
+    g = el.LSTM(M, N, S, B)
+    g.set_params(params); g.set_state(h0, c0)
+    g.load_text(alice)
+    # the GPU context carries h(stride) -> h(0) as well; park the injected state in slot `stride` by
+    # one zero-cost trick: state is in slot 0 and the first carry copies slot 1, so run the first
+    # iteration through train_step's building blocks instead
+    losses = np.zeros(1000)
+    og = orc.Oracle(M, N, S, B, "f32")  # only used as the window builder (host logic)
+    for i in range(1000):
+        og.advance(alice, 1)
+        x, t = og.window()
+        if i > 0:
+            g.carry(1)
+        losses[i] = g.forward(x, t)
+        g.backward()
+        g.adagrad(0.1)
+    nz = ref > 0
+    err = np.abs(losses[nz] - ref[nz]) / ref[nz]
+    assert err.max() <= 1e-4, (err.max(), int(err.argmax()))
+    assert np.all(losses[~nz] == 0)
+
+
+def test_cfg1_device_pipeline_equals_host_windows(alice):
+    """lstm_train_text (windows built by the K10 kernel) == lstm_train_step with host-built windows."""
+    import eigen_lstm_b200 as el
+    M, N, S, B = 256, 64, 3, 1
+    params = orc.init_params(M, N, seed=9, sd=0.01)
+    a = el.LSTM(M, N, S, B); a.set_params(params); a.load_text(alice)
+    b = el.LSTM(M, N, S, B); b.set_params(params)
+    la = a.train_text(200, stride=1, lr=0.1)
+    og = orc.Oracle(M, N, S, B, "f32")
+    lb = np.zeros(200)
+    for i in range(200):
+        og.advance(alice, 1)
+        x, t = og.window()
+        lb[i] = b.train_step(x, t, stride=1, lr=0.1)
+    assert np.array_equal(la, lb)
+    for p, q in zip(a.params(), b.params()):
+        assert np.array_equal(p, q)
+
+
+@pytest.mark.parametrize("stride", [1, 9])
+def test_batched_trajectory(enwik6, stride):
+    """cfg2-style (batched, forget bias 1, random stream positions) at a size the oracle finishes in seconds."""
+    import eigen_lstm_b200 as el
+    M, N, S, B = 256, 48, 10, 8
+    params = orc.init_params(M, N, seed=21, sd=0.01, forget_bias=1.0)
+    rng = np.random.default_rng(2)
+    pos = rng.integers(S, len(enwik6), B)
+    pos[0] = len(enwik6) - 5  # wraps to S almost immediately (OV/lstm_eigen_opt/lstm.cc:196-197)
+    o = orc.Oracle(M, N, S, B, "f32"); o.set_params(params); o.set_positions(pos)
+    g = el.LSTM(M, N, S, B); g.set_params(params); g.load_text(enwik6); g.set_positions(pos)
+    iters = 60
+    ref, _ = o.train(enwik6, iters, stride=stride, lr=0.1)
+    got = g.train_text(iters, stride=stride, lr=0.1)
+    nz = ref > 0
+    assert np.max(np.abs(got[nz] - ref[nz]) / ref[nz]) < 1e-4
+    xo, to = o.window(); xg, tg = g.window()
+    assert np.array_equal(xo[1:], xg[1:]) and np.array_equal(to[1:], tg[1:])
+    assert np.array_equal(g.positions(), o.positions())
+
+
+def test_window_kernel_bit_exact(alice):
+    """K10 vs the literal shift loop, through warm-up (-1 columns), many strides and text wrap-around."""
+    import eigen_lstm_b200 as el
+    M, N, S, B = 256, 16, 6, 5
+    text = alice[:200]
+    pos = [6, 50, 199, 120, 7]
+    o = orc.Oracle(M, N, S, B, "f32"); o.set_positions(pos)
+    g = el.LSTM(M, N, S, B); g.init_params(1); g.load_text(text); g.set_positions(pos)
+    for stride in [1, 1, 1, 2, 5, 1, 3, 5, 5, 4] * 12:
+        o.advance(text, stride)
+        g.train_text(1, stride=stride, lr=0.0, want_losses=False)
+        xo, to = o.window(); xg, tg = g.window()
+        assert np.array_equal(xo[1:], xg[1:]) and np.array_equal(to[1:], tg[1:])
+
+
+def test_enwik5_known_answer_on_gpu(golden_dir):
+    """test() on the reference's trained N=32 checkpoint: logged 3.24396 bits/char
+    (OV/lstm_eigen_class_CUDA/models/enwik5_test.txt:1)."""
+    import eigen_lstm_b200 as el
+    z = np.load(os.path.join(golden_dir, "enwik5_test.npz"))
+    params = [z["W"], z["U"], z["b"], z["Why"], z["by"]]
+    g = el.LSTM(256, 32, 2, 1); g.set_params(params)
+    bpc = g.test(z["test_bytes"].tobytes())
+    assert abs(bpc - float(z["logged_test_bpc"])) < 2e-4
+    o = orc.Oracle(256, 32, 2, 1, "f32"); o.set_params(params)
+    assert abs(bpc - o.eval_bpc(z["test_bytes"].tobytes())) < 1e-5
+
+
+def test_untrained_bpc_is_8_on_gpu(enwik6):
+    import eigen_lstm_b200 as el
+    g = el.LSTM(256, 32, 3, 4); g.init_params(1, 0.01, 1.0)
+    assert abs(g.test(enwik6[:2000]) - 8.0) < 5e-3
+
+
+def test_sampling_matches_oracle(golden_dir):
+    """sample(): same uniforms (mt19937(seed)), same weights -> same bytes (R/lstm.cc:293-356)."""
+    import eigen_lstm_b200 as el
+    z = np.load(os.path.join(golden_dir, "enwik5_test.npz"))
+    params = [z["W"], z["U"], z["b"], z["Why"], z["by"]]
+    N = 32
+    g = el.LSTM(256, N, 2, 1); g.set_params(params)
+    o = orc.Oracle(256, N, 2, 1, "f32"); o.set_params(params)
+    h0 = orc.randn(N, 1, 0, 0.1, 5).ravel(); c0 = orc.randn(N, 1, 0, 0.1, 6).ravel()
+    n = 400
+    assert np.array_equal(g.sample(n, seed=11, h0=h0, c0=c0, greedy=True), o.sample(h0, c0, 11, n, greedy=True))
+    a = g.sample(n, seed=11, h0=h0, c0=c0); b = o.sample(h0, c0, 11, n)
+    assert (a == b).mean() > 0.99, (a == b).mean()   # a draw within 1 ulp of a cdf edge may flip one byte
+
+
+def test_init_params_matches_reference_randn():
+    import eigen_lstm_b200 as el
+    M, N = 256, 16
+    g = el.LSTM(M, N, 3, 2); g.init_params(42, 0.01, 1.0)
+    ref = orc.init_params(M, N, seed=42, sd=0.01, forget_bias=1.0)
+    for a, b in zip(g.params(), ref):
+        assert np.array_equal(a, b)
+
+
+def test_text_checkpoint_roundtrip_and_format(tmp_path):
+    """Parameters::save_to_disk / load_from_disk text format (OV/lstm_eigen_class_CUDA/io.h:16-81)."""
+    import eigen_lstm_b200 as el
+    M, N = 256, 8
+    g = el.LSTM(M, N, 3, 1); g.init_params(3, 0.3, 1.0)
+    prefix = str(tmp_path / "ck")
+    g.save_to_disk(prefix)
+    before = g.params()
+    for name, p in zip(orc.NAMES, before):
+        txt = open(f"{prefix}_{name}.txt").read()
+        assert not txt.endswith("\n")
+        rows = txt.split("\n")
+        assert len(rows) == p.shape[0] and len(set(len(r) for r in rows)) == 1  # aligned columns
+        parsed = np.loadtxt(f"{prefix}_{name}.txt", ndmin=2)
+        assert parsed.shape == p.shape
+        assert np.allclose(parsed, p, rtol=1e-5, atol=0)
+    h = el.LSTM(M, N, 3, 1); h.load_from_disk(prefix)
+    for a, b in zip(h.params(), before):
+        assert np.allclose(a, b, rtol=1e-5, atol=0)
+    with pytest.raises(el.LstmError):
+        h.load_from_disk(str(tmp_path / "missing"))
+
+
+def test_bin_checkpoint_resume_bit_exact(alice, tmp_path):
+    import eigen_lstm_b200 as el
+    M, N, S, B = 256, 32, 4, 2
+    a = el.LSTM(M, N, S, B); a.init_params(5); a.load_text(alice); a.set_positions([10, 3000])
+    a.train_text(25, 1, 0.1)
+    path = str(tmp_path / "ck.bin"); a.save_bin(path)
+    la = a.train_text(15, 1, 0.1)
+    b = el.LSTM(M, N, S, B); b.load_text(alice); b.load_bin(path)
+    lb = b.train_text(15, 1, 0.1)
+    assert np.array_equal(la, lb)
+
+
+def test_errors_are_loud():
+    import eigen_lstm_b200 as el
+    g = el.LSTM(256, 8, 3, 1)
+    with pytest.raises(el.LstmError):
+        g.backward()                       # before forward
+    with pytest.raises(el.LstmError):
+        g.train_text(1)                    # no text
+    with pytest.raises(el.LstmError):
+        g.forward(np.full((3, 1), 300), np.zeros((3, 1)))   # byte out of range
+    with pytest.raises(el.LstmError):
+        el.LSTM(300, 8, 3, 1)              # M > 256
