@@ -133,9 +133,10 @@ extern "C" int lstm_create(lstm_ctx** out, int M, int N, int S, int B, int devic
   CREATE_CUDA(cudaMemsetAsync(ctx->params, 0, ctx->P * sizeof(float), ctx->st));
   CREATE_CUDA(cudaMemsetAsync(ctx->grads, 0, ctx->P * sizeof(float), ctx->st));
   CREATE_CUDA(cudaMemsetAsync(ctx->mem, 0, ctx->P * sizeof(float), ctx->st));
-  CREATE_CUDA(cudaMalloc(&ctx->Hs, (T + 1) * BN * sizeof(float)));
+  const size_t h_slots = (dtype == LSTM_BF16) ? 1 : T + 1;  // the bf16 path keeps h in bf16 (tc_path.cu); fp32 slot 0 is the API copy
+  CREATE_CUDA(cudaMalloc(&ctx->Hs, h_slots * BN * sizeof(float)));
   CREATE_CUDA(cudaMalloc(&ctx->Cs, (T + 1) * BN * sizeof(float)));
-  CREATE_CUDA(cudaMemsetAsync(ctx->Hs, 0, (T + 1) * BN * sizeof(float), ctx->st));
+  CREATE_CUDA(cudaMemsetAsync(ctx->Hs, 0, h_slots * BN * sizeof(float), ctx->st));
   CREATE_CUDA(cudaMemsetAsync(ctx->Cs, 0, (T + 1) * BN * sizeof(float), ctx->st));
   if (dtype == LSTM_F32) {
     CREATE_CUDA(cudaMalloc(&ctx->Gs, T * B * N4 * sizeof(float)));
@@ -271,6 +272,10 @@ extern "C" int lstm_set_state(lstm_ctx* ctx, const float* h0, const float* c0) {
   else LSTM_CUDA(cudaMemsetAsync(ctx->Hslot(0), 0, bytes, ctx->st));
   if (c0) LSTM_CUDA(cudaMemcpyAsync(ctx->Cslot(0), c0, bytes, cudaMemcpyHostToDevice, ctx->st));
   else LSTM_CUDA(cudaMemsetAsync(ctx->Cslot(0), 0, bytes, ctx->st));
+  if (ctx->tc) {
+    int rc = tc_state_from_f32(ctx);
+    if (rc) return rc;
+  }
   LSTM_CUDA(cudaStreamSynchronize(ctx->st));
   return LSTM_OK;
 }
@@ -279,6 +284,10 @@ extern "C" int lstm_get_state(lstm_ctx* ctx, float* h0, float* c0) {
   if (!ctx) return LSTM_ERR_ARG;
   LSTM_CUDA(cudaSetDevice(ctx->device));
   const size_t bytes = (size_t)ctx->B * ctx->N * sizeof(float);
+  if (ctx->tc && h0) {
+    int rc = tc_state_to_f32(ctx);
+    if (rc) return rc;
+  }
   if (h0) LSTM_CUDA(cudaMemcpyAsync(h0, ctx->Hslot(0), bytes, cudaMemcpyDeviceToHost, ctx->st));
   if (c0) LSTM_CUDA(cudaMemcpyAsync(c0, ctx->Cslot(0), bytes, cudaMemcpyDeviceToHost, ctx->st));
   LSTM_CUDA(cudaStreamSynchronize(ctx->st));
@@ -339,7 +348,7 @@ static int forward_device(lstm_ctx* ctx, size_t loss_slot) {
   return LSTM_OK;
 }
 
-static int allreduce_bucket(lstm_ctx* ctx, int bucket) {
+int lstm_allreduce_bucket(lstm_ctx* ctx, int bucket) {
   // bucket 0 = [W,U,b], bucket 1 = [Why,by]; both contiguous in the flat gradient vector.
   if (ctx->world <= 1) return LSTM_OK;
   float* ptr = bucket == 0 ? ctx->g(LSTM_W) : ctx->g(LSTM_WHY);
@@ -369,7 +378,7 @@ static int backward_device(lstm_ctx* ctx) {
   launch_gemm_f32(ctx->Hslot(1), 1, N, ctx->dY, M, 1, ctx->g(LSTM_WHY), M, 1, nullptr, N, M, BT, ctx->st);
   launch_colsum_f32(ctx->dY, ctx->g(LSTM_BY), BT, M, ctx->st);
   LSTM_LAUNCHED(3);
-  int rc = allreduce_bucket(ctx, 1);
+  int rc = lstm_allreduce_bucket(ctx, 1);
   if (rc) return rc;
   // K5: BPTT recurrence t = T..1
   for (int t = T; t >= 1; t--) {
@@ -386,7 +395,7 @@ static int backward_device(lstm_ctx* ctx) {
   launch_colsum_f32(ctx->dG, ctx->g(LSTM_B), BT, (int)N4, ctx->st);      // (:252)
   LSTM_LAUNCHED(3);
   PROF(6);
-  rc = allreduce_bucket(ctx, 0);
+  rc = lstm_allreduce_bucket(ctx, 0);
   if (rc) return rc;
   return LSTM_OK;
 }
@@ -476,7 +485,12 @@ extern "C" int lstm_carry_state(lstm_ctx* ctx, int stride) {
   if (stride > ctx->T) stride = ctx->T;
   LSTM_CUDA(cudaSetDevice(ctx->device));
   const size_t bytes = (size_t)ctx->B * ctx->N * sizeof(float);
-  LSTM_CUDA(cudaMemcpyAsync(ctx->Hslot(0), ctx->Hslot(stride), bytes, cudaMemcpyDeviceToDevice, ctx->st));
+  if (ctx->tc) {
+    int rc = tc_carry(ctx, stride);
+    if (rc) return rc;
+  } else {
+    LSTM_CUDA(cudaMemcpyAsync(ctx->Hslot(0), ctx->Hslot(stride), bytes, cudaMemcpyDeviceToDevice, ctx->st));
+  }
   LSTM_CUDA(cudaMemcpyAsync(ctx->Cslot(0), ctx->Cslot(stride), bytes, cudaMemcpyDeviceToDevice, ctx->st));
   return LSTM_OK;
 }
@@ -643,7 +657,7 @@ extern "C" int lstm_get_activation(lstm_ctx* ctx, int what, int t, float* out, s
   LSTM_CUDA(cudaSetDevice(ctx->device));
   const int B = ctx->B, N = ctx->N, M = ctx->M, T = ctx->T;
   if (t < 0 || t > T) return lstm_fail(ctx, LSTM_ERR_ARG, "t outside [0, S)");
-  if (ctx->dtype == LSTM_BF16 && what != LSTM_ACT_H && what != LSTM_ACT_C) return tc_get_activation(ctx, what, t, out, n);
+  if (ctx->dtype == LSTM_BF16 && what != LSTM_ACT_C) return tc_get_activation(ctx, what, t, out, n);
   const float* src = nullptr;
   size_t cnt = 0;
   switch (what) {

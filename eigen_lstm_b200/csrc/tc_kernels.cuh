@@ -1,0 +1,102 @@
+// tc_kernels.cuh — launcher prototypes of the bf16 tcgen05 kernels (tc_kernels.cu).
+//
+// Device layouts of the bf16 path (Bp = B rounded up to 128: the tensor-core tile height; padded
+// rows/columns stay zero).  r' = 4*j + gate is the UNIT-MAJOR gate-row order used wherever the four
+// gates of one hidden unit must sit next to each other (gate in {i,o,f,u} = {0,1,2,3}):
+//   Hbf   [(T+1)][Bp][N]  bf16   h_t, slot t            (A operand of K2 and K3)
+//   Urk   [4N r'][N]      bf16   U(gate*N+j, k)         (B operand of K2)
+//   Ukr   [N k][4N r']    bf16   same matrix, k-major   (B operand of K5)
+//   Wp    [M][4N r']      fp32   W permuted (gathered by K2's epilogue), bp [4N r'] fp32
+//   Wmn   [M][N]          bf16   Why(m,n)               (B operand of K3)
+//   Wnm   [N][M]          bf16   Why(m,n) transposed    (B operand of K5's second K segment)
+//   Gp    [T][B][4N r']   fp32   activated gates of timestep t at slot t-1
+//   Cs    [(T+1)][B][N]   fp32   c_t (tanh'd), slot t   (shared with the fp32 path)
+//   dYbf  [T][Bp][M]      bf16   p - onehot at slot t-1 (A operand of K5's second K segment)
+//   dYT   [M][T*Bp]       bf16   same, transposed       (A operand of K6c)
+//   dGbf  [T][Bp][4N r']  bf16   dg_t at slot t-1       (A operand of K5)
+//   dGT   [4N r][T*Bp]    bf16   dg, MASTER row order r = gate*N+j, transposed (A operand of K6a)
+//   ZT    [M+N+16][(T+1)*Bp] bf16  rows [0,M): onehot(x_{s+1}) at slot s; rows [M,M+N): h_s at slot s;
+//                                  row M+N: ones  (B operand of K6a / K6c: one GEMM yields dW|dU|db)
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tc {
+
+struct FwdStepArgs {
+  int B, Bp, N, M;
+  int a_row0;                  // first Hbf row of h_{t-1}: (t-1)*Bp
+  const int* x;                // [B] input byte of this timestep (-1 = zero column)
+  const float* Wp;             // [M][4N r']
+  const float* bp;             // [4N r']
+  const float* c_prev;         // [B][N]
+  float* c_out;                // [B][N]
+  float* Gp_t;                 // [B][4N r']
+  __nv_bfloat16* Hbf_t;        // [Bp][N]
+  __nv_bfloat16* ZT_h;         // ZT + M*ldz + t*Bp : h rows of this slot
+  long ldz;                    // ZT leading dimension (columns)
+};
+
+struct LogitsArgs {
+  int B, Bp, N, M, T;
+  const float* by;             // [M]
+  const int* tg;               // [T][B] targets of timesteps 1..T
+  __nv_bfloat16* dYbf;         // [T*Bp][M]
+  __nv_bfloat16* dYT;          // [M][T*Bp]
+  float* surp;                 // [T][B]
+};
+
+struct BwdStepArgs {
+  int B, Bp, N, M;
+  int first;                   // t == T: no dg_{t+1}, dcnext = 0
+  int dg_row0;                 // first dGbf row of dg_{t+1}: t*Bp
+  int dy_row0;                 // first dYbf row of dy_t: (t-1)*Bp
+  const float* Gp_t;           // [B][4N r'] gates of timestep t
+  const float* c_t;            // [B][N]
+  const float* c_prev;         // [B][N]
+  float* dcnext;               // [B][N] in/out
+  __nv_bfloat16* dGbf_t;       // [Bp][4N r']
+  __nv_bfloat16* dGT_t;        // dGT + (t-1)*Bp
+  long ldg;                    // dGT leading dimension (columns)
+};
+
+struct GemmArgs {
+  int rows, cols;              // valid output extent: C(row, col) for row < rows, col < cols
+  int nkb;                     // K / 64
+  int a_k0, b_k0;              // starting K coordinate (elements) in A / B
+  int b_row0;                  // first B row
+  float* C;                    // C[col*ldc + row]
+  long ldc;
+  int tiles_m, tiles_n;
+};
+
+// K2: one recurrent timestep.  BN in {32, 64, 128} gate columns per CTA.
+void launch_fwd_step(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st);
+// K3: logits + softmax + loss + dy for all timesteps
+void launch_logits(const CUtensorMap& tmH, const CUtensorMap& tmWmn, const LogitsArgs& a, cudaStream_t st);
+// K5: one BPTT timestep.  BN in {32, 64, 128} hidden units per CTA.
+void launch_bwd_step(int BN, const CUtensorMap& tmdG, const CUtensorMap& tmUkr, const CUtensorMap& tmdY,
+                     const CUtensorMap& tmWnm, const BwdStepArgs& a, cudaStream_t st);
+// K6: C = A * B^T, both K-major bf16, fp32 out, 128x128 tiles
+void launch_gemm_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st);
+
+// parameter / state conversion kernels
+void launch_permute_rows_f32(const float* in, float* out, int rows, int N, cudaStream_t st);           // out[k][4j+g] = in[k][gN+j]
+void launch_permute_rows_bf16(const float* in, __nv_bfloat16* out, int rows, int N, cudaStream_t st);  // same, cast
+// out[c'][r] = bf16(in[r][src(c')]), src(c') = (c'%4)*N4/4 + c'/4 if permute else c'   (in: [R][C] fp32)
+void launch_transpose_cast(const float* in, __nv_bfloat16* out, int R, int C, int permute, cudaStream_t st);
+void launch_cast_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t st);
+// ZT rows [0,M): one-hot of xs (slot s <- xs[(s+1)*B + b]); cols = T*Bp
+void launch_build_xt(const int* xs1, __nv_bfloat16* ZT, long ldz, int M, int T, int B, int Bp, cudaStream_t st);
+void launch_fill_bf16(__nv_bfloat16* p, float v, size_t n, cudaStream_t st);
+// h state fp32 [B][N] <-> Hbf slot [Bp][N] + ZT h-rows of one slot
+void launch_state_to_bf16(const float* h, __nv_bfloat16* Hbf_slot, __nv_bfloat16* ZT_h, long ldz, int B, int N, cudaStream_t st);
+void launch_state_to_f32(const __nv_bfloat16* Hbf_slot, float* h, int B, int N, cudaStream_t st);
+// un-permute helpers for introspection: out[b][g*N+j] = in[b][4j+g]
+void launch_unpermute_f32(const float* in, float* out, int rows, int N, cudaStream_t st);
+void launch_unpermute_bf16(const __nv_bfloat16* in, float* out, int rows, int N, cudaStream_t st);
+void launch_bf16_to_f32(const __nv_bfloat16* in, float* out, size_t n, cudaStream_t st);
+
+}  // namespace tc

@@ -1,8 +1,276 @@
-// tc_path.cu — bf16 tensor-core path (placeholder until the tcgen05 kernels land).
+// tc_path.cu — host orchestration of the bf16 tensor-core path (LSTM_BF16): device buffers in the
+// operand layouts of tc_kernels.cuh, TMA tensor maps, and the per-iteration kernel sequence.
+#include <string.h>
+
 #include "ctx.h"
-int tc_create(lstm_ctx* ctx) { return lstm_fail(ctx, LSTM_ERR_UNSUPPORTED, "LSTM_BF16 path not built yet"); }
-void tc_destroy(lstm_ctx*) {}
-int tc_params_changed(lstm_ctx*) { return LSTM_OK; }
-int tc_forward(lstm_ctx* ctx) { return lstm_fail(ctx, LSTM_ERR_UNSUPPORTED, "LSTM_BF16 path not built yet"); }
-int tc_backward(lstm_ctx* ctx) { return lstm_fail(ctx, LSTM_ERR_UNSUPPORTED, "LSTM_BF16 path not built yet"); }
-int tc_get_activation(lstm_ctx* ctx, int, int, float*, size_t) { return lstm_fail(ctx, LSTM_ERR_UNSUPPORTED, "LSTM_BF16 path not built yet"); }
+#include "kernels.h"
+#include "tc_kernels.cuh"
+
+using bf16 = __nv_bfloat16;
+
+struct Bf16State {
+  int Bp = 0, N4 = 0, RZ = 0, BN2 = 0, BN5 = 0;
+  long LDZ = 0, LDT = 0;
+  bf16 *Hbf = nullptr, *Urk = nullptr, *Ukr = nullptr, *Wmn = nullptr, *Wnm = nullptr;
+  bf16 *dYbf = nullptr, *dYT = nullptr, *dGbf = nullptr, *dGT = nullptr, *ZT = nullptr;
+  float *Wp = nullptr, *bp = nullptr, *Gp = nullptr, *dcnext = nullptr, *scratch = nullptr;
+  size_t scratch_elems = 0;
+  CUtensorMap tmH, tmUrk, tmUkr, tmWmn, tmWnm, tmdY, tmdYT, tmdG, tmdGT, tmZT;
+};
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+bool load_encode() {
+  if (g_encode) return true;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return false;
+  g_encode = (EncodeTiledFn)fn;
+  return true;
+}
+
+// K-major bf16 matrix [rows][cols] (cols contiguous); box = 64 columns (128 B, SWIZZLE_128B) x box_rows
+bool make_tmap(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstride[1] = {cols * sizeof(bf16)};
+  const cuuint32_t box[2] = {64, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int pick_bn(int total_cols, int m_tiles, int min_ctas) {
+  for (int bn : {128, 64, 32})
+    if (total_cols % bn == 0 && (total_cols / bn) * m_tiles >= min_ctas) return bn;
+  return 32;
+}
+
+}  // namespace
+
+#define TC_ALLOC(ptr, bytes)                                          \
+  do {                                                                \
+    LSTM_CUDA(cudaMalloc(&(ptr), (bytes)));                           \
+    LSTM_CUDA(cudaMemsetAsync((ptr), 0, (bytes), ctx->st));           \
+  } while (0)
+
+int tc_create(lstm_ctx* ctx) {
+  const int M = ctx->M, N = ctx->N, B = ctx->B, T = ctx->T;
+  if (M != 256) return lstm_fail(ctx, LSTM_ERR_UNSUPPORTED, "LSTM_BF16 needs M == 256 (raw bytes)");
+  if (N % 64 != 0) return lstm_fail(ctx, LSTM_ERR_UNSUPPORTED, "LSTM_BF16 needs N to be a multiple of 64 (one 128-byte swizzled K block)");
+  if (!load_encode()) return lstm_fail(ctx, LSTM_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  Bf16State* s = new Bf16State();
+  ctx->tc = s;
+  s->Bp = (B + 127) / 128 * 128;
+  s->N4 = 4 * N;
+  s->RZ = M + N + 16;
+  s->LDZ = (long)(T + 1) * s->Bp;
+  s->LDT = (long)T * s->Bp;
+  s->BN2 = pick_bn(s->N4, s->Bp / 128, 96);
+  s->BN5 = pick_bn(N, s->Bp / 128, 32);
+  const size_t Bp = s->Bp, N4 = s->N4;
+  TC_ALLOC(s->Hbf, (size_t)(T + 1) * Bp * N * sizeof(bf16));
+  TC_ALLOC(s->Urk, N4 * N * sizeof(bf16));
+  TC_ALLOC(s->Ukr, N4 * N * sizeof(bf16));
+  TC_ALLOC(s->Wmn, (size_t)M * N * sizeof(bf16));
+  TC_ALLOC(s->Wnm, (size_t)M * N * sizeof(bf16));
+  TC_ALLOC(s->dYbf, (size_t)T * Bp * M * sizeof(bf16));
+  TC_ALLOC(s->dYT, (size_t)M * s->LDT * sizeof(bf16));
+  TC_ALLOC(s->dGbf, (size_t)T * Bp * N4 * sizeof(bf16));
+  TC_ALLOC(s->dGT, N4 * (size_t)s->LDT * sizeof(bf16));
+  TC_ALLOC(s->ZT, (size_t)s->RZ * s->LDZ * sizeof(bf16));
+  TC_ALLOC(s->Wp, (size_t)M * N4 * sizeof(float));
+  TC_ALLOC(s->bp, N4 * sizeof(float));
+  TC_ALLOC(s->Gp, (size_t)T * B * N4 * sizeof(float));
+  TC_ALLOC(s->dcnext, (size_t)B * N * sizeof(float));
+  s->scratch_elems = (size_t)B * N4;
+  TC_ALLOC(s->scratch, s->scratch_elems * sizeof(float));
+  tc::launch_fill_bf16(s->ZT + (size_t)(M + N) * s->LDZ, 1.0f, (size_t)s->LDZ, ctx->st);  // the ones row (db, dby)
+  LSTM_LAUNCHED(1);
+  bool ok = true;
+  ok &= make_tmap(&s->tmH, s->Hbf, (uint64_t)(T + 1) * Bp, N, 128);
+  ok &= make_tmap(&s->tmUrk, s->Urk, N4, N, s->BN2);
+  ok &= make_tmap(&s->tmUkr, s->Ukr, N, N4, s->BN5);
+  ok &= make_tmap(&s->tmWmn, s->Wmn, M, N, 256);
+  ok &= make_tmap(&s->tmWnm, s->Wnm, N, M, s->BN5);
+  ok &= make_tmap(&s->tmdY, s->dYbf, (uint64_t)T * Bp, M, 128);
+  ok &= make_tmap(&s->tmdYT, s->dYT, M, s->LDT, 128);
+  ok &= make_tmap(&s->tmdG, s->dGbf, (uint64_t)T * Bp, N4, 128);
+  ok &= make_tmap(&s->tmdGT, s->dGT, N4, s->LDT, 128);
+  ok &= make_tmap(&s->tmZT, s->ZT, s->RZ, s->LDZ, 128);
+  if (!ok) return lstm_fail(ctx, LSTM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  return LSTM_OK;
+}
+
+void tc_destroy(lstm_ctx* ctx) {
+  Bf16State* s = ctx->tc;
+  if (!s) return;
+  void* bufs[] = {s->Hbf, s->Urk, s->Ukr, s->Wmn, s->Wnm, s->dYbf, s->dYT, s->dGbf, s->dGT, s->ZT, s->Wp, s->bp, s->Gp,
+                  s->dcnext, s->scratch};
+  for (void* b : bufs) if (b) cudaFree(b);
+  delete s;
+  ctx->tc = nullptr;
+}
+
+// fp32 masters (column-major like the reference) -> bf16 operand copies
+int tc_params_changed(lstm_ctx* ctx) {
+  Bf16State* s = ctx->tc;
+  const int M = ctx->M, N = ctx->N;
+  tc::launch_transpose_cast(ctx->p(LSTM_U), s->Urk, N, s->N4, 1, ctx->st);     // Urk[r'][k]
+  tc::launch_permute_rows_bf16(ctx->p(LSTM_U), s->Ukr, N, N, ctx->st);          // Ukr[k][r']
+  tc::launch_permute_rows_f32(ctx->p(LSTM_W), s->Wp, M, N, ctx->st);            // Wp[m][r']
+  tc::launch_permute_rows_f32(ctx->p(LSTM_B), s->bp, 1, N, ctx->st);
+  tc::launch_transpose_cast(ctx->p(LSTM_WHY), s->Wmn, N, M, 0, ctx->st);       // Wmn[m][n]
+  tc::launch_cast_bf16(ctx->p(LSTM_WHY), s->Wnm, (size_t)M * N, ctx->st);      // Wnm[n][m]
+  LSTM_LAUNCHED(6);
+  return LSTM_OK;
+}
+
+int tc_state_from_f32(lstm_ctx* ctx) {
+  Bf16State* s = ctx->tc;
+  tc::launch_state_to_bf16(ctx->Hslot(0), s->Hbf, s->ZT + (size_t)ctx->M * s->LDZ, s->LDZ, ctx->B, ctx->N, ctx->st);
+  LSTM_LAUNCHED(1);
+  return LSTM_OK;
+}
+
+int tc_state_to_f32(lstm_ctx* ctx) {
+  Bf16State* s = ctx->tc;
+  tc::launch_state_to_f32(s->Hbf, ctx->Hslot(0), ctx->B, ctx->N, ctx->st);
+  LSTM_LAUNCHED(1);
+  return LSTM_OK;
+}
+
+int tc_carry(lstm_ctx* ctx, int stride) {
+  Bf16State* s = ctx->tc;
+  const size_t Bp = s->Bp;
+  LSTM_CUDA(cudaMemcpyAsync(s->Hbf, s->Hbf + (size_t)stride * Bp * ctx->N, Bp * ctx->N * sizeof(bf16), cudaMemcpyDeviceToDevice, ctx->st));
+  bf16* zh = s->ZT + (size_t)ctx->M * s->LDZ;
+  LSTM_CUDA(cudaMemcpy2DAsync(zh, s->LDZ * sizeof(bf16), zh + (size_t)stride * Bp, s->LDZ * sizeof(bf16), Bp * sizeof(bf16), ctx->N,
+                              cudaMemcpyDeviceToDevice, ctx->st));
+  return LSTM_OK;
+}
+
+#define PROF(i) do { if (ctx->profiling) LSTM_CUDA(cudaEventRecord(ctx->pev[i], ctx->st)); } while (0)
+
+int tc_forward(lstm_ctx* ctx) {
+  Bf16State* s = ctx->tc;
+  const int M = ctx->M, N = ctx->N, B = ctx->B, T = ctx->T;
+  const size_t Bp = s->Bp, N4 = s->N4;
+  tc::launch_build_xt(ctx->xs + B, s->ZT, s->LDZ, M, T, B, s->Bp, ctx->st);
+  LSTM_LAUNCHED(1);
+  for (int t = 1; t <= T; t++) {
+    tc::FwdStepArgs a;
+    a.B = B; a.Bp = s->Bp; a.N = N; a.M = M;
+    a.a_row0 = (t - 1) * s->Bp;
+    a.x = ctx->xs + (size_t)t * B;
+    a.Wp = s->Wp; a.bp = s->bp;
+    a.c_prev = ctx->Cslot(t - 1); a.c_out = ctx->Cslot(t);
+    a.Gp_t = s->Gp + (size_t)(t - 1) * B * N4;
+    a.Hbf_t = s->Hbf + (size_t)t * Bp * N;
+    a.ZT_h = s->ZT + (size_t)M * s->LDZ + (size_t)t * Bp;
+    a.ldz = s->LDZ;
+    tc::launch_fwd_step(s->BN2, s->tmH, s->tmUrk, a, ctx->st);
+  }
+  LSTM_LAUNCHED(T);
+  PROF(2);
+  tc::LogitsArgs la;
+  la.B = B; la.Bp = s->Bp; la.N = N; la.M = M; la.T = T;
+  la.by = ctx->p(LSTM_BY); la.tg = ctx->tg + B;
+  la.dYbf = s->dYbf; la.dYT = s->dYT; la.surp = ctx->surp;
+  tc::launch_logits(s->tmH, s->tmWmn, la, ctx->st);
+  LSTM_LAUNCHED(1);
+  return LSTM_OK;
+}
+
+int tc_backward(lstm_ctx* ctx) {
+  Bf16State* s = ctx->tc;
+  const int M = ctx->M, N = ctx->N, B = ctx->B, T = ctx->T;
+  const size_t Bp = s->Bp, N4 = s->N4;
+  // K6c first (inputs complete after K3) so its allreduce bucket overlaps the BPTT recurrence:
+  // [dWhy | dby](m, n) = sum_(s,b) dY^T[m][(s,b)] * [H^T ; 1][n][(s+1,b)]
+  {
+    tc::GemmArgs g;
+    g.rows = M; g.cols = N + 1; g.nkb = (int)(s->LDT / 64); g.a_k0 = 0; g.b_k0 = s->Bp; g.b_row0 = M;
+    g.C = ctx->g(LSTM_WHY); g.ldc = M; g.tiles_m = M / 128; g.tiles_n = (N + 1 + 127) / 128;
+    tc::launch_gemm_nt(s->tmdYT, s->tmZT, g, ctx->st);
+    LSTM_LAUNCHED(1);
+  }
+  PROF(4);
+  int rc = lstm_allreduce_bucket(ctx, 1);
+  if (rc) return rc;
+  for (int t = T; t >= 1; t--) {
+    tc::BwdStepArgs a;
+    a.B = B; a.Bp = s->Bp; a.N = N; a.M = M;
+    a.first = (t == T);
+    a.dg_row0 = t * s->Bp;
+    a.dy_row0 = (t - 1) * s->Bp;
+    a.Gp_t = s->Gp + (size_t)(t - 1) * B * N4;
+    a.c_t = ctx->Cslot(t); a.c_prev = ctx->Cslot(t - 1);
+    a.dcnext = s->dcnext;
+    a.dGbf_t = s->dGbf + (size_t)(t - 1) * Bp * N4;
+    a.dGT_t = s->dGT + (size_t)(t - 1) * Bp;
+    a.ldg = s->LDT;
+    tc::launch_bwd_step(s->BN5, s->tmdG, s->tmUkr, s->tmdY, s->tmWnm, a, ctx->st);
+  }
+  LSTM_LAUNCHED(T);
+  PROF(5);
+  // K6a+b: [dW | dU | db](r, col) = sum_(s,b) dG^T[r][(s,b)] * [X^T ; H^T ; 1][col][(s,b)]  — the flat gradient
+  // vector's first three tensors are exactly this column-major 4N x (M+N+1) matrix.
+  {
+    tc::GemmArgs g;
+    g.rows = (int)N4; g.cols = M + N + 1; g.nkb = (int)(s->LDT / 64); g.a_k0 = 0; g.b_k0 = 0; g.b_row0 = 0;
+    g.C = ctx->g(LSTM_W); g.ldc = (long)N4; g.tiles_m = (int)N4 / 128; g.tiles_n = (M + N + 1 + 127) / 128;
+    tc::launch_gemm_nt(s->tmdGT, s->tmZT, g, ctx->st);
+    LSTM_LAUNCHED(1);
+  }
+  PROF(6);
+  return lstm_allreduce_bucket(ctx, 0);
+}
+
+int tc_get_activation(lstm_ctx* ctx, int what, int t, float* out, size_t n) {
+  Bf16State* s = ctx->tc;
+  const int M = ctx->M, N = ctx->N, B = ctx->B, T = ctx->T;
+  const size_t Bp = s->Bp, N4 = s->N4;
+  size_t cnt = 0;
+  if (t < 0 || t > T) return lstm_fail(ctx, LSTM_ERR_ARG, "t outside [0, S)");
+  switch (what) {
+    case LSTM_ACT_H:
+      cnt = (size_t)B * N;
+      if (n != cnt) break;
+      tc::launch_bf16_to_f32(s->Hbf + (size_t)t * Bp * N, s->scratch, cnt, ctx->st);
+      break;
+    case LSTM_ACT_G:
+      cnt = (size_t)B * N4;
+      if (t < 1 || n != cnt) break;
+      tc::launch_unpermute_f32(s->Gp + (size_t)(t - 1) * B * N4, s->scratch, B, N, ctx->st);
+      break;
+    case LSTM_ACT_DG:
+      cnt = (size_t)B * N4;
+      if (t < 1 || n != cnt) break;
+      tc::launch_unpermute_bf16(s->dGbf + (size_t)(t - 1) * Bp * N4, s->scratch, B, N, ctx->st);
+      break;
+    case LSTM_ACT_PROBS:
+      cnt = (size_t)B * M;
+      if (t < 1 || n != cnt) break;
+      tc::launch_bf16_to_f32(s->dYbf + (size_t)(t - 1) * Bp * M, s->scratch, cnt, ctx->st);
+      break;
+    default:
+      return lstm_fail(ctx, LSTM_ERR_UNSUPPORTED, "activation not materialised by the bf16 path (dHy is fused into K5)");
+  }
+  if (n != cnt || (t < 1 && what != LSTM_ACT_H)) return lstm_fail(ctx, LSTM_ERR_ARG, "lstm_get_activation: wrong size or t");
+  LSTM_LAUNCHED(1);
+  LSTM_CUDA(cudaMemcpyAsync(out, s->scratch, cnt * sizeof(float), cudaMemcpyDeviceToHost, ctx->st));
+  LSTM_CUDA(cudaStreamSynchronize(ctx->st));
+  if (what == LSTM_ACT_PROBS) {
+    std::vector<int> tgt(B);
+    LSTM_CUDA(cudaMemcpy(tgt.data(), ctx->tg + (size_t)t * B, B * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int b = 0; b < B; b++)
+      if (tgt[b] >= 0) out[(size_t)b * M + tgt[b]] += 1.0f;
+  }
+  return LSTM_OK;
+}
