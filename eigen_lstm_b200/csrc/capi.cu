@@ -500,15 +500,15 @@ extern "C" int lstm_train_step(lstm_ctx* ctx, const int32_t* x_idx, const int32_
   if (!ctx) return LSTM_ERR_ARG;
   LSTM_CUDA(cudaSetDevice(ctx->device));
   PROF(0);
-  int rc = lstm_carry_state(ctx, stride);
-  if (rc) return rc;
-  rc = upload_window(ctx, x_idx, t_idx);
+  int rc = upload_window(ctx, x_idx, t_idx);
   if (rc) return rc;
   rc = forward_device(ctx, 0);
   if (rc) return rc;
   rc = backward_device(ctx);
   if (rc) return rc;
   rc = adagrad_device(ctx, lr, 1e-10, 0.f);
+  if (rc) return rc;
+  rc = lstm_carry_state(ctx, stride);   // slot 0 now holds the state the next window starts from
   if (rc) return rc;
   rc = finish_profile(ctx);
   if (rc) return rc;
@@ -575,8 +575,6 @@ extern "C" int lstm_train_text(lstm_ctx* ctx, int iters, int stride, float lr, d
   if (rc) return rc;
   for (int it = 0; it < iters; it++) {
     PROF(0);
-    rc = lstm_carry_state(ctx, stride);
-    if (rc) return rc;
     launch_window_advance(ctx->text, ctx->text_len, ctx->pos0, ctx->vcount, stride, ctx->S, ctx->B, ctx->xs, ctx->tg, ctx->st);
     LSTM_LAUNCHED(1);
     ctx->v_host += stride;
@@ -585,6 +583,8 @@ extern "C" int lstm_train_text(lstm_ctx* ctx, int iters, int stride, float lr, d
     rc = backward_device(ctx);
     if (rc) return rc;
     rc = adagrad_device(ctx, lr, 1e-10, 0.f);
+    if (rc) return rc;
+    rc = lstm_carry_state(ctx, stride);   // slot 0 now holds the state the next window starts from
     if (rc) return rc;
   }
   rc = finish_profile(ctx);

@@ -87,7 +87,8 @@ int lstm_adagrad(lstm_ctx* ctx, float lr, double eps, float clip);
 /* after a step: h(0),c(0) <- h(stride),c(stride) (stride 1: R/lstm.cc:163-164; stride > 1:
  * OV/lstm_eigen_class_batch/lstm_segment.cc:183-184) */
 int lstm_carry_state(lstm_ctx* ctx, int stride);
-/* carry + forward + backward + (data-parallel gradient allreduce) + adagrad in one call */
+/* forward + backward + (data-parallel gradient allreduce) + adagrad + carry(stride) in one call: the window
+ * starts from the state in slot 0 (lstm_set_state / the previous step's carry) and leaves h(stride),c(stride) there */
 int lstm_train_step(lstm_ctx* ctx, const int32_t* x_idx, const int32_t* t_idx, int stride, float lr,
                     double* loss_out);
 
@@ -98,8 +99,8 @@ int lstm_load_text(lstm_ctx* ctx, const uint8_t* bytes, size_t n);
 int lstm_set_positions(lstm_ctx* ctx, const uint64_t* pos);
 int lstm_get_positions(lstm_ctx* ctx, uint64_t* pos);
 /* `iters` full training iterations on the loaded text, windows built on the device: each iteration
- * consumes `stride` new bytes per stream (1 = the reference's sliding window), carries the state,
- * runs fwd + BPTT + allreduce + Adagrad.  losses (optional, host, [iters]) gets every iteration's
+ * consumes `stride` new bytes per stream (1 = the reference's sliding window), runs fwd + BPTT + allreduce +
+ * Adagrad and carries h(stride),c(stride) into slot 0 for the next iteration.  losses (optional, host, [iters]) gets every iteration's
  * loss.  Asynchronous unless losses != NULL. */
 int lstm_train_text(lstm_ctx* ctx, int iters, int stride, float lr, double* losses);
 /* copy out the current window indices ([S][B] each) — for tests */

@@ -75,7 +75,7 @@ inline double sqrt_eps(double x) { return sqrt(x + ORACLE_EPS); }
 // (row i, col j) iteration order into a column-major matrix.  The reference seeds from
 // std::random_device; we take the seed as an argument so runs are reproducible.
 template <typename R>
-void randn_fill(R* m, int rows, int cols, double mean, double stddev, uint64_t seed) {
+void randn_fill(R* m, int rows, int cols, float mean, float stddev, uint64_t seed) {  // float args like :364
   std::mt19937 mt((uint32_t)seed);
   std::normal_distribution<> dist(mean, stddev);
   for (int i = 0; i < rows; i++)
@@ -393,7 +393,7 @@ std::vector<R>* pick(Oracle<R>* o, int kind, int which) {
   extern "C" int PFX##_get_tensor(void* o, int kind, int which, R* dst) {                             \
     auto* v = pick<R>((Oracle<R>*)o, kind, which); if (!v) return -1;                                 \
     memcpy(dst, v->data(), sizeof(R) * v->size()); return 0; }                                        \
-  extern "C" void PFX##_randn(R* m, int rows, int cols, double mean, double sd, uint64_t seed) {      \
+  extern "C" void PFX##_randn(R* m, int rows, int cols, float mean, float sd, uint64_t seed) {        \
     randn_fill<R>(m, rows, cols, mean, sd, seed); }                                                   \
   /* state access: what 0 h, 1 c (N*B), 2 g, 5 dg (4N*B), 3 probs (M*B); column-major per t */        \
   extern "C" int PFX##_get_state(void* o_, int what, int t, R* dst) {                                 \

@@ -162,7 +162,7 @@ def randn(rows, cols, mean, sd, seed, dtype=np.float32):
     lib = _load(False)
     a = np.empty((rows, cols), dtype=dtype, order="F")
     fn = lib.oracle32_randn if dtype == np.float32 else lib.oracle64_randn
-    fn(a.ctypes.data_as(C.c_void_p), rows, cols, C.c_double(mean), C.c_double(sd), C.c_uint64(seed))
+    fn(a.ctypes.data_as(C.c_void_p), rows, cols, C.c_float(mean), C.c_float(sd), C.c_uint64(seed))
     return a
 
 
