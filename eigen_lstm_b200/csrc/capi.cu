@@ -372,12 +372,12 @@ static int backward_device(lstm_ctx* ctx) {
   const int BT = T * B;
   // K4: dHy[(t,b)][n] = sum_m dY[(t,b)][m] * Why(m,n)                      (R/lstm.cc:228)
   launch_gemm_f32(ctx->dY, M, 1, ctx->p(LSTM_WHY), 1, M, ctx->dHy, N, 1, nullptr, BT, N, M, ctx->st);
-  PROF(4);
   // K6c first (its inputs are complete), so its allreduce bucket overlaps the BPTT recurrence:
   // dWhy(m,n) = sum_(t,b) dY[(t,b)][m] * H_t[(t,b)][n]  (:226) ; dby = sum dY (:227)
   launch_gemm_f32(ctx->Hslot(1), 1, N, ctx->dY, M, 1, ctx->g(LSTM_WHY), M, 1, nullptr, N, M, BT, ctx->st);
   launch_colsum_f32(ctx->dY, ctx->g(LSTM_BY), BT, M, ctx->st);
   LSTM_LAUNCHED(3);
+  PROF(4);
   int rc = lstm_allreduce_bucket(ctx, 1);
   if (rc) return rc;
   // K5: BPTT recurrence t = T..1

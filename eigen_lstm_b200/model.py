@@ -200,7 +200,7 @@ class LSTM:
     def phase_ms(self):
         a = np.zeros(16, dtype=np.float32)
         self._ck(self.lib.lstm_get_phase_ms(self.ctx, _ptr(a)))
-        names = ["window", "fwd_recurrence", "logits_softmax", "dHy", "bwd_recurrence", "weight_grads",
+        names = ["window", "fwd_recurrence", "logits_softmax", "dhy_dwhy_gemms", "bwd_recurrence", "weight_grads",
                  "allreduce_wait", "adagrad", "total"]
         return dict(zip(names, a[:9].tolist()))
 

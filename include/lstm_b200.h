@@ -139,7 +139,7 @@ int lstm_dp_init(lstm_ctx* ctx, int rank, int world, const uint8_t id[128]);
 /* ---- measurement ------------------------------------------------------------------------------ */
 /* CUDA-event time in ms of the phases of the LAST lstm_train_step / last iteration of
  * lstm_train_text when profiling is enabled: [0] window, [1] forward recurrence, [2] logits+softmax,
- * [3] dH_y, [4] backward recurrence, [5] weight gradients, [6] allreduce wait, [7] adagrad, [8] total */
+ * [3] dH_y (fp32 path) + dWhy|dby GEMM, [4] backward recurrence, [5] weight gradients, [6] allreduce wait, [7] adagrad, [8] total */
 int lstm_set_profiling(lstm_ctx* ctx, int on);
 int lstm_get_phase_ms(lstm_ctx* ctx, float ms[16]);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
