@@ -194,9 +194,8 @@ def main():
         else:
             raise
     if world > 1:
-        ident = [el.dp_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ident, src=0)
-        net.dp_init(rank, world, ident[0])
+        from eigen_lstm_b200 import dp
+        net.dp_init(rank, world, dp.broadcast_unique_id(dist, el.dp_unique_id, rank))
     net.init_params(seed=0, std=0.01, forget_bias=1.0)       # identical replicas on every rank
     net.reset_state(0, 0.0)
     total_steps = 2 * (args.steps + args.warmup) + 4

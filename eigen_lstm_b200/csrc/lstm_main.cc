@@ -1,0 +1,157 @@
+// lstm_main.cc — drop-in host program for the reference's `lstm` binary (R/lstm.cc:50-361), written
+// against the C ABI only (include/lstm_b200.h).  With no arguments it reproduces the reference's
+// compile-time defaults and its stdout contract:
+//   N = 64, M = 256, S = 3, B = 1, lr = 0.1, 1000 epochs, "alice29.txt"        (R/lstm.cc:53-63)
+//   "Read <n> bytes (<file>)" / "Empty file! (...)" / "fopen error: (...)"     (:398,410,416)
+//   every 100 iterations  "<pct>%\r"  (fixed, width 7, precision 2)            (:274-279)
+//   epoch line with t, est GFLOP/s = S(4NM*2+4NN*2)*length / 2^30 / t and avg loss = epoch_loss/(S*length)  (:140,284-291)
+//   1000 sampled characters between "************ Generated text |" markers    (:293-356)
+// Everything the reference fixes at compile time is a flag here (the reference has no argv).
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iomanip>
+#include <iostream>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/lstm_b200.h"
+
+// rawread (R/lstm.cc:382-420): whole file as bytes; prints exactly what the reference prints
+static std::vector<unsigned char> rawread(const char* filename) {
+  std::vector<unsigned char> v;
+  if (FILE* fp = fopen(filename, "rb")) {
+    char buf[1024];
+    while (size_t len = fread(buf, 1, sizeof(buf), fp)) v.insert(v.end(), buf, buf + len);
+    fclose(fp);
+    if (v.size() > 0) std::cout << "Read " << v.size() << " bytes (" << filename << ")" << std::endl;
+    else std::cout << "Empty file! (" << filename << ")" << std::endl;
+  } else {
+    std::cout << "fopen error: (" << filename << ")" << std::endl;
+  }
+  return v;
+}
+
+#define CK(call)                                                                      \
+  do {                                                                                \
+    int rc_ = (call);                                                                 \
+    if (rc_ != 0) {                                                                   \
+      std::cerr << #call << " failed (" << rc_ << "): " << lstm_last_error(ctx) << std::endl; \
+      return 1;                                                                       \
+    }                                                                                 \
+  } while (0)
+
+int main(int argc, char** argv) {
+  size_t N = 64, M = 256, S = 3, B = 1;
+  float learning_rate = 1e-1f;
+  size_t epochs = 1000;
+  std::string file = "alice29.txt", load_prefix, save_prefix;
+  uint64_t seed = std::random_device{}();   // the reference seeds from std::random_device (:370)
+  int dtype = LSTM_F32, stride = 1, device = 0;
+  size_t characters_to_generate = 1000;
+  float forget_bias = 0.f, state_std = 0.1f;
+  long max_iters = -1;
+  for (int i = 1; i < argc; i++) {
+    std::string a = argv[i];
+    auto next = [&]() -> const char* { return (i + 1 < argc) ? argv[++i] : ""; };
+    if (a == "--file") file = next();
+    else if (a == "--hidden") N = atol(next());
+    else if (a == "--seq") S = atol(next());
+    else if (a == "--batch") B = atol(next());
+    else if (a == "--epochs") epochs = atol(next());
+    else if (a == "--lr") learning_rate = (float)atof(next());
+    else if (a == "--seed") seed = strtoull(next(), nullptr, 10);
+    else if (a == "--stride") stride = atoi(next());
+    else if (a == "--device") device = atoi(next());
+    else if (a == "--bf16") dtype = LSTM_BF16;
+    else if (a == "--sample") characters_to_generate = atol(next());
+    else if (a == "--forget-bias") forget_bias = (float)atof(next());
+    else if (a == "--state-std") state_std = (float)atof(next());
+    else if (a == "--max-iters") max_iters = atol(next());
+    else if (a == "--load") load_prefix = next();
+    else if (a == "--save") save_prefix = next();
+    else {
+      std::cerr << "usage: lstm [--file F] [--hidden N] [--seq S] [--batch B] [--epochs E] [--lr LR] [--seed K] [--stride K]\n"
+                   "            [--bf16] [--device D] [--sample N] [--forget-bias X] [--state-std X] [--max-iters K]\n"
+                   "            [--load PREFIX] [--save PREFIX]\n";
+      return 2;
+    }
+  }
+
+  std::vector<unsigned char> data = rawread(file.c_str());
+  if (data.empty()) return 0;   // the reference carries on with a 0x0 matrix and does nothing
+
+  lstm_ctx* ctx = nullptr;
+  int rc = lstm_create(&ctx, (int)M, (int)N, (int)S, (int)B, device, dtype);
+  if (rc != 0) {
+    std::cerr << "lstm_create failed (" << rc << "): " << lstm_last_error(nullptr) << std::endl;
+    return 1;
+  }
+  CK(lstm_init_params(ctx, seed, 0.01f, forget_bias));              // :113-119
+  if (!load_prefix.empty() && lstm_load_text_ckpt(ctx, load_prefix.c_str()) != 0)
+    std::cout << lstm_last_error(ctx) << std::endl;                  // the reference prints and keeps the random init
+  CK(lstm_load_text(ctx, data.data(), data.size()));
+  const size_t length = data.size();
+  if (B > 1) {                                                        // OV/lstm_eigen_opt/lstm.cc:140-144
+    std::mt19937_64 g(seed + 17);
+    std::vector<uint64_t> pos(B);
+    for (auto& p : pos) p = g() % (length - S) + S;
+    CK(lstm_set_positions(ctx, pos.data()));
+  }
+  const double flops_per_epoch = (double)S * (4.0 * N * M * 2 + 4.0 * N * N * 2) * (double)length;   // :140
+  const size_t iters_per_epoch = (length - S + stride - 1) / stride;
+  std::vector<double> losses(100);
+  long total_iters = 0;
+
+  for (size_t e = 0; e < epochs; e++) {
+    double epoch_loss = 0.0;
+    CK(lstm_reset_state(ctx, seed + 100 + 2 * e, state_std));         // randn(h,0,0.1); randn(c,0,0.1)  :146-147
+    auto t0 = std::chrono::steady_clock::now();
+    size_t done = 0;
+    bool stop = false;
+    while (done < iters_per_epoch && !stop) {
+      // the reference prints when i % 100 == 0 (i = S + iteration index): run up to the next multiple of 100
+      const size_t i_now = S + done * stride;
+      size_t chunk = (100 - (i_now % 100) + stride - 1) / stride;
+      if (chunk == 0) chunk = 100 / stride ? 100 / stride : 1;
+      if (chunk > iters_per_epoch - done) chunk = iters_per_epoch - done;
+      if (max_iters >= 0 && total_iters + (long)chunk >= max_iters) { chunk = (size_t)(max_iters - total_iters); stop = true; }
+      if (chunk > losses.size()) losses.resize(chunk);
+      if (chunk > 0) CK(lstm_train_text(ctx, (int)chunk, stride, learning_rate, losses.data()));
+      for (size_t k = 0; k < chunk; k++) epoch_loss += losses[k];
+      done += chunk;
+      total_iters += (long)chunk;
+      const size_t i = S + done * stride;
+      if (i % 100 == 0 || stride > 1)
+        std::cout << std::fixed << std::setw(7) << std::setprecision(2) << 100.0f * (float)i / (float)length << "%\r" << std::flush;
+    }
+    CK(lstm_sync(ctx));
+    const double epoch_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::cout << std::endl
+              << "====================================================================================" << std::endl
+              << "Epoch " << e + 1 << "/" << epochs << std::fixed << std::setprecision(3) << ", t = " << epoch_time << " s"
+              << ", est GFLOP/s = " << (flops_per_epoch / powf(2, 30)) / epoch_time << ", avg loss = "
+              << epoch_loss / ((double)S * (double)length) << " bits/char" << std::endl;
+
+    // sampling (:293-356): _h, _c ~ N(0, 0.1), then 1000 draws
+    std::vector<float> h0(N), c0(N);
+    {
+      std::mt19937 mh((uint32_t)(seed + 1000 + 2 * e)), mc((uint32_t)(seed + 1001 + 2 * e));
+      std::normal_distribution<> d(0.0f, 0.1f);
+      for (auto& v : h0) v = (float)d(mh);
+      for (auto& v : c0) v = (float)d(mc);
+    }
+    std::vector<uint8_t> text(characters_to_generate);
+    CK(lstm_sample(ctx, seed + 5000 + e, h0.data(), c0.data(), text.data(), text.size(), 0));
+    std::cout << std::endl << std::endl << "************ Generated text |";
+    for (uint8_t ch : text) std::cout << (char)ch;
+    std::cout << "| Generated text END ************" << std::endl;
+    if (!save_prefix.empty()) CK(lstm_save_text_ckpt(ctx, save_prefix.c_str()));
+    if (stop) break;
+  }
+  lstm_destroy(ctx);
+  return 0;
+}
