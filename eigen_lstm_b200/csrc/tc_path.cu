@@ -72,7 +72,7 @@ int tc_create(lstm_ctx* ctx) {
   s->LDZ = (long)(T + 1) * s->Bp;
   s->LDT = (long)T * s->Bp;
   s->BN2 = pick_bn(s->N4, s->Bp / 128, 96);
-  s->BN5 = pick_bn(N, s->Bp / 128, 32);
+  s->BN5 = pick_bn(N, (s->Bp / 128) * 4, 96);   // K5 runs 4 split-K CTAs per output tile
   const size_t Bp = s->Bp, N4 = s->N4;
   TC_ALLOC(s->Hbf, (size_t)(T + 1) * Bp * N * sizeof(bf16));
   TC_ALLOC(s->Urk, N4 * N * sizeof(bf16));

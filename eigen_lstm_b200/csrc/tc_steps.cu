@@ -1,0 +1,267 @@
+// tc_steps.cu — the two SERIAL kernels of the bf16 path: one forward timestep (K2) and one BPTT
+// timestep (K5).  Both run the contraction on tcgen05 (tc_tile.cuh) and then re-map the 128 x BN
+// accumulator tile through shared memory so that the LSTM math runs with LANE = HIDDEN UNIT: every
+// global access of the epilogue (W row gather, gates stash, c, h, dg) is then a contiguous 128-512 B
+// warp access instead of 32 scattered rows.
+//
+//   k_fwd_step  R/lstm.cc:176-192   g = W x + U h(t-1) + b, gates, c = tanh(i u + f c(t-1)), h = o c
+//   k_bwd_step  R/lstm.cc:228-256   dh = Why^T dy + U^T dg(t+1), gate gradients, dcnext
+//
+// K5's output (B x N) is 4x smaller than K2's (B x 4N) for the same flops, so its K range
+// (4N + M) is split over a cluster of 4 CTAs; the partial accumulators are reduce-scattered through
+// distributed shared memory (each CTA finalises a quarter of the tile's hidden units).
+#include "tc_kernels.cuh"
+#include "tc_tile.cuh"
+
+namespace tc {
+
+constexpr int EPI_THREADS = 128;
+constexpr int HT_LD = 130;   // bf16 row pitch of the transposed staging tiles: 65 words -> conflict-free
+
+// ------------------------------------------------------------------------------------------------
+// K2: forward timestep.  D[b][r'] = sum_k h(t-1)[b][k] * U[r'][k], r' = 4*unit + gate.
+// grid (4N/BN, Bp/128)
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+struct FwdCfg {
+  static constexpr int STAGES = BN == 128 ? 4 : (BN == 64 ? 6 : 8);
+  static constexpr int UT = BN / 4;                        // hidden units per tile
+  static constexpr int ACC_LD = BN + 4;                    // fp32 row pitch (16-byte aligned, odd multiple of 16 B)
+  static constexpr int ACC_BYTES = 128 * ACC_LD * 4;
+  static constexpr int HT_BYTES = UT * HT_LD * 2;
+  static constexpr int X_BYTES = 128 * 4;
+  static constexpr int EPI_BYTES = ACC_BYTES + HT_BYTES + X_BYTES;
+  using C = Cfg<BN, STAGES, EPI_BYTES>;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmU, const FwdStepArgs a) {
+  using F = FwdCfg<BN>;
+  constexpr int STAGES = F::STAGES, UT = F::UT, RG = EPI_THREADS / UT, ACC_LD = F::ACC_LD;
+  extern __shared__ uint8_t smem_raw[];
+  TileCtx c = tile_prologue<BN, STAGES>(smem_raw);
+  float* acc = reinterpret_cast<float*>(c.epi);
+  __nv_bfloat16* hT = reinterpret_cast<__nv_bfloat16*>(c.epi + F::ACC_BYTES);
+  int* sx = reinterpret_cast<int*>(c.epi + F::ACC_BYTES + F::HT_BYTES);
+  const int nb = blockIdx.x, mb = blockIdx.y;
+  const KSeg s0{&tmH, &tmU, a.a_row0 + mb * BM, nb * BN, 0, 0, a.N / BK};
+  const KSeg s1{&tmH, &tmU, 0, 0, 0, 0, 0};
+  tile_mainloop<BN, STAGES>(c, s0, s1);
+  if (c.warp >= 2) {
+    const int e = threadIdx.x - 64;                        // 0..127
+    const int N = a.N, N4 = 4 * a.N;
+    const int l = e % UT, rg = e / UT;                     // phase-2 mapping: lane = hidden unit
+    const int j = nb * UT + l;                             // hidden unit
+    const int rp = 4 * j;                                  // first of its 4 gate rows (unit-major order)
+    {                                                      // input bytes of the tile's 128 streams
+      const int b = mb * BM + e;
+      sx[e] = (b < a.B) ? a.x[b] : -2;                     // -2 = padding row, -1 = all-zero input column
+    }
+    const float4 bias = *reinterpret_cast<const float4*>(a.bp + rp);
+    named_bar_sync(1, EPI_THREADS);
+    // warm L2 with what phase 2 will read, while the tensor core is busy
+#pragma unroll 4
+    for (int i = 0; i < UT; i++) {
+      const int r = rg + RG * i, x = sx[r];
+      if (x >= 0 && (l & 7) == 0) prefetch_l2(a.Wp + (size_t)x * N4 + rp);
+      if (x >= -1 && l == 0) prefetch_l2(a.c_prev + (size_t)(mb * BM + r) * N + j);
+    }
+    // phase 1: TMEM (lane = stream) -> shared memory tile acc[row][col]
+    const int quarter = c.warp & 3;
+    const int row = quarter * 32 + c.lane;
+    mbar_wait(c.accum_full, 0);
+    tcgen05_after_sync();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      tmem_ld32(c.tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+      float4* dst = reinterpret_cast<float4*>(acc + (size_t)row * ACC_LD + c0);
+#pragma unroll
+      for (int u = 0; u < 8; u++) dst[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+    }
+    named_bar_sync(1, EPI_THREADS);
+    // phase 2: lane = hidden unit; one warp instruction touches one stream's contiguous row segment
+#pragma unroll 4
+    for (int i = 0; i < UT; i++) {
+      const int r = rg + RG * i;
+      const int x = sx[r];
+      float hval = 0.f;
+      if (x >= -1) {
+        const int b = mb * BM + r;
+        const float4 pre = *reinterpret_cast<const float4*>(acc + (size_t)r * ACC_LD + 4 * l);
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (x >= 0) w = *reinterpret_cast<const float4*>(a.Wp + (size_t)x * N4 + rp);   // W*x, one-hot x
+        const float cp = a.c_prev[(size_t)b * N + j];
+        const float gi = sigmoid_fast(pre.x + w.x + bias.x);
+        const float go = sigmoid_fast(pre.y + w.y + bias.y);
+        const float gf = sigmoid_fast(pre.z + w.z + bias.z);
+        const float gu = tanh_fast(pre.w + w.w + bias.w);
+        const float cc = tanh_fast(gi * gu + gf * cp);     // the carried cell value is the tanh'd one
+        hval = go * cc;
+        *reinterpret_cast<float4*>(a.Gp_t + (size_t)b * N4 + rp) = make_float4(gi, go, gf, gu);
+        a.c_out[(size_t)b * N + j] = cc;
+        a.Hbf_t[(size_t)b * N + j] = __float2bfloat16_rn(hval);
+      }
+      hT[l * HT_LD + r] = __float2bfloat16_rn(hval);
+    }
+    named_bar_sync(1, EPI_THREADS);
+    // phase 3: h^T rows of ZT (the K6 operand), lanes along the stream index
+    {
+      const int w4 = e >> 5, lane = e & 31;
+      for (int u = w4; u < UT; u += 4) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(hT + u * HT_LD);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(a.ZT_h + (size_t)(nb * UT + u) * a.ldz + mb * BM);
+        dst[lane] = src[lane];
+        dst[lane + 32] = src[lane + 32];
+      }
+    }
+  }
+  tile_epilogue_end<BN, STAGES>(c);
+}
+
+template <int BN>
+static void launch_fwd_t(const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st) {
+  using F = FwdCfg<BN>;
+  dim3 grid(4 * a.N / BN, a.Bp / BM);
+  set_smem(k_fwd_step<BN>, F::C::SMEM_BYTES);
+  k_fwd_step<BN><<<grid, 192, F::C::SMEM_BYTES, st>>>(tmH, tmUrk, a);
+}
+void launch_fwd_step(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st) {
+  if (BN == 128) launch_fwd_t<128>(tmH, tmUrk, a, st);
+  else if (BN == 64) launch_fwd_t<64>(tmH, tmUrk, a, st);
+  else launch_fwd_t<32>(tmH, tmUrk, a, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: backward timestep.  D[b][j] = sum_r' dg(t+1)[b][r'] U[r'][j]  +  sum_m dy(t)[b][m] Why[m][j]
+// (one contraction over the concatenated K range of 4N + M), split-K over a cluster of 4 CTAs.
+// grid (N/BN, Bp/128, 4), cluster (1,1,4)
+// ------------------------------------------------------------------------------------------------
+constexpr int SPLIT = 4;
+template <int BN>
+struct BwdCfg {
+  static constexpr int STAGES = BN == 128 ? 3 : (BN == 64 ? 5 : 8);
+  static constexpr int UO = BN / SPLIT;                    // hidden units finalised by each CTA of the cluster
+  static constexpr int RV_LD = UO + 4;                     // fp32 row pitch of one received partial slice
+  static constexpr int RV_BYTES = SPLIT * 128 * RV_LD * 4; // [src rank][row][UO]
+  static constexpr int GT_BYTES = 4 * UO * HT_LD * 2;      // dg^T staging [gate*UO + unit][row]
+  static constexpr int EPI_BYTES = RV_BYTES + GT_BYTES;
+  using C = Cfg<BN, STAGES, EPI_BYTES>;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(1, 1, SPLIT) __launch_bounds__(192, 1)
+k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUtensorMap tmU,
+           const __grid_constant__ CUtensorMap tmdY, const __grid_constant__ CUtensorMap tmW, const BwdStepArgs a) {
+  using F = BwdCfg<BN>;
+  constexpr int STAGES = F::STAGES, UO = F::UO, RG = EPI_THREADS / UO, RV_LD = F::RV_LD;
+  extern __shared__ uint8_t smem_raw[];
+  TileCtx c = tile_prologue<BN, STAGES>(smem_raw);
+  float* recv = reinterpret_cast<float*>(c.epi);
+  __nv_bfloat16* gT = reinterpret_cast<__nv_bfloat16*>(c.epi + F::RV_BYTES);
+  const int nb = blockIdx.x, mb = blockIdx.y;
+  const uint32_t rank = cluster_ctarank();
+  // this CTA's quarter of the concatenated K range [0, nkb0) ++ [0, nkb1)
+  const int nkb0 = a.first ? 0 : (4 * a.N) / BK, nkb1 = a.M / BK;
+  const int per = (nkb0 + nkb1) / SPLIT;
+  const int lo = (int)rank * per, hi = lo + per;
+  const int lo0 = min(lo, nkb0), hi0 = min(hi, nkb0);
+  const int lo1 = max(lo, nkb0) - nkb0, hi1 = max(hi, nkb0) - nkb0;
+  const KSeg s0{&tmdG, &tmU, a.dg_row0 + mb * BM, nb * BN, lo0 * BK, lo0 * BK, hi0 - lo0};
+  const KSeg s1{&tmdY, &tmW, a.dy_row0 + mb * BM, nb * BN, lo1 * BK, lo1 * BK, hi1 - lo1};
+  cluster_sync_all();                                      // every CTA of the cluster is running before any DSMEM traffic
+  tile_mainloop<BN, STAGES>(c, s0, s1);
+  const int e = threadIdx.x - 64;
+  const int N = a.N, N4 = 4 * a.N;
+  const int l = e >= 0 ? e % UO : 0, rg = e >= 0 ? e / UO : 0;
+  const int j = nb * BN + (int)rank * UO + l;              // the hidden unit this thread finalises
+  if (c.warp >= 2) {
+#pragma unroll 4
+    for (int i = 0; i < UO; i++) {                         // warm L2 for phase 2
+      const int b = mb * BM + rg + RG * i;
+      if (b < a.B) {
+        if ((l & 7) == 0) prefetch_l2(a.Gp_t + (size_t)b * N4 + 4 * (size_t)j);
+        if (l == 0) { prefetch_l2(a.c_t + (size_t)b * N + j); prefetch_l2(a.c_prev + (size_t)b * N + j); }
+      }
+    }
+    // phase 1: reduce-scatter.  Column slice q of this CTA's partial accumulator goes to CTA q's recv[rank]
+    const int quarter = c.warp & 3;
+    const int row = quarter * 32 + c.lane;
+    const uint32_t my_slot = smem_u32(recv + ((size_t)rank * 128 + row) * RV_LD);
+    mbar_wait(c.accum_full, 0);
+    tcgen05_after_sync();
+#pragma unroll 1
+    for (int q = 0; q < SPLIT; q++) {
+      float v[UO];
+      tmem_ldw<UO>(c.tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(q * UO), v);
+      const uint32_t dst = mapa_u32(my_slot, (uint32_t)q);
+#pragma unroll
+      for (int u = 0; u < UO / 4; u++) st_cluster_v4(dst + 16 * u, make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]));
+    }
+  }
+  cluster_sync_all();                                      // all partial slices have landed (release/acquire)
+  if (c.warp >= 2) {
+    // phase 2: lane = hidden unit
+#pragma unroll 2
+    for (int i = 0; i < UO; i++) {
+      const int r = rg + RG * i;
+      const int b = mb * BM + r;
+      float d_i = 0.f, d_o = 0.f, d_f = 0.f, d_u = 0.f;
+      if (b < a.B) {
+        float dh = 0.f;
+#pragma unroll
+        for (int s = 0; s < SPLIT; s++) dh += recv[((size_t)s * 128 + r) * RV_LD + l];      // fixed order: deterministic
+        const float4 g = *reinterpret_cast<const float4*>(a.Gp_t + (size_t)b * N4 + 4 * (size_t)j);   // i o f u
+        const size_t bj = (size_t)b * N + j;
+        const float ct = a.c_t[bj], cp = a.c_prev[bj];
+        const float dn = a.first ? 0.f : a.dcnext[bj];
+        const float dc = (dh * g.y + dn) * (1.0f - ct * ct);               // :233-235
+        d_o = dh * ct * (g.y * (1.0f - g.y));                              // :238,244
+        d_i = dc * g.w * (g.x * (1.0f - g.x));                             // :239,244
+        d_f = dc * cp * (g.z * (1.0f - g.z));                              // :240,244
+        d_u = dc * g.x * (1.0f - g.w * g.w);                               // :241,247
+        a.dcnext[bj] = dc * g.z;                                           // :256
+        uint2 pk;
+        pk.x = pack_bf16x2(d_i, d_o);
+        pk.y = pack_bf16x2(d_f, d_u);
+        *reinterpret_cast<uint2*>(a.dGbf_t + (size_t)b * N4 + 4 * (size_t)j) = pk;
+      }
+      gT[(0 * UO + l) * HT_LD + r] = __float2bfloat16_rn(d_i);
+      gT[(1 * UO + l) * HT_LD + r] = __float2bfloat16_rn(d_o);
+      gT[(2 * UO + l) * HT_LD + r] = __float2bfloat16_rn(d_f);
+      gT[(3 * UO + l) * HT_LD + r] = __float2bfloat16_rn(d_u);
+    }
+    named_bar_sync(1, EPI_THREADS);
+    // phase 3: dg^T rows (master row order gate*N + unit), lanes along the stream index
+    {
+      const int w4 = e >> 5, lane = e & 31;
+      const int jbase = nb * BN + (int)rank * UO;
+      for (int q = w4; q < 4 * UO; q += 4) {
+        const int gate = q / UO, u = q - gate * UO;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(gT + q * HT_LD);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(a.dGT_t + (size_t)(gate * N + jbase + u) * a.ldg + mb * BM);
+        dst[lane] = src[lane];
+        dst[lane + 32] = src[lane + 32];
+      }
+    }
+  }
+  tile_epilogue_end<BN, STAGES>(c);
+}
+
+template <int BN>
+static void launch_bwd_t(const CUtensorMap& tmdG, const CUtensorMap& tmUkr, const CUtensorMap& tmdY,
+                         const CUtensorMap& tmWnm, const BwdStepArgs& a, cudaStream_t st) {
+  using F = BwdCfg<BN>;
+  dim3 grid(a.N / BN, a.Bp / BM, SPLIT);
+  set_smem(k_bwd_step<BN>, F::C::SMEM_BYTES);
+  k_bwd_step<BN><<<grid, 192, F::C::SMEM_BYTES, st>>>(tmdG, tmUkr, tmdY, tmWnm, a);
+}
+void launch_bwd_step(int BN, const CUtensorMap& tmdG, const CUtensorMap& tmUkr, const CUtensorMap& tmdY,
+                     const CUtensorMap& tmWnm, const BwdStepArgs& a, cudaStream_t st) {
+  if (BN == 128) launch_bwd_t<128>(tmdG, tmUkr, tmdY, tmWnm, a, st);
+  else if (BN == 64) launch_bwd_t<64>(tmdG, tmUkr, tmdY, tmWnm, a, st);
+  else launch_bwd_t<32>(tmdG, tmUkr, tmdY, tmWnm, a, st);
+}
+
+}  // namespace tc

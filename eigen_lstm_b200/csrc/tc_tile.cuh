@@ -1,0 +1,123 @@
+// tc_tile.cuh — the shared skeleton of every tcgen05 kernel here: one 128 x BN output tile per CTA,
+// warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer, warps 2-5 = epilogue.
+#pragma once
+#include "tc_common.cuh"
+
+namespace tc {
+
+constexpr int BM = 128;                 // tile rows = TMEM lanes
+constexpr int BK = 64;                  // bf16 per 128-byte swizzled row
+constexpr int A_TILE_BYTES = BM * BK * 2;
+
+struct KSeg {                           // one contiguous K range of the contraction
+  const CUtensorMap* ta;
+  const CUtensorMap* tb;
+  int a_row, b_row, a_k0, b_k0, nkb;
+};
+
+template <int BN, int STAGES, int EPI_BYTES = 0>
+struct Cfg {
+  static constexpr int B_TILE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int EPI = (EPI_BYTES + 127) / 128 * 128;   // epilogue staging region after the barriers
+  static constexpr int SMEM_BYTES = TILE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + EPI;
+  static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+struct TileCtx {
+  uint8_t* epi;     // epilogue staging region (Cfg::EPI bytes)
+  uint8_t* tiles;
+  uint64_t *full, *empty, *accum_full;
+  uint32_t tmem_d;
+  int warp, lane;
+};
+
+// Common prologue: carve shared memory, init barriers, allocate TMEM.
+template <int BN, int STAGES>
+__device__ __forceinline__ TileCtx tile_prologue(uint8_t* raw) {
+  using C = Cfg<BN, STAGES>;
+  TileCtx c;
+  const uint32_t base = smem_u32(raw);
+  const uint32_t pad = ((base + 1023u) & ~1023u) - base;   // SWIZZLE_128B atoms need 1024-byte alignment
+  c.tiles = raw + pad;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(c.tiles + C::TILE_BYTES);
+  c.full = bars;
+  c.empty = bars + STAGES;
+  c.accum_full = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  c.epi = c.tiles + C::TILE_BYTES + 256;
+  c.warp = threadIdx.x >> 5;
+  c.lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(&c.full[s], 1); mbar_init(&c.empty[s], 1); }
+    mbar_init(c.accum_full, 1);
+    fence_barrier_init();
+  }
+  if (c.warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  tcgen05_before_sync();
+  __syncthreads();
+  tcgen05_after_sync();
+  c.tmem_d = *tmem_slot;
+  return c;
+}
+
+template <int BN, int STAGES>
+__device__ __forceinline__ void tile_epilogue_end(const TileCtx& c) {
+  tcgen05_before_sync();
+  __syncthreads();
+  if (c.warp == 1) tmem_dealloc<Cfg<BN, STAGES>::TMEM_COLS>(c.tmem_d);
+}
+
+// Producer (warp 0, one lane) and MMA issuer (warp 1, one lane) of one output tile.
+template <int BN, int STAGES>
+__device__ __forceinline__ void tile_mainloop(const TileCtx& c, const KSeg& s0, const KSeg& s1) {
+  using C = Cfg<BN, STAGES>;
+  const int total = s0.nkb + s1.nkb;
+  if (c.warp == 0) {
+    if (c.lane == 0) {
+      for (int kb = 0; kb < total; kb++) {
+        const int st = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&c.empty[st], ph ^ 1u);
+        const bool first = kb < s0.nkb;
+        const KSeg& s = first ? s0 : s1;
+        const int k = first ? kb : kb - s0.nkb;
+        uint8_t* a = c.tiles + (size_t)st * C::STAGE_BYTES;
+        uint8_t* b = a + A_TILE_BYTES;
+        mbar_expect_tx(&c.full[st], (uint32_t)C::STAGE_BYTES);
+        tma_load_2d(a, s.ta, &c.full[st], s.a_k0 + k * BK, s.a_row);
+        tma_load_2d(b, s.tb, &c.full[st], s.b_k0 + k * BK, s.b_row);
+      }
+    }
+  } else if (c.warp == 1) {
+    if (c.lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      for (int kb = 0; kb < total; kb++) {
+        const int st = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&c.full[st], ph);
+        tcgen05_after_sync();
+        const uint32_t a_addr = smem_u32(c.tiles + (size_t)st * C::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; k++)   // UMMA_K = 16 bf16 = 32 bytes inside the swizzled row
+          umma_bf16(c.tmem_d, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32), idesc,
+                    (uint32_t)((kb | k) != 0));
+        umma_commit(&c.empty[st]);          // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(c.accum_full);            // accumulator complete -> epilogue
+    }
+  }
+}
+
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+
+
+template <typename K>
+static void set_smem(K kernel, int bytes) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+}  // namespace tc
