@@ -72,6 +72,10 @@ struct GemmArgs {
   int tiles_m, tiles_n;
 };
 
+// K2 runs in clusters of FWD_CN x fwd_cluster_m(Bp) CTAs that share operand tiles by TMA multicast: its h map needs a
+// box of 128/FWD_CN rows, its U map one of BN/fwd_cluster_m(Bp) rows.
+constexpr int FWD_CN = 4;
+inline int fwd_cluster_m(int Bp) { return ((Bp / 128) % 2 == 0) ? 2 : 1; }
 // K2: one recurrent timestep.  BN in {32, 64, 128} gate columns per CTA.
 void launch_fwd_step(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st);
 // K3: logits + softmax + loss + dy for all timesteps

@@ -15,7 +15,7 @@ struct Bf16State {
   bf16 *dYbf = nullptr, *dYT = nullptr, *dGbf = nullptr, *dGT = nullptr, *ZT = nullptr;
   float *Wp = nullptr, *bp = nullptr, *Gp = nullptr, *dcnext = nullptr, *scratch = nullptr;
   size_t scratch_elems = 0;
-  CUtensorMap tmH, tmUrk, tmUkr, tmWmn, tmWnm, tmdY, tmdYT, tmdG, tmdGT, tmZT;
+  CUtensorMap tmH, tmH2, tmUrk, tmUkr, tmWmn, tmWnm, tmdY, tmdYT, tmdG, tmdGT, tmZT;
 };
 
 namespace {
@@ -94,7 +94,8 @@ int tc_create(lstm_ctx* ctx) {
   LSTM_LAUNCHED(1);
   bool ok = true;
   ok &= make_tmap(&s->tmH, s->Hbf, (uint64_t)(T + 1) * Bp, N, 128);
-  ok &= make_tmap(&s->tmUrk, s->Urk, N4, N, s->BN2);
+  ok &= make_tmap(&s->tmH2, s->Hbf, (uint64_t)(T + 1) * Bp, N, 128 / tc::FWD_CN);            // K2: multicast slices
+  ok &= make_tmap(&s->tmUrk, s->Urk, N4, N, s->BN2 / tc::fwd_cluster_m(s->Bp));
   ok &= make_tmap(&s->tmUkr, s->Ukr, N, N4, s->BN5);
   ok &= make_tmap(&s->tmWmn, s->Wmn, M, N, 256);
   ok &= make_tmap(&s->tmWnm, s->Wnm, N, M, s->BN5);
@@ -174,7 +175,7 @@ int tc_forward(lstm_ctx* ctx) {
     a.Hbf_t = s->Hbf + (size_t)t * Bp * N;
     a.ZT_h = s->ZT + (size_t)M * s->LDZ + (size_t)t * Bp;
     a.ldz = s->LDZ;
-    tc::launch_fwd_step(s->BN2, s->tmH, s->tmUrk, a, ctx->st);
+    tc::launch_fwd_step(s->BN2, s->tmH2, s->tmUrk, a, ctx->st);
   }
   LSTM_LAUNCHED(T);
   PROF(2);

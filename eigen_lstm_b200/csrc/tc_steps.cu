@@ -34,20 +34,21 @@ struct FwdCfg {
   using C = Cfg<BN, STAGES, EPI_BYTES>;
 };
 
-template <int BN>
+// CN x CM cluster: the CN CTAs along x share the h tile, the CM CTAs along y share the U tile (TMA multicast)
+template <int BN, int CN, int CM>
 __global__ void __launch_bounds__(192, 1)
 k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmU, const FwdStepArgs a) {
   using F = FwdCfg<BN>;
   constexpr int STAGES = F::STAGES, UT = F::UT, RG = EPI_THREADS / UT, ACC_LD = F::ACC_LD;
   extern __shared__ uint8_t smem_raw[];
-  TileCtx c = tile_prologue<BN, STAGES>(smem_raw);
+  TileCtx c = tile_prologue<BN, STAGES, CN, CM>(smem_raw);
   float* acc = reinterpret_cast<float*>(c.epi);
   __nv_bfloat16* hT = reinterpret_cast<__nv_bfloat16*>(c.epi + F::ACC_BYTES);
   int* sx = reinterpret_cast<int*>(c.epi + F::ACC_BYTES + F::HT_BYTES);
   const int nb = blockIdx.x, mb = blockIdx.y;
   const KSeg s0{&tmH, &tmU, a.a_row0 + mb * BM, nb * BN, 0, 0, a.N / BK};
   const KSeg s1{&tmH, &tmU, 0, 0, 0, 0, 0};
-  tile_mainloop<BN, STAGES>(c, s0, s1);
+  tile_mainloop<BN, STAGES, CN, CM>(c, s0, s1, (int)(blockIdx.x % CN), (int)(blockIdx.y % CM));
   if (c.warp >= 2) {
     const int e = threadIdx.x - 64;                        // 0..127
     const int N = a.N, N4 = 4 * a.N;
@@ -117,20 +118,40 @@ k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUte
       }
     }
   }
-  tile_epilogue_end<BN, STAGES>(c);
+  tile_epilogue_end<BN, STAGES, CN, CM>(c);
+}
+
+template <typename Kern, typename... Args>
+static void launch_cluster(Kern kernel, dim3 grid, dim3 cluster, int smem, cudaStream_t st, Args... args) {
+  set_smem(kernel, smem);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = (size_t)smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster.x;
+  attr[0].val.clusterDim.y = cluster.y;
+  attr[0].val.clusterDim.z = cluster.z;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
 template <int BN>
-static void launch_fwd_t(const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st) {
+static void launch_fwd_t(int CM, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st) {
   using F = FwdCfg<BN>;
   dim3 grid(4 * a.N / BN, a.Bp / BM);
-  set_smem(k_fwd_step<BN>, F::C::SMEM_BYTES);
-  k_fwd_step<BN><<<grid, 192, F::C::SMEM_BYTES, st>>>(tmH, tmUrk, a);
+  if (CM == 2) launch_cluster(k_fwd_step<BN, FWD_CN, 2>, grid, dim3(FWD_CN, 2, 1), F::C::SMEM_BYTES, st, tmH, tmUrk, a);
+  else launch_cluster(k_fwd_step<BN, FWD_CN, 1>, grid, dim3(FWD_CN, 1, 1), F::C::SMEM_BYTES, st, tmH, tmUrk, a);
 }
+// tmH must have a box of 128/FWD_CN rows and tmUrk one of BN/CM rows (CM = fwd_cluster_m(Bp))
 void launch_fwd_step(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st) {
-  if (BN == 128) launch_fwd_t<128>(tmH, tmUrk, a, st);
-  else if (BN == 64) launch_fwd_t<64>(tmH, tmUrk, a, st);
-  else launch_fwd_t<32>(tmH, tmUrk, a, st);
+  const int CM = fwd_cluster_m(a.Bp);
+  if (BN == 128) launch_fwd_t<128>(CM, tmH, tmUrk, a, st);
+  else if (BN == 64) launch_fwd_t<64>(CM, tmH, tmUrk, a, st);
+  else launch_fwd_t<32>(CM, tmH, tmUrk, a, st);
 }
 
 // ------------------------------------------------------------------------------------------------

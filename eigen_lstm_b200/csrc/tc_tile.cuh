@@ -34,7 +34,9 @@ struct TileCtx {
 };
 
 // Common prologue: carve shared memory, init barriers, allocate TMEM.
-template <int BN, int STAGES>
+// CN x CM = thread-block cluster sharing operand tiles by TMA multicast (tile_mainloop): a stage of this CTA is
+// written by CN + CM - 1 CTAs' loads, so that many consumers must release it.
+template <int BN, int STAGES, int CN = 1, int CM = 1>
 __device__ __forceinline__ TileCtx tile_prologue(uint8_t* raw) {
   using C = Cfg<BN, STAGES>;
   TileCtx c;
@@ -50,30 +52,43 @@ __device__ __forceinline__ TileCtx tile_prologue(uint8_t* raw) {
   c.warp = threadIdx.x >> 5;
   c.lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) { mbar_init(&c.full[s], 1); mbar_init(&c.empty[s], 1); }
+    for (int s = 0; s < STAGES; s++) { mbar_init(&c.full[s], 1); mbar_init(&c.empty[s], CN + CM - 1); }
     mbar_init(c.accum_full, 1);
     fence_barrier_init();
   }
   if (c.warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
   tcgen05_before_sync();
   __syncthreads();
+  if (CN * CM > 1) cluster_sync_all();                     // peers' barriers are initialised before any multicast lands
   tcgen05_after_sync();
   c.tmem_d = *tmem_slot;
   return c;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CN = 1, int CM = 1>
 __device__ __forceinline__ void tile_epilogue_end(const TileCtx& c) {
   tcgen05_before_sync();
   __syncthreads();
-  if (c.warp == 1) tmem_dealloc<Cfg<BN, STAGES>::TMEM_COLS>(c.tmem_d);
+  if (CN * CM > 1) cluster_sync_all();                     // no peer may still multicast into / signal an exited CTA
+  if (c.warp == 1) {
+    __syncwarp();
+    tmem_dealloc<Cfg<BN, STAGES>::TMEM_COLS>(c.tmem_d);
+  }
 }
 
 // Producer (warp 0, one lane) and MMA issuer (warp 1, one lane) of one output tile.
-template <int BN, int STAGES>
-__device__ __forceinline__ void tile_mainloop(const TileCtx& c, const KSeg& s0, const KSeg& s1) {
+// With a CN x CM cluster (cluster rank = xr + yr*CN): the A tile (128 rows) is common to the CN CTAs of a cluster
+// row and the B tile (BN rows) to the CM CTAs of a cluster column; every CTA loads a 1/CN (1/CM) row slice and
+// multicasts it, so each operand byte crosses L2 -> SM once per cluster instead of once per CTA.
+template <int BN, int STAGES, int CN = 1, int CM = 1>
+__device__ __forceinline__ void tile_mainloop(const TileCtx& c, const KSeg& s0, const KSeg& s1, int xr = 0, int yr = 0) {
   using C = Cfg<BN, STAGES>;
+  constexpr int A_ROWS = BM / CN, B_ROWS = BN / CM;
+  static_assert(A_ROWS % 8 == 0 && B_ROWS % 8 == 0, "multicast slices must be whole 8-row swizzle atoms");
   const int total = s0.nkb + s1.nkb;
+  uint16_t mask_a = 0, mask_b = 0;
+  for (int i = 0; i < CN; i++) mask_a |= (uint16_t)(1u << (yr * CN + i));
+  for (int j = 0; j < CM; j++) mask_b |= (uint16_t)(1u << (j * CN + xr));
   if (c.warp == 0) {
     if (c.lane == 0) {
       for (int kb = 0; kb < total; kb++) {
@@ -86,8 +101,10 @@ __device__ __forceinline__ void tile_mainloop(const TileCtx& c, const KSeg& s0, 
         uint8_t* a = c.tiles + (size_t)st * C::STAGE_BYTES;
         uint8_t* b = a + A_TILE_BYTES;
         mbar_expect_tx(&c.full[st], (uint32_t)C::STAGE_BYTES);
-        tma_load_2d(a, s.ta, &c.full[st], s.a_k0 + k * BK, s.a_row);
-        tma_load_2d(b, s.tb, &c.full[st], s.b_k0 + k * BK, s.b_row);
+        if (CN == 1) tma_load_2d(a, s.ta, &c.full[st], s.a_k0 + k * BK, s.a_row);
+        else tma_load_2d_mc(a + xr * A_ROWS * 128, s.ta, &c.full[st], s.a_k0 + k * BK, s.a_row + xr * A_ROWS, mask_a);
+        if (CM == 1) tma_load_2d(b, s.tb, &c.full[st], s.b_k0 + k * BK, s.b_row);
+        else tma_load_2d_mc(b + yr * B_ROWS * 128, s.tb, &c.full[st], s.b_k0 + k * BK, s.b_row + yr * B_ROWS, mask_b);
       }
     }
   } else if (c.warp == 1) {
@@ -104,7 +121,9 @@ __device__ __forceinline__ void tile_mainloop(const TileCtx& c, const KSeg& s0, 
         for (int k = 0; k < BK / 16; k++)   // UMMA_K = 16 bf16 = 32 bytes inside the swizzled row
           umma_bf16(c.tmem_d, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32), idesc,
                     (uint32_t)((kb | k) != 0));
-        umma_commit(&c.empty[st]);          // frees the smem stage once these MMAs have read it
+        // frees the stage once these MMAs have read it — in every CTA whose loads write into this CTA's stage
+        if (CN * CM == 1) umma_commit(&c.empty[st]);
+        else umma_commit_mc(&c.empty[st], (uint16_t)(mask_a | mask_b));
       }
       umma_commit(c.accum_full);            // accumulator complete -> epilogue
     }
