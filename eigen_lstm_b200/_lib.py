@@ -42,6 +42,7 @@ SYMBOLS = {
     "lstm_load_bin": (_i, [_vp, C.c_char_p]),
     "lstm_dp_unique_id": (_i, [_vp]),
     "lstm_dp_init": (_i, [_vp, _i, _i, _vp]),
+    "lstm_debug_kernel_clocks": (_i, [_vp, _vp]),
     "lstm_set_profiling": (_i, [_vp, _i]),
     "lstm_get_phase_ms": (_i, [_vp, _vp]),
     "lstm_launch_count": (C.c_long, [_vp]),

@@ -860,6 +860,11 @@ extern "C" int lstm_dp_init(lstm_ctx* ctx, int rank, int world, const uint8_t id
 // ------------------------------------------------------------------------------------------------
 // measurement
 // ------------------------------------------------------------------------------------------------
+extern "C" int lstm_debug_kernel_clocks(lstm_ctx* ctx, long long out[32]) {
+  if (!ctx || !out) return LSTM_ERR_ARG;
+  return tc_debug_read(ctx, out);
+}
+
 extern "C" int lstm_set_profiling(lstm_ctx* ctx, int on) {
   if (!ctx) return LSTM_ERR_ARG;
   ctx->profiling = on != 0;

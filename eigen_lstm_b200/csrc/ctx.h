@@ -85,5 +85,6 @@ int tc_get_activation(lstm_ctx* ctx, int what, int t, float* out, size_t n);
 int tc_state_from_f32(lstm_ctx* ctx);  // Hs slot 0 (fp32) -> bf16 operand copies
 int tc_state_to_f32(lstm_ctx* ctx);    // bf16 h(0) -> Hs slot 0
 int tc_carry(lstm_ctx* ctx, int stride);
+int tc_debug_read(lstm_ctx* ctx, long long out[32]);
 // sum gradient bucket (0 = [W,U,b], 1 = [Why,by]) over the data-parallel ranks on the communication stream
 int lstm_allreduce_bucket(lstm_ctx* ctx, int bucket);

@@ -37,6 +37,7 @@ struct FwdStepArgs {
   __nv_bfloat16* Hbf_t;        // [Bp][N]
   __nv_bfloat16* ZT_h;         // ZT + M*ldz + t*Bp : h rows of this slot
   long ldz;                    // ZT leading dimension (columns)
+  long long* dbg;              // optional: clock64 stamps of CTA (0,0) for diagnostics (NULL = off)
 };
 
 struct LogitsArgs {
@@ -60,6 +61,7 @@ struct BwdStepArgs {
   __nv_bfloat16* dGbf_t;       // [Bp][4N r']
   __nv_bfloat16* dGT_t;        // dGT + (t-1)*Bp
   long ldg;                    // dGT leading dimension (columns)
+  long long* dbg;              // optional: clock64 stamps of CTA (0,0,0) for diagnostics (NULL = off)
 };
 
 struct GemmArgs {
@@ -72,10 +74,13 @@ struct GemmArgs {
   int tiles_m, tiles_n;
 };
 
-// K2 runs in clusters of FWD_CN x fwd_cluster_m(Bp) CTAs that share operand tiles by TMA multicast: its h map needs a
-// box of 128/FWD_CN rows, its U map one of BN/fwd_cluster_m(Bp) rows.
-constexpr int FWD_CN = 4;
-inline int fwd_cluster_m(int Bp) { return ((Bp / 128) % 2 == 0) ? 2 : 1; }
+// K2 can run in clusters of cn x cm CTAs that share operand tiles by TMA multicast (cn CTAs along the gate-column
+// tiles share the h tile, cm CTAs along the batch tiles share the U tile): its h map then needs a box of 128/cn rows,
+// its U map one of BN/cm rows.  Measured on B200 (profiles/): multicast clusters are SLOWER than independent CTAs
+// for this kernel (lock-step stage reuse across the cluster), so the default is 1 x 1; LSTM_FWD_CN / LSTM_FWD_CM
+// override it for experiments.
+int fwd_cluster_n(int n_tiles);
+int fwd_cluster_m(int Bp);
 // K2: one recurrent timestep.  BN in {32, 64, 128} gate columns per CTA.
 void launch_fwd_step(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st);
 // K3: logits + softmax + loss + dy for all timesteps

@@ -1,5 +1,6 @@
 // tc_path.cu — host orchestration of the bf16 tensor-core path (LSTM_BF16): device buffers in the
 // operand layouts of tc_kernels.cuh, TMA tensor maps, and the per-iteration kernel sequence.
+#include <stdlib.h>
 #include <string.h>
 
 #include "ctx.h"
@@ -14,6 +15,7 @@ struct Bf16State {
   bf16 *Hbf = nullptr, *Urk = nullptr, *Ukr = nullptr, *Wmn = nullptr, *Wnm = nullptr;
   bf16 *dYbf = nullptr, *dYT = nullptr, *dGbf = nullptr, *dGT = nullptr, *ZT = nullptr;
   float *Wp = nullptr, *bp = nullptr, *Gp = nullptr, *dcnext = nullptr, *scratch = nullptr;
+  long long* dbg = nullptr;   // [32] kernel-internal clock stamps (LSTM_TC_DEBUG=1)
   size_t scratch_elems = 0;
   CUtensorMap tmH, tmH2, tmUrk, tmUkr, tmWmn, tmWnm, tmdY, tmdYT, tmdG, tmdGT, tmZT;
 };
@@ -90,11 +92,12 @@ int tc_create(lstm_ctx* ctx) {
   TC_ALLOC(s->dcnext, (size_t)B * N * sizeof(float));
   s->scratch_elems = (size_t)B * N4;
   TC_ALLOC(s->scratch, s->scratch_elems * sizeof(float));
+  if (getenv("LSTM_TC_DEBUG")) TC_ALLOC(s->dbg, 32 * sizeof(long long));
   tc::launch_fill_bf16(s->ZT + (size_t)(M + N) * s->LDZ, 1.0f, (size_t)s->LDZ, ctx->st);  // the ones row (db, dby)
   LSTM_LAUNCHED(1);
   bool ok = true;
   ok &= make_tmap(&s->tmH, s->Hbf, (uint64_t)(T + 1) * Bp, N, 128);
-  ok &= make_tmap(&s->tmH2, s->Hbf, (uint64_t)(T + 1) * Bp, N, 128 / tc::FWD_CN);            // K2: multicast slices
+  ok &= make_tmap(&s->tmH2, s->Hbf, (uint64_t)(T + 1) * Bp, N, 128 / tc::fwd_cluster_n(s->N4 / s->BN2));            // K2: multicast slices
   ok &= make_tmap(&s->tmUrk, s->Urk, N4, N, s->BN2 / tc::fwd_cluster_m(s->Bp));
   ok &= make_tmap(&s->tmUkr, s->Ukr, N, N4, s->BN5);
   ok &= make_tmap(&s->tmWmn, s->Wmn, M, N, 256);
@@ -175,6 +178,7 @@ int tc_forward(lstm_ctx* ctx) {
     a.Hbf_t = s->Hbf + (size_t)t * Bp * N;
     a.ZT_h = s->ZT + (size_t)M * s->LDZ + (size_t)t * Bp;
     a.ldz = s->LDZ;
+    a.dbg = s->dbg;
     tc::launch_fwd_step(s->BN2, s->tmH2, s->tmUrk, a, ctx->st);
   }
   LSTM_LAUNCHED(T);
@@ -216,6 +220,7 @@ int tc_backward(lstm_ctx* ctx) {
     a.dGbf_t = s->dGbf + (size_t)(t - 1) * Bp * N4;
     a.dGT_t = s->dGT + (size_t)(t - 1) * Bp;
     a.ldg = s->LDT;
+    a.dbg = s->dbg ? s->dbg + 16 : nullptr;
     tc::launch_bwd_step(s->BN5, s->tmdG, s->tmUkr, s->tmdY, s->tmWnm, a, ctx->st);
   }
   LSTM_LAUNCHED(T);
@@ -231,6 +236,14 @@ int tc_backward(lstm_ctx* ctx) {
   }
   PROF(6);
   return lstm_allreduce_bucket(ctx, 0);
+}
+
+int tc_debug_read(lstm_ctx* ctx, long long out[32]) {
+  Bf16State* s = ctx->tc;
+  if (!s || !s->dbg) return lstm_fail(ctx, LSTM_ERR_STATE, "set LSTM_TC_DEBUG=1 before lstm_create (bf16 contexts only)");
+  LSTM_CUDA(cudaStreamSynchronize(ctx->st));
+  LSTM_CUDA(cudaMemcpy(out, s->dbg, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return LSTM_OK;
 }
 
 int tc_get_activation(lstm_ctx* ctx, int what, int t, float* out, size_t n) {

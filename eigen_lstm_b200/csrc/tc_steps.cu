@@ -10,6 +10,8 @@
 // K5's output (B x N) is 4x smaller than K2's (B x 4N) for the same flops, so its K range
 // (4N + M) is split over a cluster of 4 CTAs; the partial accumulators are reduce-scattered through
 // distributed shared memory (each CTA finalises a quarter of the tile's hidden units).
+#include <stdlib.h>
+
 #include "tc_kernels.cuh"
 #include "tc_tile.cuh"
 
@@ -41,7 +43,11 @@ k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUte
   using F = FwdCfg<BN>;
   constexpr int STAGES = F::STAGES, UT = F::UT, RG = EPI_THREADS / UT, ACC_LD = F::ACC_LD;
   extern __shared__ uint8_t smem_raw[];
+  const long long t_entry = clock64();
   TileCtx c = tile_prologue<BN, STAGES, CN, CM>(smem_raw);
+  c.dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0) ? a.dbg : nullptr;
+  const bool stamp = c.dbg && threadIdx.x == 64;
+  if (stamp) { c.dbg[0] = t_entry; c.dbg[4] = clock64(); }
   float* acc = reinterpret_cast<float*>(c.epi);
   __nv_bfloat16* hT = reinterpret_cast<__nv_bfloat16*>(c.epi + F::ACC_BYTES);
   int* sx = reinterpret_cast<int*>(c.epi + F::ACC_BYTES + F::HT_BYTES);
@@ -72,6 +78,7 @@ k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUte
     const int quarter = c.warp & 3;
     const int row = quarter * 32 + c.lane;
     mbar_wait(c.accum_full, 0);
+    if (stamp) c.dbg[5] = clock64();
     tcgen05_after_sync();
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -82,6 +89,7 @@ k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUte
       for (int u = 0; u < 8; u++) dst[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
     }
     named_bar_sync(1, EPI_THREADS);
+    if (stamp) c.dbg[6] = clock64();
     // phase 2: lane = hidden unit; one warp instruction touches one stream's contiguous row segment
 #pragma unroll 4
     for (int i = 0; i < UT; i++) {
@@ -107,6 +115,7 @@ k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUte
       hT[l * HT_LD + r] = __float2bfloat16_rn(hval);
     }
     named_bar_sync(1, EPI_THREADS);
+    if (stamp) c.dbg[7] = clock64();
     // phase 3: h^T rows of ZT (the K6 operand), lanes along the stream index
     {
       const int w4 = e >> 5, lane = e & 31;
@@ -119,6 +128,7 @@ k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUte
     }
   }
   tile_epilogue_end<BN, STAGES, CN, CM>(c);
+  if (stamp) c.dbg[8] = clock64();
 }
 
 template <typename Kern, typename... Args>
@@ -139,19 +149,38 @@ static void launch_cluster(Kern kernel, dim3 grid, dim3 cluster, int smem, cudaS
   cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
-template <int BN>
-static void launch_fwd_t(int CM, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st) {
-  using F = FwdCfg<BN>;
-  dim3 grid(4 * a.N / BN, a.Bp / BM);
-  if (CM == 2) launch_cluster(k_fwd_step<BN, FWD_CN, 2>, grid, dim3(FWD_CN, 2, 1), F::C::SMEM_BYTES, st, tmH, tmUrk, a);
-  else launch_cluster(k_fwd_step<BN, FWD_CN, 1>, grid, dim3(FWD_CN, 1, 1), F::C::SMEM_BYTES, st, tmH, tmUrk, a);
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
 }
-// tmH must have a box of 128/FWD_CN rows and tmUrk one of BN/CM rows (CM = fwd_cluster_m(Bp))
+int fwd_cluster_n(int n_tiles) {
+  const int cn = env_int("LSTM_FWD_CN", 1);
+  return (cn == 2 || cn == 4) && n_tiles % cn == 0 ? cn : 1;
+}
+int fwd_cluster_m(int Bp) {
+  const int cm = env_int("LSTM_FWD_CM", 1);
+  return cm == 2 && (Bp / 128) % 2 == 0 ? 2 : 1;
+}
+
+template <int BN, int CN>
+static void launch_fwd_cn(int CM, dim3 grid, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st) {
+  using F = FwdCfg<BN>;
+  if (CM == 2) launch_cluster(k_fwd_step<BN, CN, 2>, grid, dim3(CN, 2, 1), F::C::SMEM_BYTES, st, tmH, tmUrk, a);
+  else launch_cluster(k_fwd_step<BN, CN, 1>, grid, dim3(CN, 1, 1), F::C::SMEM_BYTES, st, tmH, tmUrk, a);
+}
+template <int BN>
+static void launch_fwd_t(const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st) {
+  dim3 grid(4 * a.N / BN, a.Bp / BM);
+  const int CN = fwd_cluster_n((int)grid.x), CM = fwd_cluster_m(a.Bp);
+  if (CN == 4) launch_fwd_cn<BN, 4>(CM, grid, tmH, tmUrk, a, st);
+  else if (CN == 2) launch_fwd_cn<BN, 2>(CM, grid, tmH, tmUrk, a, st);
+  else launch_fwd_cn<BN, 1>(CM, grid, tmH, tmUrk, a, st);
+}
+// tmH must have a box of 128/fwd_cluster_n rows and tmUrk one of BN/fwd_cluster_m rows
 void launch_fwd_step(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st) {
-  const int CM = fwd_cluster_m(a.Bp);
-  if (BN == 128) launch_fwd_t<128>(CM, tmH, tmUrk, a, st);
-  else if (BN == 64) launch_fwd_t<64>(CM, tmH, tmUrk, a, st);
-  else launch_fwd_t<32>(CM, tmH, tmUrk, a, st);
+  if (BN == 128) launch_fwd_t<128>(tmH, tmUrk, a, st);
+  else if (BN == 64) launch_fwd_t<64>(tmH, tmUrk, a, st);
+  else launch_fwd_t<32>(tmH, tmUrk, a, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -178,7 +207,11 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
   using F = BwdCfg<BN>;
   constexpr int STAGES = F::STAGES, UO = F::UO, RG = EPI_THREADS / UO, RV_LD = F::RV_LD;
   extern __shared__ uint8_t smem_raw[];
+  const long long t_entry = clock64();
   TileCtx c = tile_prologue<BN, STAGES>(smem_raw);
+  c.dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? a.dbg : nullptr;
+  const bool stamp = c.dbg && threadIdx.x == 64;
+  if (stamp) { c.dbg[0] = t_entry; c.dbg[4] = clock64(); }
   float* recv = reinterpret_cast<float*>(c.epi);
   __nv_bfloat16* gT = reinterpret_cast<__nv_bfloat16*>(c.epi + F::RV_BYTES);
   const int nb = blockIdx.x, mb = blockIdx.y;
@@ -211,6 +244,7 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
     const int row = quarter * 32 + c.lane;
     const uint32_t my_slot = smem_u32(recv + ((size_t)rank * 128 + row) * RV_LD);
     mbar_wait(c.accum_full, 0);
+    if (stamp) c.dbg[5] = clock64();
     tcgen05_after_sync();
 #pragma unroll 1
     for (int q = 0; q < SPLIT; q++) {
@@ -222,6 +256,7 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
     }
   }
   cluster_sync_all();                                      // all partial slices have landed (release/acquire)
+  if (stamp) c.dbg[6] = clock64();
   if (c.warp >= 2) {
     // phase 2: lane = hidden unit
 #pragma unroll 2
@@ -254,6 +289,7 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
       gT[(3 * UO + l) * HT_LD + r] = __float2bfloat16_rn(d_u);
     }
     named_bar_sync(1, EPI_THREADS);
+    if (stamp) c.dbg[7] = clock64();
     // phase 3: dg^T rows (master row order gate*N + unit), lanes along the stream index
     {
       const int w4 = e >> 5, lane = e & 31;
@@ -268,6 +304,7 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
     }
   }
   tile_epilogue_end<BN, STAGES>(c);
+  if (stamp) c.dbg[8] = clock64();
 }
 
 template <int BN>

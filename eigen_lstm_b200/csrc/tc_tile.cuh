@@ -26,6 +26,7 @@ struct Cfg {
 };
 
 struct TileCtx {
+  long long* dbg;   // diagnostics (NULL = off): [1] last TMA issued, [2] first stage landed, [3] last MMA issued
   uint8_t* epi;     // epilogue staging region (Cfg::EPI bytes)
   uint8_t* tiles;
   uint64_t *full, *empty, *accum_full;
@@ -40,6 +41,7 @@ template <int BN, int STAGES, int CN = 1, int CM = 1>
 __device__ __forceinline__ TileCtx tile_prologue(uint8_t* raw) {
   using C = Cfg<BN, STAGES>;
   TileCtx c;
+  c.dbg = nullptr;
   const uint32_t base = smem_u32(raw);
   const uint32_t pad = ((base + 1023u) & ~1023u) - base;   // SWIZZLE_128B atoms need 1024-byte alignment
   c.tiles = raw + pad;
@@ -106,6 +108,7 @@ __device__ __forceinline__ void tile_mainloop(const TileCtx& c, const KSeg& s0, 
         if (CM == 1) tma_load_2d(b, s.tb, &c.full[st], s.b_k0 + k * BK, s.b_row);
         else tma_load_2d_mc(b + yr * B_ROWS * 128, s.tb, &c.full[st], s.b_k0 + k * BK, s.b_row + yr * B_ROWS, mask_b);
       }
+      if (c.dbg) c.dbg[1] = clock64();
     }
   } else if (c.warp == 1) {
     if (c.lane == 0) {
@@ -114,6 +117,7 @@ __device__ __forceinline__ void tile_mainloop(const TileCtx& c, const KSeg& s0, 
         const int st = kb % STAGES;
         const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
         mbar_wait(&c.full[st], ph);
+        if (c.dbg && kb == 0) c.dbg[2] = clock64();
         tcgen05_after_sync();
         const uint32_t a_addr = smem_u32(c.tiles + (size_t)st * C::STAGE_BYTES);
         const uint32_t b_addr = a_addr + A_TILE_BYTES;
@@ -126,6 +130,7 @@ __device__ __forceinline__ void tile_mainloop(const TileCtx& c, const KSeg& s0, 
         else umma_commit_mc(&c.empty[st], (uint16_t)(mask_a | mask_b));
       }
       umma_commit(c.accum_full);            // accumulator complete -> epilogue
+      if (c.dbg) c.dbg[3] = clock64();
     }
   }
 }

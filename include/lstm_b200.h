@@ -142,6 +142,11 @@ int lstm_dp_init(lstm_ctx* ctx, int rank, int world, const uint8_t id[128]);
  * [3] dH_y (fp32 path) + dWhy|dby GEMM, [4] backward recurrence, [5] weight gradients, [6] allreduce wait, [7] adagrad, [8] total */
 int lstm_set_profiling(lstm_ctx* ctx, int on);
 int lstm_get_phase_ms(lstm_ctx* ctx, float ms[16]);
+/* diagnostics (LSTM_TC_DEBUG=1 in the environment at lstm_create, bf16 contexts): SM clock stamps taken inside the
+ * last forward-step kernel ([0..8]) and the last BPTT-step kernel ([16..24]) by CTA 0: [0] entry, [4] prologue done,
+ * [2] first operand stage landed, [1] last TMA issued, [3] last MMA issued, [5] accumulator complete, [6] tile
+ * re-mapped through shared memory / cluster reduce done, [7] LSTM math + stores done, [8] exit */
+int lstm_debug_kernel_clocks(lstm_ctx* ctx, long long out[32]);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 long lstm_launch_count(const lstm_ctx* ctx);
 /* raw CUDA stream (cudaStream_t) of the context, for callers that time with their own events */
