@@ -90,29 +90,44 @@ k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUte
     }
     named_bar_sync(1, EPI_THREADS);
     if (stamp) c.dbg[6] = clock64();
-    // phase 2: lane = hidden unit; one warp instruction touches one stream's contiguous row segment
-#pragma unroll 4
-    for (int i = 0; i < UT; i++) {
-      const int r = rg + RG * i;
-      const int x = sx[r];
-      float hval = 0.f;
-      if (x >= -1) {
-        const int b = mb * BM + r;
-        const float4 pre = *reinterpret_cast<const float4*>(acc + (size_t)r * ACC_LD + 4 * l);
-        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (x >= 0) w = *reinterpret_cast<const float4*>(a.Wp + (size_t)x * N4 + rp);   // W*x, one-hot x
-        const float cp = a.c_prev[(size_t)b * N + j];
-        const float gi = sigmoid_fast(pre.x + w.x + bias.x);
-        const float go = sigmoid_fast(pre.y + w.y + bias.y);
-        const float gf = sigmoid_fast(pre.z + w.z + bias.z);
-        const float gu = tanh_fast(pre.w + w.w + bias.w);
-        const float cc = tanh_fast(gi * gu + gf * cp);     // the carried cell value is the tanh'd one
-        hval = go * cc;
-        *reinterpret_cast<float4*>(a.Gp_t + (size_t)b * N4 + rp) = make_float4(gi, go, gf, gu);
-        a.c_out[(size_t)b * N + j] = cc;
-        a.Hbf_t[(size_t)b * N + j] = __float2bfloat16_rn(hval);
+    // phase 2: lane = hidden unit; one warp instruction touches one stream's contiguous row segment.
+    // Rows are processed in batches of RB with all their global loads issued up front (memory-level parallelism:
+    // this phase is latency-bound, not bandwidth-bound).
+    constexpr int RB = UT < 8 ? UT : 8;
+#pragma unroll 1
+    for (int i0 = 0; i0 < UT; i0 += RB) {
+      float4 w[RB];
+      float cpv[RB];
+      int xv[RB];
+#pragma unroll
+      for (int q = 0; q < RB; q++) {
+        const int r = rg + RG * (i0 + q);
+        const int x = sx[r];
+        xv[q] = x;
+        w[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        cpv[q] = 0.f;
+        if (x >= 0) w[q] = __ldg(reinterpret_cast<const float4*>(a.Wp + (size_t)x * N4 + rp));   // W*x, one-hot x
+        if (x >= -1) cpv[q] = a.c_prev[(size_t)(mb * BM + r) * N + j];
       }
-      hT[l * HT_LD + r] = __float2bfloat16_rn(hval);
+#pragma unroll
+      for (int q = 0; q < RB; q++) {
+        const int r = rg + RG * (i0 + q);
+        float hval = 0.f;
+        if (xv[q] >= -1) {
+          const int b = mb * BM + r;
+          const float4 pre = *reinterpret_cast<const float4*>(acc + (size_t)r * ACC_LD + 4 * l);
+          const float gi = sigmoid_fast(pre.x + w[q].x + bias.x);
+          const float go = sigmoid_fast(pre.y + w[q].y + bias.y);
+          const float gf = sigmoid_fast(pre.z + w[q].z + bias.z);
+          const float gu = tanh_fast(pre.w + w[q].w + bias.w);
+          const float cc = tanh_fast(gi * gu + gf * cpv[q]);   // the carried cell value is the tanh'd one
+          hval = go * cc;
+          *reinterpret_cast<float4*>(a.Gp_t + (size_t)b * N4 + rp) = make_float4(gi, go, gf, gu);
+          a.c_out[(size_t)b * N + j] = cc;
+          a.Hbf_t[(size_t)b * N + j] = __float2bfloat16_rn(hval);
+        }
+        hT[l * HT_LD + r] = __float2bfloat16_rn(hval);
+      }
     }
     named_bar_sync(1, EPI_THREADS);
     if (stamp) c.dbg[7] = clock64();
@@ -258,35 +273,52 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
   cluster_sync_all();                                      // all partial slices have landed (release/acquire)
   if (stamp) c.dbg[6] = clock64();
   if (c.warp >= 2) {
-    // phase 2: lane = hidden unit
-#pragma unroll 2
-    for (int i = 0; i < UO; i++) {
-      const int r = rg + RG * i;
-      const int b = mb * BM + r;
-      float d_i = 0.f, d_o = 0.f, d_f = 0.f, d_u = 0.f;
-      if (b < a.B) {
-        float dh = 0.f;
+    // phase 2: lane = hidden unit; batches of RB rows with all global loads issued up front (latency-bound phase)
+    constexpr int RB = UO < 8 ? UO : 8;
+#pragma unroll 1
+    for (int i0 = 0; i0 < UO; i0 += RB) {
+      float4 gv[RB];
+      float ctv[RB], cpv[RB], dnv[RB];
 #pragma unroll
-        for (int s = 0; s < SPLIT; s++) dh += recv[((size_t)s * 128 + r) * RV_LD + l];      // fixed order: deterministic
-        const float4 g = *reinterpret_cast<const float4*>(a.Gp_t + (size_t)b * N4 + 4 * (size_t)j);   // i o f u
-        const size_t bj = (size_t)b * N + j;
-        const float ct = a.c_t[bj], cp = a.c_prev[bj];
-        const float dn = a.first ? 0.f : a.dcnext[bj];
-        const float dc = (dh * g.y + dn) * (1.0f - ct * ct);               // :233-235
-        d_o = dh * ct * (g.y * (1.0f - g.y));                              // :238,244
-        d_i = dc * g.w * (g.x * (1.0f - g.x));                             // :239,244
-        d_f = dc * cp * (g.z * (1.0f - g.z));                              // :240,244
-        d_u = dc * g.x * (1.0f - g.w * g.w);                               // :241,247
-        a.dcnext[bj] = dc * g.z;                                           // :256
-        uint2 pk;
-        pk.x = pack_bf16x2(d_i, d_o);
-        pk.y = pack_bf16x2(d_f, d_u);
-        *reinterpret_cast<uint2*>(a.dGbf_t + (size_t)b * N4 + 4 * (size_t)j) = pk;
+      for (int q = 0; q < RB; q++) {
+        const int b = mb * BM + rg + RG * (i0 + q);
+        gv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ctv[q] = cpv[q] = dnv[q] = 0.f;
+        if (b < a.B) {
+          const size_t bj = (size_t)b * N + j;
+          gv[q] = *reinterpret_cast<const float4*>(a.Gp_t + (size_t)b * N4 + 4 * (size_t)j);   // i o f u
+          ctv[q] = a.c_t[bj];
+          cpv[q] = a.c_prev[bj];
+          if (!a.first) dnv[q] = a.dcnext[bj];
+        }
       }
-      gT[(0 * UO + l) * HT_LD + r] = __float2bfloat16_rn(d_i);
-      gT[(1 * UO + l) * HT_LD + r] = __float2bfloat16_rn(d_o);
-      gT[(2 * UO + l) * HT_LD + r] = __float2bfloat16_rn(d_f);
-      gT[(3 * UO + l) * HT_LD + r] = __float2bfloat16_rn(d_u);
+#pragma unroll
+      for (int q = 0; q < RB; q++) {
+        const int r = rg + RG * (i0 + q);
+        const int b = mb * BM + r;
+        float d_i = 0.f, d_o = 0.f, d_f = 0.f, d_u = 0.f;
+        if (b < a.B) {
+          float dh = 0.f;
+#pragma unroll
+          for (int sr = 0; sr < SPLIT; sr++) dh += recv[((size_t)sr * 128 + r) * RV_LD + l];   // fixed order: deterministic
+          const float4 g = gv[q];
+          const float ct = ctv[q];
+          const float dc = (dh * g.y + dnv[q]) * (1.0f - ct * ct);           // :233-235
+          d_o = dh * ct * (g.y * (1.0f - g.y));                              // :238,244
+          d_i = dc * g.w * (g.x * (1.0f - g.x));                             // :239,244
+          d_f = dc * cpv[q] * (g.z * (1.0f - g.z));                          // :240,244
+          d_u = dc * g.x * (1.0f - g.w * g.w);                               // :241,247
+          a.dcnext[(size_t)b * N + j] = dc * g.z;                            // :256
+          uint2 pk;
+          pk.x = pack_bf16x2(d_i, d_o);
+          pk.y = pack_bf16x2(d_f, d_u);
+          *reinterpret_cast<uint2*>(a.dGbf_t + (size_t)b * N4 + 4 * (size_t)j) = pk;
+        }
+        gT[(0 * UO + l) * HT_LD + r] = __float2bfloat16_rn(d_i);
+        gT[(1 * UO + l) * HT_LD + r] = __float2bfloat16_rn(d_o);
+        gT[(2 * UO + l) * HT_LD + r] = __float2bfloat16_rn(d_f);
+        gT[(3 * UO + l) * HT_LD + r] = __float2bfloat16_rn(d_u);
+      }
     }
     named_bar_sync(1, EPI_THREADS);
     if (stamp) c.dbg[7] = clock64();
