@@ -17,7 +17,9 @@
 
 namespace tc {
 
-constexpr int EPI_THREADS = 128;
+constexpr int EPI_WARPS = 16;            // the LSTM math is latency-bound: many warps, few rows each
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int CTA_THREADS = 64 + EPI_THREADS;
 constexpr int HT_LD = 130;   // bf16 row pitch of the transposed staging tiles: 65 words -> conflict-free
 
 // ------------------------------------------------------------------------------------------------
@@ -38,10 +40,10 @@ struct FwdCfg {
 
 // CN x CM cluster: the CN CTAs along x share the h tile, the CM CTAs along y share the U tile (TMA multicast)
 template <int BN, int CN, int CM>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(CTA_THREADS, 1)
 k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmU, const FwdStepArgs a) {
   using F = FwdCfg<BN>;
-  constexpr int STAGES = F::STAGES, UT = F::UT, RG = EPI_THREADS / UT, ACC_LD = F::ACC_LD;
+  constexpr int STAGES = F::STAGES, UT = F::UT, RG = EPI_THREADS / UT, ROWS = 128 / RG, ACC_LD = F::ACC_LD;
   extern __shared__ uint8_t smem_raw[];
   const long long t_entry = clock64();
   TileCtx c = tile_prologue<BN, STAGES, CN, CM>(smem_raw);
@@ -56,46 +58,48 @@ k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUte
   const KSeg s1{&tmH, &tmU, 0, 0, 0, 0, 0};
   tile_mainloop<BN, STAGES, CN, CM>(c, s0, s1, (int)(blockIdx.x % CN), (int)(blockIdx.y % CM));
   if (c.warp >= 2) {
-    const int e = threadIdx.x - 64;                        // 0..127
+    const int e = threadIdx.x - 64;                        // 0..EPI_THREADS-1
     const int N = a.N, N4 = 4 * a.N;
     const int l = e % UT, rg = e / UT;                     // phase-2 mapping: lane = hidden unit
     const int j = nb * UT + l;                             // hidden unit
     const int rp = 4 * j;                                  // first of its 4 gate rows (unit-major order)
-    {                                                      // input bytes of the tile's 128 streams
+    if (e < 128) {                                         // input bytes of the tile's 128 streams
       const int b = mb * BM + e;
       sx[e] = (b < a.B) ? a.x[b] : -2;                     // -2 = padding row, -1 = all-zero input column
     }
     const float4 bias = *reinterpret_cast<const float4*>(a.bp + rp);
     named_bar_sync(1, EPI_THREADS);
     // warm L2 with what phase 2 will read, while the tensor core is busy
-#pragma unroll 4
-    for (int i = 0; i < UT; i++) {
+#pragma unroll
+    for (int i = 0; i < ROWS; i++) {
       const int r = rg + RG * i, x = sx[r];
       if (x >= 0 && (l & 7) == 0) prefetch_l2(a.Wp + (size_t)x * N4 + rp);
       if (x >= -1 && l == 0) prefetch_l2(a.c_prev + (size_t)(mb * BM + r) * N + j);
     }
-    // phase 1: TMEM (lane = stream) -> shared memory tile acc[row][col]
-    const int quarter = c.warp & 3;
-    const int row = quarter * 32 + c.lane;
-    mbar_wait(c.accum_full, 0);
-    if (stamp) c.dbg[5] = clock64();
-    tcgen05_after_sync();
+    // phase 1 (warps 2-5, one per TMEM lane quarter): TMEM (lane = stream) -> shared memory tile acc[row][col]
+    if (c.warp < 6) {
+      const int quarter = c.warp & 3;
+      const int row = quarter * 32 + c.lane;
+      mbar_wait(c.accum_full, 0);
+      if (stamp) c.dbg[5] = clock64();
+      tcgen05_after_sync();
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      float v[32];
-      tmem_ld32(c.tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-      float4* dst = reinterpret_cast<float4*>(acc + (size_t)row * ACC_LD + c0);
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(c.tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+        float4* dst = reinterpret_cast<float4*>(acc + (size_t)row * ACC_LD + c0);
 #pragma unroll
-      for (int u = 0; u < 8; u++) dst[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+        for (int u = 0; u < 8; u++) dst[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+      }
     }
     named_bar_sync(1, EPI_THREADS);
     if (stamp) c.dbg[6] = clock64();
     // phase 2: lane = hidden unit; one warp instruction touches one stream's contiguous row segment.
     // Rows are processed in batches of RB with all their global loads issued up front (memory-level parallelism:
     // this phase is latency-bound, not bandwidth-bound).
-    constexpr int RB = UT < 8 ? UT : 8;
+    constexpr int RB = ROWS < 8 ? ROWS : 8;
 #pragma unroll 1
-    for (int i0 = 0; i0 < UT; i0 += RB) {
+    for (int i0 = 0; i0 < ROWS; i0 += RB) {
       float4 w[RB];
       float cpv[RB];
       int xv[RB];
@@ -134,7 +138,7 @@ k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUte
     // phase 3: h^T rows of ZT (the K6 operand), lanes along the stream index
     {
       const int w4 = e >> 5, lane = e & 31;
-      for (int u = w4; u < UT; u += 4) {
+      for (int u = w4; u < UT; u += EPI_WARPS) {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(hT + u * HT_LD);
         uint32_t* dst = reinterpret_cast<uint32_t*>(a.ZT_h + (size_t)(nb * UT + u) * a.ldz + mb * BM);
         dst[lane] = src[lane];
@@ -151,7 +155,7 @@ static void launch_cluster(Kern kernel, dim3 grid, dim3 cluster, int smem, cudaS
   set_smem(kernel, smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(192);
+  cfg.blockDim = dim3(CTA_THREADS);
   cfg.dynamicSmemBytes = (size_t)smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -216,11 +220,11 @@ struct BwdCfg {
 };
 
 template <int BN>
-__global__ void __cluster_dims__(1, 1, SPLIT) __launch_bounds__(192, 1)
+__global__ void __cluster_dims__(1, 1, SPLIT) __launch_bounds__(CTA_THREADS, 1)
 k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUtensorMap tmU,
            const __grid_constant__ CUtensorMap tmdY, const __grid_constant__ CUtensorMap tmW, const BwdStepArgs a) {
   using F = BwdCfg<BN>;
-  constexpr int STAGES = F::STAGES, UO = F::UO, RG = EPI_THREADS / UO, RV_LD = F::RV_LD;
+  constexpr int STAGES = F::STAGES, UO = F::UO, RG = EPI_THREADS / UO, ROWS = 128 / RG, RV_LD = F::RV_LD;
   extern __shared__ uint8_t smem_raw[];
   const long long t_entry = clock64();
   TileCtx c = tile_prologue<BN, STAGES>(smem_raw);
@@ -246,37 +250,39 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
   const int l = e >= 0 ? e % UO : 0, rg = e >= 0 ? e / UO : 0;
   const int j = nb * BN + (int)rank * UO + l;              // the hidden unit this thread finalises
   if (c.warp >= 2) {
-#pragma unroll 4
-    for (int i = 0; i < UO; i++) {                         // warm L2 for phase 2
+#pragma unroll
+    for (int i = 0; i < ROWS; i++) {                       // warm L2 for phase 2
       const int b = mb * BM + rg + RG * i;
       if (b < a.B) {
         if ((l & 7) == 0) prefetch_l2(a.Gp_t + (size_t)b * N4 + 4 * (size_t)j);
         if (l == 0) { prefetch_l2(a.c_t + (size_t)b * N + j); prefetch_l2(a.c_prev + (size_t)b * N + j); }
       }
     }
-    // phase 1: reduce-scatter.  Column slice q of this CTA's partial accumulator goes to CTA q's recv[rank]
-    const int quarter = c.warp & 3;
-    const int row = quarter * 32 + c.lane;
-    const uint32_t my_slot = smem_u32(recv + ((size_t)rank * 128 + row) * RV_LD);
-    mbar_wait(c.accum_full, 0);
-    if (stamp) c.dbg[5] = clock64();
-    tcgen05_after_sync();
+    // phase 1 (warps 2-5): reduce-scatter.  Column slice q of this CTA's partial accumulator goes to CTA q's recv[rank]
+    if (c.warp < 6) {
+      const int quarter = c.warp & 3;
+      const int row = quarter * 32 + c.lane;
+      const uint32_t my_slot = smem_u32(recv + ((size_t)rank * 128 + row) * RV_LD);
+      mbar_wait(c.accum_full, 0);
+      if (stamp) c.dbg[5] = clock64();
+      tcgen05_after_sync();
 #pragma unroll 1
-    for (int q = 0; q < SPLIT; q++) {
-      float v[UO];
-      tmem_ldw<UO>(c.tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(q * UO), v);
-      const uint32_t dst = mapa_u32(my_slot, (uint32_t)q);
+      for (int q = 0; q < SPLIT; q++) {
+        float v[UO];
+        tmem_ldw<UO>(c.tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(q * UO), v);
+        const uint32_t dst = mapa_u32(my_slot, (uint32_t)q);
 #pragma unroll
-      for (int u = 0; u < UO / 4; u++) st_cluster_v4(dst + 16 * u, make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]));
+        for (int u = 0; u < UO / 4; u++) st_cluster_v4(dst + 16 * u, make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]));
+      }
     }
   }
   cluster_sync_all();                                      // all partial slices have landed (release/acquire)
   if (stamp) c.dbg[6] = clock64();
   if (c.warp >= 2) {
     // phase 2: lane = hidden unit; batches of RB rows with all global loads issued up front (latency-bound phase)
-    constexpr int RB = UO < 8 ? UO : 8;
+    constexpr int RB = ROWS < 8 ? ROWS : 8;
 #pragma unroll 1
-    for (int i0 = 0; i0 < UO; i0 += RB) {
+    for (int i0 = 0; i0 < ROWS; i0 += RB) {
       float4 gv[RB];
       float ctv[RB], cpv[RB], dnv[RB];
 #pragma unroll
@@ -326,7 +332,7 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
     {
       const int w4 = e >> 5, lane = e & 31;
       const int jbase = nb * BN + (int)rank * UO;
-      for (int q = w4; q < 4 * UO; q += 4) {
+      for (int q = w4; q < 4 * UO; q += EPI_WARPS) {
         const int gate = q / UO, u = q - gate * UO;
         const uint32_t* src = reinterpret_cast<const uint32_t*>(gT + q * HT_LD);
         uint32_t* dst = reinterpret_cast<uint32_t*>(a.dGT_t + (size_t)(gate * N + jbase + u) * a.ldg + mb * BM);
@@ -345,7 +351,7 @@ static void launch_bwd_t(const CUtensorMap& tmdG, const CUtensorMap& tmUkr, cons
   using F = BwdCfg<BN>;
   dim3 grid(a.N / BN, a.Bp / BM, SPLIT);
   set_smem(k_bwd_step<BN>, F::C::SMEM_BYTES);
-  k_bwd_step<BN><<<grid, 192, F::C::SMEM_BYTES, st>>>(tmdG, tmUkr, tmdY, tmWnm, a);
+  k_bwd_step<BN><<<grid, CTA_THREADS, F::C::SMEM_BYTES, st>>>(tmdG, tmUkr, tmdY, tmWnm, a);
 }
 void launch_bwd_step(int BN, const CUtensorMap& tmdG, const CUtensorMap& tmUkr, const CUtensorMap& tmdY,
                      const CUtensorMap& tmWnm, const BwdStepArgs& a, cudaStream_t st) {
