@@ -153,6 +153,10 @@ extern "C" int lstm_create(lstm_ctx** out, int M, int N, int S, int B, int devic
   ctx->loss_cap = 1024;
   CREATE_CUDA(cudaMalloc(&ctx->d_loss, ctx->loss_cap * sizeof(double)));
   CREATE_CUDA(cudaMallocHost(&ctx->h_loss_pinned, sizeof(double)));
+  CREATE_CUDA(cudaMalloc(&ctx->d_iter, sizeof(unsigned long long)));
+  CREATE_CUDA(cudaMemsetAsync(ctx->d_iter, 0, sizeof(unsigned long long), ctx->st));
+  CREATE_CUDA(cudaMallocHost(&ctx->h_xs_pinned, (size_t)S * B * sizeof(int32_t)));
+  CREATE_CUDA(cudaMallocHost(&ctx->h_tg_pinned, (size_t)S * B * sizeof(int32_t)));
   CREATE_CUDA(cudaMalloc(&ctx->pos0, (size_t)B * sizeof(unsigned long long)));
   CREATE_CUDA(cudaMalloc(&ctx->vcount, sizeof(unsigned long long)));
   CREATE_CUDA(cudaMemsetAsync(ctx->vcount, 0, sizeof(unsigned long long), ctx->st));
@@ -183,6 +187,10 @@ extern "C" int lstm_destroy(lstm_ctx* ctx) {
                   ctx->dcnext, ctx->surp, ctx->xs, ctx->tg, ctx->d_loss, ctx->text, ctx->pos0, ctx->vcount};
   for (void* b : bufs) if (b) cudaFree(b);
   if (ctx->h_loss_pinned) cudaFreeHost(ctx->h_loss_pinned);
+  if (ctx->h_xs_pinned) cudaFreeHost(ctx->h_xs_pinned);
+  if (ctx->h_tg_pinned) cudaFreeHost(ctx->h_tg_pinned);
+  if (ctx->d_iter) cudaFree(ctx->d_iter);
+  for (auto& g : ctx->graph) if (g.exec) cudaGraphExecDestroy(g.exec);
   for (int i = 0; i < 2; i++) {
     if (ctx->ev_bucket[i]) cudaEventDestroy(ctx->ev_bucket[i]);
     if (ctx->ev_comm[i]) cudaEventDestroy(ctx->ev_comm[i]);
@@ -309,9 +317,17 @@ extern "C" int lstm_reset_state(lstm_ctx* ctx, uint64_t seed, float std) {
 // ------------------------------------------------------------------------------------------------
 // forward / backward / adagrad
 // ------------------------------------------------------------------------------------------------
+static void drop_graphs(lstm_ctx* ctx) {
+  for (auto& g : ctx->graph) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    g = lstm_ctx::IterGraph();
+  }
+}
+
 static int ensure_loss_cap(lstm_ctx* ctx, size_t need) {
   if (need <= ctx->loss_cap) return LSTM_OK;
   LSTM_CUDA(cudaStreamSynchronize(ctx->st));
+  drop_graphs(ctx);   // the ring pointer and capacity are baked into captured graphs
   LSTM_CUDA(cudaFree(ctx->d_loss));
   ctx->d_loss = nullptr;
   LSTM_CUDA(cudaMalloc(&ctx->d_loss, need * sizeof(double)));
@@ -321,7 +337,7 @@ static int ensure_loss_cap(lstm_ctx* ctx, size_t need) {
 
 #define PROF(i) do { if (ctx->profiling) LSTM_CUDA(cudaEventRecord(ctx->pev[i], ctx->st)); } while (0)
 
-static int forward_device(lstm_ctx* ctx, size_t loss_slot) {
+static int forward_device(lstm_ctx* ctx) {
   const int B = ctx->B, N = ctx->N, M = ctx->M, T = ctx->T;
   PROF(1);
   if (ctx->dtype == LSTM_BF16) {
@@ -341,7 +357,7 @@ static int forward_device(lstm_ctx* ctx, size_t loss_slot) {
     launch_softmax_ce_f32(ctx->dY, ctx->tg + B, ctx->surp, T * B, M, ctx->st);
     LSTM_LAUNCHED(2);
   }
-  launch_loss_reduce(ctx->surp, T, B, ctx->d_loss + loss_slot, ctx->st);
+  launch_loss_reduce(ctx->surp, T, B, ctx->d_loss, ctx->loss_cap, ctx->d_iter, ctx->st);
   LSTM_LAUNCHED(1);
   PROF(3);
   ctx->fwd_done = true;
@@ -413,7 +429,6 @@ static int adagrad_device(lstm_ctx* ctx, float lr, double eps, float clip) {
     if (rc) return rc;
   }
   PROF(8);
-  ctx->iteration++;
   return LSTM_OK;
 }
 
@@ -431,7 +446,9 @@ static int finish_profile(lstm_ctx* ctx) {
   return LSTM_OK;
 }
 
-static int fetch_loss(lstm_ctx* ctx, size_t slot, double* out) {
+// loss of the most recent forward
+static int fetch_loss(lstm_ctx* ctx, double* out) {
+  const size_t slot = (size_t)((ctx->fwd_count - 1) % ctx->loss_cap);
   LSTM_CUDA(cudaMemcpyAsync(ctx->h_loss_pinned, ctx->d_loss + slot, sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
   LSTM_CUDA(cudaStreamSynchronize(ctx->st));
   *out = *ctx->h_loss_pinned;
@@ -444,8 +461,79 @@ static int upload_window(lstm_ctx* ctx, const int32_t* x_idx, const int32_t* t_i
   for (size_t i = 0; i < (size_t)ctx->S * ctx->B; i++)
     if (x_idx[i] < -1 || x_idx[i] >= ctx->M || t_idx[i] < -1 || t_idx[i] >= ctx->M)
       return lstm_fail(ctx, LSTM_ERR_ARG, "window index outside [-1, M)");
-  LSTM_CUDA(cudaMemcpyAsync(ctx->xs, x_idx, bytes, cudaMemcpyHostToDevice, ctx->st));
-  LSTM_CUDA(cudaMemcpyAsync(ctx->tg, t_idx, bytes, cudaMemcpyHostToDevice, ctx->st));
+  // staged through the context's pinned buffers: the copies below are then true async DMA and can live in a graph
+  LSTM_CUDA(cudaStreamSynchronize(ctx->st));   // the previous step's DMA has read the staging buffers
+  memcpy(ctx->h_xs_pinned, x_idx, bytes);
+  memcpy(ctx->h_tg_pinned, t_idx, bytes);
+  return LSTM_OK;
+}
+
+static int window_h2d(lstm_ctx* ctx) {
+  const size_t bytes = (size_t)ctx->S * ctx->B * sizeof(int);
+  LSTM_CUDA(cudaMemcpyAsync(ctx->xs, ctx->h_xs_pinned, bytes, cudaMemcpyHostToDevice, ctx->st));
+  LSTM_CUDA(cudaMemcpyAsync(ctx->tg, ctx->h_tg_pinned, bytes, cudaMemcpyHostToDevice, ctx->st));
+  return LSTM_OK;
+}
+
+// One full training iteration on the context's stream.  mode 0: window built on the device from the loaded text;
+// mode 1: window copied from the pinned staging buffers.
+static int iteration_body(lstm_ctx* ctx, int mode, int stride, float lr) {
+  int rc;
+  if (mode == 0) {
+    launch_window_advance(ctx->text, ctx->text_len, ctx->pos0, ctx->vcount, stride, ctx->S, ctx->B, ctx->xs, ctx->tg, ctx->st);
+    LSTM_LAUNCHED(1);
+  } else {
+    rc = window_h2d(ctx);
+    if (rc) return rc;
+  }
+  rc = forward_device(ctx);
+  if (rc) return rc;
+  rc = backward_device(ctx);
+  if (rc) return rc;
+  rc = adagrad_device(ctx, lr, 1e-10, 0.f);
+  if (rc) return rc;
+  return lstm_carry_state(ctx, stride);   // slot 0 now holds the state the next window starts from
+}
+
+// Launch-bound inner loop (hundreds of short kernels per iteration): the iteration is captured once into a CUDA graph
+// and replayed.  Profiling (per-phase events) and LSTM_NO_GRAPH=1 use plain stream launches.
+static int run_iteration(lstm_ctx* ctx, int mode, int stride, float lr) {
+  static const bool no_graph = getenv("LSTM_NO_GRAPH") != nullptr;
+  lstm_ctx::IterGraph& g = ctx->graph[mode];
+  if (g.exec && (g.stride != stride || g.lr != lr)) { cudaGraphExecDestroy(g.exec); g = lstm_ctx::IterGraph(); }
+  ctx->fwd_count++;
+  ctx->iteration++;
+  if (ctx->profiling || no_graph) {
+    PROF(0);
+    const long it0 = ctx->iteration;
+    int rc = iteration_body(ctx, mode, stride, lr);
+    ctx->iteration = it0;
+    return rc;
+  }
+  if (!g.exec) {
+    const long it0 = ctx->iteration;
+    if (g.warm == 0 || g.stride != stride || g.lr != lr) {   // first time: plain launches (also sets kernel attributes)
+      g.warm = 1; g.stride = stride; g.lr = lr;
+      int rc = iteration_body(ctx, mode, stride, lr);
+      ctx->iteration = it0;
+      return rc;
+    }
+    const long l0 = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    LSTM_CUDA(cudaStreamBeginCapture(ctx->st, cudaStreamCaptureModeThreadLocal));
+    int rc = iteration_body(ctx, mode, stride, lr);
+    cudaError_t ce = cudaStreamEndCapture(ctx->st, &graph);
+    ctx->iteration = it0;
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) return lstm_fail(ctx, LSTM_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+    g.launches = ctx->launches - l0;
+    ctx->launches = l0;
+    ce = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) { g.exec = nullptr; return lstm_fail(ctx, LSTM_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)); }
+  }
+  LSTM_CUDA(cudaGraphLaunch(g.exec, ctx->st));
+  ctx->launches += g.launches;
   return LSTM_OK;
 }
 
@@ -455,9 +543,12 @@ extern "C" int lstm_forward(lstm_ctx* ctx, const int32_t* x_idx, const int32_t* 
   PROF(0);
   int rc = upload_window(ctx, x_idx, t_idx);
   if (rc) return rc;
-  rc = forward_device(ctx, 0);
+  rc = window_h2d(ctx);
   if (rc) return rc;
-  if (loss_out) return fetch_loss(ctx, 0, loss_out);
+  ctx->fwd_count++;
+  rc = forward_device(ctx);
+  if (rc) return rc;
+  if (loss_out) return fetch_loss(ctx, loss_out);
   return LSTM_OK;
 }
 
@@ -476,6 +567,7 @@ extern "C" int lstm_backward(lstm_ctx* ctx) {
 extern "C" int lstm_adagrad(lstm_ctx* ctx, float lr, double eps, float clip) {
   if (!ctx) return LSTM_ERR_ARG;
   LSTM_CUDA(cudaSetDevice(ctx->device));
+  ctx->iteration++;
   return adagrad_device(ctx, lr, eps, clip);
 }
 
@@ -499,20 +591,13 @@ extern "C" int lstm_train_step(lstm_ctx* ctx, const int32_t* x_idx, const int32_
                                double* loss_out) {
   if (!ctx) return LSTM_ERR_ARG;
   LSTM_CUDA(cudaSetDevice(ctx->device));
-  PROF(0);
   int rc = upload_window(ctx, x_idx, t_idx);
   if (rc) return rc;
-  rc = forward_device(ctx, 0);
-  if (rc) return rc;
-  rc = backward_device(ctx);
-  if (rc) return rc;
-  rc = adagrad_device(ctx, lr, 1e-10, 0.f);
-  if (rc) return rc;
-  rc = lstm_carry_state(ctx, stride);   // slot 0 now holds the state the next window starts from
+  rc = run_iteration(ctx, 1, stride, lr);
   if (rc) return rc;
   rc = finish_profile(ctx);
   if (rc) return rc;
-  if (loss_out) return fetch_loss(ctx, 0, loss_out);
+  if (loss_out) return fetch_loss(ctx, loss_out);
   return LSTM_OK;
 }
 
@@ -573,25 +658,19 @@ extern "C" int lstm_train_text(lstm_ctx* ctx, int iters, int stride, float lr, d
   LSTM_CUDA(cudaSetDevice(ctx->device));
   int rc = ensure_loss_cap(ctx, (size_t)iters);
   if (rc) return rc;
+  const uint64_t first = ctx->fwd_count;
   for (int it = 0; it < iters; it++) {
-    PROF(0);
-    launch_window_advance(ctx->text, ctx->text_len, ctx->pos0, ctx->vcount, stride, ctx->S, ctx->B, ctx->xs, ctx->tg, ctx->st);
-    LSTM_LAUNCHED(1);
     ctx->v_host += stride;
-    rc = forward_device(ctx, (size_t)it);
-    if (rc) return rc;
-    rc = backward_device(ctx);
-    if (rc) return rc;
-    rc = adagrad_device(ctx, lr, 1e-10, 0.f);
-    if (rc) return rc;
-    rc = lstm_carry_state(ctx, stride);   // slot 0 now holds the state the next window starts from
+    rc = run_iteration(ctx, 0, stride, lr);
     if (rc) return rc;
   }
   rc = finish_profile(ctx);
   if (rc) return rc;
   if (losses && iters > 0) {
-    LSTM_CUDA(cudaMemcpyAsync(losses, ctx->d_loss, (size_t)iters * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
     LSTM_CUDA(cudaStreamSynchronize(ctx->st));
+    std::vector<double> ring(ctx->loss_cap);
+    LSTM_CUDA(cudaMemcpy(ring.data(), ctx->d_loss, ctx->loss_cap * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int it = 0; it < iters; it++) losses[it] = ring[(size_t)((first + it) % ctx->loss_cap)];
   }
   return LSTM_OK;
 }

@@ -23,8 +23,13 @@ struct lstm_ctx {
   float *Hs = nullptr, *Cs = nullptr, *Gs = nullptr, *dY = nullptr, *dHy = nullptr, *dG = nullptr;
   float *dcnext = nullptr, *surp = nullptr;
   int *xs = nullptr, *tg = nullptr;
-  double* d_loss = nullptr;  // [loss_cap] per-iteration losses
+  double* d_loss = nullptr;  // [loss_cap] ring of per-iteration losses, slot = iteration % loss_cap
   size_t loss_cap = 0;
+  unsigned long long* d_iter = nullptr;  // device-side forward counter (owned by k_loss_reduce)
+  uint64_t fwd_count = 0;                // host mirror of *d_iter
+  // one training iteration captured as a CUDA graph, keyed by (mode, stride, lr)
+  struct IterGraph { cudaGraphExec_t exec = nullptr; int stride = 0; float lr = 0.f; long launches = 0; int warm = 0; } graph[2];
+  int32_t *h_xs_pinned = nullptr, *h_tg_pinned = nullptr;
   double* h_loss_pinned = nullptr;
   // device text pipeline
   uint8_t* text = nullptr;

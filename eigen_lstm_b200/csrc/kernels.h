@@ -31,8 +31,8 @@ void launch_gemm_f32(const float* A, long a_si, long a_sk, const float* Bm, long
                      long c_si, long c_sj, const float* bias_j, int I, int J, int K, cudaStream_t st);
 // rows of `y` ([rows][M] logits) -> p - onehot(tg) in place; surp[row] = -log2 p[tg] (0 if tg < 0)
 void launch_softmax_ce_f32(float* y, const int* tg, float* surp, int rows, int M, cudaStream_t st);
-// loss = sum_t (float)(sum_b surp[t][b]) / B  -> out[0] (double)
-void launch_loss_reduce(const float* surp, int T, int B, double* out, cudaStream_t st);
+// loss = sum_t (float)(sum_b surp[t][b]) / B  -> ring[*iter % cap] (double); *iter += 1
+void launch_loss_reduce(const float* surp, int T, int B, double* ring, size_t cap, unsigned long long* iter, cudaStream_t st);
 // dW[m*4N + r] = sum over (t,b) with xs[t][b] == m of dG[t][b][r]   (R/lstm.cc:251 for one-hot x)
 void launch_dw_scatter_f32(const float* dG, const int* xs, float* dW, int rows, int N4, int M, cudaStream_t st);
 // out[j] = sum_i X[i*J + j]

@@ -266,8 +266,11 @@ void launch_softmax_ce_f32(float* y, const int* tg, float* surp, int rows, int M
 }
 
 // loss = sum_t (float)(sum_b surp[t][b]) / (float)B    (OV/lstm_eigen_opt/lstm.cc:246-249)
+// The result goes to ring[*iter % cap] and the kernel bumps *iter itself, so a captured CUDA graph of one training
+// iteration can be replayed unchanged.
 __global__ void __launch_bounds__(1024) k_loss_reduce(const float* __restrict__ surp, int T, int B,
-                                                      double* __restrict__ out) {
+                                                      double* __restrict__ ring, unsigned long long cap,
+                                                      unsigned long long* __restrict__ iter) {
   extern __shared__ float st_sum[];  // [T]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int t = warp; t < T; t += 32) {
@@ -281,12 +284,14 @@ __global__ void __launch_bounds__(1024) k_loss_reduce(const float* __restrict__ 
   if (threadIdx.x == 0) {
     double l = 0.0;
     for (int t = 0; t < T; t++) l += (double)st_sum[t];
-    out[0] = l;
+    const unsigned long long it = iter[0];
+    ring[it % cap] = l;
+    iter[0] = it + 1;
   }
 }
 
-void launch_loss_reduce(const float* surp, int T, int B, double* out, cudaStream_t st) {
-  k_loss_reduce<<<1, 1024, T * sizeof(float), st>>>(surp, T, B, out);
+void launch_loss_reduce(const float* surp, int T, int B, double* ring, size_t cap, unsigned long long* iter, cudaStream_t st) {
+  k_loss_reduce<<<1, 1024, T * sizeof(float), st>>>(surp, T, B, ring, (unsigned long long)cap, iter);
 }
 
 // ------------------------------------------------------------------------------------------------
