@@ -194,6 +194,11 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, float4 v) {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// programmatic dependent launch: a kernel launched with programmaticStreamSerialization may start while its
+// predecessor is still running; pdl_wait() blocks until the predecessor grid has completed and its writes are visible,
+// pdl_launch_dependents() lets the successor start launching.  Both are no-ops without the launch attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

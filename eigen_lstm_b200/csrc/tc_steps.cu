@@ -47,6 +47,8 @@ k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUte
   extern __shared__ uint8_t smem_raw[];
   const long long t_entry = clock64();
   TileCtx c = tile_prologue<BN, STAGES, CN, CM>(smem_raw);
+  pdl_launch_dependents();   // the next timestep's CTAs may take SMs as ours drain; they block in pdl_wait()
+  pdl_wait();                // everything below reads what the previous timestep's kernel wrote
   c.dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0) ? a.dbg : nullptr;
   const bool stamp = c.dbg && threadIdx.x == 64;
   if (stamp) { c.dbg[0] = t_entry; c.dbg[4] = clock64(); }
@@ -150,6 +152,10 @@ k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUte
   if (stamp) c.dbg[8] = clock64();
 }
 
+static bool use_pdl() {
+  static const bool on = getenv("LSTM_NO_PDL") == nullptr;
+  return on;
+}
 template <typename Kern, typename... Args>
 static void launch_cluster(Kern kernel, dim3 grid, dim3 cluster, int smem, cudaStream_t st, Args... args) {
   set_smem(kernel, smem);
@@ -158,13 +164,15 @@ static void launch_cluster(Kern kernel, dim3 grid, dim3 cluster, int smem, cudaS
   cfg.blockDim = dim3(CTA_THREADS);
   cfg.dynamicSmemBytes = (size_t)smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cluster.x;
   attr[0].val.clusterDim.y = cluster.y;
   attr[0].val.clusterDim.z = cluster.z;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = use_pdl() ? 2 : 1;
   cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
@@ -220,7 +228,7 @@ struct BwdCfg {
 };
 
 template <int BN>
-__global__ void __cluster_dims__(1, 1, SPLIT) __launch_bounds__(CTA_THREADS, 1)
+__global__ void __launch_bounds__(CTA_THREADS, 1)
 k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUtensorMap tmU,
            const __grid_constant__ CUtensorMap tmdY, const __grid_constant__ CUtensorMap tmW, const BwdStepArgs a) {
   using F = BwdCfg<BN>;
@@ -228,6 +236,8 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
   extern __shared__ uint8_t smem_raw[];
   const long long t_entry = clock64();
   TileCtx c = tile_prologue<BN, STAGES>(smem_raw);
+  pdl_launch_dependents();
+  pdl_wait();
   c.dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? a.dbg : nullptr;
   const bool stamp = c.dbg && threadIdx.x == 64;
   if (stamp) { c.dbg[0] = t_entry; c.dbg[4] = clock64(); }
@@ -350,8 +360,7 @@ static void launch_bwd_t(const CUtensorMap& tmdG, const CUtensorMap& tmUkr, cons
                          const CUtensorMap& tmWnm, const BwdStepArgs& a, cudaStream_t st) {
   using F = BwdCfg<BN>;
   dim3 grid(a.N / BN, a.Bp / BM, SPLIT);
-  set_smem(k_bwd_step<BN>, F::C::SMEM_BYTES);
-  k_bwd_step<BN><<<grid, CTA_THREADS, F::C::SMEM_BYTES, st>>>(tmdG, tmUkr, tmdY, tmWnm, a);
+  launch_cluster(k_bwd_step<BN>, grid, dim3(1, 1, SPLIT), F::C::SMEM_BYTES, st, tmdG, tmUkr, tmdY, tmWnm, a);
 }
 void launch_bwd_step(int BN, const CUtensorMap& tmdG, const CUtensorMap& tmUkr, const CUtensorMap& tmdY,
                      const CUtensorMap& tmWnm, const BwdStepArgs& a, cudaStream_t st) {
