@@ -1,0 +1,42 @@
+"""North-star check: the bf16-GEMM / fp32-accumulate path reaches a final bits-per-char within 0.01 of the fp32 path
+(same text, seed, initial weights, schedule).  Runs on one B200:  python scripts/bpc_bf16_vs_f32.py [N B S iters lr]
+
+Text: the committed 64 KiB head of enwik6 (tests/golden/enwik6_head.bin; the GPU box has no /root/reference);
+first 90 % for training with B streams, last 10 % held out and scored with the reference's test() recipe
+(OV/lstm_eigen_class_CUDA/lstm.cc:661-720)."""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import eigen_lstm_b200 as el  # noqa: E402
+
+N, B, S, iters, lr = 256, 32, 51, 1500, 0.02
+if len(sys.argv) > 1:
+    N, B, S, iters = [int(v) for v in sys.argv[1:5]]
+    lr = float(sys.argv[5])
+text = open(os.path.join(ROOT, "tests", "golden", "enwik6_head.bin"), "rb").read()
+cut = len(text) * 9 // 10
+train, held = text[:cut], text[cut:]
+pos = [S + (len(train) - 2 * S) * b // B for b in range(B)]
+res = {}
+for name, dt in (("f32", el.F32), ("bf16", el.BF16)):
+    g = el.LSTM(256, N, S, B, dtype=dt)
+    g.init_params(seed=1, std=0.01, forget_bias=1.0)
+    g.load_text(train)
+    g.set_positions(pos)
+    curve = []
+    for k in range(iters // 100):
+        l = g.train_text(100, stride=S - 1, lr=lr)
+        curve.append(float(l.mean() / (S - 1)))
+    res[name] = {"train_bpc_curve": curve, "heldout_bpc": g.test(held)}
+    print(name, "train bpc (last 100 its)", curve[-1], "held-out bpc", res[name]["heldout_bpc"], flush=True)
+res["abs_diff_heldout"] = abs(res["f32"]["heldout_bpc"] - res["bf16"]["heldout_bpc"])
+res["abs_diff_train"] = abs(res["f32"]["train_bpc_curve"][-1] - res["bf16"]["train_bpc_curve"][-1])
+res["config"] = dict(N=N, B=B, S=S, iters=iters, lr=lr, text="enwik6 head 64 KiB, 90/10 split")
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", "bpc_bf16_vs_f32.json"), "w"), indent=1)
+print("held-out |bf16 - f32| =", res["abs_diff_heldout"], " train |diff| =", res["abs_diff_train"])
