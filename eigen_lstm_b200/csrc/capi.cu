@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <fstream>
 #include <iomanip>
 #include <random>
@@ -678,22 +679,66 @@ extern "C" int lstm_train_text(lstm_ctx* ctx, int iters, int stride, float lr, d
 // ------------------------------------------------------------------------------------------------
 // evaluation / sampling
 // ------------------------------------------------------------------------------------------------
+// Batch-1 recurrences run on the persistent multi-CTA kernel (K9) when the model is big enough to need more than one
+// SM; tiny models (the reference's N = 64 default) stay on the single-CTA kernel, which has no grid barriers.
+static bool use_persistent(const lstm_ctx* ctx) {
+  static const bool off = getenv("LSTM_NO_PERSIST") != nullptr;
+  return !off && ctx->N >= 128;
+}
+
+struct ScopedFree {
+  std::vector<void*> p;
+  ~ScopedFree() { for (void* q : p) if (q) cudaFree(q); }
+  template <typename T> cudaError_t alloc(T** out, size_t bytes) { cudaError_t e = cudaMalloc(out, bytes); if (e == cudaSuccess) p.push_back(*out); return e; }
+};
+
 extern "C" int lstm_eval_bpc(lstm_ctx* ctx, const uint8_t* bytes, size_t n, double* bpc_out) {
   if (!ctx || !bytes || !bpc_out || n < 2) return LSTM_ERR_ARG;
   LSTM_CUDA(cudaSetDevice(ctx->device));
+  ScopedFree mem;
   uint8_t* d_text = nullptr;
   double* d_bits = nullptr;
-  LSTM_CUDA(cudaMalloc(&d_text, n));
-  LSTM_CUDA(cudaMalloc(&d_bits, sizeof(double)));
+  LSTM_CUDA(mem.alloc(&d_text, n));
+  LSTM_CUDA(mem.alloc(&d_bits, sizeof(double)));
   LSTM_CUDA(cudaMemcpyAsync(d_text, bytes, n, cudaMemcpyHostToDevice, ctx->st));
-  launch_recur_b1_f32(ctx->p(LSTM_W), ctx->p(LSTM_U), ctx->p(LSTM_B), ctx->p(LSTM_WHY), ctx->p(LSTM_BY), ctx->M, ctx->N,
-                      0, d_text, n, nullptr, nullptr, nullptr, nullptr, d_bits, ctx->st);
-  LSTM_LAUNCHED(1);
+  LSTM_CUDA(cudaMemsetAsync(d_bits, 0, sizeof(double), ctx->st));
+  if (!use_persistent(ctx)) {
+    launch_recur_b1_f32(ctx->p(LSTM_W), ctx->p(LSTM_U), ctx->p(LSTM_B), ctx->p(LSTM_WHY), ctx->p(LSTM_BY), ctx->M, ctx->N,
+                        0, d_text, n, nullptr, nullptr, nullptr, nullptr, d_bits, ctx->st);
+    LSTM_LAUNCHED(1);
+  } else {
+    // chunks of CH characters: the per-step softmax partial sums are [CH][G] floats; state is chained on the device
+    const size_t CH = 16384;
+    int sms = 0;
+    LSTM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    float *hbuf = nullptr, *ebuf = nullptr, *sum_part = nullptr, *y_tgt = nullptr, *h_in = nullptr, *c_in = nullptr, *c_out = nullptr;
+    unsigned int* bar = nullptr;
+    LSTM_CUDA(mem.alloc(&hbuf, 2 * (size_t)ctx->N * sizeof(float)));
+    LSTM_CUDA(mem.alloc(&ebuf, 2 * (size_t)ctx->M * sizeof(float)));
+    LSTM_CUDA(mem.alloc(&sum_part, CH * (size_t)sms * sizeof(float)));
+    LSTM_CUDA(mem.alloc(&y_tgt, CH * sizeof(float)));
+    LSTM_CUDA(mem.alloc(&h_in, (size_t)ctx->N * sizeof(float)));
+    LSTM_CUDA(mem.alloc(&c_in, (size_t)ctx->N * sizeof(float)));
+    LSTM_CUDA(mem.alloc(&c_out, (size_t)ctx->N * sizeof(float)));
+    LSTM_CUDA(mem.alloc(&bar, sizeof(unsigned int)));
+    LSTM_CUDA(cudaMemsetAsync(h_in, 0, (size_t)ctx->N * sizeof(float), ctx->st));
+    LSTM_CUDA(cudaMemsetAsync(c_in, 0, (size_t)ctx->N * sizeof(float), ctx->st));
+    for (size_t off = 0; off + 1 < n; off += CH) {
+      const size_t len = std::min(CH + 1, n - off);   // len bytes -> len-1 scored pairs
+      int G = 0;
+      LSTM_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned int), ctx->st));
+      LSTM_CUDA(launch_recur_persist(ctx->p(LSTM_W), ctx->p(LSTM_U), ctx->p(LSTM_B), ctx->p(LSTM_WHY), ctx->p(LSTM_BY), ctx->M,
+                                     ctx->N, 0, d_text + off, len, nullptr, h_in, c_in, nullptr, hbuf, ebuf, sum_part, y_tgt,
+                                     c_out, bar, sms, &G, ctx->st));
+      launch_eval_finish(sum_part, y_tgt, len - 1, G, d_bits, ctx->st);
+      LSTM_LAUNCHED(2);
+      LSTM_CUDA(cudaMemcpyAsync(h_in, hbuf + ((len - 1) & 1) * (size_t)ctx->N, (size_t)ctx->N * sizeof(float), cudaMemcpyDeviceToDevice, ctx->st));
+      LSTM_CUDA(cudaMemcpyAsync(c_in, c_out, (size_t)ctx->N * sizeof(float), cudaMemcpyDeviceToDevice, ctx->st));
+    }
+  }
   double bits = 0;
   LSTM_CUDA(cudaMemcpyAsync(&bits, d_bits, sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
   LSTM_CUDA(cudaStreamSynchronize(ctx->st));
-  cudaFree(d_text);
-  cudaFree(d_bits);
   *bpc_out = bits / (double)(n - 1);
   return LSTM_OK;
 }
@@ -710,21 +755,34 @@ extern "C" int lstm_sample(lstm_ctx* ctx, uint64_t seed, const float* h0, const 
     std::uniform_real_distribution<> dis(0, 1);
     for (size_t i = 0; i < n; i++) u[i] = (float)dis(gen);
   }
+  ScopedFree mem;
   float *d_u = nullptr, *d_h = nullptr, *d_c = nullptr;
   uint8_t* d_out = nullptr;
-  LSTM_CUDA(cudaMalloc(&d_u, n * sizeof(float)));
-  LSTM_CUDA(cudaMalloc(&d_out, n));
+  LSTM_CUDA(mem.alloc(&d_u, n * sizeof(float)));
+  LSTM_CUDA(mem.alloc(&d_out, n));
   LSTM_CUDA(cudaMemcpyAsync(d_u, u.data(), n * sizeof(float), cudaMemcpyHostToDevice, ctx->st));
-  if (h0) { LSTM_CUDA(cudaMalloc(&d_h, ctx->N * sizeof(float))); LSTM_CUDA(cudaMemcpyAsync(d_h, h0, ctx->N * sizeof(float), cudaMemcpyHostToDevice, ctx->st)); }
-  if (c0) { LSTM_CUDA(cudaMalloc(&d_c, ctx->N * sizeof(float))); LSTM_CUDA(cudaMemcpyAsync(d_c, c0, ctx->N * sizeof(float), cudaMemcpyHostToDevice, ctx->st)); }
-  launch_recur_b1_f32(ctx->p(LSTM_W), ctx->p(LSTM_U), ctx->p(LSTM_B), ctx->p(LSTM_WHY), ctx->p(LSTM_BY), ctx->M, ctx->N,
-                      greedy ? 2 : 1, nullptr, n, d_u, d_h, d_c, d_out, nullptr, ctx->st);
-  LSTM_LAUNCHED(1);
+  if (h0) { LSTM_CUDA(mem.alloc(&d_h, ctx->N * sizeof(float))); LSTM_CUDA(cudaMemcpyAsync(d_h, h0, ctx->N * sizeof(float), cudaMemcpyHostToDevice, ctx->st)); }
+  if (c0) { LSTM_CUDA(mem.alloc(&d_c, ctx->N * sizeof(float))); LSTM_CUDA(cudaMemcpyAsync(d_c, c0, ctx->N * sizeof(float), cudaMemcpyHostToDevice, ctx->st)); }
+  if (!use_persistent(ctx)) {
+    launch_recur_b1_f32(ctx->p(LSTM_W), ctx->p(LSTM_U), ctx->p(LSTM_B), ctx->p(LSTM_WHY), ctx->p(LSTM_BY), ctx->M, ctx->N,
+                        greedy ? 2 : 1, nullptr, n, d_u, d_h, d_c, d_out, nullptr, ctx->st);
+    LSTM_LAUNCHED(1);
+  } else {
+    int sms = 0, G = 0;
+    LSTM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device));
+    float *hbuf = nullptr, *ebuf = nullptr;
+    unsigned int* bar = nullptr;
+    LSTM_CUDA(mem.alloc(&hbuf, 2 * (size_t)ctx->N * sizeof(float)));
+    LSTM_CUDA(mem.alloc(&ebuf, 2 * (size_t)ctx->M * sizeof(float)));
+    LSTM_CUDA(mem.alloc(&bar, sizeof(unsigned int)));
+    LSTM_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned int), ctx->st));
+    LSTM_CUDA(launch_recur_persist(ctx->p(LSTM_W), ctx->p(LSTM_U), ctx->p(LSTM_B), ctx->p(LSTM_WHY), ctx->p(LSTM_BY), ctx->M,
+                                   ctx->N, greedy ? 2 : 1, nullptr, n, d_u, d_h, d_c, d_out, hbuf, ebuf, nullptr, nullptr, nullptr,
+                                   bar, sms, &G, ctx->st));
+    LSTM_LAUNCHED(1);
+  }
   LSTM_CUDA(cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, ctx->st));
   LSTM_CUDA(cudaStreamSynchronize(ctx->st));
-  cudaFree(d_u); cudaFree(d_out);
-  if (d_h) cudaFree(d_h);
-  if (d_c) cudaFree(d_c);
   return LSTM_OK;
 }
 

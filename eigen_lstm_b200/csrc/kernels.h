@@ -46,5 +46,13 @@ void launch_recur_b1_f32(const float* W, const float* U, const float* bias, cons
                          int M, int N, int mode, const uint8_t* text, size_t n, const float* uniforms,
                          const float* h0, const float* c0, uint8_t* out, double* bits_out, cudaStream_t st);
 void launch_fill_f32(float* p, float v, size_t n, cudaStream_t st);
+// K9 persistent multi-CTA version (cooperative launch; weights resident in shared memory; grid barrier per step).
+// hbuf [2][N], ebuf [2][M], sum_part [n][G] + y_tgt [n] (eval only), bar: zeroed counter.  The state after the call is
+// NOT returned (sampling / test() start from h0, c0 each time, like the reference).
+cudaError_t launch_recur_persist(const float* W, const float* U, const float* bias, const float* Why, const float* by, int M,
+                                 int N, int mode, const uint8_t* text, size_t n, const float* uniforms, const float* h0,
+                                 const float* c0, uint8_t* out, float* hbuf, float* ebuf, float* sum_part, float* y_tgt,
+                                 float* c_out, unsigned int* bar, int num_sms, int* G_out, cudaStream_t st);
+void launch_eval_finish(const float* sum_part, const float* y_tgt, size_t steps, int G, double* bits_out, cudaStream_t st);
 
 }  // namespace lstm

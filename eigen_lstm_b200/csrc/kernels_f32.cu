@@ -535,4 +535,261 @@ void launch_recur_b1_f32(const float* W, const float* U, const float* bias, cons
   k_recur_b1_f32<<<1, 1024, smem, st>>>(W, U, bias, Why, by, M, N, mode, text, n, uniforms, h0, c0, out, bits_out);
 }
 
+// ------------------------------------------------------------------------------------------------
+// K9: PERSISTENT batch-1 recurrence (sampling R/lstm.cc:293-356, test() class_CUDA/lstm.cc:661-720).
+// Latency-bound GEMV chain: one cooperative grid of G CTAs lives for the whole sequence; CTA g owns
+// hidden units [g*UPC, (g+1)*UPC): their 4*UPC rows of U stay RESIDENT IN SHARED MEMORY across all
+// timesteps (when they fit), as do its rows of Why.  Per character: h(t) is exchanged through a
+// double-buffered global vector and one grid-wide barrier; sampling needs the full softmax, i.e. a second
+// barrier; evaluation defers the softmax normalisation to the end (per-step partial sums) and needs one.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const long long t0 = clock64();
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (clock64() - t0 > 4000000000LL) __trap();   // a protocol bug must not hang the GPU
+    } while ((int)(v - target) < 0);
+  }
+  __syncthreads();
+}
+
+struct RecurArgs {
+  const float *W, *U, *bias, *Why, *by;   // fp32 masters, column-major like the reference
+  int M, N, mode;                          // mode 0 eval, 1 sample, 2 greedy
+  int UPC, rows_resident;                  // hidden units per CTA; 1 if this CTA's U rows live in smem
+  const uint8_t* text; size_t n;
+  const float* uniforms; const float *h0, *c0;
+  uint8_t* out;
+  float* hbuf;                             // [2][N]
+  float* ebuf;                             // [2][M]   exp(y) of the current step (sampling)
+  float* sum_part;                         // [n][G]   eval: per-step per-CTA sum of exp(y)
+  float* y_tgt;                            // [n]      eval: logit of the target byte
+  float* c_out;                            // [N] final cell state (optional)
+  unsigned int* bar;
+};
+
+__global__ void __launch_bounds__(256, 1) k_recur_persist(const RecurArgs a) {
+  extern __shared__ float sm[];
+  const int N = a.N, M = a.M, N4 = 4 * N, G = gridDim.x, g = blockIdx.x, tid = threadIdx.x;
+  const int UPC = a.UPC, R = 4 * UPC;                 // gate rows owned by this CTA (unit-major: r = 4*u + gate)
+  const int MPC = (M + G - 1) / G;                    // logit rows owned by this CTA
+  float* sh = sm;                                      // [N]   h(t)
+  float* sU = sh + N;                                  // [R][N+1] resident rows of U (pitch N+1: conflict-free)
+  const int UP = N + 1;
+  float* sWhy = sU + (a.rows_resident ? (size_t)R * UP : 0);   // [MPC][N+1]
+  float* sg = sWhy + (size_t)MPC * UP;                 // [R] gate pre-activations
+  float* sc = sg + R;                                  // [UPC] cell state of the owned units
+  float* se = sc + UPC;                                // [M] exp(y) of the current step
+  __shared__ float s_sum;
+  __shared__ int s_index;
+  const int j0 = g * UPC;
+  // one-time: make the weights resident
+  if (a.rows_resident)
+    for (int idx = tid; idx < R * N; idx += blockDim.x) {
+      const int r = idx / N, k = idx - r * N;
+      const int u = r >> 2, gate = r & 3, j = j0 + u;
+      sU[(size_t)r * UP + k] = (j < N) ? a.U[(size_t)k * N4 + (size_t)gate * N + j] : 0.f;
+    }
+  for (int idx = tid; idx < MPC * N; idx += blockDim.x) {
+    const int mm = idx / N, k = idx - mm * N, m = g * MPC + mm;
+    sWhy[(size_t)mm * UP + k] = (m < M) ? a.Why[(size_t)k * M + m] : 0.f;
+  }
+  for (int u = tid; u < UPC; u += blockDim.x) sc[u] = (a.c0 && j0 + u < N) ? a.c0[j0 + u] : 0.f;
+  if (g == 0)
+    for (int k = tid; k < N; k += blockDim.x) a.hbuf[k] = a.h0 ? a.h0[k] : 0.f;
+  unsigned int epoch = 0;
+  grid_barrier(a.bar, ++epoch * G);
+
+  auto load_h = [&](int buf) {
+    for (int k = tid; k < N; k += blockDim.x) sh[k] = __ldcg(a.hbuf + (size_t)buf * N + k);
+    __syncthreads();
+  };
+  // 8 lanes per gate row (4 rows per warp and pass; every lane runs the shuffles): dot(U_row, h) + W[x][row] + b[row];
+  // then the cell update for the owned units
+  const int warp = tid >> 5, lane = tid & 31, lane8 = lane & 7, nwarps = blockDim.x >> 5;
+  auto cell = [&](int x, int buf_out) {
+    for (int base = warp * 4; base < R; base += nwarps * 4) {
+      const int r = base + (lane >> 3);
+      const int u = r >> 2, gate = r & 3, j = j0 + u;
+      const bool ok = r < R && j < N;
+      float acc = 0.f;
+      if (ok) {
+        if (a.rows_resident) {
+          const float* ur = sU + (size_t)r * UP;
+          for (int k = lane8; k < N; k += 8) acc = fmaf(ur[k], sh[k], acc);
+        } else {
+          const float* ug = a.U + (size_t)gate * N + j;
+          for (int k = lane8; k < N; k += 8) acc = fmaf(__ldg(ug + (size_t)k * N4), sh[k], acc);
+        }
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (lane8 == 0 && ok) {
+        const size_t row = (size_t)gate * N + j;
+        const float wx = (x >= 0) ? a.W[(size_t)x * N4 + row] : 0.f;
+        const float pre = __fadd_rn(__fadd_rn(wx, acc), a.bias[row]);
+        sg[r] = (gate < 3) ? logistic_f(pre) : tanhf(pre);
+      }
+    }
+    __syncthreads();
+    for (int u = tid; u < UPC; u += blockDim.x) {
+      const int j = j0 + u;
+      if (j < N) {
+        const float gi = sg[4 * u], go = sg[4 * u + 1], gf = sg[4 * u + 2], gu = sg[4 * u + 3];   // gate order i o f u
+        const float cc = tanhf(__fadd_rn(__fmul_rn(gi, gu), __fmul_rn(gf, sc[u])));
+        sc[u] = cc;
+        a.hbuf[(size_t)buf_out * N + j] = __fmul_rn(go, cc);
+      }
+    }
+  };
+  // exp(Why*h + by) for the owned logit rows (8 lanes per row)
+  auto logits = [&](float* e_out, float* y_out) {
+    for (int base = warp * 4; base < MPC; base += nwarps * 4) {
+      const int mm = base + (lane >> 3);
+      const int m = g * MPC + mm;
+      const bool ok = mm < MPC && m < M;
+      float acc = 0.f;
+      if (ok) {
+        const float* wr = sWhy + (size_t)mm * UP;
+        for (int k = lane8; k < N; k += 8) acc = fmaf(wr[k], sh[k], acc);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (lane8 == 0 && ok) {
+        const float y = __fadd_rn(acc, a.by[m]);
+        e_out[mm] = expf(y);
+        if (y_out) y_out[mm] = y;
+      }
+    }
+    __syncthreads();
+  };
+
+  if (a.mode == 0) {
+    // evaluation: step on text[i], then score text[i+1]; ONE barrier per character
+    float* my_e = se;          // [MPC]
+    float* my_y = se + MPC;    // [MPC]
+    for (size_t i = 0; i + 1 < a.n; i++) {
+      const int buf = (int)(i & 1);
+      load_h(buf);
+      cell((int)a.text[i], buf ^ 1);
+      grid_barrier(a.bar, ++epoch * G);
+      load_h(buf ^ 1);
+      logits(my_e, my_y);
+      if (tid == 0) {
+        float s = 0.f;
+        const int tgt = (int)a.text[i + 1];
+        for (int mm = 0; mm < MPC; mm++) {
+          const int m = g * MPC + mm;
+          if (m < M) { s += my_e[mm]; if (m == tgt) a.y_tgt[i] = my_y[mm]; }
+        }
+        a.sum_part[i * G + g] = s;
+      }
+      __syncthreads();
+    }
+  } else {
+    // sampling: p from the current h, draw, emit, step on the drawn byte; TWO barriers per character
+    for (size_t i = 0; i < a.n; i++) {
+      const int buf = (int)(i & 1);
+      load_h(buf);
+      logits(se, nullptr);                                           // se[0..MPC) = owned exp(y)
+      for (int mm = tid; mm < MPC; mm += blockDim.x)
+        if (g * MPC + mm < M) a.ebuf[(size_t)buf * M + g * MPC + mm] = se[mm];
+      grid_barrier(a.bar, ++epoch * G);
+      for (int m = tid; m < M; m += blockDim.x) se[m] = __ldcg(a.ebuf + (size_t)buf * M + m);
+      __syncthreads();
+      if (tid < 32) {                                                // same reduction shape as the 1-CTA kernel
+        float s = 0.f;
+        for (int q = tid; q < M; q += 32) s += se[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (tid == 0) s_sum = s;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int index = 0;
+        const float sum = s_sum;
+        if (a.mode == 2) {
+          float best = __fdiv_rn(se[0], sum);
+          for (int q = 1; q < M; q++) { const float p = __fdiv_rn(se[q], sum); if (p > best) { best = p; index = q; } }
+        } else {
+          const float r = a.uniforms[i];
+          float cdf = 0.f;
+          for (int q = 0; q < M; q++) {                              // R/lstm.cc:321-338
+            const float p = __fdiv_rn(se[q], sum);
+            cdf = (q == 0) ? p : __fadd_rn(cdf, p);
+            if (r < cdf) { index = q; break; }
+          }
+        }
+        s_index = index;
+        if (g == 0) a.out[i] = (uint8_t)index;
+      }
+      __syncthreads();
+      cell(s_index, buf ^ 1);
+      grid_barrier(a.bar, ++epoch * G);
+    }
+  }
+  // final state: h is in hbuf[(steps) & 1]; c of the owned units goes to c_out (lets the host chain chunks)
+  if (a.c_out)
+    for (int u = tid; u < UPC; u += blockDim.x)
+      if (j0 + u < N) a.c_out[j0 + u] = sc[u];
+}
+
+// host side: sizes, cooperative launch.  Returns cudaSuccess or the launch error.
+size_t recur_persist_smem(int M, int N, int G, int UPC, int resident) {
+  const int MPC = (M + G - 1) / G;
+  return sizeof(float) * ((size_t)N + (resident ? (size_t)4 * UPC * (N + 1) : 0) + (size_t)MPC * (N + 1) + 4 * UPC + UPC + M + 2 * MPC + 64);
+}
+
+cudaError_t launch_recur_persist(const float* W, const float* U, const float* bias, const float* Why, const float* by, int M,
+                                 int N, int mode, const uint8_t* text, size_t n, const float* uniforms, const float* h0,
+                                 const float* c0, uint8_t* out, float* hbuf, float* ebuf, float* sum_part, float* y_tgt,
+                                 float* c_out, unsigned int* bar, int num_sms, int* G_out, cudaStream_t st) {
+  int G = num_sms;
+  while (G > 1 && (N + G - 1) / G * (G - 1) >= N) G--;       // no CTA without units
+  if (N % 128 == 0 && num_sms >= 128) G = 128;                // even split: 128 CTAs x N/128 units
+  const int UPC = (N + G - 1) / G;
+  int resident = 1;
+  size_t smem = recur_persist_smem(M, N, G, UPC, 1);
+  if (smem > 227 * 1024) { resident = 0; smem = recur_persist_smem(M, N, G, UPC, 0); }
+  RecurArgs a;
+  a.W = W; a.U = U; a.bias = bias; a.Why = Why; a.by = by; a.M = M; a.N = N; a.mode = mode;
+  a.UPC = UPC; a.rows_resident = resident; a.text = text; a.n = n; a.uniforms = uniforms; a.h0 = h0; a.c0 = c0;
+  a.out = out; a.hbuf = hbuf; a.ebuf = ebuf; a.sum_part = sum_part; a.y_tgt = y_tgt; a.c_out = c_out; a.bar = bar;
+  cudaError_t e = cudaFuncSetAttribute(k_recur_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  void* args[] = {(void*)&a};
+  *G_out = G;
+  return cudaLaunchCooperativeKernel((void*)k_recur_persist, dim3(G), dim3(256), args, smem, st);
+}
+
+// eval epilogue: bits = sum_i -log2( exp(y_tgt[i]) / sum_g sum_part[i][g] )
+__global__ void k_eval_finish(const float* __restrict__ sum_part, const float* __restrict__ y_tgt, size_t steps, int G,
+                              double* __restrict__ bits_out) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  for (size_t i = threadIdx.x; i < steps; i += blockDim.x) {
+    float s = 0.f;
+    for (int g = 0; g < G; g++) s += sum_part[i * G + g];
+    const float p = __fdiv_rn(expf(y_tgt[i]), s);
+    acc += -log2((double)p);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) bits_out[0] += red[0];
+}
+void launch_eval_finish(const float* sum_part, const float* y_tgt, size_t steps, int G, double* bits_out, cudaStream_t st) {
+  k_eval_finish<<<1, 256, 0, st>>>(sum_part, y_tgt, steps, G, bits_out);
+}
+
 }  // namespace lstm

@@ -290,3 +290,40 @@ def test_errors_are_loud():
         g.forward(np.full((3, 1), 300), np.zeros((3, 1)))   # byte out of range
     with pytest.raises(el.LstmError):
         el.LSTM(300, 8, 3, 1)              # M > 256
+
+
+# ---- K9: persistent multi-CTA batch-1 recurrence (used for N >= 128) -------------------------------------------
+@pytest.mark.parametrize("N", [128, 200, 256])
+def test_persistent_eval_matches_oracle(enwik6, N):
+    """test() on the cooperative persistent kernel (weights resident in shared memory, one grid barrier per
+    character) vs the oracle's serial recipe."""
+    import eigen_lstm_b200 as el
+    params = orc.init_params(256, N, seed=31, sd=0.08, forget_bias=1.0)
+    g = el.LSTM(256, N, 2, 1); g.set_params(params)
+    o = orc.Oracle(256, N, 2, 1, "f32"); o.set_params(params)
+    text = enwik6[1000:1700]
+    assert abs(g.test(text) - o.eval_bpc(text)) < 2e-5
+
+
+def test_persistent_eval_chains_state_across_chunks(enwik6):
+    """40 000 bytes = three 16 384-character launches with h, c carried on the device."""
+    import eigen_lstm_b200 as el
+    N = 128
+    params = orc.init_params(256, N, seed=32, sd=0.08)
+    g = el.LSTM(256, N, 2, 1); g.set_params(params)
+    o = orc.Oracle(256, N, 2, 1, "f32"); o.set_params(params)
+    text = enwik6[:40000]
+    assert abs(g.test(text) - o.eval_bpc(text)) < 2e-5
+
+
+@pytest.mark.parametrize("N", [128, 200])
+def test_persistent_sampling_matches_oracle(N):
+    import eigen_lstm_b200 as el
+    params = orc.init_params(256, N, seed=33, sd=0.12)
+    g = el.LSTM(256, N, 2, 1); g.set_params(params)
+    o = orc.Oracle(256, N, 2, 1, "f32"); o.set_params(params)
+    h0 = orc.randn(N, 1, 0, 0.1, 5).ravel(); c0 = orc.randn(N, 1, 0, 0.1, 6).ravel()
+    n = 400
+    assert np.array_equal(g.sample(n, seed=3, h0=h0, c0=c0, greedy=True), o.sample(h0, c0, 3, n, greedy=True))
+    a = g.sample(n, seed=3, h0=h0, c0=c0); b = o.sample(h0, c0, 3, n)
+    assert (a == b).mean() > 0.99, (a == b).mean()
