@@ -606,7 +606,12 @@ __global__ void __launch_bounds__(256, 1) k_recur_persist(const RecurArgs a) {
   grid_barrier(a.bar, ++epoch * G);
 
   auto load_h = [&](int buf) {
-    for (int k = tid; k < N; k += blockDim.x) sh[k] = __ldcg(a.hbuf + (size_t)buf * N + k);
+    if ((N & 3) == 0) {
+      const float4* src = reinterpret_cast<const float4*>(a.hbuf + (size_t)buf * N);
+      for (int k = tid; k < (N >> 2); k += blockDim.x) reinterpret_cast<float4*>(sh)[k] = __ldcg(src + k);
+    } else {
+      for (int k = tid; k < N; k += blockDim.x) sh[k] = __ldcg(a.hbuf + (size_t)buf * N + k);
+    }
     __syncthreads();
   };
   // 8 lanes per gate row (4 rows per warp and pass; every lane runs the shuffles): dot(U_row, h) + W[x][row] + b[row];
@@ -648,21 +653,18 @@ __global__ void __launch_bounds__(256, 1) k_recur_persist(const RecurArgs a) {
       }
     }
   };
-  // exp(Why*h + by) for the owned logit rows (8 lanes per row)
+  // exp(Why*h + by) for the owned logit rows: one full warp per row (there are only ceil(M/G) ~ 2 rows per CTA)
   auto logits = [&](float* e_out, float* y_out) {
-    for (int base = warp * 4; base < MPC; base += nwarps * 4) {
-      const int mm = base + (lane >> 3);
+    for (int mm = warp; mm < MPC; mm += nwarps) {
       const int m = g * MPC + mm;
-      const bool ok = mm < MPC && m < M;
       float acc = 0.f;
-      if (ok) {
+      if (m < M) {
         const float* wr = sWhy + (size_t)mm * UP;
-        for (int k = lane8; k < N; k += 8) acc = fmaf(wr[k], sh[k], acc);
+        for (int k = lane; k < N; k += 32) acc = fmaf(wr[k], sh[k], acc);
       }
-      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      if (lane8 == 0 && ok) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0 && m < M) {
         const float y = __fadd_rn(acc, a.by[m]);
         e_out[mm] = expf(y);
         if (y_out) y_out[mm] = y;
@@ -712,18 +714,21 @@ __global__ void __launch_bounds__(256, 1) k_recur_persist(const RecurArgs a) {
         if (tid == 0) s_sum = s;
       }
       __syncthreads();
+      {
+        const float sum = s_sum;
+        for (int m = tid; m < M; m += blockDim.x) se[m] = __fdiv_rn(se[m], sum);   // probs = exp(y) / sum, in parallel
+      }
+      __syncthreads();
       if (tid == 0) {
         int index = 0;
-        const float sum = s_sum;
         if (a.mode == 2) {
-          float best = __fdiv_rn(se[0], sum);
-          for (int q = 1; q < M; q++) { const float p = __fdiv_rn(se[q], sum); if (p > best) { best = p; index = q; } }
+          float best = se[0];
+          for (int q = 1; q < M; q++) if (se[q] > best) { best = se[q]; index = q; }
         } else {
           const float r = a.uniforms[i];
           float cdf = 0.f;
-          for (int q = 0; q < M; q++) {                              // R/lstm.cc:321-338
-            const float p = __fdiv_rn(se[q], sum);
-            cdf = (q == 0) ? p : __fadd_rn(cdf, p);
+          for (int q = 0; q < M; q++) {                              // sequential cdf, first r < cdf  (R/lstm.cc:321-338)
+            cdf = (q == 0) ? se[0] : __fadd_rn(cdf, se[q]);
             if (r < cdf) { index = q; break; }
           }
         }
