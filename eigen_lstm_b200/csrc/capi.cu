@@ -504,7 +504,9 @@ static int run_iteration(lstm_ctx* ctx, int mode, int stride, float lr) {
   if (g.exec && (g.stride != stride || g.lr != lr)) { cudaGraphExecDestroy(g.exec); g = lstm_ctx::IterGraph(); }
   ctx->fwd_count++;
   ctx->iteration++;
-  if (ctx->profiling || no_graph) {
+  // Data parallel: plain stream launches.  (Capturing the NCCL allreduce on the side stream into the iteration graph
+  // hung at 4 and 8 ranks on B200 / NCCL 2.28; until that is understood the graph path is single-GPU only.)
+  if (ctx->profiling || no_graph || ctx->world > 1) {
     PROF(0);
     const long it0 = ctx->iteration;
     int rc = iteration_body(ctx, mode, stride, lr);
