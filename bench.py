@@ -274,17 +274,42 @@ def main():
         return 0
 
     pk = peaks()
-    # dominant kernel = the recurrent timestep kernel (forward + backward recurrences are 2/3 of the flops)
-    step_flops = 2.0 * 4 * N * N * B
+    # dominant kernel = the recurrent timestep kernel (forward + backward recurrences are 2/3 of the flops).
+    # Durations are LIVE: CUDA events around each phase of the profiled iteration, divided by its launch count.
     fwd_us = phases["fwd_recurrence"] * 1e3 / T
     bwd_us = phases["bwd_recurrence"] * 1e3 / T
-    dom = "fwd_recurrence" if phases["fwd_recurrence"] >= phases["bwd_recurrence"] else "bwd_recurrence"
-    dom_us = max(fwd_us, bwd_us)
-    achieved = step_flops / (dom_us * 1e-6) / 1e12 if dom_us > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": f"{dom} timestep ({'tcgen05 bf16' if dtype == 'bf16' else 'SIMT fp32'})",
+    fwd_flops = 2.0 * 4 * N * N * B                         # U*h(t-1) for B streams
+    bwd_flops = 2.0 * N * (4 * N + (M if dtype == "bf16" else 0)) * B   # U^T*dg (+ Why^T*dy folded into K5's K range)
+    dom = "fwd" if phases["fwd_recurrence"] >= phases["bwd_recurrence"] else "bwd"
+    dom_us, dom_flops = (fwd_us, fwd_flops) if dom == "fwd" else (bwd_us, bwd_flops)
+    dom_kernel = {"fwd": "k_fwd_step", "bwd": "k_bwd_step"}[dom] if dtype == "bf16" else {"fwd": "k_step_fwd_f32", "bwd": "k_step_bwd_f32"}[dom]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+    if dtype == "bf16" and args.workload == "cfg4" and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(dom_kernel, {}).get("dram_bytes_per_launch")
+    achieved = dom_flops / (dom_us * 1e-6) / 1e12 if dom_us > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": f"{dom_kernel} (one recurrent timestep, {'tcgen05 bf16' if dtype == 'bf16' else 'SIMT fp32'})",
                 "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
-                "traffic": None, "peak_source": f"{pk['src']} sustained bf16 (kernel timed inside a long step)",
-                "flops_per_launch": step_flops, "us_per_launch": dom_us}
+                "traffic": traffic, "traffic_source": "ncu --set full dram__bytes_read+write per launch (profiles/r01b_kernels.md)" if traffic else None,
+                "peak_source": f"{pk['src']} sustained bf16 (kernel timed inside a long step)",
+                "flops_per_launch": dom_flops, "us_per_launch": dom_us,
+                "note": "operand bytes per launch (U 33.5 MB + h/dg) exceed what the tensor pipe can be fed at: the step is bound by "
+                        "L2->SM operand delivery, see DESIGN.md section 5"}
+    BT = B * T
+    wg_flops = 2.0 * 4 * N * (M + N + 1) * BT               # dW|dU|db as one GEMM (bf16 path)
+    pre_flops = 2.0 * M * (N + 1) * BT                      # dWhy|dby
+    lg_flops = 2.0 * M * N * BT
+    P = 4 * N * M + 4 * N * N + 4 * N + M * N + M
+
+    def rate(flops, ms_):
+        return {"ms": ms_, "tflops": flops / (ms_ * 1e-3) / 1e12 if ms_ > 0 else None,
+                "frac_of_peak": flops / (ms_ * 1e-3) / 1e12 / pk["tf_sustained"] if ms_ > 0 else None}
+    kernels = {"fwd_recurrence(K2 x T)": rate(fwd_flops * T, phases["fwd_recurrence"]),
+               "bwd_recurrence(K5 x T)": rate(bwd_flops * T, phases["bwd_recurrence"]),
+               "weight_grads(K6a dW|dU|db)": rate(wg_flops, phases["weight_grads"]),
+               "logits_softmax(K3)": rate(lg_flops, phases["logits_softmax"]),
+               "adagrad(K7 + operand refresh)": {"ms": phases["adagrad"], "algorithmic_GBps": 20.0 * P / (phases["adagrad"] * 1e-3) / 1e9
+                                                  if phases["adagrad"] > 0 else None, "hbm_peak_GBps": pk["hbm_gbs"]}}
     e2e_tf = fl["alg"] * value / 1e12
     line = {"metric": "training chars/sec (fwd+BPTT+Adagrad)", "value": value, "unit": "chars/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -292,7 +317,7 @@ def main():
             "config": dict(config, l2="per-step working set (activations) is >> the 126 MB L2; no flush needed"
                            if N * B * T * 24 > 4e8 else "small working set: L2-resident by design (latency-bound config)"),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-            "us_per_recurrent_timestep": {"forward": fwd_us, "backward": bwd_us},
+            "us_per_recurrent_timestep": {"forward": fwd_us, "backward": bwd_us}, "kernels": kernels,
             "phases_ms_last_step": phases,
             "end_to_end_tflops": {"alg": e2e_tf, "dense": fl["dense"] * value / 1e12,
                                   "frac_of_peak_alg": e2e_tf / (pk["tf_sustained"] * world)},

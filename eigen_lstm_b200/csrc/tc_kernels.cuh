@@ -61,6 +61,7 @@ struct BwdStepArgs {
   __nv_bfloat16* dGbf_t;       // [Bp][4N r']
   __nv_bfloat16* dGT_t;        // dGT + (t-1)*Bp
   long ldg;                    // dGT leading dimension (columns)
+  float* red;                  // split-K exchange scratch: [tiles][4 dst][4 src][128][BN/4] fp32 (L2-resident)
   long long* dbg;              // optional: clock64 stamps of CTA (0,0,0) for diagnostics (NULL = off)
 };
 

@@ -14,7 +14,7 @@ struct Bf16State {
   long LDZ = 0, LDT = 0;
   bf16 *Hbf = nullptr, *Urk = nullptr, *Ukr = nullptr, *Wmn = nullptr, *Wnm = nullptr;
   bf16 *dYbf = nullptr, *dYT = nullptr, *dGbf = nullptr, *dGT = nullptr, *ZT = nullptr;
-  float *Wp = nullptr, *bp = nullptr, *Gp = nullptr, *dcnext = nullptr, *scratch = nullptr;
+  float *Wp = nullptr, *bp = nullptr, *Gp = nullptr, *dcnext = nullptr, *scratch = nullptr, *red = nullptr;
   long long* dbg = nullptr;   // [32] kernel-internal clock stamps (LSTM_TC_DEBUG=1)
   size_t scratch_elems = 0;
   CUtensorMap tmH, tmH2, tmUrk, tmUkr, tmWmn, tmWnm, tmdY, tmdYT, tmdG, tmdGT, tmZT;
@@ -90,6 +90,7 @@ int tc_create(lstm_ctx* ctx) {
   TC_ALLOC(s->bp, N4 * sizeof(float));
   TC_ALLOC(s->Gp, (size_t)T * B * N4 * sizeof(float));
   TC_ALLOC(s->dcnext, (size_t)B * N * sizeof(float));
+  TC_ALLOC(s->red, (size_t)(N / s->BN5) * (Bp / 128) * 16 * 128 * (s->BN5 / 4) * sizeof(float));   // K5 split-K exchange
   s->scratch_elems = (size_t)B * N4;
   TC_ALLOC(s->scratch, s->scratch_elems * sizeof(float));
   if (getenv("LSTM_TC_DEBUG")) TC_ALLOC(s->dbg, 32 * sizeof(long long));
@@ -115,7 +116,7 @@ void tc_destroy(lstm_ctx* ctx) {
   Bf16State* s = ctx->tc;
   if (!s) return;
   void* bufs[] = {s->Hbf, s->Urk, s->Ukr, s->Wmn, s->Wnm, s->dYbf, s->dYT, s->dGbf, s->dGT, s->ZT, s->Wp, s->bp, s->Gp,
-                  s->dcnext, s->scratch};
+                  s->dcnext, s->scratch, s->red, s->dbg};
   for (void* b : bufs) if (b) cudaFree(b);
   delete s;
   ctx->tc = nullptr;
@@ -220,6 +221,7 @@ int tc_backward(lstm_ctx* ctx) {
     a.dGbf_t = s->dGbf + (size_t)(t - 1) * Bp * N4;
     a.dGT_t = s->dGT + (size_t)(t - 1) * Bp;
     a.ldg = s->LDT;
+    a.red = s->red;
     a.dbg = s->dbg ? s->dbg + 16 : nullptr;
     tc::launch_bwd_step(s->BN5, s->tmdG, s->tmUkr, s->tmdY, s->tmWnm, a, ctx->st);
   }
