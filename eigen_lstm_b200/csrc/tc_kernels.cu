@@ -95,9 +95,12 @@ k_logits(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtens
 // (C[col*ldc + row]: the TMEM lane dimension is the contiguous one, so every warp store is 128 B).
 // Tiles are rasterised in groups of 16 row-tiles so concurrently resident CTAs share operand rows in L2.
 // ------------------------------------------------------------------------------------------------
-constexpr int K6_BN = 128, K6_STAGES = 6;
+// K6_BN = 256 (one N = 256 MMA per k-step) moves 48 KB of operands per 512 MMA cycles instead of 32 KB per 256: the
+// big dW|dU|db GEMM uses it; the small dWhy|dby GEMM keeps 128-wide tiles so that more CTAs share its long K loop.
+template <int K6_BN>
 __global__ void __launch_bounds__(192, 1)
 k_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs a) {
+  constexpr int K6_STAGES = K6_BN == 256 ? 4 : 6;
   extern __shared__ uint8_t smem_raw[];
   TileCtx c = tile_prologue<K6_BN, K6_STAGES>(smem_raw);
   constexpr int GROUP = 16;
@@ -141,9 +144,15 @@ void launch_logits(const CUtensorMap& tmH, const CUtensorMap& tmWmn, const Logit
   k_logits<<<a.T * a.Bp / BM, 192, Cfg<K3_BN, K3_STAGES>::SMEM_BYTES, st>>>(tmH, tmWmn, a);
 }
 
-void launch_gemm_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st) {
-  set_smem(k_gemm_nt, Cfg<K6_BN, K6_STAGES>::SMEM_BYTES);
-  k_gemm_nt<<<a.tiles_m * a.tiles_n, 192, Cfg<K6_BN, K6_STAGES>::SMEM_BYTES, st>>>(tmA, tmB, a);
+// bn = 128 or 256 = tile width; tmB must have a box of bn rows and a.tiles_n = ceil(cols / bn)
+void launch_gemm_nt(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st) {
+  if (bn == 256) {
+    set_smem(k_gemm_nt<256>, Cfg<256, 4>::SMEM_BYTES);
+    k_gemm_nt<256><<<a.tiles_m * a.tiles_n, 192, Cfg<256, 4>::SMEM_BYTES, st>>>(tmA, tmB, a);
+  } else {
+    set_smem(k_gemm_nt<128>, Cfg<128, 6>::SMEM_BYTES);
+    k_gemm_nt<128><<<a.tiles_m * a.tiles_n, 192, Cfg<128, 6>::SMEM_BYTES, st>>>(tmA, tmB, a);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -89,8 +89,8 @@ void launch_logits(const CUtensorMap& tmH, const CUtensorMap& tmWmn, const Logit
 // K5: one BPTT timestep.  BN in {32, 64, 128} hidden units per CTA.
 void launch_bwd_step(int BN, const CUtensorMap& tmdG, const CUtensorMap& tmUkr, const CUtensorMap& tmdY,
                      const CUtensorMap& tmWnm, const BwdStepArgs& a, cudaStream_t st);
-// K6: C = A * B^T, both K-major bf16, fp32 out, 128x128 tiles
-void launch_gemm_nt(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st);
+// K6: C = A * B^T, both K-major bf16, fp32 out, 128 x bn tiles (bn = 128 | 256; tmB box = bn rows)
+void launch_gemm_nt(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st);
 
 // parameter / state conversion kernels
 void launch_permute_rows_f32(const float* in, float* out, int rows, int N, cudaStream_t st);           // out[k][4j+g] = in[k][gN+j]

@@ -17,7 +17,7 @@ struct Bf16State {
   float *Wp = nullptr, *bp = nullptr, *Gp = nullptr, *dcnext = nullptr, *scratch = nullptr, *red = nullptr;
   long long* dbg = nullptr;   // [32] kernel-internal clock stamps (LSTM_TC_DEBUG=1)
   size_t scratch_elems = 0;
-  CUtensorMap tmH, tmH2, tmUrk, tmUkr, tmWmn, tmWnm, tmdY, tmdYT, tmdG, tmdGT, tmZT;
+  CUtensorMap tmH, tmH2, tmUrk, tmUkr, tmWmn, tmWnm, tmdY, tmdYT, tmdG, tmdGT, tmZT, tmZT256;
 };
 
 namespace {
@@ -108,6 +108,7 @@ int tc_create(lstm_ctx* ctx) {
   ok &= make_tmap(&s->tmdG, s->dGbf, (uint64_t)T * Bp, N4, 128);
   ok &= make_tmap(&s->tmdGT, s->dGT, N4, s->LDT, 128);
   ok &= make_tmap(&s->tmZT, s->ZT, s->RZ, s->LDZ, 128);
+  ok &= make_tmap(&s->tmZT256, s->ZT, s->RZ, s->LDZ, 256);
   if (!ok) return lstm_fail(ctx, LSTM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   return LSTM_OK;
 }
@@ -203,7 +204,7 @@ int tc_backward(lstm_ctx* ctx) {
     tc::GemmArgs g;
     g.rows = M; g.cols = N + 1; g.nkb = (int)(s->LDT / 64); g.a_k0 = 0; g.b_k0 = s->Bp; g.b_row0 = M;
     g.C = ctx->g(LSTM_WHY); g.ldc = M; g.tiles_m = M / 128; g.tiles_n = (N + 1 + 127) / 128;
-    tc::launch_gemm_nt(s->tmdYT, s->tmZT, g, ctx->st);
+    tc::launch_gemm_nt(128, s->tmdYT, s->tmZT, g, ctx->st);
     LSTM_LAUNCHED(1);
   }
   PROF(4);
@@ -232,8 +233,9 @@ int tc_backward(lstm_ctx* ctx) {
   {
     tc::GemmArgs g;
     g.rows = (int)N4; g.cols = M + N + 1; g.nkb = (int)(s->LDT / 64); g.a_k0 = 0; g.b_k0 = 0; g.b_row0 = 0;
-    g.C = ctx->g(LSTM_W); g.ldc = (long)N4; g.tiles_m = (int)N4 / 128; g.tiles_n = (M + N + 1 + 127) / 128;
-    tc::launch_gemm_nt(s->tmdGT, s->tmZT, g, ctx->st);
+    const int bn = (M + N + 1 >= 1024) ? 256 : 128;   // wide tiles once there are enough of them to fill the SMs
+    g.C = ctx->g(LSTM_W); g.ldc = (long)N4; g.tiles_m = (int)N4 / 128; g.tiles_n = (M + N + 1 + bn - 1) / bn;
+    tc::launch_gemm_nt(bn, bn == 256 ? s->tmdGT : s->tmdGT, bn == 256 ? s->tmZT256 : s->tmZT, g, ctx->st);
     LSTM_LAUNCHED(1);
   }
   PROF(6);
