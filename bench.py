@@ -145,7 +145,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=list(WORKLOADS))
     ap.add_argument("--dtype", default="auto", choices=["auto", "bf16", "f32"])
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--cpu-seconds", type=float, default=None, help="CPU work per sample (default 12 s for cpu_baseline; --impl reference sizes it from --steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -164,7 +164,7 @@ def main():
         if rank != 0:
             return 0
         text = synthetic_text(1 << 20)
-        per_step = max(2.0, min(20.0, 90.0 / (args.steps + args.warmup)))
+        per_step = args.cpu_seconds if args.cpu_seconds else max(2.0, min(20.0, 90.0 / (args.steps + args.warmup)))
         cb, secs = cpu_arm(cfg, text.tobytes(), per_step, steps=args.steps, warmup=args.warmup)
         line = {"impl": "reference", "metric": "training chars/sec (fwd+BPTT+Adagrad)", "value": cb["value"], "unit": "chars/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3,
@@ -290,7 +290,7 @@ def main():
     achieved = dom_flops / (dom_us * 1e-6) / 1e12 if dom_us > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": f"{dom_kernel} (one recurrent timestep, {'tcgen05 bf16' if dtype == 'bf16' else 'SIMT fp32'})",
                 "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
-                "traffic": traffic, "traffic_source": "ncu --set full dram__bytes_read+write per launch (profiles/r01b_kernels.md)" if traffic else None,
+                "traffic": traffic, "traffic_source": "ncu --set full dram__bytes_read+write per launch (profiles/r01c_kernels.md)" if traffic else None,
                 "peak_source": f"{pk['src']} sustained bf16 (kernel timed inside a long step)",
                 "flops_per_launch": dom_flops, "us_per_launch": dom_us,
                 "note": "operand bytes per launch (U 33.5 MB + h/dg) exceed what the tensor pipe can be fed at: the step is bound by "
@@ -324,7 +324,7 @@ def main():
             "final_loss_bits_per_char": float(losses[-1] / T) if len(losses) else None, "learning_rate": LR,
             "launch_mode": "one CUDA graph per training iteration (timed region); plain stream launches for the profiled iteration"}
     if not args.no_cpu_baseline and world == 1:
-        cb, _ = cpu_arm(cfg, text.tobytes()[: 1 << 20], args.cpu_seconds)
+        cb, _ = cpu_arm(cfg, text.tobytes()[: 1 << 20], args.cpu_seconds or 12.0)
         line["cpu_baseline"] = cb
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -508,25 +508,18 @@ static int run_iteration(lstm_ctx* ctx, int mode, int stride, float lr) {
   // hung at 4 and 8 ranks on B200 / NCCL 2.28; until that is understood the graph path is single-GPU only.)
   if (ctx->profiling || no_graph || ctx->world > 1) {
     PROF(0);
-    const long it0 = ctx->iteration;
-    int rc = iteration_body(ctx, mode, stride, lr);
-    ctx->iteration = it0;
-    return rc;
+    return iteration_body(ctx, mode, stride, lr);
   }
   if (!g.exec) {
-    const long it0 = ctx->iteration;
     if (g.warm == 0 || g.stride != stride || g.lr != lr) {   // first time: plain launches (also sets kernel attributes)
       g.warm = 1; g.stride = stride; g.lr = lr;
-      int rc = iteration_body(ctx, mode, stride, lr);
-      ctx->iteration = it0;
-      return rc;
+      return iteration_body(ctx, mode, stride, lr);
     }
     const long l0 = ctx->launches;
     cudaGraph_t graph = nullptr;
     LSTM_CUDA(cudaStreamBeginCapture(ctx->st, cudaStreamCaptureModeThreadLocal));
     int rc = iteration_body(ctx, mode, stride, lr);
     cudaError_t ce = cudaStreamEndCapture(ctx->st, &graph);
-    ctx->iteration = it0;
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (ce != cudaSuccess) return lstm_fail(ctx, LSTM_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
     g.launches = ctx->launches - l0;

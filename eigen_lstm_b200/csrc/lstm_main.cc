@@ -54,6 +54,9 @@ int main(int argc, char** argv) {
   size_t characters_to_generate = 1000;
   float forget_bias = 0.f, state_std = 0.1f;
   long max_iters = -1;
+  // held-out evaluation of the last snapshots (OV/lstm_eigen_class_CUDA/lstm.cc:73-86,188-238): off by default
+  size_t train_percent = 100;
+  double test_every_seconds = 0;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     auto next = [&]() -> const char* { return (i + 1 < argc) ? argv[++i] : ""; };
@@ -71,12 +74,14 @@ int main(int argc, char** argv) {
     else if (a == "--forget-bias") forget_bias = (float)atof(next());
     else if (a == "--state-std") state_std = (float)atof(next());
     else if (a == "--max-iters") max_iters = atol(next());
+    else if (a == "--train-percent") train_percent = atol(next());
+    else if (a == "--test-every") test_every_seconds = atof(next());
     else if (a == "--load") load_prefix = next();
     else if (a == "--save") save_prefix = next();
     else {
       std::cerr << "usage: lstm [--file F] [--hidden N] [--seq S] [--batch B] [--epochs E] [--lr LR] [--seed K] [--stride K]\n"
                    "            [--bf16] [--device D] [--sample N] [--forget-bias X] [--state-std X] [--max-iters K]\n"
-                   "            [--load PREFIX] [--save PREFIX]\n";
+                   "            [--load PREFIX] [--save PREFIX] [--train-percent P --test-every SECONDS]\n";
       return 2;
     }
   }
@@ -93,8 +98,20 @@ int main(int argc, char** argv) {
   CK(lstm_init_params(ctx, seed, 0.01f, forget_bias));              // :113-119
   if (!load_prefix.empty() && lstm_load_text_ckpt(ctx, load_prefix.c_str()) != 0)
     std::cout << lstm_last_error(ctx) << std::endl;                  // the reference prints and keeps the random init
+  // first train_percent % for training, the rest held out (class_CUDA/lstm.cc:73-86)
+  std::vector<unsigned char> testdata;
+  if (train_percent < 100) {
+    const size_t percent_size = data.size() / 100;
+    testdata.assign(data.begin() + train_percent * percent_size, data.end());
+    data.resize(train_percent * percent_size);
+    std::cout << "Train set size: " << data.size() << ", Test set size: " << testdata.size() << ", Total: "
+              << data.size() + testdata.size() << std::endl;
+  }
   CK(lstm_load_text(ctx, data.data(), data.size()));
   const size_t length = data.size();
+  auto last_test = std::chrono::steady_clock::now();
+  double window_loss = 0.0;
+  size_t window_iters = 0, results_rows = 0;
   if (B > 1) {                                                        // OV/lstm_eigen_opt/lstm.cc:140-144
     std::mt19937_64 g(seed + 17);
     std::vector<uint64_t> pos(B);
@@ -121,8 +138,28 @@ int main(int argc, char** argv) {
       if (max_iters >= 0 && total_iters + (long)chunk >= max_iters) { chunk = (size_t)(max_iters - total_iters); stop = true; }
       if (chunk > losses.size()) losses.resize(chunk);
       if (chunk > 0) CK(lstm_train_text(ctx, (int)chunk, stride, learning_rate, losses.data()));
-      for (size_t k = 0; k < chunk; k++) epoch_loss += losses[k];
+      for (size_t k = 0; k < chunk; k++) { epoch_loss += losses[k]; window_loss += losses[k]; }
+      window_iters += chunk;
       done += chunk;
+      if (test_every_seconds > 0 && testdata.size() > 1) {
+        const auto now = std::chrono::steady_clock::now();
+        const double since = std::chrono::duration<double>(now - last_test).count();
+        if (since >= test_every_seconds) {
+          double test_bpc = 0;
+          CK(lstm_eval_bpc(ctx, testdata.data(), testdata.size(), &test_bpc));
+          const double train_bpc = window_loss / ((double)window_iters * (double)(S - 1));
+          const double gflops = (double)window_iters * (double)(S - 1) * (double)B * (22.0 * N * M + 24.0 * N * N) / since / 1073741824.0;
+          std::cout << std::endl << "Train error: " << train_bpc << ", Test error: " << test_bpc << std::endl;
+          if (!save_prefix.empty()) {     // 5-column results row: idx, secs since last, train, test, GFlOP/s (class_CUDA/lstm.cc:205-226)
+            FILE* rf = fopen((save_prefix + ".txt").c_str(), "a");
+            if (rf) { fprintf(rf, "%zu %g %g %g %g\n", results_rows, since, train_bpc, test_bpc, gflops); fclose(rf); }
+            CK(lstm_save_text_ckpt(ctx, save_prefix.c_str()));
+          }
+          results_rows++;
+          window_loss = 0.0; window_iters = 0;
+          last_test = std::chrono::steady_clock::now();
+        }
+      }
       total_iters += (long)chunk;
       const size_t i = S + done * stride;
       if (i % 100 == 0 || stride > 1)
