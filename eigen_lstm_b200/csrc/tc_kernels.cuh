@@ -38,6 +38,7 @@ struct FwdStepArgs {
   __nv_bfloat16* ZT_h;         // ZT + M*ldz + t*Bp : h rows of this slot
   long ldz;                    // ZT leading dimension (columns)
   long long* dbg;              // optional: clock64 stamps of CTA (0,0) for diagnostics (NULL = off)
+  const void* pin; size_t pin_bytes;   // recurrent weights (Urk): L2-persisting access window of this launch
 };
 
 struct LogitsArgs {
@@ -63,6 +64,7 @@ struct BwdStepArgs {
   long ldg;                    // dGT leading dimension (columns)
   float* red;                  // split-K exchange scratch: [tiles][4 dst][4 src][128][BN/4] fp32 (L2-resident)
   long long* dbg;              // optional: clock64 stamps of CTA (0,0,0) for diagnostics (NULL = off)
+  const void* pin; size_t pin_bytes;   // recurrent weights (Ukr): L2-persisting access window of this launch
 };
 
 struct GemmArgs {

@@ -3,6 +3,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "ctx.h"
 #include "kernels.h"
 #include "tc_kernels.cuh"
@@ -16,7 +18,7 @@ struct Bf16State {
   bf16 *dYbf = nullptr, *dYT = nullptr, *dGbf = nullptr, *dGT = nullptr, *ZT = nullptr;
   float *Wp = nullptr, *bp = nullptr, *Gp = nullptr, *dcnext = nullptr, *scratch = nullptr, *red = nullptr;
   long long* dbg = nullptr;   // [32] kernel-internal clock stamps (LSTM_TC_DEBUG=1)
-  size_t scratch_elems = 0;
+  size_t scratch_elems = 0, pin_bytes = 0;
   CUtensorMap tmH, tmH2, tmUrk, tmUkr, tmWmn, tmWnm, tmdY, tmdYT, tmdG, tmdGT, tmZT, tmZT256;
 };
 
@@ -96,6 +98,15 @@ int tc_create(lstm_ctx* ctx) {
   if (getenv("LSTM_TC_DEBUG")) TC_ALLOC(s->dbg, 32 * sizeof(long long));
   tc::launch_fill_bf16(s->ZT + (size_t)(M + N) * s->LDZ, 1.0f, (size_t)s->LDZ, ctx->st);  // the ones row (db, dby)
   LSTM_LAUNCHED(1);
+  {  // let the recurrent weight operand (one of Urk / Ukr at a time) persist in L2 across the timestep kernels
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, ctx->device);
+    const size_t want = N4 * N * sizeof(bf16);
+    const size_t lim = std::min((size_t)prop.persistingL2CacheMaxSize, want + (want >> 2));
+    if (lim > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lim) == cudaSuccess)
+      s->pin_bytes = std::min(want, (size_t)prop.accessPolicyMaxWindowSize);
+    cudaGetLastError();
+  }
   bool ok = true;
   ok &= make_tmap(&s->tmH, s->Hbf, (uint64_t)(T + 1) * Bp, N, 128);
   ok &= make_tmap(&s->tmH2, s->Hbf, (uint64_t)(T + 1) * Bp, N, 128 / tc::fwd_cluster_n(s->N4 / s->BN2));            // K2: multicast slices
@@ -181,6 +192,7 @@ int tc_forward(lstm_ctx* ctx) {
     a.ZT_h = s->ZT + (size_t)M * s->LDZ + (size_t)t * Bp;
     a.ldz = s->LDZ;
     a.dbg = s->dbg;
+    a.pin = s->Urk; a.pin_bytes = s->pin_bytes;
     tc::launch_fwd_step(s->BN2, s->tmH2, s->tmUrk, a, ctx->st);
   }
   LSTM_LAUNCHED(T);
@@ -224,6 +236,7 @@ int tc_backward(lstm_ctx* ctx) {
     a.ldg = s->LDT;
     a.red = s->red;
     a.dbg = s->dbg ? s->dbg + 16 : nullptr;
+    a.pin = s->Ukr; a.pin_bytes = s->pin_bytes;
     tc::launch_bwd_step(s->BN5, s->tmdG, s->tmUkr, s->tmdY, s->tmWnm, a, ctx->st);
   }
   LSTM_LAUNCHED(T);

@@ -131,7 +131,7 @@ k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUte
           const float gu = tanh_fast(pre.w + w[q].w + bias.w);
           const float cc = tanh_fast(gi * gu + gf * cpv[q]);   // the carried cell value is the tanh'd one
           hval = go * cc;
-          *reinterpret_cast<float4*>(a.Gp_t + (size_t)b * N4 + rp) = make_float4(gi, go, gf, gu);
+          __stcs(reinterpret_cast<float4*>(a.Gp_t + (size_t)b * N4 + rp), make_float4(gi, go, gf, gu));   // streamed: read once, in BPTT
           a.c_out[(size_t)b * N + j] = cc;
           a.Hbf_t[(size_t)b * N + j] = __float2bfloat16_rn(hval);
         }
@@ -146,8 +146,8 @@ k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUte
       for (int u = w4; u < UT; u += EPI_WARPS) {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(hT + u * HT_LD);
         uint32_t* dst = reinterpret_cast<uint32_t*>(a.ZT_h + (size_t)(nb * UT + u) * a.ldz + mb * BM);
-        dst[lane] = src[lane];
-        dst[lane + 32] = src[lane + 32];
+        __stcs(dst + lane, src[lane]);            // read again only by the K6 GEMM: do not displace U in L2
+        __stcs(dst + lane + 32, src[lane + 32]);
       }
     }
   }
@@ -159,8 +159,15 @@ static bool use_pdl() {
   static const bool on = getenv("LSTM_NO_PDL") == nullptr;
   return on;
 }
+static bool use_l2pin() {
+  static const bool on = getenv("LSTM_NO_L2PIN") == nullptr;
+  return on;
+}
+// `pin`/`pin_bytes`: the recurrent weight operand of this launch.  It is re-read by every timestep kernel, so its L2
+// lines are marked persisting (and everything else streaming on a miss) to survive the per-step activation traffic.
 template <typename Kern, typename... Args>
-static void launch_cluster(Kern kernel, dim3 grid, dim3 cluster, int smem, cudaStream_t st, Args... args) {
+static void launch_cluster(Kern kernel, dim3 grid, dim3 cluster, int smem, cudaStream_t st, const void* pin, size_t pin_bytes,
+                           Args... args) {
   set_smem(kernel, smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -174,8 +181,21 @@ static void launch_cluster(Kern kernel, dim3 grid, dim3 cluster, int smem, cudaS
   attr[0].val.clusterDim.z = cluster.z;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = use_pdl() ? 2 : 1;
+  int na = use_pdl() ? 2 : 1;
+  cudaLaunchAttribute all[3];
+  all[0] = attr[0];
+  all[1] = attr[1];
+  if (pin && pin_bytes && use_l2pin()) {
+    all[na].id = cudaLaunchAttributeAccessPolicyWindow;
+    all[na].val.accessPolicyWindow.base_ptr = const_cast<void*>(pin);
+    all[na].val.accessPolicyWindow.num_bytes = pin_bytes;
+    all[na].val.accessPolicyWindow.hitRatio = 1.0f;
+    all[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    all[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    na++;
+  }
+  cfg.attrs = all;
+  cfg.numAttrs = na;
   cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
@@ -195,8 +215,8 @@ int fwd_cluster_m(int Bp) {
 template <int BN, int CN>
 static void launch_fwd_cn(int CM, dim3 grid, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st) {
   using F = FwdCfg<BN>;
-  if (CM == 2) launch_cluster(k_fwd_step<BN, CN, 2>, grid, dim3(CN, 2, 1), F::C::SMEM_BYTES, st, tmH, tmUrk, a);
-  else launch_cluster(k_fwd_step<BN, CN, 1>, grid, dim3(CN, 1, 1), F::C::SMEM_BYTES, st, tmH, tmUrk, a);
+  if (CM == 2) launch_cluster(k_fwd_step<BN, CN, 2>, grid, dim3(CN, 2, 1), F::C::SMEM_BYTES, st, a.pin, a.pin_bytes, tmH, tmUrk, a);
+  else launch_cluster(k_fwd_step<BN, CN, 1>, grid, dim3(CN, 1, 1), F::C::SMEM_BYTES, st, a.pin, a.pin_bytes, tmH, tmUrk, a);
 }
 template <int BN>
 static void launch_fwd_t(const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st) {
@@ -313,7 +333,7 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
 #pragma unroll
           for (int sr = 0; sr < SPLIT; sr++)
             if (sr != (int)rank) pv[q][sr] = __ldcg(red_tile + (((size_t)rank * SPLIT + sr) * 128 + r) * UO + l);
-          gv[q] = *reinterpret_cast<const float4*>(a.Gp_t + (size_t)b * N4 + 4 * (size_t)j);   // i o f u
+          gv[q] = __ldcs(reinterpret_cast<const float4*>(a.Gp_t + (size_t)b * N4 + 4 * (size_t)j));   // i o f u (last use)
           ctv[q] = a.c_t[bj];
           cpv[q] = a.c_prev[bj];
           if (!a.first) dnv[q] = a.dcnext[bj];
@@ -357,8 +377,8 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
         const int gate = q / UO, u = q - gate * UO;
         const uint32_t* src = reinterpret_cast<const uint32_t*>(gT + q * HT_LD);
         uint32_t* dst = reinterpret_cast<uint32_t*>(a.dGT_t + (size_t)(gate * N + jbase + u) * a.ldg + mb * BM);
-        dst[lane] = src[lane];
-        dst[lane + 32] = src[lane + 32];
+        __stcs(dst + lane, src[lane]);
+        __stcs(dst + lane + 32, src[lane + 32]);
       }
     }
   }
@@ -371,7 +391,7 @@ static void launch_bwd_t(const CUtensorMap& tmdG, const CUtensorMap& tmUkr, cons
                          const CUtensorMap& tmWnm, const BwdStepArgs& a, cudaStream_t st) {
   using F = BwdCfg<BN>;
   dim3 grid(a.N / BN, a.Bp / BM, SPLIT);
-  launch_cluster(k_bwd_step<BN>, grid, dim3(1, 1, SPLIT), F::C::SMEM_BYTES, st, tmdG, tmUkr, tmdY, tmWnm, a);
+  launch_cluster(k_bwd_step<BN>, grid, dim3(1, 1, SPLIT), F::C::SMEM_BYTES, st, a.pin, a.pin_bytes, tmdG, tmUkr, tmdY, tmWnm, a);
 }
 void launch_bwd_step(int BN, const CUtensorMap& tmdG, const CUtensorMap& tmUkr, const CUtensorMap& tmdY,
                      const CUtensorMap& tmWnm, const BwdStepArgs& a, cudaStream_t st) {
