@@ -86,6 +86,39 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
 }
 
+// ---- CTA pairs (cta_group::2): two SMs of one cluster execute one M = 256 MMA; each holds its own 128 rows of A, half
+// of B's rows, and the 128 accumulator lanes of its half of D.  The LEADER (even cluster rank) issues the MMAs. ----
+template <uint32_t COLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result) {   // one warp in EACH CTA, same smem offset
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t COLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+// TMA load whose completion is signalled on the LEADER CTA's mbarrier (same offset; bit 24 of a shared::cluster
+// address selects the odd CTA of a pair)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
+// arrive on the mbarrier at this offset in BOTH CTAs of the pair once the pair's MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t pair_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(pair_mask) : "memory");
+}
+
 // ---- descriptors ----
 // Shared-memory matrix descriptor, K-major operand tile stored as rows of 128 bytes (64 bf16) with the
 // 128-byte swizzle TMA applies (CU_TENSOR_MAP_SWIZZLE_128B): 8 rows x 128 B form one 1024-byte swizzle

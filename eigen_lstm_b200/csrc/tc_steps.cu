@@ -29,9 +29,9 @@ constexpr int HT_LD = 130;   // bf16 row pitch of the transposed staging tiles: 
 // K2: forward timestep.  D[b][r'] = sum_k h(t-1)[b][k] * U[r'][k], r' = 4*unit + gate.
 // grid (4N/BN, Bp/128)
 // ------------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, bool PAIR = false>
 struct FwdCfg {
-  static constexpr int STAGES = BN == 128 ? 4 : (BN == 64 ? 6 : 8);
+  static constexpr int STAGES = PAIR ? (BN == 128 ? 5 : 8) : (BN == 128 ? 4 : (BN == 64 ? 6 : 8));
   static constexpr int UT = BN / 4;                        // hidden units per tile
   static constexpr int ACC_LD = BN + 4;                    // fp32 row pitch (16-byte aligned, odd multiple of 16 B)
   static constexpr int ACC_BYTES = 128 * ACC_LD * 4;
@@ -39,17 +39,22 @@ struct FwdCfg {
   static constexpr int X_BYTES = 128 * 4;
   static constexpr int EPI_BYTES = ACC_BYTES + HT_BYTES + X_BYTES;
   using C = Cfg<BN, STAGES, EPI_BYTES>;
+  static constexpr int SMEM_BYTES = PAIR ? PairCfg<BN, STAGES>::TILE_BYTES + 1024 + 256 + (EPI_BYTES + 127) / 128 * 128 : C::SMEM_BYTES;
 };
 
-// CN x CM cluster: the CN CTAs along x share the h tile, the CM CTAs along y share the U tile (TMA multicast)
-template <int BN, int CN, int CM>
+// CN x CM cluster: the CN CTAs along x share the h tile, the CM CTAs along y share the U tile (TMA multicast).
+// PAIR: the two batch tiles of one gate-column tile form a cta_group::2 pair (cluster 1 x 2): one M = 256 MMA,
+// each CTA stages its own h tile and half of the U tile.
+template <int BN, int CN, int CM, bool PAIR = false>
 __global__ void __launch_bounds__(CTA_THREADS, 1)
 k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmU, const FwdStepArgs a) {
-  using F = FwdCfg<BN>;
+  using F = FwdCfg<BN, PAIR>;
   constexpr int STAGES = F::STAGES, UT = F::UT, RG = EPI_THREADS / UT, ROWS = 128 / RG, ACC_LD = F::ACC_LD;
   extern __shared__ uint8_t smem_raw[];
   const long long t_entry = clock64();
-  TileCtx c = tile_prologue<BN, STAGES, CN, CM>(smem_raw);
+  TileCtx c;
+  if constexpr (PAIR) c = pair_prologue<BN, STAGES>(smem_raw);
+  else c = tile_prologue<BN, STAGES, CN, CM>(smem_raw);
   pdl_launch_dependents();   // the next timestep's CTAs may take SMs as ours drain; they block in pdl_wait()
   pdl_wait();                // everything below reads what the previous timestep's kernel wrote
   c.dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0) ? a.dbg : nullptr;
@@ -61,7 +66,8 @@ k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUte
   const int nb = blockIdx.x, mb = blockIdx.y;
   const KSeg s0{&tmH, &tmU, a.a_row0 + mb * BM, nb * BN, 0, 0, a.N / BK};
   const KSeg s1{&tmH, &tmU, 0, 0, 0, 0, 0};
-  tile_mainloop<BN, STAGES, CN, CM>(c, s0, s1, (int)(blockIdx.x % CN), (int)(blockIdx.y % CM));
+  if constexpr (PAIR) pair_mainloop<BN, STAGES>(c, s0, s1, cluster_ctarank(), (uint16_t)0x3);
+  else tile_mainloop<BN, STAGES, CN, CM>(c, s0, s1, (int)(blockIdx.x % CN), (int)(blockIdx.y % CM));
   if (c.warp >= 2) {
     const int e = threadIdx.x - 64;                        // 0..EPI_THREADS-1
     const int N = a.N, N4 = 4 * a.N;
@@ -151,7 +157,8 @@ k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUte
       }
     }
   }
-  tile_epilogue_end<BN, STAGES, CN, CM>(c);
+  if constexpr (PAIR) pair_epilogue_end<BN, STAGES>(c);
+  else tile_epilogue_end<BN, STAGES, CN, CM>(c);
   if (stamp) c.dbg[8] = clock64();
 }
 
@@ -203,11 +210,17 @@ static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
 }
+// forward-step launch shape: CTA pairs (cta_group::2) when there is an even number of batch tiles, unless
+// LSTM_FWD_PAIR=0; LSTM_FWD_CN / LSTM_FWD_CM select the (slower) multicast-cluster experiment instead.
+bool fwd_pair(int Bp) {
+  return env_int("LSTM_FWD_PAIR", 0) != 0 && (Bp / 128) % 2 == 0 && env_int("LSTM_FWD_CN", 1) == 1 && env_int("LSTM_FWD_CM", 1) == 1;
+}
 int fwd_cluster_n(int n_tiles) {
   const int cn = env_int("LSTM_FWD_CN", 1);
   return (cn == 2 || cn == 4) && n_tiles % cn == 0 ? cn : 1;
 }
 int fwd_cluster_m(int Bp) {
+  if (fwd_pair(Bp)) return 2;                       // a pair stages half of the U tile per CTA: same box as CM = 2
   const int cm = env_int("LSTM_FWD_CM", 1);
   return cm == 2 && (Bp / 128) % 2 == 0 ? 2 : 1;
 }
@@ -221,6 +234,10 @@ static void launch_fwd_cn(int CM, dim3 grid, const CUtensorMap& tmH, const CUten
 template <int BN>
 static void launch_fwd_t(const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st) {
   dim3 grid(4 * a.N / BN, a.Bp / BM);
+  if (fwd_pair(a.Bp)) {
+    launch_cluster(k_fwd_step<BN, 1, 1, true>, grid, dim3(1, 2, 1), FwdCfg<BN, true>::SMEM_BYTES, st, a.pin, a.pin_bytes, tmH, tmUrk, a);
+    return;
+  }
   const int CN = fwd_cluster_n((int)grid.x), CM = fwd_cluster_m(a.Bp);
   if (CN == 4) launch_fwd_cn<BN, 4>(CM, grid, tmH, tmUrk, a, st);
   else if (CN == 2) launch_fwd_cn<BN, 2>(CM, grid, tmH, tmUrk, a, st);

@@ -135,6 +135,104 @@ __device__ __forceinline__ void tile_mainloop(const TileCtx& c, const KSeg& s0, 
   }
 }
 
+// ---- CTA-pair variant (tcgen05 cta_group::2): D = 256 rows x BN, the pair's two CTAs are the two 128-row halves ----
+// Each CTA stages its own A tile (128 rows) and HALF of the B tile (BN/2 rows): 25 % fewer operand bytes per MMA than
+// two independent 128 x BN tiles.  All loads of a stage complete on the leader's full barrier; the leader issues the
+// M = 256 MMAs and its commit frees the stage in both CTAs.
+template <int BN, int STAGES>
+struct PairCfg {
+  static constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_HALF_BYTES;
+  static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
+};
+
+template <int BN, int STAGES>
+__device__ __forceinline__ TileCtx pair_prologue(uint8_t* raw) {
+  using C = PairCfg<BN, STAGES>;
+  TileCtx c;
+  c.dbg = nullptr;
+  const uint32_t base = smem_u32(raw);
+  const uint32_t pad = ((base + 1023u) & ~1023u) - base;
+  c.tiles = raw + pad;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(c.tiles + C::TILE_BYTES);
+  c.full = bars;
+  c.empty = bars + STAGES;
+  c.accum_full = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  c.epi = c.tiles + C::TILE_BYTES + 256;
+  c.warp = threadIdx.x >> 5;
+  c.lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) { mbar_init(&c.full[s], 1); mbar_init(&c.empty[s], 1); }
+    mbar_init(c.accum_full, 1);
+    fence_barrier_init();
+  }
+  if (c.warp == 1) tmem_alloc_pair<(BN < 32 ? 32 : BN)>(tmem_slot);
+  tcgen05_before_sync();
+  __syncthreads();
+  cluster_sync_all();            // both CTAs' barriers exist before any remote completion / commit arrives
+  tcgen05_after_sync();
+  c.tmem_d = *tmem_slot;
+  return c;
+}
+
+template <int BN, int STAGES>
+__device__ __forceinline__ void pair_epilogue_end(const TileCtx& c) {
+  tcgen05_before_sync();
+  __syncthreads();
+  cluster_sync_all();
+  if (c.warp == 1) {
+    __syncwarp();
+    tmem_dealloc_pair<(BN < 32 ? 32 : BN)>(c.tmem_d);
+  }
+}
+
+// s.a_row = this CTA's own 128 A rows; s.b_row = first row of the pair's BN-row B tile (each CTA loads rows
+// [b_row + rank*BN/2, +BN/2)).  rank = cluster rank within the pair (0 = leader).
+template <int BN, int STAGES>
+__device__ __forceinline__ void pair_mainloop(const TileCtx& c, const KSeg& s0, const KSeg& s1, uint32_t rank, uint16_t pair_mask) {
+  using C = PairCfg<BN, STAGES>;
+  const int total = s0.nkb + s1.nkb;
+  if (c.warp == 0) {
+    if (c.lane == 0) {
+      for (int kb = 0; kb < total; kb++) {
+        const int st = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&c.empty[st], ph ^ 1u);
+        const bool first = kb < s0.nkb;
+        const KSeg& s = first ? s0 : s1;
+        const int k = first ? kb : kb - s0.nkb;
+        uint8_t* a = c.tiles + (size_t)st * C::STAGE_BYTES;
+        uint8_t* b = a + A_TILE_BYTES;
+        if (rank == 0) mbar_expect_tx(&c.full[st], 2u * (uint32_t)C::STAGE_BYTES);   // both CTAs' bytes land on the leader's barrier
+        tma_load_2d_pair(a, s.ta, &c.full[st], s.a_k0 + k * BK, s.a_row);
+        tma_load_2d_pair(b, s.tb, &c.full[st], s.b_k0 + k * BK, s.b_row + (int)rank * (BN / 2));
+      }
+      if (c.dbg) c.dbg[1] = clock64();
+    }
+  } else if (c.warp == 1 && rank == 0) {
+    if (c.lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
+      for (int kb = 0; kb < total; kb++) {
+        const int st = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&c.full[st], ph);
+        if (c.dbg && kb == 0) c.dbg[2] = clock64();
+        tcgen05_after_sync();
+        const uint32_t a_addr = smem_u32(c.tiles + (size_t)st * C::STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / 16; k++)
+          umma_bf16_pair(c.tmem_d, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32), idesc,
+                         (uint32_t)((kb | k) != 0));
+        umma_commit_pair(&c.empty[st], pair_mask);     // stage free in both CTAs
+      }
+      umma_commit_pair(c.accum_full, pair_mask);       // accumulator halves complete in both CTAs
+      if (c.dbg) c.dbg[3] = clock64();
+    }
+  }
+}
+
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
 
