@@ -63,7 +63,9 @@ k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUte
   float* acc = reinterpret_cast<float*>(c.epi);
   __nv_bfloat16* hT = reinterpret_cast<__nv_bfloat16*>(c.epi + F::ACC_BYTES);
   int* sx = reinterpret_cast<int*>(c.epi + F::ACC_BYTES + F::HT_BYTES);
-  const int nb = blockIdx.x, mb = blockIdx.y;
+  // PAIR: the two CTAs of a pair must be neighbours along cluster x: grid (2 * n_tiles, m_tiles / 2), cluster (2,1,1)
+  const int nb = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int mb = PAIR ? (int)(blockIdx.y * 2 + (blockIdx.x & 1)) : (int)blockIdx.y;
   const KSeg s0{&tmH, &tmU, a.a_row0 + mb * BM, nb * BN, 0, 0, a.N / BK};
   const KSeg s1{&tmH, &tmU, 0, 0, 0, 0, 0};
   if constexpr (PAIR) pair_mainloop<BN, STAGES>(c, s0, s1, cluster_ctarank(), (uint16_t)0x3);
@@ -235,7 +237,8 @@ template <int BN>
 static void launch_fwd_t(const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st) {
   dim3 grid(4 * a.N / BN, a.Bp / BM);
   if (fwd_pair(a.Bp)) {
-    launch_cluster(k_fwd_step<BN, 1, 1, true>, grid, dim3(1, 2, 1), FwdCfg<BN, true>::SMEM_BYTES, st, a.pin, a.pin_bytes, tmH, tmUrk, a);
+    launch_cluster(k_fwd_step<BN, 1, 1, true>, dim3(2 * grid.x, grid.y / 2), dim3(2, 1, 1), FwdCfg<BN, true>::SMEM_BYTES, st,
+                   a.pin, a.pin_bytes, tmH, tmUrk, a);
     return;
   }
   const int CN = fwd_cluster_n((int)grid.x), CM = fwd_cluster_m(a.Bp);
