@@ -91,12 +91,16 @@ __device__ __forceinline__ void tile_mainloop(const TileCtx& c, const KSeg& s0, 
   uint16_t mask_a = 0, mask_b = 0;
   for (int i = 0; i < CN; i++) mask_a |= (uint16_t)(1u << (yr * CN + i));
   for (int j = 0; j < CM; j++) mask_b |= (uint16_t)(1u << (j * CN + xr));
+  // Both role loops run WARP-UNIFORM (all 32 lanes take the loop and the waits) with the single-thread instructions
+  // under elect.sync: issued from a divergent `if (lane == 0)` region, every UTMALDG / UTCHMMA / UTCBAR gets wrapped
+  // by ptxas in a vote-and-branch loop, and the MMA issue thread — not the tensor pipe or the operand delivery —
+  // became the bottleneck (~530 cycles per k-block regardless of tile size).
   if (c.warp == 0) {
-    if (c.lane == 0) {
-      for (int kb = 0; kb < total; kb++) {
-        const int st = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(&c.empty[st], ph ^ 1u);
+    for (int kb = 0; kb < total; kb++) {
+      const int st = kb % STAGES;
+      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      mbar_wait(&c.empty[st], ph ^ 1u);
+      if (elect_one()) {
         const bool first = kb < s0.nkb;
         const KSeg& s = first ? s0 : s1;
         const int k = first ? kb : kb - s0.nkb;
@@ -108,30 +112,33 @@ __device__ __forceinline__ void tile_mainloop(const TileCtx& c, const KSeg& s0, 
         if (CM == 1) tma_load_2d(b, s.tb, &c.full[st], s.b_k0 + k * BK, s.b_row);
         else tma_load_2d_mc(b + yr * B_ROWS * 128, s.tb, &c.full[st], s.b_k0 + k * BK, s.b_row + yr * B_ROWS, mask_b);
       }
-      if (c.dbg) c.dbg[1] = clock64();
+      __syncwarp();
     }
+    if (c.dbg && c.lane == 0) c.dbg[1] = clock64();
   } else if (c.warp == 1) {
-    if (c.lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
-      for (int kb = 0; kb < total; kb++) {
-        const int st = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(&c.full[st], ph);
-        if (c.dbg && kb == 0) c.dbg[2] = clock64();
-        tcgen05_after_sync();
-        const uint32_t a_addr = smem_u32(c.tiles + (size_t)st * C::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + A_TILE_BYTES;
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+    const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(c.tiles));
+    const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(c.tiles) + A_TILE_BYTES);
+    for (int kb = 0; kb < total; kb++) {
+      const int st = kb % STAGES;
+      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      mbar_wait(&c.full[st], ph);
+      if (c.dbg && kb == 0 && c.lane == 0) c.dbg[2] = clock64();
+      tcgen05_after_sync();
+      if (elect_one()) {
+        const uint64_t soff = (uint64_t)((uint32_t)st * (uint32_t)(C::STAGE_BYTES >> 4));   // descriptors address smem in 16-byte units
 #pragma unroll
         for (int k = 0; k < BK / 16; k++)   // UMMA_K = 16 bf16 = 32 bytes inside the swizzled row
-          umma_bf16(c.tmem_d, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32), idesc,
-                    (uint32_t)((kb | k) != 0));
+          umma_bf16(c.tmem_d, a_desc0 + soff + 2 * k, b_desc0 + soff + 2 * k, idesc, (uint32_t)((kb | k) != 0));
         // frees the stage once these MMAs have read it — in every CTA whose loads write into this CTA's stage
         if (CN * CM == 1) umma_commit(&c.empty[st]);
         else umma_commit_mc(&c.empty[st], (uint16_t)(mask_a | mask_b));
       }
-      umma_commit(c.accum_full);            // accumulator complete -> epilogue
-      if (c.dbg) c.dbg[3] = clock64();
+      __syncwarp();
     }
+    if (elect_one()) umma_commit(c.accum_full);   // accumulator complete -> epilogue
+    __syncwarp();
+    if (c.dbg && c.lane == 0) c.dbg[3] = clock64();
   }
 }
 
@@ -194,11 +201,11 @@ __device__ __forceinline__ void pair_mainloop(const TileCtx& c, const KSeg& s0, 
   using C = PairCfg<BN, STAGES>;
   const int total = s0.nkb + s1.nkb;
   if (c.warp == 0) {
-    if (c.lane == 0) {
-      for (int kb = 0; kb < total; kb++) {
-        const int st = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(&c.empty[st], ph ^ 1u);
+    for (int kb = 0; kb < total; kb++) {
+      const int st = kb % STAGES;
+      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      mbar_wait(&c.empty[st], ph ^ 1u);
+      if (elect_one()) {
         const bool first = kb < s0.nkb;
         const KSeg& s = first ? s0 : s1;
         const int k = first ? kb : kb - s0.nkb;
@@ -208,28 +215,31 @@ __device__ __forceinline__ void pair_mainloop(const TileCtx& c, const KSeg& s0, 
         tma_load_2d_pair(a, s.ta, &c.full[st], s.a_k0 + k * BK, s.a_row);
         tma_load_2d_pair(b, s.tb, &c.full[st], s.b_k0 + k * BK, s.b_row + (int)rank * (BN / 2));
       }
-      if (c.dbg) c.dbg[1] = clock64();
+      __syncwarp();
     }
+    if (c.dbg && c.lane == 0) c.dbg[1] = clock64();
   } else if (c.warp == 1 && rank == 0) {
-    if (c.lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
-      for (int kb = 0; kb < total; kb++) {
-        const int st = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(&c.full[st], ph);
-        if (c.dbg && kb == 0) c.dbg[2] = clock64();
-        tcgen05_after_sync();
-        const uint32_t a_addr = smem_u32(c.tiles + (size_t)st * C::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + A_TILE_BYTES;
+    constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
+    const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(c.tiles));
+    const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(c.tiles) + A_TILE_BYTES);
+    for (int kb = 0; kb < total; kb++) {
+      const int st = kb % STAGES;
+      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      mbar_wait(&c.full[st], ph);
+      if (c.dbg && kb == 0 && c.lane == 0) c.dbg[2] = clock64();
+      tcgen05_after_sync();
+      if (elect_one()) {
+        const uint64_t soff = (uint64_t)((uint32_t)st * (uint32_t)(C::STAGE_BYTES >> 4));
 #pragma unroll
         for (int k = 0; k < BK / 16; k++)
-          umma_bf16_pair(c.tmem_d, make_smem_desc_sw128(a_addr + k * 32), make_smem_desc_sw128(b_addr + k * 32), idesc,
-                         (uint32_t)((kb | k) != 0));
+          umma_bf16_pair(c.tmem_d, a_desc0 + soff + 2 * k, b_desc0 + soff + 2 * k, idesc, (uint32_t)((kb | k) != 0));
         umma_commit_pair(&c.empty[st], pair_mask);     // stage free in both CTAs
       }
-      umma_commit_pair(c.accum_full, pair_mask);       // accumulator halves complete in both CTAs
-      if (c.dbg) c.dbg[3] = clock64();
+      __syncwarp();
     }
+    if (elect_one()) umma_commit_pair(c.accum_full, pair_mask);   // accumulator halves complete in both CTAs
+    __syncwarp();
+    if (c.dbg && c.lane == 0) c.dbg[3] = clock64();
   }
 }
 
