@@ -111,9 +111,9 @@ int tc_create(lstm_ctx* ctx) {
   ok &= make_tmap(&s->tmH, s->Hbf, (uint64_t)(T + 1) * Bp, N, 128);
   ok &= make_tmap(&s->tmH2, s->Hbf, (uint64_t)(T + 1) * Bp, N, 128 / tc::fwd_cluster_n(s->N4 / s->BN2));            // K2: multicast slices
   ok &= make_tmap(&s->tmUrk, s->Urk, N4, N, s->BN2 / tc::fwd_cluster_m(s->Bp));
-  ok &= make_tmap(&s->tmUkr, s->Ukr, N, N4, s->BN5);
+  ok &= make_tmap(&s->tmUkr, s->Ukr, N, N4, tc::bwd_box_rows(s->BN5, s->Bp));
   ok &= make_tmap(&s->tmWmn, s->Wmn, M, N, 256);
-  ok &= make_tmap(&s->tmWnm, s->Wnm, N, M, s->BN5);
+  ok &= make_tmap(&s->tmWnm, s->Wnm, N, M, tc::bwd_box_rows(s->BN5, s->Bp));
   ok &= make_tmap(&s->tmdY, s->dYbf, (uint64_t)T * Bp, M, 128);
   ok &= make_tmap(&s->tmdYT, s->dYT, M, s->LDT, 128);
   ok &= make_tmap(&s->tmdG, s->dGbf, (uint64_t)T * Bp, N4, 128);

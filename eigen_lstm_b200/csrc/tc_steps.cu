@@ -212,17 +212,18 @@ static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
 }
-// forward-step launch shape: CTA pairs (cta_group::2) when there is an even number of batch tiles, unless
-// LSTM_FWD_PAIR=0; LSTM_FWD_CN / LSTM_FWD_CM select the (slower) multicast-cluster experiment instead.
-bool fwd_pair(int Bp) {
-  return env_int("LSTM_FWD_PAIR", 0) != 0 && (Bp / 128) % 2 == 0 && env_int("LSTM_FWD_CN", 1) == 1 && env_int("LSTM_FWD_CM", 1) == 1;
+// timestep-kernel launch shape: CTA pairs (cta_group::2) when there is an even number of batch tiles, unless
+// LSTM_PAIR=0; LSTM_FWD_CN / LSTM_FWD_CM select the (slower) multicast-cluster experiment instead.
+bool step_pair(int Bp) {
+  return env_int("LSTM_PAIR", 1) != 0 && (Bp / 128) % 2 == 0 && env_int("LSTM_FWD_CN", 1) == 1 && env_int("LSTM_FWD_CM", 1) == 1;
 }
+int bwd_box_rows(int BN, int Bp) { return step_pair(Bp) ? BN / 2 : BN; }
 int fwd_cluster_n(int n_tiles) {
   const int cn = env_int("LSTM_FWD_CN", 1);
   return (cn == 2 || cn == 4) && n_tiles % cn == 0 ? cn : 1;
 }
 int fwd_cluster_m(int Bp) {
-  if (fwd_pair(Bp)) return 2;                       // a pair stages half of the U tile per CTA: same box as CM = 2
+  if (step_pair(Bp)) return 2;                       // a pair stages half of the U tile per CTA: same box as CM = 2
   const int cm = env_int("LSTM_FWD_CM", 1);
   return cm == 2 && (Bp / 128) % 2 == 0 ? 2 : 1;
 }
@@ -236,7 +237,7 @@ static void launch_fwd_cn(int CM, dim3 grid, const CUtensorMap& tmH, const CUten
 template <int BN>
 static void launch_fwd_t(const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st) {
   dim3 grid(4 * a.N / BN, a.Bp / BM);
-  if (fwd_pair(a.Bp)) {
+  if (step_pair(a.Bp)) {
     launch_cluster(k_fwd_step<BN, 1, 1, true>, dim3(2 * grid.x, grid.y / 2), dim3(2, 1, 1), FwdCfg<BN, true>::SMEM_BYTES, st,
                    a.pin, a.pin_bytes, tmH, tmUrk, a);
     return;
@@ -259,26 +260,30 @@ void launch_fwd_step(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, c
 // grid (N/BN, Bp/128, 4), cluster (1,1,4)
 // ------------------------------------------------------------------------------------------------
 constexpr int SPLIT = 4;
-template <int BN>
+template <int BN, bool PAIR = false>
 struct BwdCfg {
-  static constexpr int STAGES = BN == 128 ? 4 : (BN == 64 ? 6 : 8);
+  static constexpr int STAGES = PAIR ? (BN == 128 ? 5 : 8) : (BN == 128 ? 4 : (BN == 64 ? 6 : 8));
   static constexpr int UO = BN / SPLIT;                    // hidden units finalised by each CTA of the cluster
   static constexpr int RV_LD = UO + 4;                     // fp32 row pitch of this CTA's own partial slice
   static constexpr int RV_BYTES = 128 * RV_LD * 4;         // [row][UO]
   static constexpr int GT_BYTES = 4 * UO * HT_LD * 2;      // dg^T staging [gate*UO + unit][row]
   static constexpr int EPI_BYTES = RV_BYTES + GT_BYTES;
   using C = Cfg<BN, STAGES, EPI_BYTES>;
+  static constexpr int SMEM_BYTES = PAIR ? PairCfg<BN, STAGES>::TILE_BYTES + 1024 + 256 + (EPI_BYTES + 127) / 128 * 128 : C::SMEM_BYTES;
 };
 
-template <int BN>
+// PAIR: cluster (2,1,4) — x = the two batch tiles of a cta_group::2 pair, z = the 4 split-K ranks
+template <int BN, bool PAIR = false>
 __global__ void __launch_bounds__(CTA_THREADS, 1)
 k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUtensorMap tmU,
            const __grid_constant__ CUtensorMap tmdY, const __grid_constant__ CUtensorMap tmW, const BwdStepArgs a) {
-  using F = BwdCfg<BN>;
+  using F = BwdCfg<BN, PAIR>;
   constexpr int STAGES = F::STAGES, UO = F::UO, RG = EPI_THREADS / UO, ROWS = 128 / RG, RV_LD = F::RV_LD;
   extern __shared__ uint8_t smem_raw[];
   const long long t_entry = clock64();
-  TileCtx c = tile_prologue<BN, STAGES>(smem_raw);
+  TileCtx c;
+  if constexpr (PAIR) c = pair_prologue<BN, STAGES>(smem_raw);
+  else c = tile_prologue<BN, STAGES>(smem_raw);
   pdl_launch_dependents();
   pdl_wait();
   c.dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? a.dbg : nullptr;
@@ -286,9 +291,11 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
   if (stamp) { c.dbg[0] = t_entry; c.dbg[4] = clock64(); }
   float* recv = reinterpret_cast<float*>(c.epi);
   __nv_bfloat16* gT = reinterpret_cast<__nv_bfloat16*>(c.epi + F::RV_BYTES);
-  const int nb = blockIdx.x, mb = blockIdx.y;
-  const uint32_t rank = cluster_ctarank();
-  float* red_tile = a.red + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * (SPLIT * SPLIT * 128 * UO);
+  const int nb = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int mb = PAIR ? (int)(blockIdx.y * 2 + (blockIdx.x & 1)) : (int)blockIdx.y;
+  const uint32_t crank = cluster_ctarank();                  // PAIR: x (pair member) + 2 * z (split-K rank)
+  const uint32_t rank = PAIR ? crank >> 1 : crank;           // split-K rank
+  float* red_tile = a.red + (size_t)(mb * (a.N / BN) + nb) * (SPLIT * SPLIT * 128 * UO);
   // this CTA's quarter of the concatenated K range [0, nkb0) ++ [0, nkb1)
   const int nkb0 = a.first ? 0 : (4 * a.N) / BK, nkb1 = a.M / BK;
   const int per = (nkb0 + nkb1) / SPLIT;
@@ -297,7 +304,8 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
   const int lo1 = max(lo, nkb0) - nkb0, hi1 = max(hi, nkb0) - nkb0;
   const KSeg s0{&tmdG, &tmU, a.dg_row0 + mb * BM, nb * BN, lo0 * BK, lo0 * BK, hi0 - lo0};
   const KSeg s1{&tmdY, &tmW, a.dy_row0 + mb * BM, nb * BN, lo1 * BK, lo1 * BK, hi1 - lo1};
-  tile_mainloop<BN, STAGES>(c, s0, s1);
+  if constexpr (PAIR) pair_mainloop<BN, STAGES>(c, s0, s1, crank & 1u, (uint16_t)(0x3u << (2 * rank)));
+  else tile_mainloop<BN, STAGES>(c, s0, s1);
   const int e = threadIdx.x - 64;
   const int N = a.N, N4 = 4 * a.N;
   const int l = e >= 0 ? e % UO : 0, rg = e >= 0 ? e / UO : 0;
@@ -402,7 +410,8 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
       }
     }
   }
-  tile_epilogue_end<BN, STAGES>(c);
+  if constexpr (PAIR) pair_epilogue_end<BN, STAGES>(c);
+  else tile_epilogue_end<BN, STAGES>(c);
   if (stamp) c.dbg[8] = clock64();
 }
 
@@ -411,6 +420,11 @@ static void launch_bwd_t(const CUtensorMap& tmdG, const CUtensorMap& tmUkr, cons
                          const CUtensorMap& tmWnm, const BwdStepArgs& a, cudaStream_t st) {
   using F = BwdCfg<BN>;
   dim3 grid(a.N / BN, a.Bp / BM, SPLIT);
+  if (step_pair(a.Bp)) {   // tmUkr / tmWnm boxes are BN/2 rows in this mode (bwd_box_rows)
+    launch_cluster(k_bwd_step<BN, true>, dim3(2 * grid.x, grid.y / 2, SPLIT), dim3(2, 1, SPLIT), BwdCfg<BN, true>::SMEM_BYTES, st,
+                   a.pin, a.pin_bytes, tmdG, tmUkr, tmdY, tmWnm, a);
+    return;
+  }
   launch_cluster(k_bwd_step<BN>, grid, dim3(1, 1, SPLIT), F::C::SMEM_BYTES, st, a.pin, a.pin_bytes, tmdG, tmUkr, tmdY, tmWnm, a);
 }
 void launch_bwd_step(int BN, const CUtensorMap& tmdG, const CUtensorMap& tmUkr, const CUtensorMap& tmdY,
