@@ -84,9 +84,10 @@ struct GemmArgs {
 // override it for experiments.
 int fwd_cluster_n(int n_tiles);
 int fwd_cluster_m(int Bp);
-// K2 / K5 run as cta_group::2 CTA pairs over the two batch tiles when Bp/128 is even (LSTM_PAIR=0 disables): each CTA
-// then stages only half of the weight tile, so the weight maps need boxes of BN/2 rows.
+// K2 runs as cta_group::2 CTA pairs over the two batch tiles when Bp/128 is even (LSTM_PAIR=0 disables; K5 only with
+// LSTM_BWD_PAIR=1): each CTA then stages only half of the weight tile, so the weight maps need boxes of BN/2 rows.
 bool step_pair(int Bp);
+bool bwd_pair(int Bp);
 int bwd_box_rows(int BN, int Bp);
 // K2: one recurrent timestep.  BN in {32, 64, 128} gate columns per CTA.
 void launch_fwd_step(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st);

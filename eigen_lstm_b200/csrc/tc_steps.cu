@@ -217,7 +217,10 @@ static int env_int(const char* name, int dflt) {
 bool step_pair(int Bp) {
   return env_int("LSTM_PAIR", 1) != 0 && (Bp / 128) % 2 == 0 && env_int("LSTM_FWD_CN", 1) == 1 && env_int("LSTM_FWD_CM", 1) == 1;
 }
-int bwd_box_rows(int BN, int Bp) { return step_pair(Bp) ? BN / 2 : BN; }
+// K5 as pairs needs clusters of 2 x 1 x 4 = 8 CTAs; 16 of those do not all become co-resident on a B200 (GPCs of
+// 16-20 SMs, some with fewer usable): measured 37.5 us per step instead of 20.1.  Off unless LSTM_BWD_PAIR=1.
+bool bwd_pair(int Bp) { return step_pair(Bp) && env_int("LSTM_BWD_PAIR", 0) != 0; }
+int bwd_box_rows(int BN, int Bp) { return bwd_pair(Bp) ? BN / 2 : BN; }
 int fwd_cluster_n(int n_tiles) {
   const int cn = env_int("LSTM_FWD_CN", 1);
   return (cn == 2 || cn == 4) && n_tiles % cn == 0 ? cn : 1;
@@ -420,7 +423,7 @@ static void launch_bwd_t(const CUtensorMap& tmdG, const CUtensorMap& tmUkr, cons
                          const CUtensorMap& tmWnm, const BwdStepArgs& a, cudaStream_t st) {
   using F = BwdCfg<BN>;
   dim3 grid(a.N / BN, a.Bp / BM, SPLIT);
-  if (step_pair(a.Bp)) {   // tmUkr / tmWnm boxes are BN/2 rows in this mode (bwd_box_rows)
+  if (bwd_pair(a.Bp)) {   // tmUkr / tmWnm boxes are BN/2 rows in this mode (bwd_box_rows)
     launch_cluster(k_bwd_step<BN, true>, dim3(2 * grid.x, grid.y / 2, SPLIT), dim3(2, 1, SPLIT), BwdCfg<BN, true>::SMEM_BYTES, st,
                    a.pin, a.pin_bytes, tmdG, tmUkr, tmdY, tmWnm, a);
     return;
