@@ -82,12 +82,20 @@ k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUte
     }
     const float4 bias = *reinterpret_cast<const float4*>(a.bp + rp);
     named_bar_sync(1, EPI_THREADS);
-    // warm L2 with what phase 2 will read, while the tensor core is busy
+    // Operands of the LSTM math (W row gather, c(t-1)) are loaded into registers NOW, while the tensor core is still
+    // busy with the contraction: the phase-2 math then starts with its inputs already on chip.
+    float4 w[ROWS];
+    float cpv[ROWS];
+    int xv[ROWS];
 #pragma unroll
-    for (int i = 0; i < ROWS; i++) {
-      const int r = rg + RG * i, x = sx[r];
-      if (x >= 0 && (l & 7) == 0) prefetch_l2(a.Wp + (size_t)x * N4 + rp);
-      if (x >= -1 && l == 0) prefetch_l2(a.c_prev + (size_t)(mb * BM + r) * N + j);
+    for (int q = 0; q < ROWS; q++) {
+      const int r = rg + RG * q;
+      const int x = sx[r];
+      xv[q] = x;
+      w[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      cpv[q] = 0.f;
+      if (x >= 0) w[q] = __ldg(reinterpret_cast<const float4*>(a.Wp + (size_t)x * N4 + rp));   // W*x, one-hot x
+      if (x >= -1) cpv[q] = a.c_prev[(size_t)(mb * BM + r) * N + j];
     }
     // phase 1 (warps 2-5, one per TMEM lane quarter): TMEM (lane = stream) -> shared memory tile acc[row][col]
     if (c.warp < 6) {
@@ -107,25 +115,9 @@ k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUte
     }
     named_bar_sync(1, EPI_THREADS);
     if (stamp) c.dbg[6] = clock64();
-    // phase 2: lane = hidden unit; one warp instruction touches one stream's contiguous row segment.
-    // Rows are processed in batches of RB with all their global loads issued up front (memory-level parallelism:
-    // this phase is latency-bound, not bandwidth-bound).
-    constexpr int RB = ROWS < 8 ? ROWS : 8;
-#pragma unroll 1
-    for (int i0 = 0; i0 < ROWS; i0 += RB) {
-      float4 w[RB];
-      float cpv[RB];
-      int xv[RB];
-#pragma unroll
-      for (int q = 0; q < RB; q++) {
-        const int r = rg + RG * (i0 + q);
-        const int x = sx[r];
-        xv[q] = x;
-        w[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        cpv[q] = 0.f;
-        if (x >= 0) w[q] = __ldg(reinterpret_cast<const float4*>(a.Wp + (size_t)x * N4 + rp));   // W*x, one-hot x
-        if (x >= -1) cpv[q] = a.c_prev[(size_t)(mb * BM + r) * N + j];
-      }
+    // phase 2: lane = hidden unit; one warp instruction touches one stream's contiguous row segment
+    {
+      constexpr int RB = ROWS, i0 = 0;
 #pragma unroll
       for (int q = 0; q < RB; q++) {
         const int r = rg + RG * (i0 + q);
