@@ -269,7 +269,7 @@ struct BwdCfg {
 
 // PAIR: cluster (2,1,4) — x = the two batch tiles of a cta_group::2 pair, z = the 4 split-K ranks
 template <int BN, bool PAIR = false>
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(CTA_THREADS, 1)
 k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUtensorMap tmU,
            const __grid_constant__ CUtensorMap tmdY, const __grid_constant__ CUtensorMap tmW, const BwdStepArgs a) {
   using F = BwdCfg<BN, PAIR>;
@@ -305,21 +305,13 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
   const int N = a.N, N4 = 4 * a.N;
   const int l = e >= 0 ? e % UO : 0, rg = e >= 0 ? e / UO : 0;
   const int j = nb * BN + (int)rank * UO + l;              // the hidden unit this thread finalises
-  float4 gv[ROWS];
-  float ctv[ROWS], cpv[ROWS], dnv[ROWS];
   if (c.warp >= 2) {
-    // operands of the gate-gradient math are loaded into registers now, while the contraction is still running
 #pragma unroll
-    for (int q = 0; q < ROWS; q++) {
-      const int b = mb * BM + rg + RG * q;
-      gv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-      ctv[q] = cpv[q] = dnv[q] = 0.f;
+    for (int i = 0; i < ROWS; i++) {                       // warm L2 for phase 2
+      const int b = mb * BM + rg + RG * i;
       if (b < a.B) {
-        const size_t bj = (size_t)b * N + j;
-        gv[q] = __ldcs(reinterpret_cast<const float4*>(a.Gp_t + (size_t)b * N4 + 4 * (size_t)j));   // i o f u (last use)
-        ctv[q] = a.c_t[bj];
-        cpv[q] = a.c_prev[bj];
-        if (!a.first) dnv[q] = a.dcnext[bj];
+        if ((l & 7) == 0) prefetch_l2(a.Gp_t + (size_t)b * N4 + 4 * (size_t)j);
+        if (l == 0) { prefetch_l2(a.c_t + (size_t)b * N + j); prefetch_l2(a.c_prev + (size_t)b * N + j); }
       }
     }
     // phase 1 (warps 2-5): reduce-scatter.  Column slice q of this CTA's partial accumulator goes to CTA q:
@@ -345,17 +337,29 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
   cluster_sync_all();                                      // all partial slices are written (cluster-scope release/acquire)
   if (stamp) c.dbg[6] = clock64();
   if (c.warp >= 2) {
-    // phase 2: lane = hidden unit; the three foreign split-K partials of every row are fetched (L2) up front
-    {
-      constexpr int RB = ROWS, i0 = 0;
-      float pv[RB][SPLIT];
+    // phase 2: lane = hidden unit; batches of RB rows with all global loads issued up front (latency-bound phase)
+    constexpr int RB = ROWS < 4 ? ROWS : 4;
+#pragma unroll 1
+    for (int i0 = 0; i0 < ROWS; i0 += RB) {
+      float4 gv[RB];
+      float ctv[RB], cpv[RB], dnv[RB], pv[RB][SPLIT];
 #pragma unroll
       for (int q = 0; q < RB; q++) {
-        const int r = rg + RG * q;
+        const int r = rg + RG * (i0 + q);
+        const int b = mb * BM + r;
+        gv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ctv[q] = cpv[q] = dnv[q] = 0.f;
 #pragma unroll
-        for (int sr = 0; sr < SPLIT; sr++) {
-          pv[q][sr] = 0.f;
-          if (sr != (int)rank && mb * BM + r < a.B) pv[q][sr] = __ldcg(red_tile + (((size_t)rank * SPLIT + sr) * 128 + r) * UO + l);
+        for (int sr = 0; sr < SPLIT; sr++) pv[q][sr] = 0.f;
+        if (b < a.B) {
+          const size_t bj = (size_t)b * N + j;
+#pragma unroll
+          for (int sr = 0; sr < SPLIT; sr++)
+            if (sr != (int)rank) pv[q][sr] = __ldcg(red_tile + (((size_t)rank * SPLIT + sr) * 128 + r) * UO + l);
+          gv[q] = __ldcs(reinterpret_cast<const float4*>(a.Gp_t + (size_t)b * N4 + 4 * (size_t)j));   // i o f u (last use)
+          ctv[q] = a.c_t[bj];
+          cpv[q] = a.c_prev[bj];
+          if (!a.first) dnv[q] = a.dcnext[bj];
         }
       }
 #pragma unroll
