@@ -257,7 +257,7 @@ void launch_fwd_step(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, c
 constexpr int SPLIT = 4;
 template <int BN, bool PAIR = false>
 struct BwdCfg {
-  static constexpr int STAGES = PAIR ? (BN == 128 ? 5 : 8) : (BN == 128 ? 4 : (BN == 64 ? 6 : 8));
+  static constexpr int STAGES = PAIR ? (BN == 128 ? 5 : 8) : (BN == 128 ? 4 : (BN == 64 ? 6 : 8));   // 5 stages: no faster
   static constexpr int UO = BN / SPLIT;                    // hidden units finalised by each CTA of the cluster
   static constexpr int RV_LD = UO + 4;                     // fp32 row pitch of this CTA's own partial slice
   static constexpr int RV_BYTES = 128 * RV_LD * 4;         // [row][UO]
