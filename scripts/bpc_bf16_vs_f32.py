@@ -23,9 +23,15 @@ cut = len(text) * 9 // 10
 train, held = text[:cut], text[cut:]
 pos = [S + (len(train) - 2 * S) * b // B for b in range(B)]
 res = {}
-for name, dt in (("f32", el.F32), ("bf16", el.BF16)):
+# "f32_ulp": the fp32 path again with every weight moved by ~1 ulp — the trajectory noise floor of this chaotic system
+for name, dt in (("f32", el.F32), ("bf16", el.BF16), ("f32_ulp", el.F32)):
     g = el.LSTM(256, N, S, B, dtype=dt)
     g.init_params(seed=1, std=0.01, forget_bias=1.0)
+    if name == "f32_ulp":
+        rng = np.random.default_rng(0)
+        for w in range(5):
+            p = g.get(0, w)
+            g.set(0, w, (p * (1.0 + 1.2e-7 * rng.choice([-1.0, 1.0], p.shape))).astype(np.float32))
     g.load_text(train)
     g.set_positions(pos)
     curve = []
@@ -36,7 +42,9 @@ for name, dt in (("f32", el.F32), ("bf16", el.BF16)):
     print(name, "train bpc (last 100 its)", curve[-1], "held-out bpc", res[name]["heldout_bpc"], flush=True)
 res["abs_diff_heldout"] = abs(res["f32"]["heldout_bpc"] - res["bf16"]["heldout_bpc"])
 res["abs_diff_train"] = abs(res["f32"]["train_bpc_curve"][-1] - res["bf16"]["train_bpc_curve"][-1])
+res["noise_floor_heldout_f32_vs_f32_plus_1ulp"] = abs(res["f32"]["heldout_bpc"] - res["f32_ulp"]["heldout_bpc"])
 res["config"] = dict(N=N, B=B, S=S, iters=iters, lr=lr, text="enwik6 head 64 KiB, 90/10 split")
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "bpc_bf16_vs_f32.json"), "w"), indent=1)
-print("held-out |bf16 - f32| =", res["abs_diff_heldout"], " train |diff| =", res["abs_diff_train"])
+print("held-out |bf16 - f32| =", res["abs_diff_heldout"], " train |diff| =", res["abs_diff_train"],
+      " noise floor |f32 - f32(+1ulp)| =", res["noise_floor_heldout_f32_vs_f32_plus_1ulp"])
