@@ -290,7 +290,7 @@ def main():
     achieved = dom_flops / (dom_us * 1e-6) / 1e12 if dom_us > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": f"{dom_kernel} (one recurrent timestep, {'tcgen05 bf16' if dtype == 'bf16' else 'SIMT fp32'})",
                 "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
-                "traffic": traffic, "traffic_source": "ncu --set full dram__bytes_read+write per launch (profiles/r01d_kernels.md)" if traffic else None,
+                "traffic": traffic, "traffic_source": "ncu --set full dram__bytes_read+write per launch (profiles/r01e_kernels.md)" if traffic else None,
                 "peak_source": f"{pk['src']} sustained bf16 (kernel timed inside a long step)",
                 "flops_per_launch": dom_flops, "us_per_launch": dom_us,
                 "note": "operand bytes per launch (U 33.5 MB + h/dg) exceed what the tensor pipe can be fed at: the step is bound by "
