@@ -110,6 +110,8 @@ def cpu_arm(cfg, text, target_seconds, steps=1, warmup=0):
     from oracle import oracle as orc
     N, S = cfg["N"], cfg["S"]
     threads = os.cpu_count() or 1
+    if cfg["B"] * N < 4096:
+        threads = 1                                   # tiny models: fork/join costs more than the loops (the reference is 1 thread)
     Bs = min(cfg["B"], threads)                       # one stream per host thread
     # probe: a short window to find the per-char-step cost, then size the sample
     Tp = min(S - 1, 4)
