@@ -56,6 +56,18 @@ bool nccl_load() {
 
 static thread_local std::string g_create_error;
 
+static void free_iter_graph_keep_key(lstm_ctx::IterGraph& g) {
+  if (g.exec) cudaGraphExecDestroy(g.exec);
+  for (cudaGraphExec_t e : g.segs) if (e) cudaGraphExecDestroy(e);
+  g.exec = nullptr;
+  g.segs.clear();
+  g.seg_bucket.clear();
+}
+static void free_iter_graph(lstm_ctx::IterGraph& g) {
+  free_iter_graph_keep_key(g);
+  g = lstm_ctx::IterGraph();
+}
+
 int lstm_fail(lstm_ctx* c, int code, const std::string& msg) {
   if (c) c->err = msg; else g_create_error = msg;
   return code;
@@ -191,7 +203,7 @@ extern "C" int lstm_destroy(lstm_ctx* ctx) {
   if (ctx->h_xs_pinned) cudaFreeHost(ctx->h_xs_pinned);
   if (ctx->h_tg_pinned) cudaFreeHost(ctx->h_tg_pinned);
   if (ctx->d_iter) cudaFree(ctx->d_iter);
-  for (auto& g : ctx->graph) if (g.exec) cudaGraphExecDestroy(g.exec);
+  for (auto& g : ctx->graph) free_iter_graph(g);
   for (int i = 0; i < 2; i++) {
     if (ctx->ev_bucket[i]) cudaEventDestroy(ctx->ev_bucket[i]);
     if (ctx->ev_comm[i]) cudaEventDestroy(ctx->ev_comm[i]);
@@ -320,8 +332,7 @@ extern "C" int lstm_reset_state(lstm_ctx* ctx, uint64_t seed, float std) {
 // ------------------------------------------------------------------------------------------------
 static void drop_graphs(lstm_ctx* ctx) {
   for (auto& g : ctx->graph) {
-    if (g.exec) cudaGraphExecDestroy(g.exec);
-    g = lstm_ctx::IterGraph();
+    free_iter_graph(g);
   }
 }
 
@@ -365,9 +376,26 @@ static int forward_device(lstm_ctx* ctx) {
   return LSTM_OK;
 }
 
+// Segmented capture (data parallel): close the graph segment being captured on ctx->st, remember that `bucket` is
+// summed after it, and open the next segment.
+static int cut_segment(lstm_ctx* ctx, int bucket) {
+  lstm_ctx::IterGraph* g = ctx->seg_capture;
+  cudaGraph_t graph = nullptr;
+  LSTM_CUDA(cudaStreamEndCapture(ctx->st, &graph));
+  cudaGraphExec_t exec = nullptr;
+  cudaError_t ce = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) return lstm_fail(ctx, LSTM_ERR_CUDA, std::string("cudaGraphInstantiate (segment): ") + cudaGetErrorString(ce));
+  g->segs.push_back(exec);
+  g->seg_bucket.push_back(bucket);
+  LSTM_CUDA(cudaStreamBeginCapture(ctx->st, cudaStreamCaptureModeThreadLocal));
+  return LSTM_OK;
+}
+
 int lstm_allreduce_bucket(lstm_ctx* ctx, int bucket) {
   // bucket 0 = [W,U,b], bucket 1 = [Why,by]; both contiguous in the flat gradient vector.
   if (ctx->world <= 1) return LSTM_OK;
+  if (ctx->seg_capture) return cut_segment(ctx, bucket);   // capture pass: the graph ends here, NCCL runs between replays
   float* ptr = bucket == 0 ? ctx->g(LSTM_W) : ctx->g(LSTM_WHY);
   const size_t cnt = bucket == 0 ? ctx->off[LSTM_WHY] : ctx->P - ctx->off[LSTM_WHY];
   LSTM_CUDA(cudaEventRecord(ctx->ev_bucket[bucket], ctx->st));
@@ -418,7 +446,7 @@ static int backward_device(lstm_ctx* ctx) {
 }
 
 static int adagrad_device(lstm_ctx* ctx, float lr, double eps, float clip) {
-  if (ctx->world > 1) {
+  if (ctx->world > 1 && !ctx->seg_capture) {   // segmented replay issues these waits itself, before the last segment
     LSTM_CUDA(cudaStreamWaitEvent(ctx->st, ctx->ev_comm[0], 0));
     LSTM_CUDA(cudaStreamWaitEvent(ctx->st, ctx->ev_comm[1], 0));
   }
@@ -498,37 +526,68 @@ static int iteration_body(lstm_ctx* ctx, int mode, int stride, float lr) {
 
 // Launch-bound inner loop (hundreds of short kernels per iteration): the iteration is captured once into a CUDA graph
 // and replayed.  Profiling (per-phase events) and LSTM_NO_GRAPH=1 use plain stream launches.
+//
+// Data parallel: NCCL is kept OUT of the graphs (capturing the allreduce on the side stream into the iteration graph
+// hung at 4 and 8 ranks on B200 / NCCL 2.28).  The iteration is captured as segments cut at each gradient bucket
+// (lstm_allreduce_bucket -> cut_segment); a replay launches segment, eager allreduce on the communication stream,
+// next segment, ..., and joins the communication stream before the last segment (Adagrad).  LSTM_DP_GRAPH=0 falls
+// back to plain stream launches.
 static int run_iteration(lstm_ctx* ctx, int mode, int stride, float lr) {
   static const bool no_graph = getenv("LSTM_NO_GRAPH") != nullptr;
+  static const bool dp_graph = !(getenv("LSTM_DP_GRAPH") && atoi(getenv("LSTM_DP_GRAPH")) == 0);
   lstm_ctx::IterGraph& g = ctx->graph[mode];
-  if (g.exec && (g.stride != stride || g.lr != lr)) { cudaGraphExecDestroy(g.exec); g = lstm_ctx::IterGraph(); }
+  const bool dp = ctx->world > 1;
+  if ((g.exec || !g.segs.empty()) && (g.stride != stride || g.lr != lr)) free_iter_graph(g);
   ctx->fwd_count++;
   ctx->iteration++;
-  // Data parallel: plain stream launches.  (Capturing the NCCL allreduce on the side stream into the iteration graph
-  // hung at 4 and 8 ranks on B200 / NCCL 2.28; until that is understood the graph path is single-GPU only.)
-  if (ctx->profiling || no_graph || ctx->world > 1) {
+  if (ctx->profiling || no_graph || (dp && !dp_graph)) {
     PROF(0);
     return iteration_body(ctx, mode, stride, lr);
   }
-  if (!g.exec) {
+  if (!g.exec && g.segs.empty()) {
     if (g.warm == 0 || g.stride != stride || g.lr != lr) {   // first time: plain launches (also sets kernel attributes)
       g.warm = 1; g.stride = stride; g.lr = lr;
       return iteration_body(ctx, mode, stride, lr);
     }
     const long l0 = ctx->launches;
-    cudaGraph_t graph = nullptr;
     LSTM_CUDA(cudaStreamBeginCapture(ctx->st, cudaStreamCaptureModeThreadLocal));
+    if (dp) ctx->seg_capture = &g;
     int rc = iteration_body(ctx, mode, stride, lr);
+    ctx->seg_capture = nullptr;
+    cudaGraph_t graph = nullptr;
     cudaError_t ce = cudaStreamEndCapture(ctx->st, &graph);
-    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-    if (ce != cudaSuccess) return lstm_fail(ctx, LSTM_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+    if (rc) { if (graph) cudaGraphDestroy(graph); free_iter_graph_keep_key(g); return rc; }
+    if (ce != cudaSuccess) {
+      free_iter_graph_keep_key(g);
+      return lstm_fail(ctx, LSTM_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+    }
     g.launches = ctx->launches - l0;
     ctx->launches = l0;
-    ce = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphExec_t exec = nullptr;
+    ce = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
-    if (ce != cudaSuccess) { g.exec = nullptr; return lstm_fail(ctx, LSTM_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce)); }
+    if (ce != cudaSuccess) {
+      free_iter_graph_keep_key(g);
+      return lstm_fail(ctx, LSTM_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+    }
+    if (dp) { g.segs.push_back(exec); g.seg_bucket.push_back(-1); }
+    else g.exec = exec;
   }
-  LSTM_CUDA(cudaGraphLaunch(g.exec, ctx->st));
+  if (!dp) {
+    LSTM_CUDA(cudaGraphLaunch(g.exec, ctx->st));
+  } else {
+    for (size_t i = 0; i < g.segs.size(); i++) {
+      if (i + 1 == g.segs.size() && i > 0) {                  // Adagrad reads the summed gradients
+        LSTM_CUDA(cudaStreamWaitEvent(ctx->st, ctx->ev_comm[0], 0));
+        LSTM_CUDA(cudaStreamWaitEvent(ctx->st, ctx->ev_comm[1], 0));
+      }
+      LSTM_CUDA(cudaGraphLaunch(g.segs[i], ctx->st));
+      if (g.seg_bucket[i] >= 0) {
+        int rc = lstm_allreduce_bucket(ctx, g.seg_bucket[i]);
+        if (rc) return rc;
+      }
+    }
+  }
   ctx->launches += g.launches;
   return LSTM_OK;
 }

@@ -28,7 +28,16 @@ struct lstm_ctx {
   unsigned long long* d_iter = nullptr;  // device-side forward counter (owned by k_loss_reduce)
   uint64_t fwd_count = 0;                // host mirror of *d_iter
   // one training iteration captured as a CUDA graph, keyed by (mode, stride, lr)
-  struct IterGraph { cudaGraphExec_t exec = nullptr; int stride = 0; float lr = 0.f; long launches = 0; int warm = 0; } graph[2];
+  // Data-parallel contexts replay the iteration as SEGMENTS: the graph is cut at every gradient bucket and the
+  // ncclAllReduce is issued eagerly on the communication stream between two segment launches (NCCL stays outside
+  // the graphs).  seg_bucket[i] = bucket to sum after segment i, -1 = none.
+  struct IterGraph {
+    cudaGraphExec_t exec = nullptr;
+    std::vector<cudaGraphExec_t> segs;
+    std::vector<int> seg_bucket;
+    int stride = 0; float lr = 0.f; long launches = 0; int warm = 0;
+  } graph[2];
+  IterGraph* seg_capture = nullptr;      // non-null while run_iteration captures a segmented graph
   int32_t *h_xs_pinned = nullptr, *h_tg_pinned = nullptr;
   double* h_loss_pinned = nullptr;
   // device text pipeline

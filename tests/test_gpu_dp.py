@@ -29,13 +29,13 @@ def _worker(rank, world, port, dtype, out):
     g.dp_init(rank, world, dp.broadcast_unique_id(dist, el.dp_unique_id, rank))
     g.init_params(7, 0.05, 1.0)
     g.load_text(text); g.set_positions(dp.stream_positions(B * world, rank, world, S, chunk))
-    losses = g.train_text(3, stride=S - 1, lr=0.01)
+    losses = g.train_text(5, stride=S - 1, lr=0.01)   # plain, capture + replay, 3 more segmented-graph replays
     flat = np.concatenate([p.ravel(order="F") for p in g.params()])
     if rank == 0:
         one = el.LSTM(M, N, S, B * world, device=0, dtype=dtype)
         one.init_params(7, 0.05, 1.0)
         one.load_text(text); one.set_positions(dp.stream_positions(B * world, 0, 1, S, chunk))
-        one.train_text(3, stride=S - 1, lr=0.01)
+        one.train_text(5, stride=S - 1, lr=0.01)
         ref = np.concatenate([p.ravel(order="F") for p in one.params()])
         out["err"] = float(np.max(np.abs(flat - ref)) / np.max(np.abs(ref)))
     t = torch.from_numpy(flat).cuda()
