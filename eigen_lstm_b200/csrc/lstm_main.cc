@@ -123,9 +123,30 @@ int main(int argc, char** argv) {
   std::vector<double> losses(100);
   long total_iters = 0;
 
+  // Seeding follows the ORDER in which the reference constructs its generators, the k-th one seeded seed + k
+  // (oracle/eigen_shim/deterministic_random_device.h gives the reference program the same schedule): W, U, Why
+  // (k = 0, 1, 2, inside lstm_init_params), then per epoch h, c (:146-147), _h, _c (:306-307) and the sampling
+  // generator (:309-310) — so `lstm --seed K` and the reference started with REF_SEED=K walk the same trajectory
+  // up to float rounding.
+  uint64_t gen_k = seed + 3;
   for (size_t e = 0; e < epochs; e++) {
     double epoch_loss = 0.0;
-    CK(lstm_reset_state(ctx, seed + 100 + 2 * e, state_std));         // randn(h,0,0.1); randn(c,0,0.1)  :146-147
+    if (B == 1 && state_std != 0.f) {
+      // randn(h,0,0.1); randn(c,0,0.1) draw the whole N x S matrices in (row, col) order (:146-147, :375); the column
+      // that the first shift (:163-164) moves into slot 0 is column 1.
+      std::vector<float> h0(N), c0(N);
+      std::mt19937 mh((uint32_t)gen_k), mc((uint32_t)(gen_k + 1));
+      std::normal_distribution<> dh(0.0f, state_std), dc(0.0f, state_std);
+      for (size_t i = 0; i < N; i++)
+        for (size_t j = 0; j < S; j++) {
+          const float vh = (float)dh(mh), vc = (float)dc(mc);
+          if (j == 1) { h0[i] = vh; c0[i] = vc; }
+        }
+      CK(lstm_set_state(ctx, h0.data(), c0.data()));
+    } else {
+      CK(lstm_reset_state(ctx, gen_k, state_std));                    // N x B draws for the carried-in column
+    }
+    gen_k += 2;
     auto t0 = std::chrono::steady_clock::now();
     size_t done = 0;
     bool stop = false;
@@ -176,13 +197,14 @@ int main(int argc, char** argv) {
     // sampling (:293-356): _h, _c ~ N(0, 0.1), then 1000 draws
     std::vector<float> h0(N), c0(N);
     {
-      std::mt19937 mh((uint32_t)(seed + 1000 + 2 * e)), mc((uint32_t)(seed + 1001 + 2 * e));
-      std::normal_distribution<> d(0.0f, 0.1f);
-      for (auto& v : h0) v = (float)d(mh);
-      for (auto& v : c0) v = (float)d(mc);
+      std::mt19937 mh((uint32_t)gen_k), mc((uint32_t)(gen_k + 1));
+      std::normal_distribution<> dh(0.0f, 0.1f), dc(0.0f, 0.1f);
+      for (auto& v : h0) v = (float)dh(mh);
+      for (auto& v : c0) v = (float)dc(mc);
     }
     std::vector<uint8_t> text(characters_to_generate);
-    CK(lstm_sample(ctx, seed + 5000 + e, h0.data(), c0.data(), text.data(), text.size(), 0));
+    CK(lstm_sample(ctx, gen_k + 2, h0.data(), c0.data(), text.data(), text.size(), 0));
+    gen_k += 3;
     std::cout << std::endl << std::endl << "************ Generated text |";
     for (uint8_t ch : text) std::cout << (char)ch;
     std::cout << "| Generated text END ************" << std::endl;

@@ -4,17 +4,19 @@
 // as the checker for the CUDA path (tests/, __graft_entry__.smoke(), bench.py's cpu_baseline /
 // --impl reference leg).  Nothing under eigen_lstm_b200/ may include, link or call it.
 //
-// Parity status: the reference itself cannot be built in this image (needs Eigen, which is not
-// installed).  The restatement is PINNED against the reference's own
-// artefacts:
-//   * forward semantics (gate order [i,o,f,u], tanh'd carried cell, softmax, log2 loss) by the
-//     known-answer fixture models/enwik5_test_{W,U,Why,b,by}.txt -> 3.24396 bits/char
-//     (tests/test_oracle_golden.py),
-//   * backward semantics by the reference's own acceptance rule for its numerical gradient
-//     check (max rel.err < 1e-1, mean < 1e-3; we hold 1e-6) in double precision
-//     (tests/test_oracle_gradcheck.py).
-//   * the Adagrad trajectory is unpinned by any reference artefact (the reference is seeded
-//     from std::random_device); it follows R/lstm.cc:259-272 statement by statement.
+// Parity status: PINNED.
+//   * Against the reference's own SOURCE: the unmodified /root/reference/lstm.cc is compiled by `make -C oracle ref`
+//     into oracle/_ref/lstm_ref.  Its one external dependency, Eigen, is not installed in this image (no network), so
+//     it is built against oracle/eigen_shim/ — a from-scratch stand-in for the few Eigen members lstm.cc uses — with
+//     std::random_device replaced by a seed counter.  Driven with the same seeds, this oracle reproduces that
+//     program's output EXACTLY: the printed epoch losses and all 4 x 1000 sampled characters after 3 000 .. 12 000
+//     Adagrad iterations (tests/test_oracle_vs_reference_source.py; committed output: tests/golden/ref_lstm_cc_run.json).
+//     That pins the window shift, state carry, loss normalisation, Adagrad order, seeding order and sampling.  What a
+//     shim cannot pin is Eigen's internal float summation order (the shim, like this file, sums sequentially).
+//   * forward semantics (gate order [i,o,f,u], tanh'd carried cell, softmax, log2 loss) by the reference's
+//     known-answer fixture models/enwik5_test_{W,U,Why,b,by}.txt -> 3.24396 bits/char (tests/test_oracle_golden.py),
+//   * backward semantics by the reference's own acceptance rule for its numerical gradient check (max rel.err
+//     < 1e-1, mean < 1e-3; we hold 1e-6) in double precision (tests/test_oracle_gradcheck.py).
 //
 // Reference shorthand: R/ = /root/reference/, OV/ = R/optimized-obsfuscated_versions/.
 // All matrices are column-major like Eigen's default (R/lstm.cc:65-84): element (r,c) of an

@@ -1,0 +1,49 @@
+"""The drop-in `lstm` host program (eigen_lstm_b200/csrc/lstm_main.cc) against the stdout of the reference program.
+
+tests/golden/ref_lstm_cc_run.json is what the unmodified R/lstm.cc printed (built against oracle/eigen_shim, see
+tests/golden/make_ref_run.py) for seed 1234 on the first 3000 bytes of alice29.txt.  `lstm --seed 1234` seeds its
+generators in the same order, so it starts from the SAME weights and state and must print the same text structure
+(R/lstm.cc:274-291, 352-356, 398) and — the fp32 trajectory being chaotic in its last bits — epoch
+losses that agree to a few percent rather than to the digit."""
+import json
+import os
+import re
+import subprocess
+
+import pytest
+
+from tests.conftest import GOLDEN, ROOT
+
+pytestmark = pytest.mark.gpu
+FIX = json.load(open(os.path.join(GOLDEN, "ref_lstm_cc_run.json")))
+BIN = os.path.join(ROOT, "eigen_lstm_b200", "lstm")
+
+
+def test_lstm_binary_prints_what_the_reference_program_prints(tmp_path, alice):
+    assert os.path.exists(BIN), "eigen_lstm_b200/lstm is not built (python -m eigen_lstm_b200.build)"
+    (tmp_path / "alice29.txt").write_bytes(alice[: FIX["corpus_bytes"]])
+    epochs = 3
+    out = subprocess.run([BIN, "--seed", str(FIX["seed"]), "--epochs", str(epochs)], cwd=tmp_path, stdout=subprocess.PIPE,
+                         stderr=subprocess.PIPE, timeout=300)
+    assert out.returncode == 0, out.stderr.decode(errors="replace")
+    so = out.stdout
+    # line 1: rawread's report (R/lstm.cc:398)
+    assert so.split(b"\n", 1)[0].decode() == FIX["read_line"]
+    # progress fields of epoch 1: same count, same text (:274-279)
+    first = so[: so.find(b"====")]
+    assert [m.decode() for m in re.findall(rb"([ 0-9.]{7})%\r", first)] == FIX["progress_fields"]
+    # epoch lines: same format as the reference's, epoch counter out of the same total, loss close (:284-291)
+    lines = [m.decode() for m in re.findall(rb"Epoch \d+/\d+, t = [^\n]*", so)]
+    assert len(lines) == epochs
+    pat = r"Epoch (\d+)/(\d+), t = \d+\.\d{3} s, est GFLOP/s = \d+\.\d{3}, avg loss = (\d+\.\d{3}) bits/char"
+    for e, (line, ref_line) in enumerate(zip(lines, FIX["epoch_lines"])):
+        m, mr = re.fullmatch(pat, line), re.fullmatch(pat, ref_line)
+        assert m and mr, (line, ref_line)
+        assert int(m.group(1)) == e + 1
+        got, want = float(m.group(3)), float(mr.group(3))
+        print(f"epoch {e + 1}: lstm {got:.3f} reference {want:.3f} bits/char")
+        assert abs(got - want) / want < 0.08, (e, got, want)
+    # the separator and the sample block (:284, :352-356): 1000 characters between the reference's markers
+    assert so.count(b"\n" + b"=" * 84 + b"\n") == epochs
+    gen = re.findall(rb"\n\n\*{12} Generated text \|(.*?)\| Generated text END \*{12}\n", so, flags=re.S)
+    assert len(gen) == epochs and all(len(g) == 1000 for g in gen)

@@ -1,0 +1,78 @@
+"""The oracle against the reference's OWN SOURCE.
+
+tests/golden/ref_lstm_cc_run.json holds what oracle/_ref/lstm_ref printed — the unmodified /root/reference/lstm.cc,
+compiled against oracle/eigen_shim with std::random_device replaced by a seed counter (tests/golden/make_ref_run.py).
+The oracle, driven with the same seeds in the order the reference constructs its generators (R/lstm.cc:113-115 W, U,
+Why; then per epoch h, c :146-147, _h, _c :306-307 and the sampling generator :309-310), must reproduce it EXACTLY:
+the printed epoch losses (which are sums over ~3000 Adagrad iterations each) and all 4 x 1000 sampled characters,
+which depend on every weight after 3000..12000 updates.  This pins the window shift, state carry, loss
+normalisation (epoch_loss / (S * length), :290), Adagrad order and sampling of the restatement to the reference's
+control flow; what it cannot pin is Eigen's internal summation order (the shim sums sequentially).
+"""
+import base64
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from tests.conftest import GOLDEN, ROOT
+
+FIX = json.load(open(os.path.join(GOLDEN, "ref_lstm_cc_run.json")))
+M, N, S = 256, 64, 3   # R/lstm.cc:53-57
+
+
+def replay_with_oracle(text, seed, epochs, dense_onehot=1):
+    """Yield (avg_loss, sampled_bytes) per epoch, following R/lstm.cc:142-356 with the k-th generator seeded seed+k."""
+    L = len(text)
+    o = orc.Oracle(M, N, S, 1, "f32")
+    o.set_options(dense_onehot=dense_onehot)
+    o.set_params(orc.init_params(M, N, seed, 0.01))          # generators 0, 1, 2
+    o.set_positions([S])                                      # for (i = S; ...)  :151
+    k = seed + 3
+    for _ in range(epochs):
+        h = orc.randn(N, S, 0, 0.1, k)                        # ALL S columns are re-drawn (:146-147)
+        c = orc.randn(N, S, 0, 0.1, k + 1)
+        for t in range(S):
+            o.set_state("h", t, h[:, t])
+            o.set_state("c", t, c[:, t])
+        losses, _ = o.train(text, L - S, stride=1, lr=0.1)    # i = S .. length-1; position wraps to S by itself
+        epoch_loss = 0.0
+        for v in losses:                                      # double accumulation in iteration order (:209)
+            epoch_loss += v
+        _h = orc.randn(N, 1, 0, 0.1, k + 2)
+        _c = orc.randn(N, 1, 0, 0.1, k + 3)
+        sampled = o.sample(_h, _c, k + 4, 1000).tobytes()
+        k += 5
+        yield epoch_loss / (S * L), sampled
+
+
+@pytest.mark.parametrize("dense_onehot", [1, 0])
+def test_oracle_reproduces_the_reference_programs_output(alice, dense_onehot):
+    text = alice[: FIX["corpus_bytes"]]
+    assert FIX["read_line"] == f"Read {len(text)} bytes (alice29.txt)"
+    for e, (avg, sampled) in enumerate(replay_with_oracle(text, FIX["seed"], FIX["epochs"], dense_onehot)):
+        assert f"{avg:.3f}" == FIX["avg_loss"][e], (e, avg, FIX["avg_loss"][e])
+        want = base64.b64decode(FIX["generated_b64"][e])
+        assert sampled == want, f"epoch {e + 1}: sampled text differs from the reference program's at byte " \
+                                f"{next(i for i in range(1000) if sampled[i] != want[i])}"
+
+
+def test_progress_fields_follow_the_reference_format():
+    # "%7.2f%%\r" every 100 iterations (R/lstm.cc:274-279), i = 100, 200, ... of a 3000-byte corpus
+    L = FIX["corpus_bytes"]
+    want = ["%7.2f" % (100.0 * np.float32(i) / np.float32(L)) for i in range(100, L, 100)]
+    assert FIX["progress_fields"] == want
+
+
+@pytest.mark.skipif(not (os.path.exists("/root/reference/lstm.cc") and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "lstm_ref"))),
+                    reason="needs the reference checkout and `make -C oracle ref` (build container only)")
+def test_live_reference_binary_matches_the_fixture_and_the_oracle(alice):
+    """Re-run the reference program here with another seed and corpus length: not just the committed fixture."""
+    from tests.golden import make_ref_run as mk
+    out = mk.run_reference(seed=77, corpus_bytes=1500, epochs=2)
+    _, _, avg, gen, _ = mk.parse(out)
+    for e, (a, sampled) in enumerate(replay_with_oracle(alice[:1500], 77, 2)):
+        assert f"{a:.3f}" == avg[e]
+        assert sampled == gen[e]
