@@ -124,7 +124,7 @@ int main(int argc, char** argv) {
   long total_iters = 0;
 
   // Seeding follows the ORDER in which the reference constructs its generators, the k-th one seeded seed + k
-  // (oracle/eigen_shim/deterministic_random_device.h gives the reference program the same schedule): W, U, Why
+  // (the test build of the reference program, tests/golden/make_ref_run.py, is given the same schedule): W, U, Why
   // (k = 0, 1, 2, inside lstm_init_params), then per epoch h, c (:146-147), _h, _c (:306-307) and the sampling
   // generator (:309-310) — so `lstm --seed K` and the reference started with REF_SEED=K walk the same trajectory
   // up to float rounding.
