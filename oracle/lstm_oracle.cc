@@ -211,15 +211,22 @@ struct Oracle {
         const int k = ti[(size_t)t * B + bb];
         for (int m = 0; m < M; m++) dy[(size_t)M * bb + m] = pt(t)[(size_t)M * bb + m] - (m == k ? R(1) : R(0));
       }
-      // dWhy += dy * h(t)^T (:226)
+      // dWhy += dy * h(t)^T (:226).  Batched (OV/lstm_eigen_BLAS/lstm.cc:295): the product over the B streams is
+      // evaluated first (summed over b from zero) and THEN added — the association `dWhy += (dy * h^T)` has.
       parallel_for(N, [&](int n) {
+        std::vector<R> tmp(M, R(0));
         for (int bb = 0; bb < B; bb++) {
           const R hn = ht(t)[(size_t)N * bb + n];
-          for (int m = 0; m < M; m++) dWhy[(size_t)M * n + m] += dy[(size_t)M * bb + m] * hn;
-        } });
-      // dby += dy (rowwise sum over the batch) (:227)
-      for (int bb = 0; bb < B; bb++)
-        for (int m = 0; m < M; m++) dby[m] += dy[(size_t)M * bb + m];
+          for (int m = 0; m < M; m++) tmp[m] += dy[(size_t)M * bb + m] * hn;
+        }
+        for (int m = 0; m < M; m++) dWhy[(size_t)M * n + m] += tmp[m]; });
+      // dby += dy.rowwise().sum() (:227; batched OV/lstm_eigen_BLAS/lstm.cc:297)
+      {
+        std::vector<R> tmp(M, R(0));
+        for (int bb = 0; bb < B; bb++)
+          for (int m = 0; m < M; m++) tmp[m] += dy[(size_t)M * bb + m];
+        for (int m = 0; m < M; m++) dby[m] += tmp[m];
+      }
       parallel_for(B, [&](int bb) {
         const R* gcol = gt(t) + (size_t)n4 * bb;
         const R* ccol = ct(t) + (size_t)N * bb;
@@ -243,35 +250,52 @@ struct Oracle {
           dcnext[(size_t)N * bb + n] = dcv * gcol[2 * N + n];                             // :256
         }
       });
-      // dU += dg * h(t-1)^T (:250)
+      // dU += dg * h(t-1)^T (:250): product over the streams first, then the add (see dWhy above)
       parallel_for(N, [&](int k) {
+        std::vector<R> tmp(n4, R(0));
         for (int bb = 0; bb < B; bb++) {
           const R hk = ht(t - 1)[(size_t)N * bb + k];
           const R* dgc = dg + (size_t)n4 * bb;
-          R* dUk = &dU[(size_t)n4 * k];
-          for (int r = 0; r < n4; r++) dUk[r] += dgc[r] * hk;
-        } });
-      // dW += dg * x(t)^T (:251) — x one-hot: only column x receives dg
+          for (int r = 0; r < n4; r++) tmp[r] += dgc[r] * hk;
+        }
+        R* dUk = &dU[(size_t)n4 * k];
+        for (int r = 0; r < n4; r++) dUk[r] += tmp[r]; });
+      // dW += dg * x(t)^T (:251) — x one-hot: column m receives the sum of dg over the streams whose input is m
       if (dense_onehot) {
         parallel_for(M, [&](int m) {
+          std::vector<R> tmp(n4, R(0));
           for (int bb = 0; bb < B; bb++) {
             const R xm = (xi[(size_t)t * B + bb] == m) ? R(1) : R(0);
             const R* dgc = dg + (size_t)n4 * bb;
-            R* dWm = &dW[(size_t)n4 * m];
-            for (int r = 0; r < n4; r++) dWm[r] += dgc[r] * xm;
-          } });
+            for (int r = 0; r < n4; r++) tmp[r] += dgc[r] * xm;
+          }
+          R* dWm = &dW[(size_t)n4 * m];
+          for (int r = 0; r < n4; r++) dWm[r] += tmp[r]; });
       } else {
+        std::vector<R> tmp(n4);
         for (int bb = 0; bb < B; bb++) {
           const int x = xi[(size_t)t * B + bb];
           if (x < 0) continue;
-          const R* dgc = dg + (size_t)n4 * bb;
+          bool seen = false;   // column x was already handled by an earlier stream with the same input byte
+          for (int b2 = 0; b2 < bb && !seen; b2++) seen = (xi[(size_t)t * B + b2] == x);
+          if (seen) continue;
+          std::fill(tmp.begin(), tmp.end(), R(0));
+          for (int b2 = bb; b2 < B; b2++) {
+            if (xi[(size_t)t * B + b2] != x) continue;
+            const R* dgc = dg + (size_t)n4 * b2;
+            for (int r = 0; r < n4; r++) tmp[r] += dgc[r];
+          }
           R* dWm = &dW[(size_t)n4 * x];
-          for (int r = 0; r < n4; r++) dWm[r] += dgc[r];
+          for (int r = 0; r < n4; r++) dWm[r] += tmp[r];
         }
       }
-      // db += dg (rowwise sum) (:252)
-      for (int bb = 0; bb < B; bb++)
-        for (int r = 0; r < n4; r++) db[r] += dg[(size_t)n4 * bb + r];
+      // db += dg.rowwise().sum() (:252; batched OV/lstm_eigen_BLAS/lstm.cc:335)
+      {
+        std::vector<R> tmp(n4, R(0));
+        for (int bb = 0; bb < B; bb++)
+          for (int r = 0; r < n4; r++) tmp[r] += dg[(size_t)n4 * bb + r];
+        for (int r = 0; r < n4; r++) db[r] += tmp[r];
+      }
       // dhnext = U^T * dg (:255)
       parallel_for(B, [&](int bb) {
         for (int k = 0; k < N; k++) {

@@ -8,6 +8,12 @@ has no arguments: it reads "alice29.txt" from its working directory and runs 100
 scratch directory holding the first CORPUS_BYTES bytes of R/alice29.txt (= tests/golden/alice29_head.bin[:3000])
 and stopped after EPOCHS epoch reports.
 
+The batched snapshot OV/lstm_eigen_BLAS/lstm.cc (B = 4 streams, S = 3; built without -DUSE_BLAS = its pure-Eigen
+branch) is recorded the same way as oracle/_ref/lstm_blas_ref on the first 2000 bytes of R/enwik5.txt
+(= tests/golden/enwik6_head.bin[:2000], the corpora share their prefix) -> tests/golden/ref_lstm_eigen_blas_run.json.
+Its stream start positions come from the C library's unseeded rand() (OV/lstm_eigen_BLAS/lstm.cc:150-154); the
+values it drew are stored in the fixture (`positions`) so the replay does not depend on the libc.
+
 Output: tests/golden/ref_lstm_cc_run.json
   seed, corpus_bytes, epochs
   read_line        the "Read <n> bytes (alice29.txt)" line                      (R/lstm.cc:398)
@@ -27,16 +33,23 @@ import tempfile
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 BIN = os.path.join(ROOT, "oracle", "_ref", "lstm_ref")
+BIN_BLAS = os.path.join(ROOT, "oracle", "_ref", "lstm_blas_ref")
 SEED, CORPUS_BYTES, EPOCHS = 1234, 3000, 4
+BLAS_SEED, BLAS_CORPUS_BYTES, BLAS_EPOCHS, BLAS_B, BLAS_S = 99, 2000, 3, 4, 3
 END = b"| Generated text END ************"
+PROGRAMS = {   # binary, file name the program opens, committed corpus it is a prefix of
+    "lstm.cc": (BIN, "alice29.txt", "alice29_head.bin"),
+    "lstm_eigen_BLAS": (BIN_BLAS, "enwik5.txt", "enwik6_head.bin"),
+}
 
 
-def run_reference(seed=SEED, corpus_bytes=CORPUS_BYTES, epochs=EPOCHS, timeout=120):
-    """Start lstm_ref on the truncated corpus, read its stdout until `epochs` samples were printed, stop it."""
-    text = open(os.path.join(HERE, "alice29_head.bin"), "rb").read()[:corpus_bytes]
+def run_reference(seed=SEED, corpus_bytes=CORPUS_BYTES, epochs=EPOCHS, program="lstm.cc"):
+    """Start the reference program on the truncated corpus, read its stdout until `epochs` samples were printed, stop it."""
+    binary, fname, corpus = PROGRAMS[program]
+    text = open(os.path.join(HERE, corpus), "rb").read()[:corpus_bytes]
     with tempfile.TemporaryDirectory() as d:
-        open(os.path.join(d, "alice29.txt"), "wb").write(text)
-        p = subprocess.Popen([BIN], cwd=d, stdout=subprocess.PIPE, env=dict(os.environ, REF_SEED=str(seed)))
+        open(os.path.join(d, fname), "wb").write(text)
+        p = subprocess.Popen([binary], cwd=d, stdout=subprocess.PIPE, env=dict(os.environ, REF_SEED=str(seed)))
         out = b""
         try:
             while out.count(END) < epochs:
@@ -71,6 +84,23 @@ def main():
                    "cwd holding alice29.txt = first %d bytes of R/alice29.txt" % (SEED, CORPUS_BYTES))
     json.dump(doc, open(os.path.join(HERE, "ref_lstm_cc_run.json"), "w"), indent=1)
     print("\n".join(epoch_lines[:EPOCHS]))
+
+    # batched snapshot
+    import ctypes
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(1)                                     # the program never calls srand: rand() starts from seed 1
+    positions = [libc.rand() % (BLAS_CORPUS_BYTES - BLAS_S) + BLAS_S for _ in range(BLAS_B)]
+    out = run_reference(BLAS_SEED, BLAS_CORPUS_BYTES, BLAS_EPOCHS, program="lstm_eigen_BLAS")
+    read_line, epoch_lines, avg, gen, _ = parse(out)
+    assert len(gen) >= BLAS_EPOCHS and all(len(g) == 2000 for g in gen[:BLAS_EPOCHS]), [len(g) for g in gen]
+    doc = dict(seed=BLAS_SEED, corpus_bytes=BLAS_CORPUS_BYTES, epochs=BLAS_EPOCHS, B=BLAS_B, S=BLAS_S, N=64, positions=positions,
+               read_line=read_line, epoch_lines=epoch_lines[:BLAS_EPOCHS], avg_loss=avg[:BLAS_EPOCHS],
+               generated_b64=[base64.b64encode(g).decode() for g in gen[:BLAS_EPOCHS]],
+               how="oracle/_ref/lstm_blas_ref = unmodified OV/lstm_eigen_BLAS/lstm.cc (no -DUSE_BLAS) + oracle/eigen_shim, "
+                   "REF_SEED=%d, cwd holding enwik5.txt = first %d bytes of R/enwik5.txt; positions = glibc rand() "
+                   "from its default seed" % (BLAS_SEED, BLAS_CORPUS_BYTES))
+    json.dump(doc, open(os.path.join(HERE, "ref_lstm_eigen_blas_run.json"), "w"), indent=1)
+    print("\n".join(epoch_lines[:BLAS_EPOCHS]))
 
 
 if __name__ == "__main__":

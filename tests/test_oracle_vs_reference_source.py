@@ -8,6 +8,10 @@ the printed epoch losses (which are sums over ~3000 Adagrad iterations each) and
 which depend on every weight after 3000..12000 updates.  This pins the window shift, state carry, loss
 normalisation (epoch_loss / (S * length), :290), Adagrad order and sampling of the restatement to the reference's
 control flow; what it cannot pin is Eigen's internal summation order (the shim sums sequentially).
+
+The batched semantics (B streams: positions, per-stream shift, loss / B, batch-summed gradients) are pinned the same
+way against the unmodified batched snapshot OV/lstm_eigen_BLAS/lstm.cc (its pure-Eigen branch, B = 4):
+tests/golden/ref_lstm_eigen_blas_run.json.
 """
 import base64
 import json
@@ -20,6 +24,7 @@ from oracle import oracle as orc
 from tests.conftest import GOLDEN, ROOT
 
 FIX = json.load(open(os.path.join(GOLDEN, "ref_lstm_cc_run.json")))
+FIXB = json.load(open(os.path.join(GOLDEN, "ref_lstm_eigen_blas_run.json")))
 M, N, S = 256, 64, 3   # R/lstm.cc:53-57
 
 
@@ -59,6 +64,44 @@ def test_oracle_reproduces_the_reference_programs_output(alice, dense_onehot):
                                 f"{next(i for i in range(1000) if sampled[i] != want[i])}"
 
 
+def replay_batched_with_oracle(text, seed, epochs, positions, B, S_, dense_onehot=1):
+    """OV/lstm_eigen_BLAS/lstm.cc:56-455 (pure-Eigen branch): B streams; per epoch randn(h[t]), randn(c[t]) for
+    t = 0..S-1 interleaved (:187-192); 2000 sampled characters at batch 1 (:409)."""
+    L = len(text)
+    o = orc.Oracle(M, N, S_, B, "f32")
+    o.set_options(dense_onehot=dense_onehot)
+    o.set_params(orc.init_params(M, N, seed, 0.01))
+    o.set_positions(positions)                                # rand() % (length - S) + S  (:150-154)
+    k = seed + 3
+    for _ in range(epochs):
+        for t in range(S_):
+            o.set_state("h", t, orc.randn(N, B, 0, 0.1, k))
+            o.set_state("c", t, orc.randn(N, B, 0, 0.1, k + 1))
+            k += 2
+        losses, _ = o.train(text, L - S_, stride=1, lr=0.1)   # for (i = S; i < length; i++): one event per stream
+        epoch_loss = 0.0
+        for v in losses:
+            epoch_loss += v
+        one = orc.Oracle(M, N, S_, 1, "f32")
+        one.set_params(o.params())
+        sampled = one.sample(orc.randn(N, 1, 0, 0.1, k), orc.randn(N, 1, 0, 0.1, k + 1), k + 2, 2000).tobytes()
+        k += 3
+        yield epoch_loss / (S_ * L), sampled
+
+
+@pytest.mark.parametrize("dense_onehot", [1, 0])
+def test_batched_oracle_reproduces_the_batched_reference_programs_output(enwik6, dense_onehot):
+    """B = 4 streams: positions, per-stream window shift and wrap, loss / B, gradients summed over the batch, Adagrad —
+    3 epochs x ~2000 iterations, then 2000 sampled characters per epoch, all identical to the reference program's."""
+    f = FIXB
+    text = enwik6[: f["corpus_bytes"]]
+    assert f["read_line"] == f"Read {len(text)} bytes (enwik5.txt)"
+    for e, (avg, sampled) in enumerate(replay_batched_with_oracle(text, f["seed"], f["epochs"], f["positions"], f["B"], f["S"],
+                                                                  dense_onehot)):
+        assert f"{avg:.3f}" == f["avg_loss"][e], (e, avg, f["avg_loss"][e])
+        assert sampled == base64.b64decode(f["generated_b64"][e]), f"epoch {e + 1}: sampled text differs"
+
+
 def test_progress_fields_follow_the_reference_format():
     # "%7.2f%%\r" every 100 iterations (R/lstm.cc:274-279), i = 100, 200, ... of a 3000-byte corpus
     L = FIX["corpus_bytes"]
@@ -74,5 +117,21 @@ def test_live_reference_binary_matches_the_fixture_and_the_oracle(alice):
     out = mk.run_reference(seed=77, corpus_bytes=1500, epochs=2)
     _, _, avg, gen, _ = mk.parse(out)
     for e, (a, sampled) in enumerate(replay_with_oracle(alice[:1500], 77, 2)):
+        assert f"{a:.3f}" == avg[e]
+        assert sampled == gen[e]
+
+
+@pytest.mark.skipif(not (os.path.exists("/root/reference/lstm.cc") and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "lstm_blas_ref"))),
+                    reason="needs the reference checkout and `make -C oracle ref` (build container only)")
+def test_live_batched_reference_binary_matches_the_oracle(enwik6):
+    import ctypes
+    from tests.golden import make_ref_run as mk
+    L = 1200
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(1)
+    positions = [libc.rand() % (L - 3) + 3 for _ in range(4)]
+    out = mk.run_reference(seed=5, corpus_bytes=L, epochs=2, program="lstm_eigen_BLAS")
+    _, _, avg, gen, _ = mk.parse(out)
+    for e, (a, sampled) in enumerate(replay_batched_with_oracle(enwik6[:L], 5, 2, positions, 4, 3)):
         assert f"{a:.3f}" == avg[e]
         assert sampled == gen[e]
