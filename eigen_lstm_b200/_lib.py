@@ -36,6 +36,7 @@ SYMBOLS = {
     "lstm_eval_bpc": (_i, [_vp, _vp, _sz, _dp]),
     "lstm_sample": (_i, [_vp, _u64, _vp, _vp, _vp, _sz, _i]),
     "lstm_get_activation": (_i, [_vp, _i, _i, _vp, _sz]),
+    "lstm_gradcheck": (_i, [_vp, _vp, _vp, _i, _u64, C.c_double, _vp, _vp, _vp, _vp, C.POINTER(_i)]),
     "lstm_save_text_ckpt": (_i, [_vp, C.c_char_p]),
     "lstm_load_text_ckpt": (_i, [_vp, C.c_char_p]),
     "lstm_save_bin": (_i, [_vp, C.c_char_p]),

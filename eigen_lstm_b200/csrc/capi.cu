@@ -873,6 +873,92 @@ extern "C" int lstm_get_activation(lstm_ctx* ctx, int what, int t, float* out, s
 }
 
 // ------------------------------------------------------------------------------------------------
+// gradient check
+// ------------------------------------------------------------------------------------------------
+extern "C" int lstm_gradcheck(lstm_ctx* ctx, const int32_t* x_idx, const int32_t* t_idx, int per_tensor, uint64_t seed,
+                              double delta, double report[5][6], long long* probe_idx, double* numeric, double* analytic,
+                              int* passed) {
+  if (!ctx) return LSTM_ERR_ARG;
+  if (per_tensor < 1 || !(delta > 0.0) || !report) return lstm_fail(ctx, LSTM_ERR_ARG, "lstm_gradcheck: need per_tensor >= 1, delta > 0, report");
+  LSTM_CUDA(cudaSetDevice(ctx->device));
+  // analytic gradients: the context's own forward + backward (OV/lstm_eigen_class_batch/lstm.cc:291-293)
+  int rc = lstm_forward(ctx, x_idx, t_idx, nullptr);
+  if (rc) return rc;
+  rc = lstm_backward(ctx);
+  if (rc) return rc;
+  if (ctx->tc) {                                   // bf16 contexts keep h(0) as bf16: hand the kernel the fp32 view of it
+    rc = tc_state_to_f32(ctx);
+    if (rc) return rc;
+  }
+  std::vector<float> grads(ctx->P);
+  LSTM_CUDA(cudaMemcpyAsync(grads.data(), ctx->grads, ctx->P * sizeof(float), cudaMemcpyDeviceToHost, ctx->st));
+  // probes: per tensor, distinct uniformly drawn entries (the reference keeps each entry with probability 100 / size)
+  std::vector<unsigned long long> pos;
+  std::vector<long long> idx((size_t)5 * per_tensor, -1);
+  for (int w = 0; w < 5; w++) {
+    const size_t size = ctx->sz[w];
+    const size_t want = std::min((size_t)per_tensor, size);
+    std::mt19937_64 gen(seed + (uint64_t)w);
+    std::vector<long long> chosen;
+    if (want == size) {
+      for (size_t i = 0; i < size; i++) chosen.push_back((long long)i);
+    } else {
+      while (chosen.size() < want) {
+        const long long i = (long long)(gen() % size);
+        if (std::find(chosen.begin(), chosen.end(), i) == chosen.end()) chosen.push_back(i);
+      }
+    }
+    for (size_t q = 0; q < chosen.size(); q++) {
+      idx[(size_t)w * per_tensor + q] = chosen[q];
+      pos.push_back((unsigned long long)(ctx->off[w] + (size_t)chosen[q]));
+    }
+  }
+  const int np = (int)pos.size();
+  unsigned long long* d_pos = nullptr;
+  double* d_out = nullptr;
+  LSTM_CUDA(cudaMalloc(&d_pos, (size_t)np * sizeof(unsigned long long)));
+  cudaError_t ce = cudaMalloc(&d_out, (size_t)np * 2 * sizeof(double));
+  if (ce != cudaSuccess) { cudaFree(d_pos); return lstm_fail(ctx, LSTM_ERR_CUDA, cudaGetErrorString(ce)); }
+  std::vector<double> loss((size_t)np * 2);
+  ce = cudaMemcpyAsync(d_pos, pos.data(), (size_t)np * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->st);
+  if (ce == cudaSuccess)
+    ce = launch_window_loss_f64(ctx->params, ctx->off, ctx->Hslot(0), ctx->Cslot(0), ctx->xs, ctx->tg, ctx->M, ctx->N, ctx->S,
+                                ctx->B, d_pos, np, delta, d_out, ctx->st);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(loss.data(), d_out, loss.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->st);
+  cudaFree(d_pos);
+  cudaFree(d_out);
+  if (ce != cudaSuccess) return lstm_fail(ctx, LSTM_ERR_CUDA, std::string("lstm_gradcheck: ") + cudaGetErrorString(ce));
+  ctx->launches += 1;
+  // check_gradient_error (OV/lstm_eigen_class_batch/lstm.cc:440-492)
+  bool ok = true;
+  size_t q0 = 0;
+  for (int w = 0; w < 5; w++) {
+    double mx = 0.0, sum = 0.0, nmin = INFINITY, nmax = -INFINITY, amin = INFINITY, amax = -INFINITY;
+    size_t cnt = 0;
+    for (int q = 0; q < per_tensor; q++) {
+      const long long i = idx[(size_t)w * per_tensor + q];
+      if (i < 0) continue;
+      const double n = (loss[2 * q0 + 1] - loss[2 * q0]) / (2.0 * delta);
+      const double a = (double)grads[ctx->off[w] + (size_t)i];
+      q0++;
+      const double den = fabs(a + n);
+      const double err = den > 0.0 ? fabs(a - n) / den : 0.0;
+      mx = std::max(mx, err); sum += err; cnt++;
+      nmin = std::min(nmin, n); nmax = std::max(nmax, n); amin = std::min(amin, a); amax = std::max(amax, a);
+      if (numeric) numeric[(size_t)w * per_tensor + q] = n;
+      if (analytic) analytic[(size_t)w * per_tensor + q] = a;
+    }
+    const double mean = cnt ? sum / (double)cnt : 0.0;
+    report[w][0] = mx; report[w][1] = mean; report[w][2] = nmin; report[w][3] = nmax; report[w][4] = amin; report[w][5] = amax;
+    if (mx > 1e-1 || mean > 1e-3) ok = false;
+  }
+  if (probe_idx) memcpy(probe_idx, idx.data(), idx.size() * sizeof(long long));
+  if (passed) *passed = ok ? 1 : 0;
+  return LSTM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // checkpoints
 // ------------------------------------------------------------------------------------------------
 static const char* kNames[5] = {"W", "U", "b", "Why", "by"};

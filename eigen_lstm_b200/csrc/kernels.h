@@ -53,6 +53,11 @@ cudaError_t launch_recur_persist(const float* W, const float* U, const float* bi
                                  int N, int mode, const uint8_t* text, size_t n, const float* uniforms, const float* h0,
                                  const float* c0, uint8_t* out, float* hbuf, float* ebuf, float* sum_part, float* y_tgt,
                                  float* c_out, unsigned int* bar, int num_sms, int* G_out, cudaStream_t st);
+// gradient check (gradcheck.cu): loss of the current window in double with ONE flat-parameter entry shifted by -/+ delta;
+// out[2 * probe + {0: minus, 1: plus}] = sum_b sum_t -ln p[target]   (OV/lstm_eigen_class_batch/lstm.h:203-245)
+cudaError_t launch_window_loss_f64(const float* params, const size_t off[5], const float* h0, const float* c0, const int* xs,
+                                   const int* tg, int M, int N, int S, int B, const unsigned long long* probe_pos,
+                                   int n_probes, double delta, double* out, cudaStream_t st);
 void launch_eval_finish(const float* sum_part, const float* y_tgt, size_t steps, int G, double* bits_out, cudaStream_t st);
 
 }  // namespace lstm

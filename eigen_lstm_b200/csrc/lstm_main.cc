@@ -7,6 +7,10 @@
 //   epoch line with t, est GFLOP/s = S(4NM*2+4NN*2)*length / 2^30 / t and avg loss = epoch_loss/(S*length)  (:140,284-291)
 //   1000 sampled characters between "************ Generated text |" markers    (:293-356)
 // Everything the reference fixes at compile time is a flag here (the reference has no argv).
+#include <dirent.h>
+#include <sys/stat.h>
+
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -48,7 +52,8 @@ int main(int argc, char** argv) {
   size_t N = 64, M = 256, S = 3, B = 1;
   float learning_rate = 1e-1f;
   size_t epochs = 1000;
-  std::string file = "alice29.txt", load_prefix, save_prefix;
+  std::string load_prefix, save_prefix;
+  std::vector<std::string> files;            // default "alice29.txt" (:63); several --file flags / a directory = one corpus
   uint64_t seed = std::random_device{}();   // the reference seeds from std::random_device (:370)
   int dtype = LSTM_F32, stride = 1, device = 0;
   size_t characters_to_generate = 1000;
@@ -57,10 +62,12 @@ int main(int argc, char** argv) {
   // held-out evaluation of the last snapshots (OV/lstm_eigen_class_CUDA/lstm.cc:73-86,188-238): off by default
   size_t train_percent = 100;
   double test_every_seconds = 0;
+  // the reference's self-test (OV/lstm_eigen_class_batch/lstm.cc:286-318): numerical vs analytic gradients, then exit
+  bool gradcheck = false;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     auto next = [&]() -> const char* { return (i + 1 < argc) ? argv[++i] : ""; };
-    if (a == "--file") file = next();
+    if (a == "--file") files.push_back(next());
     else if (a == "--hidden") N = atol(next());
     else if (a == "--seq") S = atol(next());
     else if (a == "--batch") B = atol(next());
@@ -78,15 +85,38 @@ int main(int argc, char** argv) {
     else if (a == "--test-every") test_every_seconds = atof(next());
     else if (a == "--load") load_prefix = next();
     else if (a == "--save") save_prefix = next();
+    else if (a == "--gradcheck") gradcheck = true;
     else {
-      std::cerr << "usage: lstm [--file F] [--hidden N] [--seq S] [--batch B] [--epochs E] [--lr LR] [--seed K] [--stride K]\n"
+      std::cerr << "usage: lstm [--file F|DIR]... [--hidden N] [--seq S] [--batch B] [--epochs E] [--lr LR] [--seed K] [--stride K]\n"
                    "            [--bf16] [--device D] [--sample N] [--forget-bias X] [--state-std X] [--max-iters K]\n"
-                   "            [--load PREFIX] [--save PREFIX] [--train-percent P --test-every SECONDS]\n";
+                   "            [--load PREFIX] [--save PREFIX] [--train-percent P --test-every SECONDS] [--gradcheck]\n";
       return 2;
     }
   }
 
-  std::vector<unsigned char> data = rawread(file.c_str());
+  // Multi-corpus input (the reference ships whole corpora next to its snapshots: OV/lstm_eigen_BLAS/cantrbry/, calgary/,
+  // reuters21578/ ...): every --file is read with rawread() in the order given, a directory contributes its regular files
+  // in name order, and the bytes are concatenated into one training text.
+  if (files.empty()) files.push_back("alice29.txt");
+  std::vector<unsigned char> data;
+  for (const std::string& f : files) {
+    std::vector<std::string> members;
+    if (DIR* d = opendir(f.c_str())) {
+      while (struct dirent* e = readdir(d)) {
+        const std::string path = f + "/" + e->d_name;
+        struct stat sb;
+        if (stat(path.c_str(), &sb) == 0 && S_ISREG(sb.st_mode)) members.push_back(path);
+      }
+      closedir(d);
+      std::sort(members.begin(), members.end());
+    } else {
+      members.push_back(f);
+    }
+    for (const std::string& m : members) {
+      const std::vector<unsigned char> part = rawread(m.c_str());
+      data.insert(data.end(), part.begin(), part.end());
+    }
+  }
   if (data.empty()) return 0;   // the reference carries on with a 0x0 matrix and does nothing
 
   lstm_ctx* ctx = nullptr;
@@ -117,6 +147,38 @@ int main(int argc, char** argv) {
     std::vector<uint64_t> pos(B);
     for (auto& p : pos) p = g() % (length - S) + S;
     CK(lstm_set_positions(ctx, pos.data()));
+  }
+  if (gradcheck) {
+    // window of every stream taken from the text at its start position: x_t = data[p - S + t], target_t = data[p - S + t + 1]
+    std::vector<uint64_t> pos(B);
+    CK(lstm_get_positions(ctx, pos.data()));
+    std::vector<int32_t> xw(S * B, -1), tw(S * B, -1);
+    for (size_t b = 0; b < B; b++)
+      for (size_t t = 1; t < S; t++) {
+        const size_t p = (size_t)pos[b] - S + t;
+        xw[t * B + b] = data[p % length];
+        tw[t * B + b] = data[(p + 1) % length];
+      }
+    CK(lstm_reset_state(ctx, seed + 3, state_std));
+    double rep[5][6];
+    int passed = 0;
+    CK(lstm_gradcheck(ctx, xw.data(), tw.data(), 100, seed, 1e-5, rep, nullptr, nullptr, nullptr, &passed));
+    const char* names[5] = {"W", "U", "b", "Why", "by"};
+    const int order[5] = {LSTM_U, LSTM_W, LSTM_WHY, LSTM_B, LSTM_BY};       // check_gradients(): U, W, Why, b, by
+    for (int q = 0; q < 5; q++) {                                            // layout of check_gradient_error()
+      const int w = order[q];
+      std::cout << std::endl << std::setw(15) << std::setprecision(12) << "[" << names[w] << "]" << std::endl
+                << std::setw(20) << " numerical range (" << std::setw(20) << rep[w][2] << ", " << std::setw(20) << rep[w][3] << ")" << std::endl
+                << std::setw(20) << " analytical range (" << std::setw(20) << rep[w][4] << ", " << std::setw(20) << rep[w][5] << ")" << std::endl
+                << std::setw(20) << " max rel. error " << std::setw(20) << rep[w][0];
+      if (rep[w][0] > 1e-1) std::cout << std::setw(23) << "!!!  >1e-1 !!!";
+      std::cout << std::endl << std::setw(20) << " mean rel. error " << std::setw(20) << rep[w][1];
+      if (rep[w][1] > 1e-3) std::cout << std::setw(23) << "!!!  >1e-3  !!!";
+      std::cout << std::endl;
+    }
+    std::cout << std::endl << (passed ? "gradient check OK" : "gradient check FAILED") << std::endl;
+    lstm_destroy(ctx);
+    return passed ? 0 : 1;
   }
   const double flops_per_epoch = (double)S * (4.0 * N * M * 2 + 4.0 * N * N * 2) * (double)length;   // :140
   const size_t iters_per_epoch = (length - S + stride - 1) / stride;

@@ -133,6 +133,23 @@ class LSTM:
     def backward(self):
         self._ck(self.lib.lstm_backward(self.ctx))
 
+    def gradcheck(self, x_idx, t_idx, per_tensor=100, seed=0, delta=1e-5):
+        """compute_all_numerical_grads + check_gradients (OV/lstm_eigen_class_batch/lstm.h:203-261, lstm.cc:440-510):
+        analytic gradients of this context vs double-precision central differences evaluated on the device.
+        Returns dict(passed, report{name: dict(max, mean, n_range, a_range)}, idx, numeric, analytic) with the three
+        arrays shaped (5, per_tensor) (idx = column-major index inside the tensor, -1 = unused slot)."""
+        x, t = self._win(x_idx), self._win(t_idx)
+        rep = np.zeros((5, 6), dtype=np.float64)
+        idx = np.full((5, per_tensor), -1, dtype=np.int64)
+        num = np.zeros((5, per_tensor), dtype=np.float64)
+        ana = np.zeros((5, per_tensor), dtype=np.float64)
+        ok = C.c_int(0)
+        self._ck(self.lib.lstm_gradcheck(self.ctx, _ptr(x), _ptr(t), int(per_tensor), int(seed), float(delta), _ptr(rep),
+                                         _ptr(idx), _ptr(num), _ptr(ana), C.byref(ok)))
+        report = {NAMES[w]: dict(max=rep[w, 0], mean=rep[w, 1], n_range=(rep[w, 2], rep[w, 3]), a_range=(rep[w, 4], rep[w, 5]))
+                  for w in range(5)}
+        return dict(passed=bool(ok.value), report=report, idx=idx, numeric=num, analytic=ana)
+
     def adagrad(self, lr=0.1, eps=1e-10, clip=0.0):
         self._ck(self.lib.lstm_adagrad(self.ctx, lr, eps, clip))
 

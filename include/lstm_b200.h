@@ -118,6 +118,21 @@ int lstm_sample(lstm_ctx* ctx, uint64_t seed, const float* h0, const float* c0, 
 /* what: LSTM_ACT_*; t in [0,S): column-major (rows x B) like the reference's per-timestep matrices */
 int lstm_get_activation(lstm_ctx* ctx, int what, int t, float* out, size_t n);
 
+/* ---- gradient check (compute_all_numerical_grads + check_gradients, OV/lstm_eigen_class_batch/lstm.h:203-261,
+ * lstm.cc:440-510; GPU snapshot: OV/lstm_eigen_class_CUDA/lstm.cc:420-500) ----------------------------------------- */
+/* Runs forward + backward on the given window (same arguments as lstm_forward) from the current h(0), c(0), then, for
+ * `per_tensor` randomly chosen entries of each of the five tensors (mt19937_64(seed + which), without replacement; all
+ * entries if the tensor is smaller), evaluates the window's loss in DOUBLE precision on the device at p - delta and
+ * p + delta and compares the central difference n with the analytic gradient a of the context's own arithmetic:
+ * error = |a - n| / |a + n| (0 where a + n == 0), exactly the reference's rule.
+ *   report[which][0..5] = max rel. error, mean rel. error, min n, max n, min a, max a     (which = LSTM_W .. LSTM_BY)
+ *   probe_idx / numeric / analytic (optional, each [5][per_tensor]): the sampled column-major indices (-1 = unused
+ *   slot) and both gradient values, for callers that want their own statistics.
+ * Returns LSTM_OK when the check RAN; the verdict (reference thresholds: max <= 1e-1 and mean <= 1e-3 for every tensor)
+ * goes to *passed.  The loss differentiated is sum_b sum_t -ln p[target] (the gradients carry no 1/B, R/lstm.cc:225). */
+int lstm_gradcheck(lstm_ctx* ctx, const int32_t* x_idx, const int32_t* t_idx, int per_tensor, uint64_t seed, double delta,
+                   double report[5][6], long long* probe_idx, double* numeric, double* analytic, int* passed);
+
 /* ---- checkpoints ------------------------------------------------------------------------------ */
 /* Eigen-text format of Parameters::save_to_disk: <prefix>_{W,U,Why,b,by}.txt, one matrix row per
  * line, 6 significant digits (OV/lstm_eigen_class_CUDA/io.h:16-32) — interchangeable with the
