@@ -881,6 +881,12 @@ extern "C" int lstm_gradcheck(lstm_ctx* ctx, const int32_t* x_idx, const int32_t
   if (!ctx) return LSTM_ERR_ARG;
   if (per_tensor < 1 || !(delta > 0.0) || !report) return lstm_fail(ctx, LSTM_ERR_ARG, "lstm_gradcheck: need per_tensor >= 1, delta > 0, report");
   LSTM_CUDA(cudaSetDevice(ctx->device));
+  // An all-zero TARGET column (-1, the window warm-up of R/lstm.cc:124,169) contributes nothing to the loss (:204) but
+  // dy = probs - 0 still enters the reference's gradients (:225): there the analytic gradient is, by the reference's own
+  // construction, not the derivative of the loss, and a gradient check is meaningless.  (-1 INPUT columns are fine.)
+  if (t_idx)
+    for (size_t i = (size_t)ctx->B; i < (size_t)ctx->S * ctx->B; i++)
+      if (t_idx[i] < 0) return lstm_fail(ctx, LSTM_ERR_ARG, "lstm_gradcheck: every target of timesteps 1..S-1 must be a real byte (not -1)");
   // analytic gradients: the context's own forward + backward (OV/lstm_eigen_class_batch/lstm.cc:291-293)
   int rc = lstm_forward(ctx, x_idx, t_idx, nullptr);
   if (rc) return rc;
@@ -930,12 +936,21 @@ extern "C" int lstm_gradcheck(lstm_ctx* ctx, const int32_t* x_idx, const int32_t
   cudaFree(d_out);
   if (ce != cudaSuccess) return lstm_fail(ctx, LSTM_ERR_CUDA, std::string("lstm_gradcheck: ") + cudaGetErrorString(ce));
   ctx->launches += 1;
-  // check_gradient_error (OV/lstm_eigen_class_batch/lstm.cc:440-492)
+  // check_gradient_error (OV/lstm_eigen_class_batch/lstm.cc:440-492).  The reference's analytic gradients are doubles and
+  // it exempts only a + n == 0; ours are fp32 sums over B*T terms, which cannot resolve entries far below the tensor's
+  // typical gradient: entries with |a + n| <= 1e-4 * max|n| of the tensor's probes count as error 0 as well.
   bool ok = true;
   size_t q0 = 0;
   for (int w = 0; w < 5; w++) {
-    double mx = 0.0, sum = 0.0, nmin = INFINITY, nmax = -INFINITY, amin = INFINITY, amax = -INFINITY;
+    double mx = 0.0, sum = 0.0, nmin = INFINITY, nmax = -INFINITY, amin = INFINITY, amax = -INFINITY, nabs = 0.0;
     size_t cnt = 0;
+    const size_t qbase = q0;
+    for (int q = 0; q < per_tensor; q++) {
+      if (idx[(size_t)w * per_tensor + q] < 0) continue;
+      nabs = std::max(nabs, fabs((loss[2 * q0 + 1] - loss[2 * q0]) / (2.0 * delta)));
+      q0++;
+    }
+    q0 = qbase;
     for (int q = 0; q < per_tensor; q++) {
       const long long i = idx[(size_t)w * per_tensor + q];
       if (i < 0) continue;
@@ -943,7 +958,7 @@ extern "C" int lstm_gradcheck(lstm_ctx* ctx, const int32_t* x_idx, const int32_t
       const double a = (double)grads[ctx->off[w] + (size_t)i];
       q0++;
       const double den = fabs(a + n);
-      const double err = den > 0.0 ? fabs(a - n) / den : 0.0;
+      const double err = den > 1e-4 * nabs ? fabs(a - n) / den : 0.0;
       mx = std::max(mx, err); sum += err; cnt++;
       nmin = std::min(nmin, n); nmax = std::max(nmax, n); amin = std::min(amin, a); amax = std::max(amax, a);
       if (numeric) numeric[(size_t)w * per_tensor + q] = n;

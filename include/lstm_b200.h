@@ -124,12 +124,15 @@ int lstm_get_activation(lstm_ctx* ctx, int what, int t, float* out, size_t n);
  * `per_tensor` randomly chosen entries of each of the five tensors (mt19937_64(seed + which), without replacement; all
  * entries if the tensor is smaller), evaluates the window's loss in DOUBLE precision on the device at p - delta and
  * p + delta and compares the central difference n with the analytic gradient a of the context's own arithmetic:
- * error = |a - n| / |a + n| (0 where a + n == 0), exactly the reference's rule.
+ * error = |a - n| / |a + n|, the reference's rule; it counts 0 where a + n == 0 and — the analytic side being fp32
+ * sums here, not doubles — also where |a + n| <= 1e-4 * max|n| over the tensor's probes.
  *   report[which][0..5] = max rel. error, mean rel. error, min n, max n, min a, max a     (which = LSTM_W .. LSTM_BY)
  *   probe_idx / numeric / analytic (optional, each [5][per_tensor]): the sampled column-major indices (-1 = unused
  *   slot) and both gradient values, for callers that want their own statistics.
  * Returns LSTM_OK when the check RAN; the verdict (reference thresholds: max <= 1e-1 and mean <= 1e-3 for every tensor)
- * goes to *passed.  The loss differentiated is sum_b sum_t -ln p[target] (the gradients carry no 1/B, R/lstm.cc:225). */
+ * goes to *passed.  Targets of timesteps 1..S-1 must be real bytes: for an all-zero target column (-1) the reference's
+ * dy = probs - target (R/lstm.cc:225) is not the derivative of its loss (:204), so LSTM_ERR_ARG is returned; -1 INPUT
+ * columns are fine.  The loss differentiated is sum_b sum_t -ln p[target] (the gradients carry no 1/B, R/lstm.cc:225). */
 int lstm_gradcheck(lstm_ctx* ctx, const int32_t* x_idx, const int32_t* t_idx, int per_tensor, uint64_t seed, double delta,
                    double report[5][6], long long* probe_idx, double* numeric, double* analytic, int* passed);
 

@@ -61,12 +61,15 @@ def test_device_gradcheck_api_agrees_with_the_double_oracle_and_passes():
     params = [rng.normal(0, 0.2, s).astype(np.float32) for s in [(4 * N, M), (4 * N, N), (4 * N, 1), (M, N), (M, 1)]]
     x = rng.integers(0, M, (S, B)).astype(np.int32)
     t = rng.integers(0, M, (S, B)).astype(np.int32)
-    x[1, 0] = -1                                  # a warm-up (all-zero) input column and a missing target
-    t[2, 1] = -1
+    x[1, 0] = -1                                  # a warm-up (all-zero) INPUT column is a legitimate part of the function
     h0 = rng.normal(0, 0.1, (N, B)).astype(np.float32)
     c0 = rng.normal(0, 0.1, (N, B)).astype(np.float32)
     g = el.LSTM(M, N, S, B)
     g.set_params(params); g.set_state(h0, c0)
+    # an all-zero TARGET column is refused: there the reference's dy = probs - 0 is not the gradient of its loss
+    bad = t.copy(); bad[2, 1] = -1
+    with pytest.raises(el.LstmError):
+        g.gradcheck(x, bad, per_tensor=4)
     per = 40
     res = g.gradcheck(x, t, per_tensor=per, seed=3, delta=1e-5)
     assert res["passed"], res["report"]
