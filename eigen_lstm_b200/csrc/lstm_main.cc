@@ -245,7 +245,7 @@ int main(int argc, char** argv) {
       }
       total_iters += (long)chunk;
       const size_t i = S + done * stride;
-      if (i % 100 == 0 || stride > 1)
+      if ((i % 100 == 0 && i < length) || stride > 1)   // the reference's loop ends at i = length - 1 (:151): no print at i = length
         std::cout << std::fixed << std::setw(7) << std::setprecision(2) << 100.0f * (float)i / (float)length << "%\r" << std::flush;
     }
     CK(lstm_sync(ctx));
