@@ -233,10 +233,19 @@ int main(int argc, char** argv) {
           const double train_bpc = window_loss / ((double)window_iters * (double)(S - 1));
           const double gflops = (double)window_iters * (double)(S - 1) * (double)B * (22.0 * N * M + 24.0 * N * N) / since / 1073741824.0;
           std::cout << std::endl << "Train error: " << train_bpc << ", Test error: " << test_bpc << std::endl;
-          if (!save_prefix.empty()) {     // 5-column results row: idx, secs since last, train, test, GFlOP/s (class_CUDA/lstm.cc:205-226)
+          // the results row: idx, secs since last, train, test, GFlOP/s (class_CUDA/lstm.cc:205-226), printed and logged
+          char row[160];
+          snprintf(row, sizeof(row), "%zu %g %g %g %g", results_rows, since, train_bpc, test_bpc, gflops);
+          std::cout << row << std::endl << std::endl;
+          if (!save_prefix.empty()) {
             FILE* rf = fopen((save_prefix + ".txt").c_str(), "a");
-            if (rf) { fprintf(rf, "%zu %g %g %g %g\n", results_rows, since, train_bpc, test_bpc, gflops); fclose(rf); }
+            if (rf) { fprintf(rf, "%s\n", row); fclose(rf); }
             CK(lstm_save_text_ckpt(ctx, save_prefix.c_str()));
+            // 5000 sampled characters next to the checkpoint (class_CUDA/lstm.cc:228-234; h = c = 0 there: reset_std = 0)
+            std::vector<uint8_t> smp(5000);
+            CK(lstm_sample(ctx, seed + 7919 * (results_rows + 1), nullptr, nullptr, smp.data(), smp.size(), 0));
+            FILE* sf = fopen((save_prefix + "_sample.txt").c_str(), "wb");
+            if (sf) { fwrite(smp.data(), 1, smp.size(), sf); fclose(sf); }
           }
           results_rows++;
           window_loss = 0.0; window_iters = 0;

@@ -47,3 +47,36 @@ def test_lstm_binary_prints_what_the_reference_program_prints(tmp_path, alice):
     assert so.count(b"\n" + b"=" * 84 + b"\n") == epochs
     gen = re.findall(rb"\n\n\*{12} Generated text \|(.*?)\| Generated text END \*{12}\n", so, flags=re.S)
     assert len(gen) == epochs and all(len(g) == 1000 for g in gen)
+
+
+def test_lstm_binary_heldout_eval_results_log_and_checkpoint_roundtrip(tmp_path, enwik6):
+    """The long-run workflow of the last snapshot (OV/lstm_eigen_class_CUDA/lstm.cc:73-86,188-238): train/test split,
+    timed held-out evaluation, 5-column results log, text checkpoint + sample file; then --load resumes from the
+    checkpoint (io.h:16-81) and scores the same held-out bits/char the log recorded (to the 6 digits the text keeps)."""
+    import numpy as np
+    (tmp_path / "corpus.txt").write_bytes(enwik6[:20000])
+    prefix = str(tmp_path / "run")
+    common = [BIN, "--file", "corpus.txt", "--hidden", "48", "--seq", "12", "--batch", "8", "--stride", "11", "--seed", "3",
+              "--forget-bias", "1", "--state-std", "0", "--train-percent", "95"]
+    out = subprocess.run(common + ["--epochs", "2", "--max-iters", "3000", "--test-every", "0.05", "--save", prefix],
+                         cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert out.returncode == 0, out.stderr.decode(errors="replace")
+    so = out.stdout.decode(errors="replace")
+    assert "Train set size: 19000, Test set size: 1000, Total: 20000" in so
+    assert "Train error: " in so and ", Test error: " in so
+    rows = np.loadtxt(prefix + ".txt", ndmin=2)
+    assert rows.shape[1] == 5 and rows.shape[0] >= 2
+    assert list(rows[:, 0]) == list(range(rows.shape[0]))            # running index
+    assert np.all(rows[:, 1] >= 0.05) and np.all(rows[:, 4] > 0)      # seconds since the last evaluation, GFlOP/s
+    assert rows[-1, 3] < rows[0, 3] < 8.5                             # held-out bits/char falls while training
+    for name, shape in [("W", (192, 256)), ("U", (192, 48)), ("Why", (256, 48)), ("b", (192,)), ("by", (256,))]:
+        assert np.loadtxt(f"{prefix}_{name}.txt").shape == shape
+    assert os.path.getsize(prefix + "_sample.txt") == 5000
+    # resume: zero further iterations, immediate evaluation -> the held-out error of the saved weights
+    out2 = subprocess.run(common + ["--epochs", "1", "--max-iters", "1", "--lr", "0", "--test-every", "0.000001", "--load", prefix],
+                          cwd=tmp_path, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=300)
+    assert out2.returncode == 0, out2.stderr.decode(errors="replace")
+    m = re.search(r"Test error: ([0-9.eE+-]+)", out2.stdout.decode(errors="replace"))
+    assert m, out2.stdout.decode(errors="replace")
+    # the checkpoint was written at the LAST evaluation or at the end of the epoch (later): at least as good as the last row
+    assert float(m.group(1)) < rows[-1, 3] + 0.3        # (an unloaded, untrained model scores 8.0)
