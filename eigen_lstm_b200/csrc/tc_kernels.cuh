@@ -39,6 +39,7 @@ struct FwdStepArgs {
   long ldz;                    // ZT leading dimension (columns)
   long long* dbg;              // optional: clock64 stamps of CTA (0,0) for diagnostics (NULL = off)
   const void* pin; size_t pin_bytes;   // recurrent weights (Urk): L2-persisting access window of this launch
+  int early_b;                 // weight tiles of the pipeline fill are issued before griddepcontrol.wait (set by the launcher)
 };
 
 struct LogitsArgs {
@@ -65,6 +66,7 @@ struct BwdStepArgs {
   float* red;                  // split-K exchange scratch: [tiles][4 dst][4 src][128][BN/4] fp32 (L2-resident)
   long long* dbg;              // optional: clock64 stamps of CTA (0,0,0) for diagnostics (NULL = off)
   const void* pin; size_t pin_bytes;   // recurrent weights (Ukr): L2-persisting access window of this launch
+  int early_b;                 // see FwdStepArgs
 };
 
 struct GemmArgs {

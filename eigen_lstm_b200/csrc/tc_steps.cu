@@ -56,7 +56,14 @@ k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUte
   if constexpr (PAIR) c = pair_prologue<BN, STAGES>(smem_raw);
   else c = tile_prologue<BN, STAGES, CN, CM>(smem_raw);
   pdl_launch_dependents();   // the next timestep's CTAs may take SMs as ours drain; they block in pdl_wait()
-  pdl_wait();                // everything below reads what the previous timestep's kernel wrote
+  // early_b: the U tiles of the pipeline fill (weights: no predecessor writes them) go in flight before the wait; the
+  // producer warp and the epilogue warps then wait on their own (tc_tile.cuh).  Otherwise: wait here, all threads.
+  const bool early = a.early_b != 0 && CN * CM == 1;
+  if (early) {
+    if (c.warp == 0 && elect_one()) { tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmU); }
+  } else {
+    pdl_wait();              // everything below reads what the previous timestep's kernel wrote
+  }
   c.dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0) ? a.dbg : nullptr;
   const bool stamp = c.dbg && threadIdx.x == 64;
   if (stamp) { c.dbg[0] = t_entry; c.dbg[4] = clock64(); }
@@ -68,9 +75,10 @@ k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUte
   const int mb = PAIR ? (int)(blockIdx.y * 2 + (blockIdx.x & 1)) : (int)blockIdx.y;
   const KSeg s0{&tmH, &tmU, a.a_row0 + mb * BM, nb * BN, 0, 0, a.N / BK};
   const KSeg s1{&tmH, &tmU, 0, 0, 0, 0, 0};
-  if constexpr (PAIR) pair_mainloop<BN, STAGES>(c, s0, s1, cluster_ctarank(), (uint16_t)0x3);
-  else tile_mainloop<BN, STAGES, CN, CM>(c, s0, s1, (int)(blockIdx.x % CN), (int)(blockIdx.y % CM));
+  if constexpr (PAIR) pair_mainloop<BN, STAGES>(c, s0, s1, cluster_ctarank(), (uint16_t)0x3, early);
+  else tile_mainloop<BN, STAGES, CN, CM>(c, s0, s1, (int)(blockIdx.x % CN), (int)(blockIdx.y % CM), early);
   if (c.warp >= 2) {
+    if (early) pdl_wait();                                 // c(t-1) below is the previous timestep kernel's output
     const int e = threadIdx.x - 64;                        // 0..EPI_THREADS-1
     const int N = a.N, N4 = 4 * a.N;
     const int l = e % UT, rg = e / UT;                     // phase-2 mapping: lane = hidden unit
@@ -204,6 +212,11 @@ static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
 }
+// LSTM_EARLY_B=1: issue the weight tiles of the pipeline fill before griddepcontrol.wait (needs PDL; see tc_tile.cuh)
+static int early_b() {
+  static const int on = env_int("LSTM_EARLY_B", 0) != 0 && use_pdl();
+  return on;
+}
 // timestep-kernel launch shape: CTA pairs (cta_group::2) when there is an even number of batch tiles, unless
 // LSTM_PAIR=0; LSTM_FWD_CN / LSTM_FWD_CM select the (slower) multicast-cluster experiment instead.
 bool step_pair(int Bp) {
@@ -243,7 +256,9 @@ static void launch_fwd_t(const CUtensorMap& tmH, const CUtensorMap& tmUrk, const
   else launch_fwd_cn<BN, 1>(CM, grid, tmH, tmUrk, a, st);
 }
 // tmH must have a box of 128/fwd_cluster_n rows and tmUrk one of BN/fwd_cluster_m rows
-void launch_fwd_step(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st) {
+void launch_fwd_step(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a0, cudaStream_t st) {
+  FwdStepArgs a = a0;
+  a.early_b = early_b();
   if (BN == 128) launch_fwd_t<128>(tmH, tmUrk, a, st);
   else if (BN == 64) launch_fwd_t<64>(tmH, tmUrk, a, st);
   else launch_fwd_t<32>(tmH, tmUrk, a, st);
@@ -280,7 +295,14 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
   if constexpr (PAIR) c = pair_prologue<BN, STAGES>(smem_raw);
   else c = tile_prologue<BN, STAGES>(smem_raw);
   pdl_launch_dependents();
-  pdl_wait();
+  const bool early = a.early_b != 0;                         // see k_fwd_step
+  if (early) {
+    if (c.warp == 0 && elect_one()) {
+      tma_prefetch_desc(&tmdG); tma_prefetch_desc(&tmU); tma_prefetch_desc(&tmdY); tma_prefetch_desc(&tmW);
+    }
+  } else {
+    pdl_wait();
+  }
   c.dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? a.dbg : nullptr;
   const bool stamp = c.dbg && threadIdx.x == 64;
   if (stamp) { c.dbg[0] = t_entry; c.dbg[4] = clock64(); }
@@ -299,13 +321,14 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
   const int lo1 = max(lo, nkb0) - nkb0, hi1 = max(hi, nkb0) - nkb0;
   const KSeg s0{&tmdG, &tmU, a.dg_row0 + mb * BM, nb * BN, lo0 * BK, lo0 * BK, hi0 - lo0};
   const KSeg s1{&tmdY, &tmW, a.dy_row0 + mb * BM, nb * BN, lo1 * BK, lo1 * BK, hi1 - lo1};
-  if constexpr (PAIR) pair_mainloop<BN, STAGES>(c, s0, s1, crank & 1u, (uint16_t)(0x3u << (2 * rank)));
-  else tile_mainloop<BN, STAGES>(c, s0, s1);
+  if constexpr (PAIR) pair_mainloop<BN, STAGES>(c, s0, s1, crank & 1u, (uint16_t)(0x3u << (2 * rank)), early);
+  else tile_mainloop<BN, STAGES>(c, s0, s1, 0, 0, early);
   const int e = threadIdx.x - 64;
   const int N = a.N, N4 = 4 * a.N;
   const int l = e >= 0 ? e % UO : 0, rg = e >= 0 ? e / UO : 0;
   const int j = nb * BN + (int)rank * UO + l;              // the hidden unit this thread finalises
   if (c.warp >= 2) {
+    if (early) pdl_wait();                                 // dcnext and the exchange scratch belong to the previous step until now
 #pragma unroll
     for (int i = 0; i < ROWS; i++) {                       // warm L2 for phase 2
       const int b = mb * BM + rg + RG * i;
@@ -423,7 +446,9 @@ static void launch_bwd_t(const CUtensorMap& tmdG, const CUtensorMap& tmUkr, cons
   launch_cluster(k_bwd_step<BN>, grid, dim3(1, 1, SPLIT), F::C::SMEM_BYTES, st, a.pin, a.pin_bytes, tmdG, tmUkr, tmdY, tmWnm, a);
 }
 void launch_bwd_step(int BN, const CUtensorMap& tmdG, const CUtensorMap& tmUkr, const CUtensorMap& tmdY,
-                     const CUtensorMap& tmWnm, const BwdStepArgs& a, cudaStream_t st) {
+                     const CUtensorMap& tmWnm, const BwdStepArgs& a0, cudaStream_t st) {
+  BwdStepArgs a = a0;
+  a.early_b = early_b();
   if (BN == 128) launch_bwd_t<128>(tmdG, tmUkr, tmdY, tmWnm, a, st);
   else if (BN == 64) launch_bwd_t<64>(tmdG, tmUkr, tmdY, tmWnm, a, st);
   else launch_bwd_t<32>(tmdG, tmUkr, tmdY, tmWnm, a, st);
