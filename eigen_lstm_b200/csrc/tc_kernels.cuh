@@ -42,6 +42,20 @@ struct FwdStepArgs {
   int early_b;                 // weight tiles of the pipeline fill are issued before griddepcontrol.wait (set by the launcher)
 };
 
+// persistent forward recurrence (tc_persist.cu, experimental): all T timesteps in one launch
+struct FwdPersistArgs {
+  int B, Bp, N, M, T;
+  const int* xs;               // [S][B] input bytes; timestep t reads row t
+  const float* Wp;             // [M][4N r']
+  const float* bp;             // [4N r']
+  float* Cs;                   // [(T+1)][B][N]: slot 0 read once, slot t written by timestep t
+  float* Gp;                   // [T][B][4N r']
+  __nv_bfloat16* Hbf;          // [(T+1)][Bp][N]: slot t-1 read (TMA), slot t written by timestep t
+  __nv_bfloat16* ZT_h0;        // ZT + M*ldz: the h rows; timestep t writes columns [t*Bp, (t+1)*Bp)
+  long ldz;
+  unsigned int* bar;           // [Bp/128][8] arrival counters of the grid barrier (zeroed by the launcher)
+};
+
 struct LogitsArgs {
   int B, Bp, N, M, T;
   const float* by;             // [M]
@@ -93,6 +107,9 @@ bool bwd_pair(int Bp);
 int bwd_box_rows(int BN, int Bp);
 // K2: one recurrent timestep.  BN in {32, 64, 128} gate columns per CTA.
 void launch_fwd_step(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st);
+// experimental persistent variant of K2 (LSTM_PERSIST_FWD=1): returns false if the shape cannot run persistently
+bool fwd_persist_enabled();
+bool launch_fwd_persist(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdPersistArgs& a, cudaStream_t st);
 // K3: logits + softmax + loss + dy for all timesteps
 void launch_logits(const CUtensorMap& tmH, const CUtensorMap& tmWmn, const LogitsArgs& a, cudaStream_t st);
 // K5: one BPTT timestep.  BN in {32, 64, 128} hidden units per CTA.

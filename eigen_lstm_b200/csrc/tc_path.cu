@@ -17,6 +17,7 @@ struct Bf16State {
   bf16 *Hbf = nullptr, *Urk = nullptr, *Ukr = nullptr, *Wmn = nullptr, *Wnm = nullptr;
   bf16 *dYbf = nullptr, *dYT = nullptr, *dGbf = nullptr, *dGT = nullptr, *ZT = nullptr;
   float *Wp = nullptr, *bp = nullptr, *Gp = nullptr, *dcnext = nullptr, *scratch = nullptr, *red = nullptr;
+  unsigned int* gbar = nullptr;   // grid-barrier arrival counters of the experimental persistent recurrence
   long long* dbg = nullptr;   // [32] kernel-internal clock stamps (LSTM_TC_DEBUG=1)
   size_t scratch_elems = 0, pin_bytes = 0;
   CUtensorMap tmH, tmH2, tmUrk, tmUkr, tmWmn, tmWnm, tmdY, tmdYT, tmdG, tmdGT, tmZT, tmZT256;
@@ -95,6 +96,7 @@ int tc_create(lstm_ctx* ctx) {
   TC_ALLOC(s->red, (size_t)(N / s->BN5) * (Bp / 128) * 16 * 128 * (s->BN5 / 4) * sizeof(float));   // K5 split-K exchange
   s->scratch_elems = (size_t)B * N4;
   TC_ALLOC(s->scratch, s->scratch_elems * sizeof(float));
+  TC_ALLOC(s->gbar, (size_t)(Bp / 128) * 8 * sizeof(unsigned int));
   if (getenv("LSTM_TC_DEBUG")) TC_ALLOC(s->dbg, 32 * sizeof(long long));
   tc::launch_fill_bf16(s->ZT + (size_t)(M + N) * s->LDZ, 1.0f, (size_t)s->LDZ, ctx->st);  // the ones row (db, dby)
   LSTM_LAUNCHED(1);
@@ -128,7 +130,7 @@ void tc_destroy(lstm_ctx* ctx) {
   Bf16State* s = ctx->tc;
   if (!s) return;
   void* bufs[] = {s->Hbf, s->Urk, s->Ukr, s->Wmn, s->Wnm, s->dYbf, s->dYT, s->dGbf, s->dGT, s->ZT, s->Wp, s->bp, s->Gp,
-                  s->dcnext, s->scratch, s->red, s->dbg};
+                  s->dcnext, s->scratch, s->red, s->dbg, s->gbar};
   for (void* b : bufs) if (b) cudaFree(b);
   delete s;
   ctx->tc = nullptr;
@@ -180,7 +182,16 @@ int tc_forward(lstm_ctx* ctx) {
   const size_t Bp = s->Bp, N4 = s->N4;
   tc::launch_build_xt(ctx->xs + B, s->ZT, s->LDZ, M, T, B, s->Bp, ctx->st);
   LSTM_LAUNCHED(1);
-  for (int t = 1; t <= T; t++) {
+  bool persistent = false;
+  if (tc::fwd_persist_enabled() && !ctx->profiling) {   // experimental: the whole recurrence in one persistent launch
+    tc::FwdPersistArgs pa;
+    pa.B = B; pa.Bp = s->Bp; pa.N = N; pa.M = M; pa.T = T;
+    pa.xs = ctx->xs; pa.Wp = s->Wp; pa.bp = s->bp; pa.Cs = ctx->Cs; pa.Gp = s->Gp; pa.Hbf = s->Hbf;
+    pa.ZT_h0 = s->ZT + (size_t)M * s->LDZ; pa.ldz = s->LDZ; pa.bar = s->gbar;
+    persistent = tc::launch_fwd_persist(s->BN2, s->tmH2, s->tmUrk, pa, ctx->st);
+    if (persistent) LSTM_LAUNCHED(1);
+  }
+  for (int t = 1; t <= T && !persistent; t++) {
     tc::FwdStepArgs a;
     a.B = B; a.Bp = s->Bp; a.N = N; a.M = M;
     a.a_row0 = (t - 1) * s->Bp;
@@ -195,7 +206,7 @@ int tc_forward(lstm_ctx* ctx) {
     a.pin = s->Urk; a.pin_bytes = s->pin_bytes;
     tc::launch_fwd_step(s->BN2, s->tmH2, s->tmUrk, a, ctx->st);
   }
-  LSTM_LAUNCHED(T);
+  if (!persistent) LSTM_LAUNCHED(T);
   PROF(2);
   tc::LogitsArgs la;
   la.B = B; la.Bp = s->Bp; la.N = N; la.M = M; la.T = T;
