@@ -53,7 +53,8 @@ struct FwdPersistArgs {
   __nv_bfloat16* Hbf;          // [(T+1)][Bp][N]: slot t-1 read (TMA), slot t written by timestep t
   __nv_bfloat16* ZT_h0;        // ZT + M*ldz: the h rows; timestep t writes columns [t*Bp, (t+1)*Bp)
   long ldz;
-  unsigned int* bar;           // [Bp/128][8] arrival counters of the grid barrier (zeroed by the launcher)
+  unsigned int* bar;           // [Bp/128][8][32] words for the grid barrier's arrival counters (zeroed by the launcher)
+  int bar_stride;              // words between two counters: 1 (one sector) or 32 (one 128-byte line each); set by the launcher
 };
 
 struct LogitsArgs {

@@ -96,7 +96,7 @@ int tc_create(lstm_ctx* ctx) {
   TC_ALLOC(s->red, (size_t)(N / s->BN5) * (Bp / 128) * 16 * 128 * (s->BN5 / 4) * sizeof(float));   // K5 split-K exchange
   s->scratch_elems = (size_t)B * N4;
   TC_ALLOC(s->scratch, s->scratch_elems * sizeof(float));
-  TC_ALLOC(s->gbar, (size_t)(Bp / 128) * 8 * sizeof(unsigned int));
+  TC_ALLOC(s->gbar, (size_t)(Bp / 128) * 8 * 32 * sizeof(unsigned int));
   if (getenv("LSTM_TC_DEBUG")) TC_ALLOC(s->dbg, 32 * sizeof(long long));
   tc::launch_fill_bf16(s->ZT + (size_t)(M + N) * s->LDZ, 1.0f, (size_t)s->LDZ, ctx->st);  // the ones row (db, dby)
   LSTM_LAUNCHED(1);

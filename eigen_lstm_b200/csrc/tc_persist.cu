@@ -81,10 +81,10 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   return v;
 }
 // whole warp: wait until all GBAR_SLOTS counters of this batch tile have reached `target` (bounded)
-__device__ __forceinline__ void grid_wait(const unsigned int* slots, unsigned int target, int lane) {
+__device__ __forceinline__ void grid_wait(const unsigned int* slots, int stride, unsigned int target, int lane) {
   const long long t0 = clock64();
   for (;;) {
-    const unsigned int v = lane < GBAR_SLOTS ? ld_acquire_gpu(slots + lane) : target;
+    const unsigned int v = lane < GBAR_SLOTS ? ld_acquire_gpu(slots + (size_t)lane * stride) : target;
     if (__all_sync(0xffffffffu, (int)(v - target) >= 0)) break;
     if (clock64() - t0 > 4000000000LL) __trap();
   }
@@ -109,7 +109,11 @@ k_fwd_persist(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ C
   const int n_tiles = (int)(gridDim.x >> 1);
   const int nkb = a.N / BK;
   const unsigned int per_slot = (unsigned int)(n_tiles / GBAR_SLOTS);   // arrivals per counter per timestep
-  unsigned int* my_slots = a.bar + (size_t)mb * GBAR_SLOTS;
+  // bar_stride = 1: the 8 counters of a batch tile share one 32-byte sector (the variant verified on the B200);
+  // bar_stride = 32 (LSTM_PERSIST_SPREAD=1, untested): one 128-byte line per counter, so the 64 pollers and 64 `red`s of a
+  // batch tile spread over 8 L2 lines instead of serialising on one.
+  const int bstride = a.bar_stride;
+  unsigned int* my_slots = a.bar + (size_t)mb * GBAR_SLOTS * bstride;
   const int N = a.N, N4 = 4 * a.N, B = a.B;
 
   if (c.warp == 0) {
@@ -132,7 +136,7 @@ k_fwd_persist(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ C
         __syncwarp();
       }
       if (t > 1) {                                           // h(t-1) of this batch tile is complete in global memory
-        grid_wait(my_slots, (unsigned int)(t - 1) * per_slot, c.lane);
+        grid_wait(my_slots, bstride, (unsigned int)(t - 1) * per_slot, c.lane);
         fence_proxy_async_global();                          // generic-proxy writes (observed via acquire) -> async-proxy reads
       }
       for (int kb = 0; kb < nkb; kb++) {
@@ -258,7 +262,7 @@ k_fwd_persist(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ C
       }
       fence_proxy_async_global();                            // this thread's Hbf stores are ordered before later TMA reads
       named_bar_sync(1, P_EPI_THREADS);
-      if (e == 0) red_release_gpu_add(my_slots + (nb % GBAR_SLOTS), 1u);   // release: cumulative over the barrier-ordered stores
+      if (e == 0) red_release_gpu_add(my_slots + (size_t)(nb % GBAR_SLOTS) * bstride, 1u);   // release: cumulative over the barrier-ordered stores
 #pragma unroll
       for (int q = 0; q < ROWS; q++) {
         if (xv[q] >= -1) {
@@ -302,7 +306,7 @@ bool launch_persist_t(const CUtensorMap& tmH, const CUtensorMap& tmUrk, const Fw
   int max_clusters = 0;
   if (cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return false; }
   if (max_clusters < n_tiles * m_tiles / 2) return false;
-  if (cudaMemsetAsync(a.bar, 0, (size_t)m_tiles * GBAR_SLOTS * sizeof(unsigned int), st) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (cudaMemsetAsync(a.bar, 0, (size_t)m_tiles * GBAR_SLOTS * a.bar_stride * sizeof(unsigned int), st) != cudaSuccess) { cudaGetLastError(); return false; }
   return cudaLaunchKernelEx(&cfg, kernel, tmH, tmUrk, a) == cudaSuccess;
 }
 
@@ -315,8 +319,11 @@ bool fwd_persist_enabled() {
 
 // Returns false when the shape cannot run persistently (the caller then launches one kernel per timestep).
 // tmH must have a 128-row box and tmUrk a BN/2-row box — the maps the pair variant of k_fwd_step uses.
-bool launch_fwd_persist(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdPersistArgs& a, cudaStream_t st) {
-  if (!step_pair(a.Bp)) return false;
+bool launch_fwd_persist(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdPersistArgs& a0, cudaStream_t st) {
+  if (!step_pair(a0.Bp)) return false;
+  static const bool spread = getenv("LSTM_PERSIST_SPREAD") != nullptr && atoi(getenv("LSTM_PERSIST_SPREAD")) != 0;
+  FwdPersistArgs a = a0;
+  a.bar_stride = spread ? 32 : 1;                            // the counter buffer holds [Bp/128][8][32] words either way
   if (BN == 128) return launch_persist_t<128>(tmH, tmUrk, a, st);
   if (BN == 64) return launch_persist_t<64>(tmH, tmUrk, a, st);
   return false;
