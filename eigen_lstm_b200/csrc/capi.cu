@@ -68,6 +68,10 @@ static void free_iter_graph(lstm_ctx::IterGraph& g) {
   g = lstm_ctx::IterGraph();
 }
 
+// captured iteration graphs bake in device pointers, sizes and the launch structure: anything that changes one of
+// those (a new corpus, a resized loss ring, joining a communicator) must drop them
+static void drop_graphs(lstm_ctx* ctx);
+
 int lstm_fail(lstm_ctx* c, int code, const std::string& msg) {
   if (c) c->err = msg; else g_create_error = msg;
   return code;
@@ -664,6 +668,7 @@ extern "C" int lstm_load_text(lstm_ctx* ctx, const uint8_t* bytes, size_t n) {
   if (n < (size_t)ctx->S + 2) return lstm_fail(ctx, LSTM_ERR_ARG, "text shorter than the window");
   LSTM_CUDA(cudaSetDevice(ctx->device));
   LSTM_CUDA(cudaStreamSynchronize(ctx->st));
+  drop_graphs(ctx);   // the text pointer and length are kernel arguments inside the captured iteration
   if (ctx->text) { LSTM_CUDA(cudaFree(ctx->text)); ctx->text = nullptr; }
   LSTM_CUDA(cudaMalloc(&ctx->text, n));
   LSTM_CUDA(cudaMemcpyAsync(ctx->text, bytes, n, cudaMemcpyHostToDevice, ctx->st));
@@ -1063,25 +1068,26 @@ extern "C" int lstm_save_bin(lstm_ctx* ctx, const char* path) {
   if (!ctx || !path) return LSTM_ERR_ARG;
   int rc = lstm_sync(ctx);
   if (rc) return rc;
+  // everything is copied to the host first, so no error path leaves a file handle open
+  std::vector<float> pbuf(ctx->P), mbuf(ctx->P);
+  LSTM_CUDA(cudaMemcpy(pbuf.data(), ctx->params, ctx->P * sizeof(float), cudaMemcpyDeviceToHost));
+  LSTM_CUDA(cudaMemcpy(mbuf.data(), ctx->mem, ctx->P * sizeof(float), cudaMemcpyDeviceToHost));
+  const size_t bn = (size_t)ctx->B * ctx->N;
+  std::vector<float> hb(bn), cb(bn);
+  rc = lstm_get_state(ctx, hb.data(), cb.data());   // bf16 contexts carry h(0) in bf16: this converts it to the fp32 view
+  if (rc) return rc;
   FILE* f = fopen(path, "wb");
   if (!f) return lstm_fail(ctx, LSTM_ERR_IO, std::string("cannot open ") + path);
   BinHeader h;
   memcpy(h.magic, "LSTMB200", 8);
   h.M = ctx->M; h.N = ctx->N; h.S = ctx->S; h.B = ctx->B; h.iteration = ctx->iteration; h.v = ctx->v_host;
   bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
-  std::vector<float> buf(ctx->P);
-  for (const float* src : {ctx->params, ctx->mem}) {
-    LSTM_CUDA(cudaMemcpy(buf.data(), src, ctx->P * sizeof(float), cudaMemcpyDeviceToHost));
-    ok = ok && fwrite(buf.data(), sizeof(float), ctx->P, f) == ctx->P;
-  }
-  const size_t bn = (size_t)ctx->B * ctx->N;
-  std::vector<float> st(bn);
-  for (const float* src : {ctx->Hslot(0), ctx->Cslot(0)}) {
-    LSTM_CUDA(cudaMemcpy(st.data(), src, bn * sizeof(float), cudaMemcpyDeviceToHost));
-    ok = ok && fwrite(st.data(), sizeof(float), bn, f) == bn;
-  }
+  ok = ok && fwrite(pbuf.data(), sizeof(float), ctx->P, f) == ctx->P;
+  ok = ok && fwrite(mbuf.data(), sizeof(float), ctx->P, f) == ctx->P;
+  ok = ok && fwrite(hb.data(), sizeof(float), bn, f) == bn;
+  ok = ok && fwrite(cb.data(), sizeof(float), bn, f) == bn;
   ok = ok && fwrite(ctx->h_pos0.data(), sizeof(uint64_t), ctx->B, f) == (size_t)ctx->B;
-  fclose(f);
+  ok = (fclose(f) == 0) && ok;
   return ok ? LSTM_OK : lstm_fail(ctx, LSTM_ERR_IO, std::string("short write to ") + path);
 }
 
@@ -1144,6 +1150,8 @@ extern "C" int lstm_dp_init(lstm_ctx* ctx, int rank, int world, const uint8_t id
   memcpy(&u, id, 128);
   if (!nccl_load()) return lstm_fail(ctx, LSTM_ERR_NCCL, "libnccl.so.2 not found");
   LSTM_NCCL(g_nccl.CommInitRank(&ctx->comm, world, u, rank));
+  LSTM_CUDA(cudaStreamSynchronize(ctx->st));
+  drop_graphs(ctx);   // a graph captured before joining has no gradient buckets; data-parallel iterations replay as segments
   ctx->rank = rank;
   ctx->world = world;
   return LSTM_OK;
