@@ -187,7 +187,7 @@ int tc_forward(lstm_ctx* ctx) {
     tc::FwdPersistArgs pa;
     pa.B = B; pa.Bp = s->Bp; pa.N = N; pa.M = M; pa.T = T;
     pa.xs = ctx->xs; pa.Wp = s->Wp; pa.bp = s->bp; pa.Cs = ctx->Cs; pa.Gp = s->Gp; pa.Hbf = s->Hbf;
-    pa.ZT_h0 = s->ZT + (size_t)M * s->LDZ; pa.ldz = s->LDZ; pa.bar = s->gbar;
+    pa.ZT_h0 = s->ZT + (size_t)M * s->LDZ; pa.ldz = s->LDZ; pa.bar = s->gbar; pa.bar_stride = 1; pa.dbg = s->dbg;
     persistent = tc::launch_fwd_persist(s->BN2, s->tmH2, s->tmUrk, pa, ctx->st);
     if (persistent) LSTM_LAUNCHED(1);
   }

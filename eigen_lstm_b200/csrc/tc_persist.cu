@@ -115,6 +115,12 @@ k_fwd_persist(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ C
   const int bstride = a.bar_stride;
   unsigned int* my_slots = a.bar + (size_t)mb * GBAR_SLOTS * bstride;
   const int N = a.N, N4 = 4 * a.N, B = a.B;
+  // diagnostics (LSTM_TC_DEBUG=1): SM-clock stamps of CTA (0,0) around timestep DBG_T, read with lstm_debug_kernel_clocks:
+  // [0] producer reaches the grid barrier  [1] barrier passed  [2] first operand stage landed  [3] last MMA issued
+  // [4] accumulator complete  [5] accumulator in shared memory  [6] h(t) announced  [7] timestep's stores done
+  // [8] producer reaches the NEXT timestep's grid barrier ([8] - [0] = one timestep period)
+  constexpr int DBG_T = 4;
+  long long* dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && a.T > DBG_T) ? a.dbg : nullptr;
 
   if (c.warp == 0) {
     // ---------------- producer ----------------
@@ -136,8 +142,10 @@ k_fwd_persist(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ C
         __syncwarp();
       }
       if (t > 1) {                                           // h(t-1) of this batch tile is complete in global memory
+        if (dbg && c.lane == 0 && (t == DBG_T || t == DBG_T + 1)) dbg[t == DBG_T ? 0 : 8] = clock64();
         grid_wait(my_slots, bstride, (unsigned int)(t - 1) * per_slot, c.lane);
         fence_proxy_async_global();                          // generic-proxy writes (observed via acquire) -> async-proxy reads
+        if (dbg && c.lane == 0 && t == DBG_T) dbg[1] = clock64();
       }
       for (int kb = 0; kb < nkb; kb++) {
         const int st = (g + kb) % STAGES;
@@ -171,6 +179,7 @@ k_fwd_persist(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ C
           const int st = (g + kb) % STAGES;
           const uint32_t ph = (uint32_t)((g + kb) / STAGES) & 1u;
           mbar_wait(&c.full[st], ph);
+          if (dbg && c.lane == 0 && t == DBG_T && kb == 0) dbg[2] = clock64();
           tcgen05_after_sync();
           if (elect_one()) {
             const uint64_t soff = (uint64_t)((uint32_t)st * (uint32_t)(PC::STAGE_BYTES >> 4));
@@ -183,6 +192,7 @@ k_fwd_persist(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ C
         }
         if (elect_one()) umma_commit_pair(c.accum_full, (uint16_t)0x3);
         __syncwarp();
+        if (dbg && c.lane == 0 && t == DBG_T) dbg[3] = clock64();
         g += nkb;
       }
     }
@@ -226,6 +236,7 @@ k_fwd_persist(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ C
         const int quarter = c.warp & 3;
         const int row = quarter * 32 + c.lane;
         mbar_wait(c.accum_full, (uint32_t)(t - 1) & 1u);
+        if (dbg && e == 0 && t == DBG_T) dbg[4] = clock64();
         tcgen05_after_sync();
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -238,6 +249,7 @@ k_fwd_persist(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ C
         tcgen05_before_sync();
       }
       named_bar_sync(1, P_EPI_THREADS);
+      if (dbg && e == 0 && t == DBG_T) dbg[5] = clock64();
       if (e == 0) mbar_arrive_remote(tmem_free, 0);          // this CTA's half of the accumulator is drained
       // Only h(t) is on the critical path of the other CTAs: it is stored FIRST, fenced and announced; the gate stash and
       // c(t) (registers until then) follow after the arrival, so the release does not wait for their 10x larger traffic.
@@ -263,6 +275,7 @@ k_fwd_persist(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ C
       fence_proxy_async_global();                            // this thread's Hbf stores are ordered before later TMA reads
       named_bar_sync(1, P_EPI_THREADS);
       if (e == 0) red_release_gpu_add(my_slots + (size_t)(nb % GBAR_SLOTS) * bstride, 1u);   // release: cumulative over the barrier-ordered stores
+      if (dbg && e == 0 && t == DBG_T) dbg[6] = clock64();
 #pragma unroll
       for (int q = 0; q < ROWS; q++) {
         if (xv[q] >= -1) {
@@ -280,6 +293,7 @@ k_fwd_persist(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ C
           __stcs(dst + lane + 32, src[lane + 32]);
         }
       }
+      if (dbg && e == 0 && t == DBG_T) dbg[7] = clock64();
     }
   }
   pair_epilogue_end<BN, STAGES>(c);
