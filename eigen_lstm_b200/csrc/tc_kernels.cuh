@@ -55,6 +55,7 @@ struct FwdPersistArgs {
   long ldz;
   unsigned int* bar;           // [Bp/128][8][32] words for the grid barrier's arrival counters (zeroed by the launcher)
   int bar_stride;              // words between two counters: 1 (one sector) or 32 (one 128-byte line each); set by the launcher
+  int writer_fence;            // 1 every writer thread executes fence.proxy.async.global, 2 only the announcing thread, 0 none
   long long* dbg;              // optional clock64 stamps of CTA (0,0) around one timestep (NULL = off)
 };
 

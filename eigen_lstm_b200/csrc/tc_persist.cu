@@ -272,8 +272,11 @@ k_fwd_persist(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ C
         }
         hT[l * P_HT_LD + r] = __float2bfloat16_rn(hval);
       }
-      fence_proxy_async_global();                            // this thread's Hbf stores are ordered before later TMA reads
+      // writer-side proxy fence: 1 (default, the verified variant) = every writing thread; 2 = only the announcing thread,
+      // after the barrier; 0 = none (the readers fence after their acquire in any case).  LSTM_PERSIST_WFENCE selects.
+      if (a.writer_fence == 1) fence_proxy_async_global();
       named_bar_sync(1, P_EPI_THREADS);
+      if (a.writer_fence == 2 && e == 0) fence_proxy_async_global();
       if (e == 0) red_release_gpu_add(my_slots + (size_t)(nb % GBAR_SLOTS) * bstride, 1u);   // release: cumulative over the barrier-ordered stores
       if (dbg && e == 0 && t == DBG_T) dbg[6] = clock64();
 #pragma unroll
@@ -338,6 +341,8 @@ bool launch_fwd_persist(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk
   static const bool spread = getenv("LSTM_PERSIST_SPREAD") != nullptr && atoi(getenv("LSTM_PERSIST_SPREAD")) != 0;
   FwdPersistArgs a = a0;
   a.bar_stride = spread ? 32 : 1;                            // the counter buffer holds [Bp/128][8][32] words either way
+  static const int wfence = getenv("LSTM_PERSIST_WFENCE") ? atoi(getenv("LSTM_PERSIST_WFENCE")) : 1;
+  a.writer_fence = wfence;
   if (BN == 128) return launch_persist_t<128>(tmH, tmUrk, a, st);
   if (BN == 64) return launch_persist_t<64>(tmH, tmUrk, a, st);
   return false;
