@@ -13,8 +13,10 @@ OV/lstm_eigen_class_batch/lstm_segment.cc:130,187), so one step consumes B*T new
              device copy of the step's window and a device -> host read of its loss every step
   roofline   the dominant kernel's achieved TFLOP/s (live CUDA-event phase timing) vs the measured
              dense bf16 peak in MEASURED_PEAKS.json
-  cpu_baseline  the CPU oracle (port of R/lstm.cc; the reference needs Eigen and cannot be built
-             here) on the box's host cores, on a bounded sample of the same workload
+  cpu_baseline  the CPU oracle (port of R/lstm.cc / OV/lstm_eigen_BLAS; the reference needs Eigen and
+             OpenBLAS and cannot be built here) on the box's host cores, on a bounded sample of the same
+             workload: BLAS-backed (numpy's OpenBLAS) for the large configurations, the single-thread
+             C++ port for the reference's own tiny default
 
 --impl reference runs only the CPU arm (the reference's own algorithm on host cores).
 """
@@ -106,9 +108,57 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (port of the reference's algorithm) on host cores, bounded sample
 # -------------------------------------------------------------------------------------------------
+def blas_threads():
+    """Threads numpy's BLAS will use (threadpoolctl when present, else the core count)."""
+    try:
+        from threadpoolctl import threadpool_info
+        n = [d.get("num_threads", 0) for d in threadpool_info() if d.get("user_api") == "blas"]
+        if n:
+            return int(max(n))
+    except Exception:
+        pass
+    return os.cpu_count() or 1
+
+
+def cpu_arm_blas(cfg, text, target_seconds, steps=1, warmup=0):
+    """Large configurations: the structure of OV/lstm_eigen_BLAS/lstm.cc (every contraction a multi-threaded BLAS GEMM,
+    dense one-hot products) on numpy's OpenBLAS — oracle/oracle_blas.py — over ALL B streams and a bounded number of
+    timesteps."""
+    from oracle import oracle as orc
+    from oracle import oracle_blas as ob
+    N, S, B = cfg["N"], cfg["S"], cfg["B"]
+    params = orc.init_params(M, N, seed=0, sd=0.01)
+
+    def make(Tw):
+        q = ob.BlasOracle(M, N, Tw + 1, B)
+        q.set_params(params)
+        return q, [Tw + 1 + i * 1000 for i in range(B)]
+
+    q, pos = make(2)                                   # probe: cost of one timestep of B streams (+ one Adagrad sweep)
+    q.train_windows(text, pos, 1, 2, LR)
+    _, secs = q.train_windows(text, pos, 1, 2, LR)
+    Ts = int(max(2, min(S - 1, target_seconds / max(secs / 2, 1e-9))))
+    del q
+    q, pos = make(Ts)
+    for _ in range(warmup):
+        q.train_windows(text, pos, 1, Ts, LR)
+    t = []
+    for _ in range(steps):
+        _, secs = q.train_windows(text, pos, 1, Ts, LR)
+        t.append(secs)
+    secs = sum(t) / len(t)
+    th = blas_threads()
+    return dict(value=B * Ts / secs, unit="chars/s", cores=th, kind="port",
+                sample=f"{B} streams x {Ts} timesteps of the same N={N} model per step (full workload: {B} x {S - 1}), "
+                       f"oracle/oracle_blas.py: the lstm_eigen_BLAS structure (every contraction a BLAS sgemm, dense one-hot "
+                       f"products like the reference) on numpy's OpenBLAS, {th} threads"), secs
+
+
 def cpu_arm(cfg, text, target_seconds, steps=1, warmup=0):
     from oracle import oracle as orc
     N, S = cfg["N"], cfg["S"]
+    if cfg["B"] * N >= 4096 and not os.environ.get("BENCH_CPU_PORT"):
+        return cpu_arm_blas(cfg, text, target_seconds, steps, warmup)   # GEMM throughput decides: use the best BLAS present
     threads = os.cpu_count() or 1
     if cfg["B"] * N < 4096:
         threads = 1                                   # tiny models: fork/join costs more than the loops (the reference is 1 thread)
@@ -173,8 +223,9 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "chars/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "note": "R/lstm.cc needs <Eigen/Dense>, which is not installed (no network): the CPU arm is the oracle port of "
-                        "its algorithm, all host threads"}
+                "note": "R/lstm.cc and OV/lstm_eigen_BLAS need Eigen / OpenBLAS, which are not installed (no network): the CPU arm is "
+                        "the oracle's port of the algorithm on the best BLAS present, all host threads (the reference sources "
+                        "compiled against oracle/eigen_shim pin the oracle's semantics but are not a timing baseline)"}
         print(json.dumps(line), flush=True)
         return 0
 

@@ -44,3 +44,13 @@ def test_non_rank0_reference_arm_exits_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, timeout=120, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_reference_arm_uses_the_blas_port_for_large_configurations():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg2",
+                          "--steps", "1", "--warmup", "3", "--cpu-seconds", "0.5"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    cb = line["cpu_baseline"]
+    assert line["impl"] == "reference" and line["value"] > 0 and cb["value"] == line["value"]
+    assert cb["kind"] == "port" and "oracle_blas" in cb["sample"] and "64 streams" in cb["sample"] and cb["cores"] >= 1
