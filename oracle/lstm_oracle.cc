@@ -177,11 +177,11 @@ struct Oracle {
         // OV/lstm_eigen_class_batch/lstm.h:175 subtracts the max over the whole M x B logit matrix
         R mx = -INFINITY;
         std::vector<R> y(M);
-        for (int bb = 0; bb < B; bb++) {
-          for (int m = 0; m < M; m++) y[m] = by[m];
+        for (int bb = 0; bb < B; bb++) {   // y = Why * h + by: the product first, then the bias (same association as softmax_col)
+          for (int m = 0; m < M; m++) y[m] = 0;
           for (int n = 0; n < N; n++)
             for (int m = 0; m < M; m++) y[m] += Why[(size_t)M * n + m] * ht(t)[(size_t)N * bb + n];
-          for (int m = 0; m < M; m++) mx = y[m] > mx ? y[m] : mx;
+          for (int m = 0; m < M; m++) { const R v = y[m] + by[m]; mx = v > mx ? v : mx; }
         }
         shift = mx;
       }
@@ -384,7 +384,7 @@ struct Oracle {
       if (greedy) {
         for (int ii = 1; ii < M; ii++) if (p[ii] > p[index]) index = ii;
       } else {
-        const float r = (float)dis(gen);  // `float r = dis(gen)` :326
+        const R r = (R)dis(gen);  // `float r = dis(gen)` R/lstm.cc:326; `double r` in the double snapshots (OV/lstm_eigen_class_batch/lstm.cc:378)
         for (int ii = 0; ii < M; ii++) if (r < cdf[ii]) { index = ii; break; }
       }
       out[i] = (uint8_t)index;
@@ -470,6 +470,21 @@ std::vector<R>* pick(Oracle<R>* o, int kind, int which) {
 
 ORACLE_API(oracle32, float)
 ORACLE_API(oracle64, double)
+
+// the double-precision snapshots call randn(MatrixXd&, double mean, double stddev) (OV/lstm_eigen_class_batch/lstm.cc:513)
+extern "C" void oracle64_randn_d(double* m, int rows, int cols, double mean, double sd, uint64_t seed) {
+  std::mt19937 mt((uint32_t)seed);
+  std::normal_distribution<> dist(mean, sd);
+  for (int i = 0; i < rows; i++)
+    for (int j = 0; j < cols; j++) m[i + (size_t)rows * j] = dist(mt);
+}
+// n draws of mt19937(seed) + uniform_real_distribution<double>(0,1): the generator of the reference's sampled gradient
+// check (OV/lstm_eigen_class_batch/lstm.h:211-219) and of its sampling loop
+extern "C" void oracle_uniform01(uint64_t seed, size_t n, double* out) {
+  std::mt19937 gen((uint32_t)seed);
+  std::uniform_real_distribution<> dis(0, 1);
+  for (size_t i = 0; i < n; i++) out[i] = dis(gen);
+}
 
 extern "C" int oracle_set_threads(int n) {
   if (n <= 0) n = (int)std::thread::hardware_concurrency();

@@ -166,6 +166,22 @@ def randn(rows, cols, mean, sd, seed, dtype=np.float32):
     return a
 
 
+def randn_d(rows, cols, mean, sd, seed):
+    """The double-precision snapshots' randn(MatrixXd&, double, double) (OV/lstm_eigen_class_batch/lstm.cc:513-529)."""
+    lib = _load(False)
+    a = np.empty((rows, cols), dtype=np.float64, order="F")
+    lib.oracle64_randn_d(a.ctypes.data_as(C.c_void_p), rows, cols, C.c_double(mean), C.c_double(sd), C.c_uint64(seed))
+    return a
+
+
+def uniform01(seed, n):
+    """n draws of mt19937(seed) + uniform_real_distribution<double>(0, 1)."""
+    lib = _load(False)
+    a = np.empty(n, dtype=np.float64)
+    lib.oracle_uniform01(C.c_uint64(seed), C.c_size_t(n), a.ctypes.data_as(C.c_void_p))
+    return a
+
+
 def init_params(M, N, seed, sd=0.01, forget_bias=0.0, dtype=np.float32):
     """R/lstm.cc:113-119 (k-th randn call seeded seed+k); forget bias per OV/lstm_eigen_class_batch/lstm.cc:81."""
     Wm = randn(4 * N, M, 0, sd, seed + 0, dtype)

@@ -14,6 +14,11 @@ branch) is recorded the same way as oracle/_ref/lstm_blas_ref on the first 2000 
 Its stream start positions come from the C library's unseeded rand() (OV/lstm_eigen_BLAS/lstm.cc:150-154); the
 values it drew are stored in the fixture (`positions`) so the replay does not depend on the libc.
 
+The double-precision class snapshot OV/lstm_eigen_class_batch/lstm.cc (+ lstm.h; N = 32, S = 5, B = 4, 95 % of
+alice29.txt for training) likewise as oracle/_ref/lstm_class_batch_ref -> tests/golden/ref_lstm_class_batch_run.json;
+besides the epoch lines and samples it records the running loss the program prints every 100 iterations with 6
+decimals (`progress_loss`) and the stream positions of every epoch (again glibc rand(), continuing sequence).
+
 Output: tests/golden/ref_lstm_cc_run.json
   seed, corpus_bytes, epochs
   read_line        the "Read <n> bytes (alice29.txt)" line                      (R/lstm.cc:398)
@@ -37,8 +42,11 @@ BIN_BLAS = os.path.join(ROOT, "oracle", "_ref", "lstm_blas_ref")
 SEED, CORPUS_BYTES, EPOCHS = 1234, 3000, 4
 BLAS_SEED, BLAS_CORPUS_BYTES, BLAS_EPOCHS, BLAS_B, BLAS_S = 99, 2000, 3, 4, 3
 END = b"| Generated text END ************"
+BIN_CLASS = os.path.join(ROOT, "oracle", "_ref", "lstm_class_batch_ref")
+CLASS_SEED, CLASS_CORPUS_BYTES, CLASS_EPOCHS, CLASS_B, CLASS_S = 42, 3000, 2, 4, 5
 PROGRAMS = {   # binary, file name the program opens, committed corpus it is a prefix of
     "lstm.cc": (BIN, "alice29.txt", "alice29_head.bin"),
+    "lstm_eigen_class_batch": (BIN_CLASS, "alice29.txt", "alice29_head.bin"),
     "lstm_eigen_BLAS": (BIN_BLAS, "enwik5.txt", "enwik6_head.bin"),
 }
 
@@ -101,6 +109,27 @@ def main():
                    "from its default seed" % (BLAS_SEED, BLAS_CORPUS_BYTES))
     json.dump(doc, open(os.path.join(HERE, "ref_lstm_eigen_blas_run.json"), "w"), indent=1)
     print("\n".join(epoch_lines[:BLAS_EPOCHS]))
+
+    # double-precision class snapshot
+    out = run_reference(CLASS_SEED, CLASS_CORPUS_BYTES, CLASS_EPOCHS, program="lstm_eigen_class_batch")
+    read_line, epoch_lines, avg, gen, _ = parse(out)
+    assert len(gen) >= CLASS_EPOCHS and all(len(g) == 1500 for g in gen[:CLASS_EPOCHS]), [len(g) for g in gen]
+    train_len = 95 * (CLASS_CORPUS_BYTES // 100)
+    libc.srand(1)
+    positions = [[libc.rand() % (train_len - CLASS_S) + CLASS_S for _ in range(CLASS_B)] for _ in range(CLASS_EPOCHS)]
+    per_epoch = len([i for i in range(CLASS_S, train_len) if (i + 1) % 100 == 0])
+    prog = re.findall(rb"\[Epoch (\d+)/1000\]\s+[0-9.]+%.*?loss = ([0-9.]+)", out)
+    progress = [p[1].decode() for p in prog if int(p[0]) <= CLASS_EPOCHS]
+    assert len(progress) == per_epoch * CLASS_EPOCHS, (len(progress), per_epoch)
+    doc = dict(seed=CLASS_SEED, corpus_bytes=CLASS_CORPUS_BYTES, train_bytes=train_len, epochs=CLASS_EPOCHS, B=CLASS_B, S=CLASS_S, N=32,
+               positions=positions, read_line=read_line, split_line=out.split(b"\n")[1].decode(),
+               epoch_lines=epoch_lines[:CLASS_EPOCHS], avg_loss=avg[:CLASS_EPOCHS], progress_loss=progress,
+               generated_b64=[base64.b64encode(g).decode() for g in gen[:CLASS_EPOCHS]],
+               how="oracle/_ref/lstm_class_batch_ref = unmodified OV/lstm_eigen_class_batch/lstm.cc + lstm.h (no -DUSE_BLAS) + "
+                   "oracle/eigen_shim, REF_SEED=%d, cwd holding alice29.txt = first %d bytes of R/alice29.txt"
+                   % (CLASS_SEED, CLASS_CORPUS_BYTES))
+    json.dump(doc, open(os.path.join(HERE, "ref_lstm_class_batch_run.json"), "w"), indent=1)
+    print("\n".join(epoch_lines[:CLASS_EPOCHS]))
 
 
 if __name__ == "__main__":

@@ -11,10 +11,13 @@ control flow; what it cannot pin is Eigen's internal summation order (the shim s
 
 The batched semantics (B streams: positions, per-stream shift, loss / B, batch-summed gradients) are pinned the same
 way against the unmodified batched snapshot OV/lstm_eigen_BLAS/lstm.cc (its pure-Eigen branch, B = 4):
-tests/golden/ref_lstm_eigen_blas_run.json.
+tests/golden/ref_lstm_eigen_blas_run.json; and the double-precision "class_batch" semantics (config 2's style: float64,
+global-max softmax shift, forget bias 1, 95/5 split, sampled gradient check every epoch) against the unmodified
+OV/lstm_eigen_class_batch/lstm.cc + lstm.h: tests/golden/ref_lstm_class_batch_run.json.
 """
 import base64
 import json
+import math
 import os
 
 import numpy as np
@@ -25,6 +28,7 @@ from tests.conftest import GOLDEN, ROOT
 
 FIX = json.load(open(os.path.join(GOLDEN, "ref_lstm_cc_run.json")))
 FIXB = json.load(open(os.path.join(GOLDEN, "ref_lstm_eigen_blas_run.json")))
+FIXC = json.load(open(os.path.join(GOLDEN, "ref_lstm_class_batch_run.json")))
 M, N, S = 256, 64, 3   # R/lstm.cc:53-57
 
 
@@ -99,6 +103,90 @@ def test_batched_oracle_reproduces_the_batched_reference_programs_output(enwik6,
     for e, (avg, sampled) in enumerate(replay_batched_with_oracle(text, f["seed"], f["epochs"], f["positions"], f["B"], f["S"],
                                                                   dense_onehot)):
         assert f"{avg:.3f}" == f["avg_loss"][e], (e, avg, f["avg_loss"][e])
+        assert sampled == base64.b64decode(f["generated_b64"][e]), f"epoch {e + 1}: sampled text differs"
+
+
+def replay_class_batch_with_oracle(full_text, seed, epochs, positions, N, S_, B):
+    """OV/lstm_eigen_class_batch/lstm.cc:36-420 + lstm.h, pure-Eigen branch, in DOUBLE precision.  Yields per epoch
+    (progress losses as printed every 100 iterations, avg loss, sampled bytes).  What this walks through, quirks included:
+      * 95 % of the file is the training text (:55-59); forget-gate bias 1 (:81); weights N(0, 0.01) drawn with DOUBLE
+        mean/stddev (:513); softmax shifted by the global maximum of the M x B logits (lstm.h:175);
+      * the window is rebuilt from the stream positions every iteration (:271-278): x_t = data[p-S+t], target_t = data[p-S+t+1];
+      * randn(h[0],0,0) at the top of an epoch (:158-159) zeroes a column the first shift (:281-285) overwrites at once, so
+        the state simply carries over; the per-stream reset at a wrap (:266-270) passes its matrix BY VALUE — a no-op that
+        still constructs two generators;
+      * the reported loss is the LAST timestep's, in nats, divided by B*length (:297-310), while backward() uses all timesteps;
+      * at the last iteration of an epoch the sampled numerical gradient check (lstm.h:203-261) runs between backward() and
+        adagrad(): its perturbed forward passes overwrite h[t], c[t], so the state the next epoch starts from is that of the
+        LAST perturbed forward (W entry + 1e-5) — reproduced here by replaying the check's own generator."""
+    data = np.frombuffer(full_text, dtype=np.uint8)
+    L = len(data)
+    o = orc.Oracle(M, N, S_, B, "f64")
+    o.set_options(softmax_shift=1, dense_onehot=1)
+    b = np.zeros((4 * N, 1)); b[2 * N:3 * N] = 1.0
+    o.set_params([orc.randn_d(4 * N, M, 0, 0.01, seed), orc.randn_d(4 * N, N, 0, 0.01, seed + 1), b,
+                  orc.randn_d(M, N, 0, 0.01, seed + 2), np.zeros((M, 1))])
+    k = seed + 3
+    check_order = [(orc.BY, (M, 1)), (orc.WHY, (M, N)), (orc.B_, (4 * N, 1)), (orc.U, (4 * N, N)), (orc.W, (4 * N, M))]
+    for e in range(epochs):
+        pos = list(positions[e])
+        k += 2                                               # randn(h[0], 0, 0), randn(c[0], 0, 0)
+        o.set_state("h", 0, np.zeros((N, B))); o.set_state("c", 0, np.zeros((N, B)))
+        epoch_loss, progress = 0.0, []
+        for i in range(S_, L):
+            if (i + 1) % 100 == 0:
+                progress.append("%.6f" % (epoch_loss * L / i))    # printed before this iteration's loss is added (:252-262)
+            x = np.zeros((S_, B), dtype=np.int32); t = np.zeros((S_, B), dtype=np.int32)
+            for bb in range(B):
+                if pos[bb] == S_:
+                    k += 2                                   # randnblock(...) x 2: by-value no-ops that consume two generators
+                x[:, bb] = data[pos[bb] - S_: pos[bb]]
+                t[:, bb] = data[pos[bb] - S_ + 1: pos[bb] + 1]
+                pos[bb] += 1
+                if pos[bb] >= L:
+                    pos[bb] = S_
+            o.set_window(x, t)
+            o.carry(1)
+            o.forward()
+            p = o.state("probs", S_ - 1)
+            loss = 0.0
+            for bb in range(B):
+                loss += -math.log(p[t[S_ - 1, bb], bb])
+            epoch_loss += loss / (B * L)
+            o.backward()
+            if i == L - 1:                                   # "Checking gradients..." (:325-327)
+                last = None
+                for q, (w, (r, c)) in enumerate(check_order):
+                    hit = np.nonzero(orc.uniform01(k + q, r * c) < 100.0 / (r * c))[0]   # row-major (i, j) scan, lstm.h:216-221
+                    if len(hit):
+                        last = (w, int(hit[-1]) // c, int(hit[-1]) % c)
+                k += 5
+                w, ii, jj = last
+                P = o.get(orc.PARAM, w)
+                orig = P[ii, jj]
+                P[ii, jj] = orig + 1e-5; o.set(orc.PARAM, w, P); o.forward()          # the last forward_loss() of the check
+                P[ii, jj] = orig; o.set(orc.PARAM, w, P)
+            o.adagrad(0.1)
+        one = orc.Oracle(M, N, S_, 1, "f64")
+        one.set_params(o.params())
+        sampled = one.sample(orc.randn_d(N, 1, 0, 0.1, k), orc.randn_d(N, 1, 0, 0.1, k + 1), k + 2, 1500).tobytes()
+        k += 3
+        yield progress, epoch_loss, sampled
+
+
+def test_double_oracle_reproduces_the_class_batch_reference_programs_output(alice):
+    """Float64 path, global-max softmax shift, forget bias, index-built windows, gradient-check side effect: two epochs of
+    the unmodified OV/lstm_eigen_class_batch program — every 6-decimal running loss it prints (56 of them), both epoch
+    losses and 2 x 1500 sampled characters — reproduced exactly."""
+    f = FIXC
+    text = alice[: f["corpus_bytes"]]
+    assert f["split_line"] == f"Train set size: {f['train_bytes']}, Test set size: {len(text) - f['train_bytes']}, Total: {len(text)}"
+    want_progress = f["progress_loss"]
+    n = len(want_progress) // f["epochs"]
+    for e, (progress, avg, sampled) in enumerate(replay_class_batch_with_oracle(text[: f["train_bytes"]], f["seed"], f["epochs"],
+                                                                               f["positions"], f["N"], f["S"], f["B"])):
+        assert progress == want_progress[e * n:(e + 1) * n], (e, [(a, b) for a, b in zip(progress, want_progress[e * n:]) if a != b][:3])
+        assert f"{avg:.3f}" == f["avg_loss"][e]
         assert sampled == base64.b64decode(f["generated_b64"][e]), f"epoch {e + 1}: sampled text differs"
 
 
