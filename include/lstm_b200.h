@@ -84,8 +84,11 @@ int lstm_backward(lstm_ctx* ctx);   /* BPTT over the window of the last forward;
 /* m += d*d; p -= lr * d / sqrtf(m + eps)  (R/lstm.cc:259-272; eps = 1e-10 is a double there, :25).  clip > 0 clamps each gradient
  * entry to [-clip, clip] first — an ADDITION of the north-star; 0 = off = the reference. */
 int lstm_adagrad(lstm_ctx* ctx, float lr, double eps, float clip);
-/* after a step: h(0),c(0) <- h(stride),c(stride) (stride 1: R/lstm.cc:163-164; stride > 1:
- * OV/lstm_eigen_class_batch/lstm_segment.cc:183-184) */
+/* after a step: h(0),c(0) <- h(stride),c(stride) — the state the shifted window's first input needs (stride 1:
+ * R/lstm.cc:163-164).  The reference's one stride > 1 program, OV/lstm_eigen_class_batch/lstm_segment.cc:183-184, copies
+ * h[stride-1] instead, i.e. carries a state one character short of its window shift; a caller that wants exactly that
+ * reads slot stride-1 with lstm_get_activation and writes it back with lstm_set_state
+ * (tests/test_oracle_vs_reference_source.py replays that program this way). */
 int lstm_carry_state(lstm_ctx* ctx, int stride);
 /* forward + backward + (data-parallel gradient allreduce) + adagrad + carry(stride) in one call: the window
  * starts from the state in slot 0 (lstm_set_state / the previous step's carry) and leaves h(stride),c(stride) there */

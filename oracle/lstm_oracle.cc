@@ -5,14 +5,17 @@
 // --impl reference leg).  Nothing under eigen_lstm_b200/ may include, link or call it.
 //
 // Parity status: PINNED.
-//   * Against the reference's own SOURCE: the unmodified /root/reference/lstm.cc is compiled by `make -C oracle ref`
-//     into oracle/_ref/lstm_ref.  Its one external dependency, Eigen, is not installed in this image (no network), so
-//     it is built against oracle/eigen_shim/ — a from-scratch stand-in for the few Eigen members lstm.cc uses — with
-//     std::random_device replaced by a seed counter.  Driven with the same seeds, this oracle reproduces that
-//     program's output EXACTLY: the printed epoch losses and all 4 x 1000 sampled characters after 3 000 .. 12 000
-//     Adagrad iterations (tests/test_oracle_vs_reference_source.py; committed output: tests/golden/ref_lstm_cc_run.json).
-//     That pins the window shift, state carry, loss normalisation, Adagrad order, seeding order and sampling.  What a
-//     shim cannot pin is Eigen's internal float summation order (the shim, like this file, sums sequentially).
+//   * Against the reference's own SOURCE: four UNMODIFIED reference programs — R/lstm.cc, OV/lstm_eigen_BLAS/lstm.cc (its
+//     pure-Eigen branch, B = 4), OV/lstm_eigen_class_batch/lstm.cc + lstm.h (double precision, softmax shift, gradient
+//     check) and OV/lstm_eigen_class_batch/lstm_segment.cc (window stride > 1) — are compiled by `make -C oracle ref` into
+//     oracle/_ref/.  Their one external dependency, Eigen, is not installed in this image (no network), so they are built
+//     against oracle/eigen_shim/ — a from-scratch stand-in for the Eigen members they use — with std::random_device
+//     replaced by a seed counter.  Driven with the same seeds, this oracle reproduces those programs' output EXACTLY: every
+//     printed loss and every sampled character after thousands of Adagrad iterations
+//     (tests/test_oracle_vs_reference_source.py; committed outputs: tests/golden/ref_*_run.json).  That pins window
+//     construction, state carry, loss normalisation, batch summation, Adagrad order, seeding order and sampling in float
+//     and double.  What a shim cannot pin is Eigen's internal float summation order (the shim, like this file, sums
+//     sequentially).
 //   * forward semantics (gate order [i,o,f,u], tanh'd carried cell, softmax, log2 loss) by the reference's
 //     known-answer fixture models/enwik5_test_{W,U,Why,b,by}.txt -> 3.24396 bits/char (tests/test_oracle_golden.py),
 //   * backward semantics by the reference's own acceptance rule for its numerical gradient check (max rel.err

@@ -47,6 +47,8 @@ CLASS_SEED, CLASS_CORPUS_BYTES, CLASS_EPOCHS, CLASS_B, CLASS_S = 42, 3000, 2, 4,
 PROGRAMS = {   # binary, file name the program opens, committed corpus it is a prefix of
     "lstm.cc": (BIN, "alice29.txt", "alice29_head.bin"),
     "lstm_eigen_class_batch": (BIN_CLASS, "alice29.txt", "alice29_head.bin"),
+    # lstm_segment.cc trains on the file called "lstm.h" in its working directory (:50): it gets prose, not source
+    "lstm_segment": (os.path.join(ROOT, "oracle", "_ref", "lstm_segment_ref"), "lstm.h", "alice29_head.bin"),
     "lstm_eigen_BLAS": (BIN_BLAS, "enwik5.txt", "enwik6_head.bin"),
 }
 
@@ -130,6 +132,21 @@ def main():
                    % (CLASS_SEED, CLASS_CORPUS_BYTES))
     json.dump(doc, open(os.path.join(HERE, "ref_lstm_class_batch_run.json"), "w"), indent=1)
     print("\n".join(epoch_lines[:CLASS_EPOCHS]))
+
+    # strided-window variant.  The corpus length is 3001 so that the last window of an epoch satisfies the program's
+    # `i > length - seg` (:209): only then does it print its epoch line.
+    SEG = dict(seed=7, corpus_bytes=3001, epochs=2, B=4, S=12, N=64)
+    out = run_reference(SEG["seed"], SEG["corpus_bytes"], SEG["epochs"], program="lstm_segment")
+    read_line, epoch_lines, avg, gen, _ = parse(out)
+    assert len(gen) >= SEG["epochs"] and all(len(g) == 1500 for g in gen[:SEG["epochs"]]), [len(g) for g in gen]
+    libc.srand(1)
+    positions = [[libc.rand() % (SEG["corpus_bytes"] - SEG["S"]) + SEG["S"] for _ in range(SEG["B"])] for _ in range(SEG["epochs"])]
+    doc = dict(SEG, positions=positions, read_line=read_line, epoch_lines=epoch_lines[:SEG["epochs"]], avg_loss=avg[:SEG["epochs"]],
+               generated_b64=[base64.b64encode(g).decode() for g in gen[:SEG["epochs"]]],
+               how="oracle/_ref/lstm_segment_ref = unmodified OV/lstm_eigen_class_batch/lstm_segment.cc + lstm.h + oracle/eigen_shim, "
+                   "REF_SEED=7, cwd holding a file named lstm.h = first 3001 bytes of R/alice29.txt")
+    json.dump(doc, open(os.path.join(HERE, "ref_lstm_segment_run.json"), "w"), indent=1)
+    print("\n".join(epoch_lines[:SEG["epochs"]]))
 
 
 if __name__ == "__main__":

@@ -29,6 +29,7 @@ from tests.conftest import GOLDEN, ROOT
 FIX = json.load(open(os.path.join(GOLDEN, "ref_lstm_cc_run.json")))
 FIXB = json.load(open(os.path.join(GOLDEN, "ref_lstm_eigen_blas_run.json")))
 FIXC = json.load(open(os.path.join(GOLDEN, "ref_lstm_class_batch_run.json")))
+FIXS = json.load(open(os.path.join(GOLDEN, "ref_lstm_segment_run.json")))
 M, N, S = 256, 64, 3   # R/lstm.cc:53-57
 
 
@@ -187,6 +188,70 @@ def test_double_oracle_reproduces_the_class_batch_reference_programs_output(alic
                                                                                f["positions"], f["N"], f["S"], f["B"])):
         assert progress == want_progress[e * n:(e + 1) * n], (e, [(a, b) for a, b in zip(progress, want_progress[e * n:]) if a != b][:3])
         assert f"{avg:.3f}" == f["avg_loss"][e]
+        assert sampled == base64.b64decode(f["generated_b64"][e]), f"epoch {e + 1}: sampled text differs"
+
+
+def test_strided_windows_reproduce_the_segment_reference_programs_output(alice):
+    """OV/lstm_eigen_class_batch/lstm_segment.cc — the reference's only stride > 1 program (window stride S/2 = 6, N = 64,
+    S = 12, B = 4, double, loss over all timesteps in nats).  NOTE the carried state: the program copies h[seg-1]
+    (:183-184) although the window moves by seg, i.e. its state is one character short; the oracle's carry(stride) and
+    the C ABI's lstm_carry_state(stride) carry h[stride].  The replay therefore sets the state by hand."""
+    f = FIXS
+    data = np.frombuffer(alice[: f["corpus_bytes"]], dtype=np.uint8)
+    N, S_, B, seed = f["N"], f["S"], f["B"], f["seed"]
+    seg, L = S_ // 2, len(data)
+    o = orc.Oracle(M, N, S_, B, "f64")
+    o.set_options(softmax_shift=1, dense_onehot=1)
+    o.set_params([orc.randn_d(4 * N, M, 0, 0.01, seed), orc.randn_d(4 * N, N, 0, 0.01, seed + 1), np.zeros((4 * N, 1)),
+                  orc.randn_d(M, N, 0, 0.01, seed + 2), np.zeros((M, 1))])
+    k = seed + 3
+    check_order = [(orc.BY, (M, 1)), (orc.WHY, (M, N)), (orc.B_, (4 * N, 1)), (orc.U, (4 * N, N)), (orc.W, (4 * N, M))]
+    for e in range(f["epochs"]):
+        pos = list(f["positions"][e])
+        o.set_state("h", 0, orc.randn_d(N, B, 0, 0.01, k)); o.set_state("c", 0, orc.randn_d(N, B, 0, 0.01, k + 1))   # :124-125
+        k += 2
+        epoch_loss = 0.0
+        for i in range(S_, L, seg):
+            x = np.zeros((S_, B), dtype=np.int32); t = np.zeros((S_, B), dtype=np.int32)
+            hs, cs = o.state("h", seg - 1), o.state("c", seg - 1)
+            for bb in range(B):
+                if pos[bb] == S_:
+                    k += 2                                   # by-value randnblock no-ops (:160-163)
+                x[:, bb] = data[pos[bb] - S_: pos[bb]]
+                t[:, bb] = data[pos[bb] - S_ + 1: pos[bb] + 1]
+                pos[bb] += seg
+                if pos[bb] >= L:
+                    pos[bb] = S_
+            o.set_state("h", 0, hs); o.set_state("c", 0, cs)  # lstm.h[0] = lstm.h[seg - 1]  (:183-184)
+            o.set_window(x, t)
+            o.forward()
+            loss = 0.0
+            for tt in range(1, S_):                           # all timesteps, natural log (:195-205)
+                p = o.state("probs", tt)
+                s = 0.0
+                for bb in range(B):
+                    s += -math.log(p[t[tt, bb], bb])
+                loss += s
+            epoch_loss += loss / (S_ * B * L / seg)           # (:207) size_t arithmetic: S*B*length/seg
+            o.backward()
+            if i > L - seg:                                   # (:209) gradient check on the last window of the epoch
+                last = None
+                for q, (w, (r, c)) in enumerate(check_order):
+                    hit = np.nonzero(orc.uniform01(k + q, r * c) < 100.0 / (r * c))[0]
+                    if len(hit):
+                        last = (w, int(hit[-1]) // c, int(hit[-1]) % c)
+                k += 5
+                w, ii, jj = last
+                P = o.get(orc.PARAM, w)
+                orig = P[ii, jj]
+                P[ii, jj] = orig + 1e-5; o.set(orc.PARAM, w, P); o.forward()
+                P[ii, jj] = orig; o.set(orc.PARAM, w, P)
+            o.adagrad(0.1)
+        assert f"{epoch_loss:.3f}" == f["avg_loss"][e], (e, epoch_loss, f["avg_loss"][e])
+        one = orc.Oracle(M, N, S_, 1, "f64")
+        one.set_params(o.params())
+        sampled = one.sample(orc.randn_d(N, 1, 0, 0.01, k), orc.randn_d(N, 1, 0, 0.01, k + 1), k + 2, 1500).tobytes()
+        k += 3
         assert sampled == base64.b64decode(f["generated_b64"][e]), f"epoch {e + 1}: sampled text differs"
 
 
