@@ -20,8 +20,9 @@
 //
 // STATUS (end of round 1): runs on the B200 with a loss trajectory BITWISE identical to the launch-per-step kernels
 // (config 4, profiles/r01f_bench_cfg4_persist_fwd_v*.json), i.e. the cross-proxy / cross-SM protocol is sound, but it is
-// not yet faster: ~14.0 us per timestep against 12.9 us.  Suspect: the 8 arrival counters of a batch tile share one
-// 32-byte sector that 64 producer warps poll while 64 CTAs `red` into it.  See DESIGN.md section 5 for the plan.
+// not yet faster: ~14.0 us per timestep against 12.9 us.  The grid barrier is not the reason (scripts/gridbar_bench.cu:
+// 1.17 us per 128-CTA barrier, independent of the counter layout); the suspects are the 512 per-thread proxy fences and
+// the MEMBAR inside the release (LSTM_PERSIST_WFENCE=0|2, scripts/persist_clocks.py).  See DESIGN.md sections 5 and 9.
 #include <stdlib.h>
 
 #include "tc_kernels.cuh"
