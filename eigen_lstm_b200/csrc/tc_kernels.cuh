@@ -84,6 +84,13 @@ struct BwdStepArgs {
   long long* dbg;              // optional: clock64 stamps of CTA (0,0,0) for diagnostics (NULL = off)
   const void* pin; size_t pin_bytes;   // recurrent weights (Ukr): L2-persisting access window of this launch
   int early_b;                 // see FwdStepArgs
+  // LSTM_BWD_PAIR=2 (experimental): cta_group::2 pairs in clusters of 2 only; the four split-K ranks of a tile are then
+  // different clusters and exchange their partial sums through `red` ordered by a per-tile arrival counter
+  // (red.release.gpu / ld.acquire.gpu) instead of the cluster barrier.  xcnt[tile] is zeroed once per iteration and
+  // reaches 4 * epoch when the four ranks of this launch have written (epoch = 1 for the first BPTT step, 2 for the next ...)
+  int flag_exchange;
+  int epoch;
+  unsigned int* xcnt;
 };
 
 struct GemmArgs {
@@ -107,6 +114,7 @@ int fwd_cluster_m(int Bp);
 // LSTM_BWD_PAIR=1): each CTA then stages only half of the weight tile, so the weight maps need boxes of BN/2 rows.
 bool step_pair(int Bp);
 bool bwd_pair(int Bp);
+bool bwd_flag_exchange(int Bp);   // LSTM_BWD_PAIR=2: pair clusters of 2 + counter-ordered split-K exchange (experimental)
 int bwd_box_rows(int BN, int Bp);
 // K2: one recurrent timestep.  BN in {32, 64, 128} gate columns per CTA.
 void launch_fwd_step(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st);

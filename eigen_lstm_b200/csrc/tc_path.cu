@@ -18,6 +18,8 @@ struct Bf16State {
   bf16 *dYbf = nullptr, *dYT = nullptr, *dGbf = nullptr, *dGT = nullptr, *ZT = nullptr;
   float *Wp = nullptr, *bp = nullptr, *Gp = nullptr, *dcnext = nullptr, *scratch = nullptr, *red = nullptr;
   unsigned int* gbar = nullptr;   // grid-barrier arrival counters of the experimental persistent recurrence
+  unsigned int* xcnt = nullptr;   // per-tile arrival counters of K5's counter-ordered split-K exchange (LSTM_BWD_PAIR=2)
+  size_t xcnt_bytes = 0;
   long long* dbg = nullptr;   // [32] kernel-internal clock stamps (LSTM_TC_DEBUG=1)
   size_t scratch_elems = 0, pin_bytes = 0;
   CUtensorMap tmH, tmH2, tmUrk, tmUkr, tmWmn, tmWnm, tmdY, tmdYT, tmdG, tmdGT, tmZT, tmZT256;
@@ -97,6 +99,8 @@ int tc_create(lstm_ctx* ctx) {
   s->scratch_elems = (size_t)B * N4;
   TC_ALLOC(s->scratch, s->scratch_elems * sizeof(float));
   TC_ALLOC(s->gbar, (size_t)(Bp / 128) * 8 * 32 * sizeof(unsigned int));
+  s->xcnt_bytes = (size_t)(N / s->BN5) * (Bp / 128) * sizeof(unsigned int);
+  TC_ALLOC(s->xcnt, s->xcnt_bytes);
   if (getenv("LSTM_TC_DEBUG")) TC_ALLOC(s->dbg, 32 * sizeof(long long));
   tc::launch_fill_bf16(s->ZT + (size_t)(M + N) * s->LDZ, 1.0f, (size_t)s->LDZ, ctx->st);  // the ones row (db, dby)
   LSTM_LAUNCHED(1);
@@ -130,7 +134,7 @@ void tc_destroy(lstm_ctx* ctx) {
   Bf16State* s = ctx->tc;
   if (!s) return;
   void* bufs[] = {s->Hbf, s->Urk, s->Ukr, s->Wmn, s->Wnm, s->dYbf, s->dYT, s->dGbf, s->dGT, s->ZT, s->Wp, s->bp, s->Gp,
-                  s->dcnext, s->scratch, s->red, s->dbg, s->gbar};
+                  s->dcnext, s->scratch, s->red, s->dbg, s->gbar, s->xcnt};
   for (void* b : bufs) if (b) cudaFree(b);
   delete s;
   ctx->tc = nullptr;
@@ -233,6 +237,7 @@ int tc_backward(lstm_ctx* ctx) {
   PROF(4);
   int rc = lstm_allreduce_bucket(ctx, 1);
   if (rc) return rc;
+  if (tc::bwd_flag_exchange(s->Bp)) LSTM_CUDA(cudaMemsetAsync(s->xcnt, 0, s->xcnt_bytes, ctx->st));
   for (int t = T; t >= 1; t--) {
     tc::BwdStepArgs a;
     a.B = B; a.Bp = s->Bp; a.N = N; a.M = M;
@@ -246,6 +251,7 @@ int tc_backward(lstm_ctx* ctx) {
     a.dGT_t = s->dGT + (size_t)(t - 1) * Bp;
     a.ldg = s->LDT;
     a.red = s->red;
+    a.xcnt = s->xcnt; a.epoch = T - t + 1; a.flag_exchange = 0;
     a.dbg = s->dbg ? s->dbg + 16 : nullptr;
     a.pin = s->Ukr; a.pin_bytes = s->pin_bytes;
     tc::launch_bwd_step(s->BN5, s->tmdG, s->tmUkr, s->tmdY, s->tmWnm, a, ctx->st);

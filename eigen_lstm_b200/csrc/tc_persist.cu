@@ -73,14 +73,6 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 // generic-proxy <-> async-proxy ordering for GLOBAL memory only (FENCE.VIEW.ASYNC.G): the all-space form adds a
 // MEMBAR.ALL.GPU per executing thread, which 512 epilogue threads would pay on the critical path
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
-__device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 // whole warp: wait until all GBAR_SLOTS counters of this batch tile have reached `target` (bounded)
 __device__ __forceinline__ void grid_wait(const unsigned int* slots, int stride, unsigned int target, int lane) {
   const long long t0 = clock64();

@@ -225,6 +225,8 @@ bool step_pair(int Bp) {
 // K5 as pairs needs clusters of 2 x 1 x 4 = 8 CTAs; 16 of those do not all become co-resident on a B200 (GPCs of
 // 16-20 SMs, some with fewer usable): measured 37.5 us per step instead of 20.1.  Off unless LSTM_BWD_PAIR=1.
 bool bwd_pair(int Bp) { return step_pair(Bp) && env_int("LSTM_BWD_PAIR", 0) != 0; }
+// LSTM_BWD_PAIR=2: pairs in clusters of 2 + split-K exchange through a global arrival counter (BwdStepArgs::flag_exchange)
+bool bwd_flag_exchange(int Bp) { return bwd_pair(Bp) && env_int("LSTM_BWD_PAIR", 0) == 2; }
 int bwd_box_rows(int BN, int Bp) { return bwd_pair(Bp) ? BN / 2 : BN; }
 int fwd_cluster_n(int n_tiles) {
   const int cn = env_int("LSTM_FWD_CN", 1);
@@ -311,7 +313,9 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
   const int nb = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int mb = PAIR ? (int)(blockIdx.y * 2 + (blockIdx.x & 1)) : (int)blockIdx.y;
   const uint32_t crank = cluster_ctarank();                  // PAIR: x (pair member) + 2 * z (split-K rank)
-  const uint32_t rank = PAIR ? crank >> 1 : crank;           // split-K rank
+  // flagx: clusters of 2 (just the pair); the split-K rank is blockIdx.z and the exchange is ordered by a global counter
+  const bool flagx = PAIR && a.flag_exchange != 0;
+  const uint32_t rank = PAIR ? (flagx ? (uint32_t)blockIdx.z : crank >> 1) : crank;   // split-K rank
   float* red_tile = a.red + (size_t)(mb * (a.N / BN) + nb) * (SPLIT * SPLIT * 128 * UO);
   // this CTA's quarter of the concatenated K range [0, nkb0) ++ [0, nkb1)
   const int nkb0 = a.first ? 0 : (4 * a.N) / BK, nkb1 = a.M / BK;
@@ -321,7 +325,7 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
   const int lo1 = max(lo, nkb0) - nkb0, hi1 = max(hi, nkb0) - nkb0;
   const KSeg s0{&tmdG, &tmU, a.dg_row0 + mb * BM, nb * BN, lo0 * BK, lo0 * BK, hi0 - lo0};
   const KSeg s1{&tmdY, &tmW, a.dy_row0 + mb * BM, nb * BN, lo1 * BK, lo1 * BK, hi1 - lo1};
-  if constexpr (PAIR) pair_mainloop<BN, STAGES>(c, s0, s1, crank & 1u, (uint16_t)(0x3u << (2 * rank)), early);
+  if constexpr (PAIR) pair_mainloop<BN, STAGES>(c, s0, s1, crank & 1u, (uint16_t)(flagx ? 0x3u : 0x3u << (2 * rank)), early);
   else tile_mainloop<BN, STAGES>(c, s0, s1, 0, 0, early);
   const int e = threadIdx.x - 64;
   const int N = a.N, N4 = 4 * a.N;
@@ -357,7 +361,24 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
       }
     }
   }
-  cluster_sync_all();                                      // all partial slices are written (cluster-scope release/acquire)
+  if (flagx) {
+    // the four ranks of this tile sit in four different clusters: announce our slices, wait for the other three
+    unsigned int* cnt = a.xcnt + (size_t)(mb * (a.N / BN) + nb);
+    if (c.warp >= 2 && c.warp < 6) named_bar_sync(2, 128);   // the four writer warps have issued their stores
+    if (threadIdx.x == 64) red_release_gpu_add(cnt, 1u);     // release: cumulative over the stores ordered by the barrier
+    if (c.warp == 6) {
+      const unsigned int target = (unsigned int)SPLIT * (unsigned int)a.epoch;
+      const long long t0 = clock64();
+      for (;;) {
+        const unsigned int v = c.lane == 0 ? ld_acquire_gpu(cnt) : target;
+        if (__all_sync(0xffffffffu, (int)(v - target) >= 0)) break;
+        if (clock64() - t0 > 4000000000LL) __trap();         // bounded: a protocol error must not hang the GPU
+      }
+    }
+    if (c.warp >= 2) named_bar_sync(1, EPI_THREADS);         // every reader is ordered after the acquire
+  } else {
+    cluster_sync_all();                                    // all partial slices are written (cluster-scope release/acquire)
+  }
   if (stamp) c.dbg[6] = clock64();
   if (c.warp >= 2) {
     // phase 2: lane = hidden unit; batches of RB rows with all global loads issued up front (latency-bound phase)
@@ -439,8 +460,8 @@ static void launch_bwd_t(const CUtensorMap& tmdG, const CUtensorMap& tmUkr, cons
   using F = BwdCfg<BN>;
   dim3 grid(a.N / BN, a.Bp / BM, SPLIT);
   if (bwd_pair(a.Bp)) {   // tmUkr / tmWnm boxes are BN/2 rows in this mode (bwd_box_rows)
-    launch_cluster(k_bwd_step<BN, true>, dim3(2 * grid.x, grid.y / 2, SPLIT), dim3(2, 1, SPLIT), BwdCfg<BN, true>::SMEM_BYTES, st,
-                   a.pin, a.pin_bytes, tmdG, tmUkr, tmdY, tmWnm, a);
+    launch_cluster(k_bwd_step<BN, true>, dim3(2 * grid.x, grid.y / 2, SPLIT), dim3(2, 1, a.flag_exchange ? 1 : SPLIT),
+                   BwdCfg<BN, true>::SMEM_BYTES, st, a.pin, a.pin_bytes, tmdG, tmUkr, tmdY, tmWnm, a);
     return;
   }
   launch_cluster(k_bwd_step<BN>, grid, dim3(1, 1, SPLIT), F::C::SMEM_BYTES, st, a.pin, a.pin_bytes, tmdG, tmUkr, tmdY, tmWnm, a);
@@ -449,6 +470,7 @@ void launch_bwd_step(int BN, const CUtensorMap& tmdG, const CUtensorMap& tmUkr, 
                      const CUtensorMap& tmWnm, const BwdStepArgs& a0, cudaStream_t st) {
   BwdStepArgs a = a0;
   a.early_b = early_b();
+  a.flag_exchange = (bwd_flag_exchange(a.Bp) && a.xcnt) ? 1 : 0;
   if (BN == 128) launch_bwd_t<128>(tmdG, tmUkr, tmdY, tmWnm, a, st);
   else if (BN == 64) launch_bwd_t<64>(tmdG, tmUkr, tmdY, tmWnm, a, st);
   else launch_bwd_t<32>(tmdG, tmUkr, tmdY, tmWnm, a, st);
