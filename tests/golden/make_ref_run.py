@@ -46,6 +46,7 @@ BIN_CLASS = os.path.join(ROOT, "oracle", "_ref", "lstm_class_batch_ref")
 CLASS_SEED, CLASS_CORPUS_BYTES, CLASS_EPOCHS, CLASS_B, CLASS_S = 42, 3000, 2, 4, 5
 PROGRAMS = {   # binary, file name the program opens, committed corpus it is a prefix of
     "lstm.cc": (BIN, "alice29.txt", "alice29_head.bin"),
+    "lstm.cc+fma": (os.path.join(ROOT, "oracle", "_ref", "lstm_ref_fma"), "alice29.txt", "alice29_head.bin"),
     "lstm_eigen_class_batch": (BIN_CLASS, "alice29.txt", "alice29_head.bin"),
     # lstm_segment.cc trains on the file called "lstm.h" in its working directory (:50): it gets prose, not source
     "lstm_segment": (os.path.join(ROOT, "oracle", "_ref", "lstm_segment_ref"), "lstm.h", "alice29_head.bin"),

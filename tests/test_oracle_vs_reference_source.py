@@ -288,3 +288,20 @@ def test_live_batched_reference_binary_matches_the_oracle(enwik6):
     for e, (a, sampled) in enumerate(replay_batched_with_oracle(enwik6[:L], 5, 2, positions, 4, 3)):
         assert f"{a:.3f}" == avg[e]
         assert sampled == gen[e]
+
+
+@pytest.mark.skipif(not (os.path.exists("/root/reference/lstm.cc") and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "lstm_ref_fma"))),
+                    reason="needs the reference checkout and `make -C oracle ref` (build container only)")
+def test_the_reference_source_does_not_reproduce_itself_under_another_rounding():
+    """Why the 1e-4-per-step bar over 1000 free-running iterations is ill-posed: the SAME unmodified
+    R/lstm.cc, same seeds, compiled once with and once without FMA contraction — two equally valid float evaluations of
+    its expressions.  The epoch losses agree to the 3 decimals the program prints (the runs are statistically the same
+    training), but the sampled text, which depends on the exact weights, no longer matches: the trajectory has diverged
+    in its low bits within the first epoch."""
+    from tests.golden import make_ref_run as mk
+    a = mk.parse(mk.run_reference(seed=1234, corpus_bytes=3000, epochs=2, program="lstm.cc"))
+    b = mk.parse(mk.run_reference(seed=1234, corpus_bytes=3000, epochs=2, program="lstm.cc+fma"))
+    for e in range(2):
+        assert abs(float(a[2][e]) - float(b[2][e])) <= 0.005          # same training, statistically
+    same = [sum(x == y for x, y in zip(a[3][e], b[3][e])) for e in range(2)]
+    assert same[0] < 1000 and same[1] < 900, same                       # but not the same weights any more
