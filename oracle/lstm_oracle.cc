@@ -5,7 +5,8 @@
 // --impl reference leg).  Nothing under eigen_lstm_b200/ may include, link or call it.
 //
 // Parity status: PINNED.
-//   * Against the reference's own SOURCE: four UNMODIFIED reference programs — R/lstm.cc, OV/lstm_eigen_BLAS/lstm.cc (its
+//   * Against the reference's own SOURCE: all six UNMODIFIED CPU programs of the reference — R/lstm.cc, OV/lstm_eigen_opt,
+//     OV/lstm_eigen_class, OV/lstm_eigen_BLAS/lstm.cc (its
 //     pure-Eigen branch, B = 4), OV/lstm_eigen_class_batch/lstm.cc + lstm.h (double precision, softmax shift, gradient
 //     check) and OV/lstm_eigen_class_batch/lstm_segment.cc (window stride > 1) — are compiled by `make -C oracle ref` into
 //     oracle/_ref/.  Their one external dependency, Eigen, is not installed in this image (no network), so they are built

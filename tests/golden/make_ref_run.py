@@ -50,6 +50,8 @@ PROGRAMS = {   # binary, file name the program opens, committed corpus it is a p
     "lstm_eigen_class_batch": (BIN_CLASS, "alice29.txt", "alice29_head.bin"),
     # lstm_segment.cc trains on the file called "lstm.h" in its working directory (:50): it gets prose, not source
     "lstm_segment": (os.path.join(ROOT, "oracle", "_ref", "lstm_segment_ref"), "lstm.h", "alice29_head.bin"),
+    "lstm_eigen_opt": (os.path.join(ROOT, "oracle", "_ref", "lstm_eigen_opt_ref"), "alice29.txt", "alice29_head.bin"),
+    "lstm_eigen_class": (os.path.join(ROOT, "oracle", "_ref", "lstm_eigen_class_ref"), "alice29.txt", "alice29_head.bin"),
     "lstm_eigen_BLAS": (BIN_BLAS, "enwik5.txt", "enwik6_head.bin"),
 }
 
@@ -148,6 +150,29 @@ def main():
                    "REF_SEED=7, cwd holding a file named lstm.h = first 3001 bytes of R/alice29.txt")
     json.dump(doc, open(os.path.join(HERE, "ref_lstm_segment_run.json"), "w"), indent=1)
     print("\n".join(epoch_lines[:SEG["epochs"]]))
+
+    # the two remaining CPU snapshots: OV/lstm_eigen_opt (f32, "batched" with B = 1, S = 5, 2000 sampled characters) and
+    # OV/lstm_eigen_class (double, N = 20, S = 50, B = 1, FULL numerical gradient check at the end of every epoch: slow, 1 epoch)
+    OPT = dict(seed=321, corpus_bytes=2500, epochs=3, B=1, S=5, N=64)
+    libc.srand(1)
+    OPT["positions"] = [libc.rand() % (OPT["corpus_bytes"] - OPT["S"]) + OPT["S"]]
+    out = run_reference(OPT["seed"], OPT["corpus_bytes"], OPT["epochs"], program="lstm_eigen_opt")
+    read_line, epoch_lines, avg, gen, _ = parse(out)
+    assert all(len(g) == 2000 for g in gen[:OPT["epochs"]])
+    json.dump(dict(OPT, read_line=read_line, epoch_lines=epoch_lines[:OPT["epochs"]], avg_loss=avg[:OPT["epochs"]],
+                   generated_b64=[base64.b64encode(g).decode() for g in gen[:OPT["epochs"]]],
+                   how="oracle/_ref/lstm_eigen_opt_ref = unmodified OV/lstm_eigen_opt/lstm.cc + oracle/eigen_shim, REF_SEED=321"),
+              open(os.path.join(HERE, "ref_lstm_eigen_opt_run.json"), "w"), indent=1)
+    print("\n".join(epoch_lines[:OPT["epochs"]]))
+    CLS = dict(seed=55, corpus_bytes=2000, epochs=1, B=1, S=50, N=20)
+    out = run_reference(CLS["seed"], CLS["corpus_bytes"], CLS["epochs"], program="lstm_eigen_class")
+    read_line, epoch_lines, avg, gen, _ = parse(out)
+    assert all(len(g) == 2500 for g in gen[:CLS["epochs"]])
+    json.dump(dict(CLS, read_line=read_line, epoch_lines=epoch_lines[:CLS["epochs"]], avg_loss=avg[:CLS["epochs"]],
+                   generated_b64=[base64.b64encode(g).decode() for g in gen[:CLS["epochs"]]],
+                   how="oracle/_ref/lstm_eigen_class_ref = unmodified OV/lstm_eigen_class/lstm.cc + lstm.h + oracle/eigen_shim, REF_SEED=55"),
+              open(os.path.join(HERE, "ref_lstm_eigen_class_run.json"), "w"), indent=1)
+    print("\n".join(epoch_lines[:CLS["epochs"]]))
 
 
 if __name__ == "__main__":

@@ -255,6 +255,43 @@ def test_strided_windows_reproduce_the_segment_reference_programs_output(alice):
         assert sampled == base64.b64decode(f["generated_b64"][e]), f"epoch {e + 1}: sampled text differs"
 
 
+def test_the_two_remaining_cpu_snapshots_are_reproduced_too(alice):
+    """OV/lstm_eigen_opt/lstm.cc (f32, B = 1, S = 5: the first batched snapshot) through the batched replay, and
+    OV/lstm_eigen_class/lstm.cc (double, N = 20, S = 50, shift-built window like R/lstm.cc, loss in nats over all
+    timesteps / (S * length), h and c ~ N(0, 0.01) per epoch, full numerical gradient check at the end of the epoch)."""
+    f = json.load(open(os.path.join(GOLDEN, "ref_lstm_eigen_opt_run.json")))
+    for e, (avg, sampled) in enumerate(replay_batched_with_oracle(alice[: f["corpus_bytes"]], f["seed"], f["epochs"], f["positions"],
+                                                                  f["B"], f["S"])):
+        assert f"{avg:.3f}" == f["avg_loss"][e]
+        assert sampled == base64.b64decode(f["generated_b64"][e])
+    f = json.load(open(os.path.join(GOLDEN, "ref_lstm_eigen_class_run.json")))
+    text, N, S_, seed = alice[: f["corpus_bytes"]], f["N"], f["S"], f["seed"]
+    L = len(text)
+    o = orc.Oracle(M, N, S_, 1, "f64")
+    o.set_options(dense_onehot=1)
+    o.set_params([orc.randn_d(4 * N, M, 0, 0.01, seed), orc.randn_d(4 * N, N, 0, 0.01, seed + 1), np.zeros((4 * N, 1)),
+                  orc.randn_d(M, N, 0, 0.01, seed + 2), np.zeros((M, 1))])
+    o.set_positions([S_])
+    k = seed + 3
+    for e in range(f["epochs"]):
+        h, c = orc.randn_d(N, S_, 0, 0.01, k), orc.randn_d(N, S_, 0, 0.01, k + 1)     # OV/lstm_eigen_class/lstm.cc:85-86
+        for t in range(S_):
+            o.set_state("h", t, h[:, t]); o.set_state("c", t, c[:, t])
+        losses, _ = o.train(text, L - S_, stride=1, lr=0.1)
+        # the program sums -ln p over all timesteps (:118-127); the oracle's trace is in bits.  Its numerical gradient check
+        # (:112-113) perturbs every entry in turn and ends on W(4N-1, 255): byte 255 is not in the window, so the state it
+        # leaves behind is the unperturbed one.
+        epoch_loss = 0.0
+        for v in losses:
+            epoch_loss += v * math.log(2.0) / (S_ * L)
+        assert f"{epoch_loss:.3f}" == f["avg_loss"][e]
+        one = orc.Oracle(M, N, S_, 1, "f64")
+        one.set_params(o.params())
+        sampled = one.sample(orc.randn_d(N, 1, 0, 0.01, k + 2), orc.randn_d(N, 1, 0, 0.01, k + 3), k + 4, 2500).tobytes()
+        k += 5
+        assert sampled == base64.b64decode(f["generated_b64"][e])
+
+
 def test_progress_fields_follow_the_reference_format():
     # "%7.2f%%\r" every 100 iterations (R/lstm.cc:274-279), i = 100, 200, ... of a 3000-byte corpus
     L = FIX["corpus_bytes"]
