@@ -59,6 +59,20 @@ struct FwdPersistArgs {
   long long* dbg;              // optional clock64 stamps of CTA (0,0) around one timestep (NULL = off)
 };
 
+// persistent BPTT recurrence (tc_persist.cu, experimental): all T timesteps in one launch
+struct BwdPersistArgs {
+  int B, Bp, N, M, T;
+  const float* Gp;             // [T][B][4N r'] activated gates
+  const float* Cs;             // [(T+1)][B][N]
+  __nv_bfloat16* dGbf;         // [T][Bp][4N r']: slot t (= dg(t+1)) read by TMA, slot t-1 written by timestep t
+  __nv_bfloat16* dGT;          // [4N][T*Bp]: timestep t writes columns [(t-1)*Bp, t*Bp)
+  long ldg;
+  float* red;                  // split-K exchange scratch (same layout as BwdStepArgs::red)
+  unsigned int* bar;           // grid-barrier arrival counters (same buffer as the forward variant; zeroed by the launcher)
+  int bar_stride;
+  int writer_fence;
+};
+
 struct LogitsArgs {
   int B, Bp, N, M, T;
   const float* by;             // [M]
@@ -121,6 +135,9 @@ void launch_fwd_step(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, c
 // experimental persistent variant of K2 (LSTM_PERSIST_FWD=1): returns false if the shape cannot run persistently
 bool fwd_persist_enabled();
 bool launch_fwd_persist(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdPersistArgs& a, cudaStream_t st);
+bool bwd_persist_enabled();
+bool launch_bwd_persist(int BN, const CUtensorMap& tmdG, const CUtensorMap& tmUkr, const CUtensorMap& tmdY, const CUtensorMap& tmWnm,
+                        const BwdPersistArgs& a, cudaStream_t st);
 // K3: logits + softmax + loss + dy for all timesteps
 void launch_logits(const CUtensorMap& tmH, const CUtensorMap& tmWmn, const LogitsArgs& a, cudaStream_t st);
 // K5: one BPTT timestep.  BN in {32, 64, 128} hidden units per CTA.

@@ -238,7 +238,16 @@ int tc_backward(lstm_ctx* ctx) {
   int rc = lstm_allreduce_bucket(ctx, 1);
   if (rc) return rc;
   if (tc::bwd_flag_exchange(s->Bp)) LSTM_CUDA(cudaMemsetAsync(s->xcnt, 0, s->xcnt_bytes, ctx->st));
-  for (int t = T; t >= 1; t--) {
+  bool persistent = false;
+  if (tc::bwd_persist_enabled() && !ctx->profiling) {   // experimental: the whole BPTT recurrence in one persistent launch
+    tc::BwdPersistArgs pa;
+    pa.B = B; pa.Bp = s->Bp; pa.N = N; pa.M = M; pa.T = T;
+    pa.Gp = s->Gp; pa.Cs = ctx->Cs; pa.dGbf = s->dGbf; pa.dGT = s->dGT; pa.ldg = s->LDT; pa.red = s->red;
+    pa.bar = s->gbar; pa.bar_stride = 1; pa.writer_fence = 1;
+    persistent = tc::launch_bwd_persist(s->BN5, s->tmdG, s->tmUkr, s->tmdY, s->tmWnm, pa, ctx->st);
+    if (persistent) LSTM_LAUNCHED(1);
+  }
+  for (int t = T; t >= 1 && !persistent; t--) {
     tc::BwdStepArgs a;
     a.B = B; a.Bp = s->Bp; a.N = N; a.M = M;
     a.first = (t == T);
@@ -256,7 +265,7 @@ int tc_backward(lstm_ctx* ctx) {
     a.pin = s->Ukr; a.pin_bytes = s->pin_bytes;
     tc::launch_bwd_step(s->BN5, s->tmdG, s->tmUkr, s->tmdY, s->tmWnm, a, ctx->st);
   }
-  LSTM_LAUNCHED(T);
+  if (!persistent) LSTM_LAUNCHED(T);
   PROF(5);
   // K6a+b: [dW | dU | db](r, col) = sum_(s,b) dG^T[r][(s,b)] * [X^T ; H^T ; 1][col][(s,b)]  — the flat gradient
   // vector's first three tensors are exactly this column-major 4N x (M+N+1) matrix.

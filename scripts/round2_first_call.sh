@@ -34,6 +34,10 @@ done
 echo "== 3. K5 as CTA pairs in clusters of 2 with the counter-ordered split-K exchange"
 LSTM_BWD_PAIR=2 timeout 120 python -m pytest tests/test_gpu_parity_bf16.py -x -q 2>&1 | tail -3 | tee $OUT/r02a_pytest_bwdpair2.txt
 LSTM_BWD_PAIR=2 timeout 120 $B > $OUT/r02a_bench_bwdpair2.json 2> $OUT/r02a_bench_bwdpair2.err; line $OUT/r02a_bench_bwdpair2.json
+echo "== 3b. persistent BPTT recurrence (LSTM_PERSIST_BWD=1): parity first, then the bench (identical loss = still correct)"
+LSTM_PERSIST_BWD=1 timeout 120 python -m pytest tests/test_gpu_parity_bf16.py -x -q 2>&1 | tail -3 | tee $OUT/r02a_pytest_persist_bwd.txt
+LSTM_PERSIST_BWD=1 timeout 120 $B > $OUT/r02a_bench_persist_bwd.json 2> $OUT/r02a_bench_persist_bwd.err; line $OUT/r02a_bench_persist_bwd.json
+LSTM_PERSIST_BWD=1 LSTM_PERSIST_FWD=1 timeout 120 $B > $OUT/r02a_bench_persist_both.json 2> $OUT/r02a_bench_persist_both.err; line $OUT/r02a_bench_persist_both.json
 echo "== 4. grid barrier microbenchmark"
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/gridbar scripts/gridbar_bench.cu && timeout 30 /tmp/gridbar 128 2000 | tee $OUT/r02a_gridbar.txt
 echo "== 5. regression checks the end of round 1 could not run (DESIGN section 9, item 5)"
