@@ -16,6 +16,8 @@ SYMBOLS = {
     "lstm_destroy": (_i, [_vp]),
     "lstm_last_error": (C.c_char_p, [_vp]),
     "lstm_sync": (_i, [_vp]),
+    "lstm_set_option": (_i, [_vp, _i, C.c_double]),
+    "lstm_debug_variant": (_i, [_vp, _vp]),
     "lstm_tensor_size": (C.c_long, [_vp, _i]),
     "lstm_set_tensor": (_i, [_vp, _i, _i, _vp, _sz]),
     "lstm_get_tensor": (_i, [_vp, _i, _i, _vp, _sz]),

@@ -161,6 +161,7 @@ extern "C" int lstm_create(lstm_ctx** out, int M, int N, int S, int B, int devic
     CREATE_CUDA(cudaMalloc(&ctx->dY, T * B * (size_t)M * sizeof(float)));
     CREATE_CUDA(cudaMalloc(&ctx->dHy, T * BN * sizeof(float)));
     CREATE_CUDA(cudaMalloc(&ctx->dcnext, BN * sizeof(float)));
+    CREATE_CUDA(cudaMalloc(&ctx->logit_shift, T * sizeof(float)));
   }
   CREATE_CUDA(cudaMalloc(&ctx->surp, T * B * sizeof(float)));
   CREATE_CUDA(cudaMalloc(&ctx->xs, (size_t)S * B * sizeof(int)));
@@ -201,7 +202,7 @@ extern "C" int lstm_destroy(lstm_ctx* ctx) {
   if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
   if (ctx->tc) tc_destroy(ctx);
   void* bufs[] = {ctx->params, ctx->grads, ctx->mem, ctx->Hs, ctx->Cs, ctx->Gs, ctx->dY, ctx->dHy, ctx->dG,
-                  ctx->dcnext, ctx->surp, ctx->xs, ctx->tg, ctx->d_loss, ctx->text, ctx->pos0, ctx->vcount};
+                  ctx->dcnext, ctx->surp, ctx->xs, ctx->tg, ctx->d_loss, ctx->text, ctx->pos0, ctx->vcount, ctx->logit_shift};
   for (void* b : bufs) if (b) cudaFree(b);
   if (ctx->h_loss_pinned) cudaFreeHost(ctx->h_loss_pinned);
   if (ctx->h_xs_pinned) cudaFreeHost(ctx->h_xs_pinned);
@@ -233,6 +234,37 @@ extern "C" long lstm_tensor_size(const lstm_ctx* ctx, int which) {
 }
 extern "C" long lstm_launch_count(const lstm_ctx* ctx) { return ctx ? ctx->launches : -1; }
 extern "C" void* lstm_stream(lstm_ctx* ctx) { return ctx ? (void*)ctx->st : nullptr; }
+
+extern "C" int lstm_set_option(lstm_ctx* ctx, int key, double value) {
+  if (!ctx) return LSTM_ERR_ARG;
+  switch (key) {
+    case LSTM_OPT_CLIP:
+      if (!(value >= 0.0)) return lstm_fail(ctx, LSTM_ERR_ARG, "clip must be >= 0 (0 = off)");
+      ctx->clip = (float)value;
+      break;
+    case LSTM_OPT_LOSS_MODE:
+      if (value != 0.0 && value != 1.0) return lstm_fail(ctx, LSTM_ERR_ARG, "loss mode: 0 = log2 over all timesteps, 1 = last timestep in nats");
+      ctx->loss_mode = (int)value;
+      break;
+    case LSTM_OPT_SOFTMAX_SHIFT:
+      if (value != 0.0 && value != 1.0) return lstm_fail(ctx, LSTM_ERR_ARG, "softmax shift: 0 = none, 1 = global maximum of the timestep");
+      ctx->softmax_shift = (int)value;
+      break;
+    default:
+      return lstm_fail(ctx, LSTM_ERR_ARG, "unknown option key");
+  }
+  LSTM_CUDA(cudaSetDevice(ctx->device));
+  LSTM_CUDA(cudaStreamSynchronize(ctx->st));
+  drop_graphs(ctx);   // options are baked into the captured iteration
+  return LSTM_OK;
+}
+
+extern "C" int lstm_debug_variant(lstm_ctx* ctx, int out[8]) {
+  if (!ctx || !out) return LSTM_ERR_ARG;
+  for (int i = 0; i < 8; i++) out[i] = 0;
+  if (ctx->tc) tc_variant(ctx, out);
+  return LSTM_OK;
+}
 
 static float* tensor_ptr(lstm_ctx* ctx, int kind, int which) {
   if (which < 0 || which > 4) return nullptr;
@@ -370,10 +402,14 @@ static int forward_device(lstm_ctx* ctx) {
     PROF(2);
     // K3: Y[(t,b)][m] = sum_n H[(t,b)][n] * Why(m,n) + by[m]            (R/lstm.cc:195)
     launch_gemm_f32(ctx->Hslot(1), N, 1, ctx->p(LSTM_WHY), M, 1, ctx->dY, M, 1, ctx->p(LSTM_BY), T * B, M, N, ctx->st);
-    launch_softmax_ce_f32(ctx->dY, ctx->tg + B, ctx->surp, T * B, M, ctx->st);
+    if (ctx->softmax_shift) {
+      launch_logit_max_f32(ctx->dY, ctx->logit_shift, T, B * M, ctx->st);
+      LSTM_LAUNCHED(1);
+    }
+    launch_softmax_ce_f32(ctx->dY, ctx->tg + B, ctx->surp, T * B, M, ctx->softmax_shift ? ctx->logit_shift : nullptr, B, ctx->st);
     LSTM_LAUNCHED(2);
   }
-  launch_loss_reduce(ctx->surp, T, B, ctx->d_loss, ctx->loss_cap, ctx->d_iter, ctx->st);
+  launch_loss_reduce(ctx->surp, T, B, ctx->d_loss, ctx->loss_cap, ctx->d_iter, ctx->loss_mode, ctx->st);
   LSTM_LAUNCHED(1);
   PROF(3);
   ctx->fwd_done = true;
@@ -523,7 +559,7 @@ static int iteration_body(lstm_ctx* ctx, int mode, int stride, float lr) {
   if (rc) return rc;
   rc = backward_device(ctx);
   if (rc) return rc;
-  rc = adagrad_device(ctx, lr, 1e-10, 0.f);
+  rc = adagrad_device(ctx, lr, 1e-10, ctx->clip);
   if (rc) return rc;
   return lstm_carry_state(ctx, stride);   // slot 0 now holds the state the next window starts from
 }
@@ -542,16 +578,20 @@ static int run_iteration(lstm_ctx* ctx, int mode, int stride, float lr) {
   lstm_ctx::IterGraph& g = ctx->graph[mode];
   const bool dp = ctx->world > 1;
   if ((g.exec || !g.segs.empty()) && (g.stride != stride || g.lr != lr)) free_iter_graph(g);
-  ctx->fwd_count++;
-  ctx->iteration++;
+  // the host mirrors of the device counters (fwd_count ~ *d_iter, iteration) move only once the iteration is enqueued
+  struct Bump { lstm_ctx* c; bool ok = false; ~Bump() { if (ok) { c->fwd_count++; c->iteration++; } } } bump{ctx};
   if (ctx->profiling || no_graph || (dp && !dp_graph)) {
     PROF(0);
-    return iteration_body(ctx, mode, stride, lr);
+    int rc = iteration_body(ctx, mode, stride, lr);
+    bump.ok = rc == LSTM_OK;
+    return rc;
   }
   if (!g.exec && g.segs.empty()) {
     if (g.warm == 0 || g.stride != stride || g.lr != lr) {   // first time: plain launches (also sets kernel attributes)
       g.warm = 1; g.stride = stride; g.lr = lr;
-      return iteration_body(ctx, mode, stride, lr);
+      int rc = iteration_body(ctx, mode, stride, lr);
+      bump.ok = rc == LSTM_OK;
+      return rc;
     }
     const long l0 = ctx->launches;
     LSTM_CUDA(cudaStreamBeginCapture(ctx->st, cudaStreamCaptureModeThreadLocal));
@@ -593,6 +633,7 @@ static int run_iteration(lstm_ctx* ctx, int mode, int stride, float lr) {
     }
   }
   ctx->launches += g.launches;
+  bump.ok = true;
   return LSTM_OK;
 }
 
@@ -604,9 +645,9 @@ extern "C" int lstm_forward(lstm_ctx* ctx, const int32_t* x_idx, const int32_t* 
   if (rc) return rc;
   rc = window_h2d(ctx);
   if (rc) return rc;
-  ctx->fwd_count++;
   rc = forward_device(ctx);
   if (rc) return rc;
+  ctx->fwd_count++;
   if (loss_out) return fetch_loss(ctx, loss_out);
   return LSTM_OK;
 }
@@ -720,9 +761,9 @@ extern "C" int lstm_train_text(lstm_ctx* ctx, int iters, int stride, float lr, d
   if (rc) return rc;
   const uint64_t first = ctx->fwd_count;
   for (int it = 0; it < iters; it++) {
-    ctx->v_host += stride;
     rc = run_iteration(ctx, 0, stride, lr);
     if (rc) return rc;
+    ctx->v_host += stride;   // host mirror of *vcount: moves only once the iteration is enqueued
   }
   rc = finish_profile(ctx);
   if (rc) return rc;
@@ -885,6 +926,8 @@ extern "C" int lstm_gradcheck(lstm_ctx* ctx, const int32_t* x_idx, const int32_t
                               int* passed) {
   if (!ctx) return LSTM_ERR_ARG;
   if (per_tensor < 1 || !(delta > 0.0) || !report) return lstm_fail(ctx, LSTM_ERR_ARG, "lstm_gradcheck: need per_tensor >= 1, delta > 0, report");
+  if (ctx->world > 1)
+    return lstm_fail(ctx, LSTM_ERR_STATE, "lstm_gradcheck on a data-parallel context: backward sums gradients over ranks, the numeric side sees the local window only");
   LSTM_CUDA(cudaSetDevice(ctx->device));
   // An all-zero TARGET column (-1, the window warm-up of R/lstm.cc:124,169) contributes nothing to the loss (:204) but
   // dy = probs - 0 still enters the reference's gradients (:225): there the analytic gradient is, by the reference's own
@@ -1108,6 +1151,10 @@ extern "C" int lstm_load_bin(lstm_ctx* ctx, const char* path) {
   fclose(f);
   if (!ok) return lstm_fail(ctx, LSTM_ERR_IO, "truncated checkpoint");
   LSTM_CUDA(cudaSetDevice(ctx->device));
+  {  // in-flight iterations (lstm_train_text is asynchronous) and allreduces must not land on the restored tensors
+    int src = lstm_sync(ctx);
+    if (src) return src;
+  }
   LSTM_CUDA(cudaMemcpy(ctx->params, pbuf.data(), ctx->P * sizeof(float), cudaMemcpyHostToDevice));
   LSTM_CUDA(cudaMemcpy(ctx->mem, mbuf.data(), ctx->P * sizeof(float), cudaMemcpyHostToDevice));
   int rc = lstm_set_state(ctx, hb.data(), cb.data());

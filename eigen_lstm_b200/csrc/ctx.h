@@ -23,6 +23,11 @@ struct lstm_ctx {
   float *Hs = nullptr, *Cs = nullptr, *Gs = nullptr, *dY = nullptr, *dHy = nullptr, *dG = nullptr;
   float *dcnext = nullptr, *surp = nullptr;
   int *xs = nullptr, *tg = nullptr;
+  // options (lstm_set_option): clip <= 0 = off (the reference); loss_mode 0 = log2 over all timesteps, 1 = last timestep in nats;
+  // softmax_shift 0 = none (R/lstm.cc:199-201), 1 = the timestep's global maximum (OV/lstm_eigen_class_batch/lstm.h:175)
+  float clip = 0.f;
+  int loss_mode = 0, softmax_shift = 0;
+  float* logit_shift = nullptr;   // [T] (fp32 path, softmax_shift = 1)
   double* d_loss = nullptr;  // [loss_cap] ring of per-iteration losses, slot = iteration % loss_cap
   size_t loss_cap = 0;
   unsigned long long* d_iter = nullptr;  // device-side forward counter (owned by k_loss_reduce)
@@ -35,7 +40,7 @@ struct lstm_ctx {
     cudaGraphExec_t exec = nullptr;
     std::vector<cudaGraphExec_t> segs;
     std::vector<int> seg_bucket;
-    int stride = 0; float lr = 0.f; long launches = 0; int warm = 0;
+    int stride = 0; float lr = 0.f; float clip = 0.f; long launches = 0; int warm = 0;
   } graph[2];
   IterGraph* seg_capture = nullptr;      // non-null while run_iteration captures a segmented graph
   int32_t *h_xs_pinned = nullptr, *h_tg_pinned = nullptr;
@@ -100,5 +105,6 @@ int tc_state_from_f32(lstm_ctx* ctx);  // Hs slot 0 (fp32) -> bf16 operand copie
 int tc_state_to_f32(lstm_ctx* ctx);    // bf16 h(0) -> Hs slot 0
 int tc_carry(lstm_ctx* ctx, int stride);
 int tc_debug_read(lstm_ctx* ctx, long long out[32]);
+void tc_variant(lstm_ctx* ctx, int out[8]);   // which kernel instantiations this context's shape selects
 // sum gradient bucket (0 = [W,U,b], 1 = [Why,by]) over the data-parallel ranks on the communication stream
 int lstm_allreduce_bucket(lstm_ctx* ctx, int bucket);

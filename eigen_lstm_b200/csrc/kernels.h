@@ -30,9 +30,13 @@ void launch_step_bwd_f32(const float* U, const float* dg_next, const float* dHy_
 void launch_gemm_f32(const float* A, long a_si, long a_sk, const float* Bm, long b_sk, long b_sj, float* C,
                      long c_si, long c_sj, const float* bias_j, int I, int J, int K, cudaStream_t st);
 // rows of `y` ([rows][M] logits) -> p - onehot(tg) in place; surp[row] = -log2 p[tg] (0 if tg < 0)
-void launch_softmax_ce_f32(float* y, const int* tg, float* surp, int rows, int M, cudaStream_t st);
+// shift (optional): [rows / B] value subtracted from every logit of the timestep before exp (global-max softmax shift)
+void launch_softmax_ce_f32(float* y, const int* tg, float* surp, int rows, int M, const float* shift, int B, cudaStream_t st);
+// shift[t] = max over the timestep's per_t = B*M logits (OV/lstm_eigen_class_batch/lstm.h:175)
+void launch_logit_max_f32(const float* y, float* shift, int T, int per_t, cudaStream_t st);
 // loss = sum_t (float)(sum_b surp[t][b]) / B  -> ring[*iter % cap] (double); *iter += 1
-void launch_loss_reduce(const float* surp, int T, int B, double* ring, size_t cap, unsigned long long* iter, cudaStream_t st);
+// mode 1: last timestep only, natural log (OV/lstm_eigen_class_batch/lstm.cc:308-319)
+void launch_loss_reduce(const float* surp, int T, int B, double* ring, size_t cap, unsigned long long* iter, int mode, cudaStream_t st);
 // dW[m*4N + r] = sum over (t,b) with xs[t][b] == m of dG[t][b][r]   (R/lstm.cc:251 for one-hot x)
 void launch_dw_scatter_f32(const float* dG, const int* xs, float* dW, int rows, int N4, int M, cudaStream_t st);
 // out[j] = sum_i X[i*J + j]

@@ -239,14 +239,17 @@ void launch_gemm_f32(const float* A, long a_si, long a_sk, const float* Bm, long
 //   dy = p - onehot(target).  One warp per (t,b) row.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_softmax_ce_f32(float* __restrict__ y, const int* __restrict__ tg,
-                                                        float* __restrict__ surp, int rows, int M) {
+                                                        float* __restrict__ surp, int rows, int M,
+                                                        const float* __restrict__ shift, int B) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   float* yr = y + (size_t)row * M;
+  // shift != NULL: OV/lstm_eigen_class_batch/lstm.h:175 subtracts the maximum of the timestep's whole M x B logit matrix
+  const float sh = shift ? shift[row / B] : 0.f;
   float s = 0.f;
   for (int m = lane; m < M; m += 32) {
-    const float e = expf(yr[m]);
+    const float e = expf(shift ? __fsub_rn(yr[m], sh) : yr[m]);
     yr[m] = e;
     s += e;
   }
@@ -261,16 +264,36 @@ __global__ void __launch_bounds__(256) k_softmax_ce_f32(float* __restrict__ y, c
   if (k < 0 && lane == 0) surp[row] = 0.f;
 }
 
-void launch_softmax_ce_f32(float* y, const int* tg, float* surp, int rows, int M, cudaStream_t st) {
-  k_softmax_ce_f32<<<(rows + 7) / 8, 256, 0, st>>>(y, tg, surp, rows, M);
+// maximum logit of every timestep's [B][M] block (the "global" softmax shift of OV/lstm_eigen_class_batch/lstm.h:175)
+__global__ void __launch_bounds__(256) k_logit_max_f32(const float* __restrict__ y, float* __restrict__ shift, int n) {
+  __shared__ float red[8];
+  const float* yt = y + (size_t)blockIdx.x * n;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += 256) mx = fmaxf(mx, yt[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; w++) mx = fmaxf(mx, red[w]);
+    shift[blockIdx.x] = mx;
+  }
+}
+
+void launch_softmax_ce_f32(float* y, const int* tg, float* surp, int rows, int M, const float* shift, int B, cudaStream_t st) {
+  k_softmax_ce_f32<<<(rows + 7) / 8, 256, 0, st>>>(y, tg, surp, rows, M, shift, B);
+}
+void launch_logit_max_f32(const float* y, float* shift, int T, int per_t, cudaStream_t st) {
+  k_logit_max_f32<<<T, 256, 0, st>>>(y, shift, per_t);
 }
 
 // loss = sum_t (float)(sum_b surp[t][b]) / (float)B    (OV/lstm_eigen_opt/lstm.cc:246-249)
 // The result goes to ring[*iter % cap] and the kernel bumps *iter itself, so a captured CUDA graph of one training
 // iteration can be replayed unchanged.
+// mode 1 (OV/lstm_eigen_class_batch/lstm.cc:308-319): the LAST timestep only, in nats: sum_b -ln p[target] / B
 __global__ void __launch_bounds__(1024) k_loss_reduce(const float* __restrict__ surp, int T, int B,
                                                       double* __restrict__ ring, unsigned long long cap,
-                                                      unsigned long long* __restrict__ iter) {
+                                                      unsigned long long* __restrict__ iter, int mode) {
   extern __shared__ float st_sum[];  // [T]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int t = warp; t < T; t += 32) {
@@ -283,15 +306,16 @@ __global__ void __launch_bounds__(1024) k_loss_reduce(const float* __restrict__ 
   __syncthreads();
   if (threadIdx.x == 0) {
     double l = 0.0;
-    for (int t = 0; t < T; t++) l += (double)st_sum[t];
+    if (mode == 1) l = (double)st_sum[T - 1] * 0.6931471805599453;
+    else for (int t = 0; t < T; t++) l += (double)st_sum[t];
     const unsigned long long it = iter[0];
     ring[it % cap] = l;
     iter[0] = it + 1;
   }
 }
 
-void launch_loss_reduce(const float* surp, int T, int B, double* ring, size_t cap, unsigned long long* iter, cudaStream_t st) {
-  k_loss_reduce<<<1, 1024, T * sizeof(float), st>>>(surp, T, B, ring, (unsigned long long)cap, iter);
+void launch_loss_reduce(const float* surp, int T, int B, double* ring, size_t cap, unsigned long long* iter, int mode, cudaStream_t st) {
+  k_loss_reduce<<<1, 1024, T * sizeof(float), st>>>(surp, T, B, ring, (unsigned long long)cap, iter, mode);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -40,6 +40,7 @@ struct FwdStepArgs {
   long long* dbg;              // optional: clock64 stamps of CTA (0,0) for diagnostics (NULL = off)
   const void* pin; size_t pin_bytes;   // recurrent weights (Urk): L2-persisting access window of this launch
   int early_b;                 // weight tiles of the pipeline fill are issued before griddepcontrol.wait (set by the launcher)
+  int l2hint;                  // bit 0: weight loads evict_last, bit 1: activation loads evict_first (set by the launcher)
 };
 
 // persistent forward recurrence (tc_persist.cu, experimental): all T timesteps in one launch
@@ -98,6 +99,7 @@ struct BwdStepArgs {
   long long* dbg;              // optional: clock64 stamps of CTA (0,0,0) for diagnostics (NULL = off)
   const void* pin; size_t pin_bytes;   // recurrent weights (Ukr): L2-persisting access window of this launch
   int early_b;                 // see FwdStepArgs
+  int l2hint;
   // LSTM_BWD_PAIR=2 (experimental): cta_group::2 pairs in clusters of 2 only; the four split-K ranks of a tile are then
   // different clusters and exchange their partial sums through `red` ordered by a per-tile arrival counter
   // (red.release.gpu / ld.acquire.gpu) instead of the cluster barrier.  xcnt[tile] is zeroed once per iteration and

@@ -281,6 +281,17 @@ int tc_backward(lstm_ctx* ctx) {
   return lstm_allreduce_bucket(ctx, 0);
 }
 
+void tc_variant(lstm_ctx* ctx, int out[8]) {
+  Bf16State* s = ctx->tc;
+  out[0] = s->BN2;
+  out[1] = tc::step_pair(s->Bp) ? 1 : 0;
+  out[2] = s->BN5;
+  out[3] = tc::bwd_pair(s->Bp) ? (tc::bwd_flag_exchange(s->Bp) ? 2 : 1) : 0;
+  out[4] = (ctx->M + ctx->N + 1 >= 1024) ? 256 : 128;
+  out[5] = tc::fwd_persist_enabled() ? 1 : 0;
+  out[6] = tc::bwd_persist_enabled() ? 1 : 0;
+}
+
 int tc_debug_read(lstm_ctx* ctx, long long out[32]) {
   Bf16State* s = ctx->tc;
   if (!s || !s->dbg) return lstm_fail(ctx, LSTM_ERR_STATE, "set LSTM_TC_DEBUG=1 before lstm_create (bf16 contexts only)");

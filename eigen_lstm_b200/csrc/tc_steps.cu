@@ -65,6 +65,8 @@ k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUte
     pdl_wait();              // everything below reads what the previous timestep's kernel wrote
   }
   c.dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0) ? a.dbg : nullptr;
+  if (a.l2hint & 1) c.hint_b = L2_EVICT_LAST;
+  if (a.l2hint & 2) c.hint_a = L2_EVICT_FIRST;
   const bool stamp = c.dbg && threadIdx.x == 64;
   if (stamp) { c.dbg[0] = t_entry; c.dbg[4] = clock64(); }
   float* acc = reinterpret_cast<float*>(c.epi);
@@ -261,6 +263,7 @@ static void launch_fwd_t(const CUtensorMap& tmH, const CUtensorMap& tmUrk, const
 void launch_fwd_step(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a0, cudaStream_t st) {
   FwdStepArgs a = a0;
   a.early_b = early_b();
+  a.l2hint = env_int("LSTM_L2HINT", 0);
   if (BN == 128) launch_fwd_t<128>(tmH, tmUrk, a, st);
   else if (BN == 64) launch_fwd_t<64>(tmH, tmUrk, a, st);
   else launch_fwd_t<32>(tmH, tmUrk, a, st);
@@ -306,6 +309,8 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
     pdl_wait();
   }
   c.dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? a.dbg : nullptr;
+  if (a.l2hint & 1) c.hint_b = L2_EVICT_LAST;
+  if (a.l2hint & 2) c.hint_a = L2_EVICT_FIRST;
   const bool stamp = c.dbg && threadIdx.x == 64;
   if (stamp) { c.dbg[0] = t_entry; c.dbg[4] = clock64(); }
   float* recv = reinterpret_cast<float*>(c.epi);
@@ -470,6 +475,7 @@ void launch_bwd_step(int BN, const CUtensorMap& tmdG, const CUtensorMap& tmUkr, 
                      const CUtensorMap& tmWnm, const BwdStepArgs& a0, cudaStream_t st) {
   BwdStepArgs a = a0;
   a.early_b = early_b();
+  a.l2hint = env_int("LSTM_L2HINT", 0);
   a.flag_exchange = (bwd_flag_exchange(a.Bp) && a.xcnt) ? 1 : 0;
   if (BN == 128) launch_bwd_t<128>(tmdG, tmUkr, tmdY, tmWnm, a, st);
   else if (BN == 64) launch_bwd_t<64>(tmdG, tmUkr, tmdY, tmWnm, a, st);

@@ -32,7 +32,16 @@ struct TileCtx {
   uint64_t *full, *empty, *accum_full;
   uint32_t tmem_d;
   int warp, lane;
+  uint64_t hint_a, hint_b;   // L2 eviction-priority hints of the A / B operand loads (0 = none)
 };
+__device__ __forceinline__ void tma_ld(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, uint64_t hint) {
+  if (hint) tma_load_2d_hint(dst, tm, bar, c0, c1, hint);
+  else tma_load_2d(dst, tm, bar, c0, c1);
+}
+__device__ __forceinline__ void tma_ld_pair(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, uint64_t hint) {
+  if (hint) tma_load_2d_pair_hint(dst, tm, bar, c0, c1, hint);
+  else tma_load_2d_pair(dst, tm, bar, c0, c1);
+}
 
 // Common prologue: carve shared memory, init barriers, allocate TMEM.
 // CN x CM = thread-block cluster sharing operand tiles by TMA multicast (tile_mainloop): a stage of this CTA is
@@ -42,6 +51,7 @@ __device__ __forceinline__ TileCtx tile_prologue(uint8_t* raw) {
   using C = Cfg<BN, STAGES>;
   TileCtx c;
   c.dbg = nullptr;
+  c.hint_a = c.hint_b = 0;
   const uint32_t base = smem_u32(raw);
   const uint32_t pad = ((base + 1023u) & ~1023u) - base;   // SWIZZLE_128B atoms need 1024-byte alignment
   c.tiles = raw + pad;
@@ -113,7 +123,7 @@ __device__ __forceinline__ void tile_mainloop(const TileCtx& c, const KSeg& s0, 
           const int k = first ? kb : kb - s0.nkb;
           uint8_t* b = c.tiles + (size_t)kb * C::STAGE_BYTES + A_TILE_BYTES;
           mbar_expect_tx(&c.full[kb], (uint32_t)C::STAGE_BYTES);   // armed once for both operands of the stage
-          tma_load_2d(b, s.tb, &c.full[kb], s.b_k0 + k * BK, s.b_row);
+          tma_ld(b, s.tb, &c.full[kb], s.b_k0 + k * BK, s.b_row, c.hint_b);
         }
         __syncwarp();
       }
@@ -130,10 +140,10 @@ __device__ __forceinline__ void tile_mainloop(const TileCtx& c, const KSeg& s0, 
         uint8_t* a = c.tiles + (size_t)st * C::STAGE_BYTES;
         uint8_t* b = a + A_TILE_BYTES;
         if (kb >= pre) mbar_expect_tx(&c.full[st], (uint32_t)C::STAGE_BYTES);
-        if (CN == 1) tma_load_2d(a, s.ta, &c.full[st], s.a_k0 + k * BK, s.a_row);
+        if (CN == 1) tma_ld(a, s.ta, &c.full[st], s.a_k0 + k * BK, s.a_row, c.hint_a);
         else tma_load_2d_mc(a + xr * A_ROWS * 128, s.ta, &c.full[st], s.a_k0 + k * BK, s.a_row + xr * A_ROWS, mask_a);
         if (kb >= pre) {
-          if (CM == 1) tma_load_2d(b, s.tb, &c.full[st], s.b_k0 + k * BK, s.b_row);
+          if (CM == 1) tma_ld(b, s.tb, &c.full[st], s.b_k0 + k * BK, s.b_row, c.hint_b);
           else tma_load_2d_mc(b + yr * B_ROWS * 128, s.tb, &c.full[st], s.b_k0 + k * BK, s.b_row + yr * B_ROWS, mask_b);
         }
       }
@@ -183,6 +193,7 @@ __device__ __forceinline__ TileCtx pair_prologue(uint8_t* raw) {
   using C = PairCfg<BN, STAGES>;
   TileCtx c;
   c.dbg = nullptr;
+  c.hint_a = c.hint_b = 0;
   const uint32_t base = smem_u32(raw);
   const uint32_t pad = ((base + 1023u) & ~1023u) - base;
   c.tiles = raw + pad;
@@ -237,7 +248,7 @@ __device__ __forceinline__ void pair_mainloop(const TileCtx& c, const KSeg& s0, 
           const int k = first ? kb : kb - s0.nkb;
           uint8_t* b = c.tiles + (size_t)kb * C::STAGE_BYTES + A_TILE_BYTES;
           if (rank == 0) mbar_expect_tx(&c.full[kb], 2u * (uint32_t)C::STAGE_BYTES);
-          tma_load_2d_pair(b, s.tb, &c.full[kb], s.b_k0 + k * BK, s.b_row + (int)rank * (BN / 2));
+          tma_ld_pair(b, s.tb, &c.full[kb], s.b_k0 + k * BK, s.b_row + (int)rank * (BN / 2), c.hint_b);
         }
         __syncwarp();
       }
@@ -254,8 +265,8 @@ __device__ __forceinline__ void pair_mainloop(const TileCtx& c, const KSeg& s0, 
         uint8_t* a = c.tiles + (size_t)st * C::STAGE_BYTES;
         uint8_t* b = a + A_TILE_BYTES;
         if (rank == 0 && kb >= pre) mbar_expect_tx(&c.full[st], 2u * (uint32_t)C::STAGE_BYTES);   // both CTAs' bytes land on the leader's barrier
-        tma_load_2d_pair(a, s.ta, &c.full[st], s.a_k0 + k * BK, s.a_row);
-        if (kb >= pre) tma_load_2d_pair(b, s.tb, &c.full[st], s.b_k0 + k * BK, s.b_row + (int)rank * (BN / 2));
+        tma_ld_pair(a, s.ta, &c.full[st], s.a_k0 + k * BK, s.a_row, c.hint_a);
+        if (kb >= pre) tma_ld_pair(b, s.tb, &c.full[st], s.b_k0 + k * BK, s.b_row + (int)rank * (BN / 2), c.hint_b);
       }
       __syncwarp();
     }

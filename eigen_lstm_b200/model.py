@@ -221,6 +221,25 @@ class LSTM:
                  "allreduce_wait", "adagrad", "total"]
         return dict(zip(names, a[:9].tolist()))
 
+    # ---- options of the training path (include/lstm_b200.h LSTM_OPT_*) ----
+    def set_clip(self, clip):
+        self._ck(self.lib.lstm_set_option(self.ctx, 0, float(clip)))
+
+    def set_loss_mode(self, mode):
+        """'log2-all' (R/lstm.cc:204-207) or 'last-ln' (OV/lstm_eigen_class_batch/lstm.cc:308-319)."""
+        self._ck(self.lib.lstm_set_option(self.ctx, 1, float({"log2-all": 0, "last-ln": 1}[mode])))
+
+    def set_softmax_shift(self, mode):
+        """'none' (R/lstm.cc:199-201) or 'global' (OV/lstm_eigen_class_batch/lstm.h:175)."""
+        self._ck(self.lib.lstm_set_option(self.ctx, 2, float({"none": 0, "global": 1}[mode])))
+
+    def variant(self):
+        """Kernel instantiations this context's shape selects (bf16 contexts), see lstm_debug_variant."""
+        a = np.zeros(8, dtype=np.int32)
+        self._ck(self.lib.lstm_debug_variant(self.ctx, _ptr(a)))
+        keys = ["fwd_bn", "fwd_pair", "bwd_bn", "bwd_variant", "wgrad_bn", "fwd_persistent", "bwd_persistent"]
+        return dict(zip(keys, a[:7].tolist()))
+
     def launch_count(self):
         return int(self.lib.lstm_launch_count(self.ctx))
 

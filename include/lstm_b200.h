@@ -44,6 +44,16 @@ enum { LSTM_F32 = 0,      /* fp32 SIMT FFMA everywhere: the parity path (1e-4 re
  * OV/lstm_eigen_class_CUDA/cu_lstm.h:398-415) */
 enum { LSTM_ACT_H = 0, LSTM_ACT_C = 1, LSTM_ACT_G = 2, LSTM_ACT_PROBS = 3, LSTM_ACT_DHY = 4, LSTM_ACT_DG = 5 };
 
+/* option keys for lstm_set_option */
+enum { LSTM_OPT_CLIP = 0,           /* gradient clipping fused into Adagrad for lstm_train_step / lstm_train_text: each gradient
+                                     * entry is clamped to [-clip, clip] first; 0 = off = the reference (R/lstm.cc:259-272) */
+       LSTM_OPT_LOSS_MODE = 1,      /* reported loss: 0 = sum_t (sum_b -log2 p_t[k_t]) / B (R/lstm.cc:204-207, OV/lstm_eigen_opt/
+                                     * lstm.cc:246-249); 1 = the LAST timestep only, natural log: (sum_b -ln p_{S-1}[k]) / B
+                                     * (OV/lstm_eigen_class_batch/lstm.cc:308-319).  Gradients flow from all timesteps either way. */
+       LSTM_OPT_SOFTMAX_SHIFT = 2 };/* 0 = exp(y) unshifted (R/lstm.cc:199-201); 1 = the maximum of the timestep's whole M x B logit
+                                     * matrix is subtracted first (OV/lstm_eigen_class_batch/lstm.h:175).  LSTM_F32 only: the bf16
+                                     * path always subtracts each column's own maximum (the same probabilities up to rounding). */
+
 /* error codes */
 enum { LSTM_OK = 0, LSTM_ERR_ARG = -1, LSTM_ERR_CUDA = -2, LSTM_ERR_STATE = -3, LSTM_ERR_IO = -4,
        LSTM_ERR_NCCL = -5, LSTM_ERR_UNSUPPORTED = -6 };
@@ -56,6 +66,8 @@ int lstm_create(lstm_ctx** out, int M, int N, int S, int B, int device, int dtyp
 int lstm_destroy(lstm_ctx* ctx);
 const char* lstm_last_error(const lstm_ctx* ctx);   /* ctx may be NULL: error of the last failed lstm_create */
 int lstm_sync(lstm_ctx* ctx);                       /* wait for the context's stream */
+/* options of the training path (see LSTM_OPT_*); drops captured iteration graphs */
+int lstm_set_option(lstm_ctx* ctx, int key, double value);
 /* elements of tensor `which` (rows*cols), or <0 */
 long lstm_tensor_size(const lstm_ctx* ctx, int which);
 
@@ -168,6 +180,11 @@ int lstm_get_phase_ms(lstm_ctx* ctx, float ms[16]);
  * [2] first operand stage landed, [1] last TMA issued, [3] last MMA issued, [5] accumulator complete, [6] tile
  * re-mapped through shared memory / cluster reduce done, [7] LSTM math + stores done, [8] exit */
 int lstm_debug_kernel_clocks(lstm_ctx* ctx, long long out[32]);
+/* which kernel instantiations this context's shape selects (bf16 contexts; zeros otherwise), so that parity tests can assert
+ * that they cover the variants the benchmark runs: [0] K2 gate columns per CTA (BN), [1] K2 as cta_group::2 pairs,
+ * [2] K5 hidden units per tile, [3] K5 variant (0 = split-K cluster of 4, 1 = pairs + 8-way split-K), [4] K6a tile width,
+ * [5] K2 persistent, [6] K5 persistent, [7] reserved */
+int lstm_debug_variant(lstm_ctx* ctx, int out[8]);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 long lstm_launch_count(const lstm_ctx* ctx);
 /* raw CUDA stream (cudaStream_t) of the context, for callers that time with their own events */

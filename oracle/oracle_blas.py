@@ -43,6 +43,7 @@ class BlasOracle:
         self.target = [z(M, B) for _ in range(S)]
         self.probs = [z(M, B) for _ in range(S)]
         self.grads = None
+        self.dg = [None] * S        # per-timestep gate gradients of the last backward (differential tests)
 
     def set_params(self, params):
         self.W, self.U, self.b, self.Why, self.by = [_f(np.array(p, copy=True)) for p in params]
@@ -102,6 +103,7 @@ class BlasOracle:
             dg[3 * N:] = dc * g[:N]                                  # du   :316
             dg[:3 * N] *= g[:3 * N] * (1.0 - g[:3 * N])              # :319-320
             dg[3 * N:] *= 1.0 - g[3 * N:] * g[3 * N:]                # :323-324
+            self.dg[t] = dg
             dU += dg @ self.h[t - 1].T                               # :327
             dW += dg @ self.x[t].T                                   # :328 (dense, like the reference)
             db += dg.sum(axis=1, keepdims=True)                      # :335

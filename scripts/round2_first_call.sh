@@ -62,4 +62,19 @@ c.train_text(8, S - 1, 0.05); c.save_bin(path); lc = c.train_text(5, S - 1, 0.05
 d = el.LSTM(M, N, S, B, dtype=el.BF16); d.load_text(enwik); d.load_bin(path); ld = d.train_text(5, S - 1, 0.05)
 print("bf16 save_bin/load_bin resume bit-exact:", bool(np.array_equal(lc, ld)))
 PY
+echo "== 6. K2 operand-sharing A/B (after the elect.sync fix): no pair / multicast clusters"
+for V in "LSTM_PAIR=0" "LSTM_FWD_CN=2" "LSTM_FWD_CN=4" "LSTM_FWD_CN=4 LSTM_FWD_CM=2" "LSTM_FWD_CN=2 LSTM_FWD_CM=2" "LSTM_NO_L2PIN=1" "LSTM_NO_PDL=1"; do
+  F=$OUT/r02a_bench_$(echo $V | tr ' =' '__').json
+  env $V timeout 120 $B > $F 2> ${F%.json}.err
+  echo -n "   $V: "; line $F
+done
+echo "== 7. in-kernel clock stamps of the default per-step kernels"
+LSTM_TC_DEBUG=1 timeout 60 python scripts/kernel_clocks.py cfg4 2>&1 | tail -3 | tee $OUT/r02a_kernel_clocks.txt
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv | tee $OUT/r02a_smi.txt
+python - <<'PY' | tee $OUT/r02a_devprops.txt
+import torch
+p = torch.cuda.get_device_properties(0)
+print(p)
+print("L2", p.L2_cache_size, "smem/SM", p.shared_memory_per_multiprocessor, "smem/block optin", p.shared_memory_per_block_optin)
+PY
 echo "== done; copy what is worth keeping from gpurun_out/r02a_* into profiles/"

@@ -1,0 +1,90 @@
+"""The kernel instantiations the BENCHMARK runs, against the oracle.
+
+`pick_bn` (csrc/tc_path.cu) chooses the tile width from the number of CTAs a shape yields, so the small shapes of
+tests/test_gpu_parity_bf16.py all resolve to the narrowest instantiation.  Here the hidden size and batch are those of
+BASELINE.json's configurations (window shortened to S = 3 so the CPU side finishes in seconds), the test ASSERTS which
+variant the library selected (lstm_debug_variant), and every intermediate and all five gradients are compared —
+the reference's own practice of running both implementations in lock-step and diffing every matrix
+(OV/lstm_eigen_CUDA/lstm.cu:416-497,564-648).  CPU side: oracle/oracle_blas.py (the lstm_eigen_BLAS structure on
+numpy's BLAS, itself checked against the C++ oracle in tests/test_oracle_blas.py)."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from oracle import oracle_blas as ob
+from tests.util import random_window
+
+pytestmark = pytest.mark.gpu
+
+
+def frob_rel(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+# (N, S, B, expected variant): config 4, the BN = 64 middle case, config 3, config 2
+CASES = [
+    (2048, 3, 256, dict(fwd_bn=128, fwd_pair=1, wgrad_bn=256)),
+    (1024, 3, 256, dict(fwd_bn=64, fwd_pair=1, wgrad_bn=256)),
+    (1024, 4, 128, dict(fwd_bn=32, fwd_pair=0, wgrad_bn=256)),
+    (512, 4, 64, dict(fwd_bn=32, fwd_pair=0, wgrad_bn=128)),
+]
+
+
+def _pair(M, N, S, B, seed):
+    import eigen_lstm_b200 as el
+    sd = 0.5 / np.sqrt(N)                      # pre-activations of O(1) whatever the width
+    params = orc.init_params(M, N, seed=seed, sd=sd, forget_bias=0.5)
+    rng = np.random.default_rng(seed + 100)
+    params[2] = (params[2] + rng.normal(0, 0.1, params[2].shape)).astype(np.float32)
+    params[4] = rng.normal(0, 0.1, params[4].shape).astype(np.float32)
+    q = ob.BlasOracle(M, N, S, B)
+    q.set_params(params)
+    g = el.LSTM(M, N, S, B, dtype=el.BF16)
+    g.set_params(params)
+    h0 = rng.normal(0, 0.3, (N, B)).astype(np.float32)
+    c0 = rng.normal(0, 0.3, (N, B)).astype(np.float32)
+    q.h[0][...] = h0; q.c[0][...] = c0
+    g.set_state(h0, c0)
+    return q, g
+
+
+@pytest.mark.parametrize("N,S,B,want", CASES)
+def test_benchmark_instantiations_vs_oracle(N, S, B, want):
+    M = 256
+    q, g = _pair(M, N, S, B, seed=3)
+    v = g.variant()
+    for k, val in want.items():
+        assert v[k] == val, (k, v)
+    rng = np.random.default_rng(5)
+    x, t = random_window(rng, M, S, B)
+    q.set_window(x, t)
+    lq = q.forward()
+    lg = g.forward(x, t)
+    assert abs(lg - lq) <= 2e-2 * abs(lq), (lg, lq)
+    for tt in range(1, S):
+        assert np.max(np.abs(g.activation("g", tt) - q.g[tt])) < 4e-2, ("g", tt)
+        assert np.max(np.abs(g.activation("c", tt) - q.c[tt])) < 4e-2, ("c", tt)
+        assert np.max(np.abs(g.activation("h", tt) - q.h[tt])) < 4e-2, ("h", tt)
+        assert np.max(np.abs(g.activation("probs", tt) - q.probs[tt])) < 2e-2, ("probs", tt)
+    q.backward()
+    g.backward()
+    for tt in range(S - 1, 0, -1):
+        assert frob_rel(g.activation("dg", tt), q.dg[tt]) < 6e-2, ("dg", tt)
+    for name, a, b in zip(orc.NAMES, g.grads(), q.grads):
+        assert frob_rel(a, b) < 6e-2, name
+
+
+def test_benchmark_shape_training_iterations_follow_the_oracle():
+    """Five full iterations (forward, BPTT, Adagrad, carry) at config 4's width and batch: graph capture + replay included."""
+    M, N, S, B = 256, 2048, 3, 256
+    q, g = _pair(M, N, S, B, seed=9)
+    rng = np.random.default_rng(1)
+    for it in range(5):
+        x, t = random_window(rng, M, S, B, nulls=False)
+        q.set_window(x, t)
+        lq = q.forward(); q.backward(); q.adagrad(0.002); q.carry(S - 1)
+        lg = g.train_step(x, t, stride=S - 1, lr=0.002)
+        assert abs(lg - lq) <= 3e-2 * abs(lq), (it, lg, lq)
+    for name, a, b in zip(orc.NAMES, g.params(), q.params()):
+        assert frob_rel(a, b) < 3e-2, name
