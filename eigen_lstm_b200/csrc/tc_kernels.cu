@@ -255,6 +255,32 @@ void launch_state_to_f32(const __nv_bfloat16* Hbf_slot, float* h, int B, int N, 
   launch_bf16_to_f32(Hbf_slot, h, (size_t)B * N, st);
 }
 
+// blocked copy of the BPTT weights (tc_recur.cu): one contiguous [bnj][64] block per (tile, k-block)
+__global__ void k_block_bwd_weights(const float* __restrict__ U, const float* __restrict__ Why, __nv_bfloat16* __restrict__ Wb,
+                                    int N, int M, int bnj, size_t total) {
+  const int N4 = 4 * N, nkbu = N4 / 64, nkbg = nkbu + M / 64;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx & 63);
+    const size_t q = idx >> 6;
+    const int row = (int)(q % bnj);
+    const size_t q2 = q / bnj;
+    const int kbg = (int)(q2 % nkbg), tile = (int)(q2 / nkbg);
+    const int j = tile * bnj + row;
+    float v;
+    if (kbg < nkbu) {
+      const int rp = kbg * 64 + c;                           // unit-major gate row r' = 4*unit + gate
+      v = U[(size_t)j * N4 + (size_t)(rp & 3) * N + (rp >> 2)];
+    } else {
+      v = Why[(size_t)j * M + (kbg - nkbu) * 64 + c];
+    }
+    Wb[idx] = __float2bfloat16_rn(v);
+  }
+}
+void launch_block_bwd_weights(const float* U, const float* Why, __nv_bfloat16* Wb, int N, int M, int bnj, cudaStream_t st) {
+  const size_t total = (size_t)N * (4 * (size_t)N + M);
+  k_block_bwd_weights<<<148 * 8, 256, 0, st>>>(U, Why, Wb, N, M, bnj, total);
+}
+
 template <typename T>
 __global__ void k_unpermute(const T* __restrict__ in, float* __restrict__ out, int N) {
   const int N4 = 4 * N;

@@ -74,6 +74,20 @@ struct BwdPersistArgs {
   int writer_fence;
 };
 
+// persistent BPTT recurrence (tc_recur.cu): all T timesteps in one launch, cta_group::2 pairs + KS-way split-K
+struct BwdRecurArgs {
+  int B, Bp, N, M, T;
+  const float* Gp;             // [T][B][4N r'] activated gates
+  const float* Cs;             // [(T+1)][B][N]
+  __nv_bfloat16* dGbf;         // [T][Bp][4N r']: slot t (= dg(t+1)) read by TMA, slot t-1 written by timestep t
+  __nv_bfloat16* dGT;          // [4N][T*Bp]: timestep t writes columns [(t-1)*Bp, t*Bp)
+  long ldg;
+  float* red;                  // split-K exchange scratch [tile][dst][src][8][128][4] fp32 (bwd_recur_red_floats)
+  unsigned int* xcnt;          // [N/BNJ * 2] per-(tile, batch half) arrival counters of the exchange (zeroed by the launcher)
+  unsigned int* gbar;          // [2][8] per-batch-half arrival counters of the dg barrier (zeroed by the launcher)
+  long long* dbg;              // optional clock64 stamps of CTA 0 around one timestep (NULL = off)
+};
+
 struct LogitsArgs {
   int B, Bp, N, M, T;
   const float* by;             // [M]
@@ -140,6 +154,14 @@ bool launch_fwd_persist(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk
 bool bwd_persist_enabled();
 bool launch_bwd_persist(int BN, const CUtensorMap& tmdG, const CUtensorMap& tmUkr, const CUtensorMap& tmdY, const CUtensorMap& tmWnm,
                         const BwdPersistArgs& a, cudaStream_t st);
+// persistent BPTT recurrence: bwd_recur_bnj() = hidden units per tile (256 | 128) if this shape runs persistently, else 0;
+// tmWb = the blocked weight copy [N/bnj][4N/64 + M/64][bnj][64] as a 2D map with a box of bnj/2 rows
+int bwd_recur_bnj(int N, int Bp, int M);
+size_t bwd_recur_red_floats(int N, int bnj);
+bool launch_bwd_recur(int bnj, const CUtensorMap& tmdG, const CUtensorMap& tmWb, const CUtensorMap& tmdY, const BwdRecurArgs& a,
+                      cudaStream_t st);
+// Wb[(tile*NKBG + kbg)*bnj + row][c]: kbg < 4N/64: U(r' = kbg*64 + c, j = tile*bnj + row), else Why(m = (kbg - 4N/64)*64 + c, j)
+void launch_block_bwd_weights(const float* U, const float* Why, __nv_bfloat16* Wb, int N, int M, int bnj, cudaStream_t st);
 // K3: logits + softmax + loss + dy for all timesteps
 void launch_logits(const CUtensorMap& tmH, const CUtensorMap& tmWmn, const LogitsArgs& a, cudaStream_t st);
 // K5: one BPTT timestep.  BN in {32, 64, 128} hidden units per CTA.

@@ -13,6 +13,10 @@ using bf16 = __nv_bfloat16;
 
 struct Bf16State {
   int Bp = 0, N4 = 0, RZ = 0, BN2 = 0, BN5 = 0;
+  int bnj5 = 0;                   // persistent BPTT recurrence (tc_recur.cu): hidden units per tile, 0 = per-timestep kernels
+  bf16* Wb5 = nullptr;            // its blocked weight copy
+  float* red5 = nullptr;
+  CUtensorMap tmWb5;
   long LDZ = 0, LDT = 0;
   bf16 *Hbf = nullptr, *Urk = nullptr, *Ukr = nullptr, *Wmn = nullptr, *Wnm = nullptr;
   bf16 *dYbf = nullptr, *dYT = nullptr, *dGbf = nullptr, *dGT = nullptr, *ZT = nullptr;
@@ -102,6 +106,12 @@ int tc_create(lstm_ctx* ctx) {
   s->xcnt_bytes = (size_t)(N / s->BN5) * (Bp / 128) * sizeof(unsigned int);
   TC_ALLOC(s->xcnt, s->xcnt_bytes);
   if (getenv("LSTM_TC_DEBUG")) TC_ALLOC(s->dbg, 32 * sizeof(long long));
+  s->bnj5 = tc::bwd_recur_bnj(N, s->Bp, M);
+  if (s->bnj5) {
+    TC_ALLOC(s->Wb5, (size_t)N * (N4 + M) * sizeof(bf16));
+    TC_ALLOC(s->red5, tc::bwd_recur_red_floats(N, s->bnj5) * sizeof(float));
+    if (s->xcnt_bytes < (size_t)(N / s->bnj5) * 2 * sizeof(unsigned int)) return lstm_fail(ctx, LSTM_ERR_STATE, "xcnt too small");
+  }
   tc::launch_fill_bf16(s->ZT + (size_t)(M + N) * s->LDZ, 1.0f, (size_t)s->LDZ, ctx->st);  // the ones row (db, dby)
   LSTM_LAUNCHED(1);
   {  // let the recurrent weight operand (one of Urk / Ukr at a time) persist in L2 across the timestep kernels
@@ -126,6 +136,7 @@ int tc_create(lstm_ctx* ctx) {
   ok &= make_tmap(&s->tmdGT, s->dGT, N4, s->LDT, 128);
   ok &= make_tmap(&s->tmZT, s->ZT, s->RZ, s->LDZ, 128);
   ok &= make_tmap(&s->tmZT256, s->ZT, s->RZ, s->LDZ, 256);
+  if (s->bnj5) ok &= make_tmap(&s->tmWb5, s->Wb5, (uint64_t)N * ((N4 + M) / 64), 64, (uint32_t)s->bnj5 / 2);
   if (!ok) return lstm_fail(ctx, LSTM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   return LSTM_OK;
 }
@@ -134,7 +145,7 @@ void tc_destroy(lstm_ctx* ctx) {
   Bf16State* s = ctx->tc;
   if (!s) return;
   void* bufs[] = {s->Hbf, s->Urk, s->Ukr, s->Wmn, s->Wnm, s->dYbf, s->dYT, s->dGbf, s->dGT, s->ZT, s->Wp, s->bp, s->Gp,
-                  s->dcnext, s->scratch, s->red, s->dbg, s->gbar, s->xcnt};
+                  s->dcnext, s->scratch, s->red, s->dbg, s->gbar, s->xcnt, s->Wb5, s->red5};
   for (void* b : bufs) if (b) cudaFree(b);
   delete s;
   ctx->tc = nullptr;
@@ -151,6 +162,10 @@ int tc_params_changed(lstm_ctx* ctx) {
   tc::launch_transpose_cast(ctx->p(LSTM_WHY), s->Wmn, N, M, 0, ctx->st);       // Wmn[m][n]
   tc::launch_cast_bf16(ctx->p(LSTM_WHY), s->Wnm, (size_t)M * N, ctx->st);      // Wnm[n][m]
   LSTM_LAUNCHED(6);
+  if (s->bnj5) {
+    tc::launch_block_bwd_weights(ctx->p(LSTM_U), ctx->p(LSTM_WHY), s->Wb5, N, M, s->bnj5, ctx->st);
+    LSTM_LAUNCHED(1);
+  }
   return LSTM_OK;
 }
 
@@ -239,7 +254,15 @@ int tc_backward(lstm_ctx* ctx) {
   if (rc) return rc;
   if (tc::bwd_flag_exchange(s->Bp)) LSTM_CUDA(cudaMemsetAsync(s->xcnt, 0, s->xcnt_bytes, ctx->st));
   bool persistent = false;
-  if (tc::bwd_persist_enabled() && !ctx->profiling) {   // experimental: the whole BPTT recurrence in one persistent launch
+  if (s->bnj5) {                                         // the whole BPTT recurrence in one persistent launch (tc_recur.cu)
+    tc::BwdRecurArgs pa;
+    pa.B = B; pa.Bp = s->Bp; pa.N = N; pa.M = M; pa.T = T;
+    pa.Gp = s->Gp; pa.Cs = ctx->Cs; pa.dGbf = s->dGbf; pa.dGT = s->dGT; pa.ldg = s->LDT; pa.red = s->red5;
+    pa.xcnt = s->xcnt; pa.gbar = s->gbar; pa.dbg = s->dbg ? s->dbg + 16 : nullptr;
+    persistent = tc::launch_bwd_recur(s->bnj5, s->tmdG, s->tmWb5, s->tmdY, pa, ctx->st);
+    if (persistent) LSTM_LAUNCHED(1);
+  }
+  if (!persistent && tc::bwd_persist_enabled() && !ctx->profiling) {   // experimental: the whole BPTT recurrence in one persistent launch
     tc::BwdPersistArgs pa;
     pa.B = B; pa.Bp = s->Bp; pa.N = N; pa.M = M; pa.T = T;
     pa.Gp = s->Gp; pa.Cs = ctx->Cs; pa.dGbf = s->dGbf; pa.dGT = s->dGT; pa.ldg = s->LDT; pa.red = s->red;
@@ -289,7 +312,7 @@ void tc_variant(lstm_ctx* ctx, int out[8]) {
   out[3] = tc::bwd_pair(s->Bp) ? (tc::bwd_flag_exchange(s->Bp) ? 2 : 1) : 0;
   out[4] = (ctx->M + ctx->N + 1 >= 1024) ? 256 : 128;
   out[5] = tc::fwd_persist_enabled() ? 1 : 0;
-  out[6] = tc::bwd_persist_enabled() ? 1 : 0;
+  out[6] = s->bnj5 ? s->bnj5 : (tc::bwd_persist_enabled() ? 1 : 0);
 }
 
 int tc_debug_read(lstm_ctx* ctx, long long out[32]) {

@@ -1,0 +1,414 @@
+// tc_recur.cu — the BPTT recurrence of a whole window as ONE persistent kernel (K5).
+//
+//   R/lstm.cc:223-257   for t = S-1 .. 1:  dh = Why^T dy(t) + U^T dg(t+1);  gate gradients;  dcnext
+//
+// Per timestep the contraction is D[b][j] = sum_r' dg(t+1)[b][r'] U[r'][j] + sum_m dy(t)[b][m] Why[m][j]: a 256 x N output
+// over K = 4N + M.  The output is tiny and K is long, so the work is split over K:
+//
+//   * tile = 256 streams x BNJ hidden units, computed by a cta_group::2 PAIR (each CTA owns 128 streams = 128 TMEM lanes and
+//     stages its own dg tile plus HALF of the weight tile: (128 + BNJ/2) operand rows per k-block instead of 128 + BNJ);
+//   * KS split-K ranks per tile; rank ks contracts NKB_U/KS k-blocks of U (+ one k-block of Why for ks < M/64);
+//   * grid = N/BNJ tiles x KS ranks pairs = 128 CTAs at N = 2048 for <256, 8> and <128, 4>, all co-resident for the whole
+//     window (one launch; every spin is bounded and traps instead of hanging).
+//
+// One timestep of a CTA (tile jt, rank ks, batch half mb):
+//   producer warp   weight tiles (and the dy / Why k-block, which no timestep produces) of the NEXT timestep are prefetched
+//                   while the epilogue still runs; the dg(t+1) tiles wait for the batch half's grid barrier (global arrival
+//                   counters, red.release.gpu / ld.acquire.gpu + fence.proxy.async: generic-proxy stores -> TMA reads)
+//   MMA warp        (pair leader) M = 256, N = BNJ tcgen05.mma into the pair's TMEM accumulator
+//   16 epilogue warps
+//     1. drain      TMEM -> the KS column slices of 32 hidden units: the own slice to shared memory, the other KS-1 to an
+//                   L2-resident exchange buffer laid out so that every warp store is 512 contiguous bytes
+//     2. exchange   one release-add on the tile's arrival counter; acquire-poll until all KS ranks have arrived
+//     3. reduce     every thread sums the KS partials of its float4 positions in a FIXED order (deterministic), coalesced
+//                   512-byte warp loads, all issued before the first use
+//     4. math       lane = hidden unit: gate gradients from the stashed activations; dcnext never leaves its registers;
+//                   dg(t) goes to the bf16 operand buffer (+ fence) and the batch half's barrier is released
+//     5. off the critical path: dg^T rows for the weight-gradient GEMM (K6a), coalesced through shared memory
+//
+// Weights are read from a BLOCKED copy (tc_path.cu: Wb5[tile][k-block][BNJ rows][64]) so that each TMA box is one contiguous
+// 8-16 KB run of memory instead of 64-128 rows 16 KB apart.
+#include <stdlib.h>
+
+#include "tc_kernels.cuh"
+#include "tc_tile.cuh"
+
+namespace tc {
+
+namespace {
+
+constexpr int R_EPI_WARPS = 16;
+constexpr int R_EPI_THREADS = R_EPI_WARPS * 32;
+constexpr int R_CTA_THREADS = 64 + R_EPI_THREADS;
+constexpr int R_HT_LD = 130;             // bf16 row pitch of the transposed staging tile: 65 words -> conflict-free
+constexpr int R_SLOTS = 8;               // arrival counters per batch half (spreads the same-address atomics)
+
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* local_bar, uint32_t cta_rank) {
+  const uint32_t addr = mapa_u32(smem_u32(local_bar), cta_rank);
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+// generic-proxy <-> async-proxy ordering for global memory
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+// whole warp: wait until the first `n` counters at `slots` (stride words apart) have all reached `target` (bounded)
+__device__ __forceinline__ void counters_wait(const unsigned int* slots, int n, unsigned int target, int lane) {
+  const long long t0 = clock64();
+  for (;;) {
+    const unsigned int v = lane < n ? ld_acquire_gpu(slots + lane) : target;
+    if (__all_sync(0xffffffffu, (int)(v - target) >= 0)) break;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+template <int BNJ, int KS>
+struct BwdRecurCfg {
+  static constexpr int STAGES = BNJ == 256 ? 4 : 5;
+  static constexpr int UO = BNJ / KS;                      // hidden units finalised by each CTA
+  static_assert(UO == 32, "the epilogue maps one warp lane to each of the 32 hidden units a CTA finalises");
+  using PC = PairCfg<BNJ, STAGES>;
+  static constexpr int DH_LD = UO + 4;                     // fp32 row pitch of the dh tile (16-byte aligned rows)
+  static constexpr int DH_BYTES = 128 * DH_LD * 4;
+  static constexpr int GT_BYTES = 4 * UO * R_HT_LD * 2;    // dg^T staging [gate*UO + unit][row]
+  static constexpr int ST_BYTES = 128 * UO * 8;            // per (stream, unit): dcnext and c(t), carried across timesteps
+  static constexpr int EPI_BYTES = DH_BYTES + GT_BYTES + ST_BYTES;
+  static constexpr int SMEM_BYTES = PC::TILE_BYTES + 1024 + 256 + (EPI_BYTES + 127) / 128 * 128;
+  static constexpr int CHUNKS_PER_WARP = KS / 4;           // 32-column slices each drain warp moves
+};
+
+// grid (2 * JT * KS), cluster (2,1,1): blockIdx.x & 1 = pair member = batch half
+template <int BNJ, int KS>
+__global__ void __launch_bounds__(R_CTA_THREADS, 1)
+k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUtensorMap tmWb,
+            const __grid_constant__ CUtensorMap tmdY, const BwdRecurArgs a) {
+  using F = BwdRecurCfg<BNJ, KS>;
+  using PC = typename F::PC;
+  constexpr int STAGES = F::STAGES, UO = F::UO, RG = R_EPI_THREADS / UO, ROWS = 128 / RG, DH_LD = F::DH_LD;
+  extern __shared__ uint8_t smem_raw[];
+  TileCtx c = pair_prologue<BNJ, STAGES>(smem_raw);
+  uint64_t* tmem_free = c.accum_full + 2;                    // (leader) both CTAs have read the accumulator out of TMEM
+  if (threadIdx.x == 0) { mbar_init(tmem_free, 2); fence_barrier_init(); }
+  __syncthreads();
+  cluster_sync_all();
+  const uint32_t rank = cluster_ctarank();                   // pair member = batch half
+  const int mb = (int)rank;
+  const int pairi = (int)(blockIdx.x >> 1);
+  const int jt = pairi / KS, ks = pairi - jt * KS;
+  const int N = a.N, N4 = 4 * a.N, B = a.B, T = a.T;
+  const int nkbu = N4 / BK / KS;                             // U k-blocks per rank and timestep
+  const int nkbw = (ks < a.M / BK) ? 1 : 0;                  // one Why k-block for the first M/64 ranks
+  const int NKBG = N4 / BK + a.M / BK;                       // k-blocks per tile in the blocked weight copy
+  const int wrow0 = jt * NKBG * BNJ + (int)rank * (BNJ / 2); // + kbg * BNJ
+  const int tile = jt * 2 + mb;
+  unsigned int* my_slots = a.gbar + (size_t)mb * R_SLOTS;
+  unsigned int* xcnt = a.xcnt + tile;
+  const unsigned int per_slot = (unsigned int)(gridDim.x / 2 / R_SLOTS);   // arrivals per counter and timestep
+  float* red_tile = a.red + (size_t)tile * KS * KS * 8 * 128 * 4;          // [dst][src][u][row][4]
+  long long* dbg = (a.dbg && blockIdx.x == 0) ? a.dbg : nullptr;
+  constexpr int DBG_S = 4;                                   // the timestep (0-based from the end of the window) that is stamped
+
+  if (c.warp == 0) {
+    // ---------------- producer ----------------
+    if (elect_one()) { tma_prefetch_desc(&tmdG); tma_prefetch_desc(&tmWb); tma_prefetch_desc(&tmdY); }
+    __syncwarp();
+    int g = 0;                                               // k-blocks issued so far (ring position)
+    for (int s = 0; s < T; s++) {
+      const int t = T - s;
+      const int nu = s == 0 ? 0 : nkbu;                      // dg(T+1) = 0: the first timestep has no U part
+      const int total = nkbw + nu;
+      // Phase A: everything of this timestep that no other CTA produces: the dy / Why k-block completely, and the weight
+      // tiles of the first U k-blocks (as many as fit in the ring)
+      const int pre = total < STAGES ? total : STAGES;
+      for (int i = 0; i < pre; i++) {
+        const int st = (g + i) % STAGES;
+        const uint32_t ph = (uint32_t)((g + i) / STAGES) & 1u;
+        mbar_wait(&c.empty[st], ph ^ 1u);
+        if (elect_one()) {
+          uint8_t* adst = c.tiles + (size_t)st * PC::STAGE_BYTES;
+          if (rank == 0) mbar_expect_tx(&c.full[st], 2u * (uint32_t)PC::STAGE_BYTES);
+          if (i < nkbw) {
+            tma_load_2d_pair_hint(adst + A_TILE_BYTES, &tmWb, &c.full[st], 0, wrow0 + (N4 / BK + ks) * BNJ, L2_EVICT_LAST);
+            tma_load_2d_pair(adst, &tmdY, &c.full[st], ks * BK, (t - 1) * a.Bp + mb * BM);
+          } else {
+            const int kbg = ks * nkbu + (i - nkbw);
+            tma_load_2d_pair_hint(adst + A_TILE_BYTES, &tmWb, &c.full[st], 0, wrow0 + kbg * BNJ, L2_EVICT_LAST);
+          }
+        }
+        __syncwarp();
+      }
+      if (s > 0) {                                           // dg(t+1) of this batch half is complete in global memory
+        if (dbg && c.lane == 0 && (s == DBG_S || s == DBG_S + 1)) dbg[s == DBG_S ? 0 : 8] = clock64();
+        counters_wait(my_slots, R_SLOTS, (unsigned int)s * per_slot, c.lane);
+        fence_proxy_async_global();                          // generic-proxy writes (observed via acquire) -> async-proxy reads
+        if (dbg && c.lane == 0 && s == DBG_S) dbg[1] = clock64();
+      }
+      for (int i = nkbw; i < total; i++) {
+        const int st = (g + i) % STAGES;
+        const uint32_t ph = (uint32_t)((g + i) / STAGES) & 1u;
+        const int kbg = ks * nkbu + (i - nkbw);
+        if (i >= pre) mbar_wait(&c.empty[st], ph ^ 1u);
+        if (elect_one()) {
+          uint8_t* adst = c.tiles + (size_t)st * PC::STAGE_BYTES;
+          if (i >= pre) {
+            if (rank == 0) mbar_expect_tx(&c.full[st], 2u * (uint32_t)PC::STAGE_BYTES);
+            tma_load_2d_pair_hint(adst + A_TILE_BYTES, &tmWb, &c.full[st], 0, wrow0 + kbg * BNJ, L2_EVICT_LAST);
+          }
+          tma_load_2d_pair(adst, &tmdG, &c.full[st], kbg * BK, t * a.Bp + mb * BM);
+        }
+        __syncwarp();
+      }
+      g += total;
+    }
+  } else if (c.warp == 1) {
+    // ---------------- MMA issuer (leader CTA of the pair) ----------------
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BNJ);
+      const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(c.tiles));
+      const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(c.tiles) + A_TILE_BYTES);
+      int g = 0, used = 0;                                   // used = timesteps that produced an accumulator so far
+      for (int s = 0; s < T; s++) {
+        const int total = nkbw + (s == 0 ? 0 : nkbu);
+        if (total == 0) continue;
+        if (used > 0) {                                      // both CTAs have drained the previous accumulator
+          mbar_wait_cluster(tmem_free, (uint32_t)(used - 1) & 1u);
+          tcgen05_after_sync();
+        }
+        for (int i = 0; i < total; i++) {
+          const int st = (g + i) % STAGES;
+          const uint32_t ph = (uint32_t)((g + i) / STAGES) & 1u;
+          mbar_wait(&c.full[st], ph);
+          if (dbg && c.lane == 0 && s == DBG_S && i == nkbw) dbg[2] = clock64();
+          tcgen05_after_sync();
+          if (elect_one()) {
+            const uint64_t soff = (uint64_t)((uint32_t)st * (uint32_t)(PC::STAGE_BYTES >> 4));
+#pragma unroll
+            for (int k = 0; k < BK / 16; k++)
+              umma_bf16_pair(c.tmem_d, a_desc0 + soff + 2 * k, b_desc0 + soff + 2 * k, idesc, (uint32_t)((i | k) != 0));
+            umma_commit_pair(&c.empty[st], (uint16_t)0x3);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit_pair(c.accum_full, (uint16_t)0x3);
+        __syncwarp();
+        if (dbg && c.lane == 0 && s == DBG_S) dbg[3] = clock64();
+        g += total;
+        used++;
+      }
+    }
+  } else {
+    // ---------------- epilogue ----------------
+    float* dh = reinterpret_cast<float*>(c.epi);             // [128][DH_LD]: own partial slice, then the summed dh
+    __nv_bfloat16* gT = reinterpret_cast<__nv_bfloat16*>(c.epi + F::DH_BYTES);
+    const int e = threadIdx.x - 64;
+    const int w = e >> 5, lane = e & 31;
+    const int quarter = c.warp & 3;                          // the TMEM lane quarter this warp may read
+    const int cgrp = w >> 2;                                 // which of the four column groups of this quarter's warps
+    const int l = e % UO, rg = e / UO;
+    const int j = jt * BNJ + ks * UO + l;                    // the hidden unit this thread finalises
+    // dcnext and c(t) of this thread's (stream, unit) pairs live in shared memory for the whole window: [q][thread] float2
+    float2* carry = reinterpret_cast<float2*>(c.epi + F::DH_BYTES + F::GT_BYTES);
+#pragma unroll
+    for (int q = 0; q < ROWS; q++) {
+      const int b = mb * BM + rg + RG * q;
+      carry[q * R_EPI_THREADS + e] = make_float2(0.f, b < B ? a.Cs[((size_t)T * B + b) * N + j] : 0.f);   // (dcnext = 0, c(T))
+    }
+    int used = 0;
+    for (int s = 0; s < T; s++) {
+      const int t = T - s;
+      const bool has_acc = nkbw + (s == 0 ? 0 : nkbu) > 0;
+      const float* Gp_t = a.Gp + (size_t)(t - 1) * B * N4;
+      const float* c_prev = a.Cs + (size_t)(t - 1) * B * N;
+      __nv_bfloat16* dGbf_t = a.dGbf + (size_t)(t - 1) * a.Bp * N4;
+      __nv_bfloat16* dGT_t = a.dGT + (size_t)(t - 1) * a.Bp;
+      // 1. drain: TMEM (lane = stream) -> KS slices of 32 hidden units
+      {
+        const int row = quarter * 32 + lane;
+        if (has_acc) {
+          mbar_wait(c.accum_full, (uint32_t)used & 1u);
+          if (dbg && e == 0 && s == DBG_S) dbg[4] = clock64();
+          tcgen05_after_sync();
+        }
+#pragma unroll 1
+        for (int ch = 0; ch < F::CHUNKS_PER_WARP; ch++) {
+          const int d = cgrp * F::CHUNKS_PER_WARP + ch;      // destination rank of this 32-column slice
+          float v[32];
+          if (has_acc) {
+            tmem_ld32(c.tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(d * UO), v);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = 0.f;
+          }
+          if (d == ks) {
+            float4* dst = reinterpret_cast<float4*>(dh + (size_t)row * DH_LD);
+#pragma unroll
+            for (int u = 0; u < 8; u++) dst[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+          } else {
+            float4* dst = reinterpret_cast<float4*>(red_tile + ((size_t)(d * KS + ks) * 8 * 128 + row) * 4);
+#pragma unroll
+            for (int u = 0; u < 8; u++) dst[(size_t)u * 128] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+          }
+        }
+        if (has_acc) tcgen05_before_sync();
+      }
+      named_bar_sync(1, R_EPI_THREADS);
+      if (dbg && e == 0 && s == DBG_S) dbg[5] = clock64();
+      // 2. exchange: announce our slices, free the accumulator, wait for the other ranks
+      if (e == 0) {
+        red_release_gpu_add(xcnt, 1u);                       // release: cumulative over the barrier-ordered stores
+        if (has_acc) mbar_arrive_remote(tmem_free, 0);
+      }
+      // operands of the gate math that no timestep of this launch produces: in flight while the exchange is awaited
+      float4 gv[ROWS];
+      float cpp[ROWS];
+#pragma unroll
+      for (int q = 0; q < ROWS; q++) {
+        const int b = mb * BM + rg + RG * q;
+        gv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        cpp[q] = 0.f;
+        if (b < B) {
+          gv[q] = __ldcs(reinterpret_cast<const float4*>(Gp_t + (size_t)b * N4 + 4 * (size_t)j));   // i o f u (last use)
+          cpp[q] = c_prev[(size_t)b * N + j];
+        }
+      }
+      if (w == 1) counters_wait(xcnt, 1, (unsigned int)KS * (unsigned int)(s + 1), lane);
+      named_bar_sync(1, R_EPI_THREADS);                      // every reader is ordered after the acquire
+      if (dbg && e == 0 && s == DBG_S) dbg[6] = clock64();
+      // 3. reduce: float4 position p = (u, row); sum over the KS sources in a fixed order
+#pragma unroll 1
+      for (int p = e; p < 8 * 128; p += R_EPI_THREADS) {
+        const int u = p >> 7, row = p & 127;
+        float4 pv[KS];
+#pragma unroll
+        for (int sr = 0; sr < KS; sr++)
+          if (sr != ks) pv[sr] = __ldcg(reinterpret_cast<const float4*>(red_tile + ((size_t)(ks * KS + sr) * 8 * 128 + (size_t)u * 128 + row) * 4));
+        float4* own = reinterpret_cast<float4*>(dh + (size_t)row * DH_LD + 4 * u);
+        const float4 o = *own;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int sr = 0; sr < KS; sr++) {
+          const float4 x = (sr == ks) ? o : pv[sr];
+          acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+        }
+        *own = acc;
+      }
+      named_bar_sync(1, R_EPI_THREADS);
+      // 4. gate gradients, lane = hidden unit (R/lstm.cc:233-256)
+#pragma unroll
+      for (int q = 0; q < ROWS; q++) {
+        const int r = rg + RG * q;
+        const int b = mb * BM + r;
+        float d_i = 0.f, d_o = 0.f, d_f = 0.f, d_u = 0.f;
+        if (b < B) {
+          const float dhv = dh[(size_t)r * DH_LD + l];
+          const float4 gg = gv[q];
+          const float2 cr = carry[q * R_EPI_THREADS + e];                      // (dcnext, c(t))
+          const float ct = cr.y;
+          const float dc = (dhv * gg.y + cr.x) * (1.0f - ct * ct);             // :233-235
+          d_o = dhv * ct * (gg.y * (1.0f - gg.y));                             // :238,244
+          d_i = dc * gg.w * (gg.x * (1.0f - gg.x));                            // :239,244
+          d_f = dc * cpp[q] * (gg.z * (1.0f - gg.z));                          // :240,244
+          d_u = dc * gg.x * (1.0f - gg.w * gg.w);                              // :241,247
+          carry[q * R_EPI_THREADS + e] = make_float2(dc * gg.z, cpp[q]);       // :256; c(t-1) is the next timestep's c(t)
+          uint2 pk;
+          pk.x = pack_bf16x2(d_i, d_o);
+          pk.y = pack_bf16x2(d_f, d_u);
+          *reinterpret_cast<uint2*>(dGbf_t + (size_t)b * N4 + 4 * (size_t)j) = pk;
+        }
+        gT[(0 * UO + l) * R_HT_LD + r] = __float2bfloat16_rn(d_i);
+        gT[(1 * UO + l) * R_HT_LD + r] = __float2bfloat16_rn(d_o);
+        gT[(2 * UO + l) * R_HT_LD + r] = __float2bfloat16_rn(d_f);
+        gT[(3 * UO + l) * R_HT_LD + r] = __float2bfloat16_rn(d_u);
+      }
+      fence_proxy_async_global();                            // dg(t) is read by other CTAs' TMA loads
+      named_bar_sync(1, R_EPI_THREADS);
+      if (e == 0) red_release_gpu_add(my_slots + (pairi % R_SLOTS), 1u);
+      if (dbg && e == 0 && s == DBG_S) dbg[7] = clock64();
+      // 5. dg^T rows (master row order gate*N + unit) for K6a: off the critical path
+      {
+        const int jbase = jt * BNJ + ks * UO;
+        for (int q = w; q < 4 * UO; q += R_EPI_WARPS) {
+          const int gate = q / UO, u = q - gate * UO;
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(gT + q * R_HT_LD);
+          uint32_t* dst = reinterpret_cast<uint32_t*>(dGT_t + (size_t)(gate * N + jbase + u) * a.ldg + mb * BM);
+          __stcs(dst + lane, src[lane]);
+          __stcs(dst + lane + 32, src[lane + 32]);
+        }
+      }
+      named_bar_sync(1, R_EPI_THREADS);                      // gT and dh are rewritten by the next timestep
+      if (has_acc) used++;
+    }
+  }
+  pair_epilogue_end<BNJ, STAGES>(c);
+}
+
+template <int BNJ, int KS>
+bool launch_bwd_recur_t(const CUtensorMap& tmdG, const CUtensorMap& tmWb, const CUtensorMap& tmdY, const BwdRecurArgs& a,
+                        cudaStream_t st) {
+  using F = BwdRecurCfg<BNJ, KS>;
+  const int JT = a.N / BNJ;
+  auto kernel = k_bwd_recur<BNJ, KS>;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES) != cudaSuccess) { cudaGetLastError(); return false; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * JT * KS, 1, 1);
+  cfg.blockDim = dim3(R_CTA_THREADS);
+  cfg.dynamicSmemBytes = (size_t)F::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // every CTA must be resident at once (the grid barrier spins): refuse unless all pairs fit on an idle GPU
+  int max_clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (max_clusters < JT * KS) return false;
+  if (cudaMemsetAsync(a.gbar, 0, 2 * R_SLOTS * sizeof(unsigned int), st) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (cudaMemsetAsync(a.xcnt, 0, (size_t)JT * 2 * sizeof(unsigned int), st) != cudaSuccess) { cudaGetLastError(); return false; }
+  return cudaLaunchKernelEx(&cfg, kernel, tmdG, tmWb, tmdY, a) == cudaSuccess;
+}
+
+}  // namespace
+
+// Which <BNJ, KS> instantiation (if any) runs this shape persistently: 0 = none (per-timestep kernels), else BNJ.
+// Needs one pair of batch tiles (Bp == 256), N/BNJ * KS pairs <= 74 and (N/BNJ * KS) % 8 == 0 for the barrier counters.
+int bwd_recur_bnj(int N, int Bp, int M) {
+  if (Bp != 256 || M != 256) return 0;
+  static const int force = getenv("LSTM_BWD_RECUR") ? atoi(getenv("LSTM_BWD_RECUR")) : -1;
+  if (force == 0) return 0;
+  const int nkbu = 4 * N / BK;
+  auto fits = [&](int bnj, int ks) {
+    const int pairs = (N / bnj) * ks;
+    return N % bnj == 0 && nkbu % ks == 0 && pairs <= 74 && pairs % R_SLOTS == 0;
+  };
+  if (force == 128) return fits(128, 4) ? 128 : 0;
+  if (fits(256, 8)) return 256;
+  if (fits(128, 4)) return 128;
+  return 0;
+}
+size_t bwd_recur_red_floats(int N, int bnj) {
+  const int ks = bnj == 256 ? 8 : 4;
+  return (size_t)(N / bnj) * 2 * ks * ks * 8 * 128 * 4;
+}
+bool launch_bwd_recur(int bnj, const CUtensorMap& tmdG, const CUtensorMap& tmWb, const CUtensorMap& tmdY, const BwdRecurArgs& a,
+                      cudaStream_t st) {
+  if (bnj == 256) return launch_bwd_recur_t<256, 8>(tmdG, tmWb, tmdY, a, st);
+  if (bnj == 128) return launch_bwd_recur_t<128, 4>(tmdG, tmWb, tmdY, a, st);
+  return false;
+}
+
+}  // namespace tc

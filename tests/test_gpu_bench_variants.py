@@ -24,7 +24,8 @@ def frob_rel(a, b):
 
 # (N, S, B, expected variant): config 4, the BN = 64 middle case, config 3, config 2
 CASES = [
-    (2048, 3, 256, dict(fwd_bn=128, fwd_pair=1, wgrad_bn=256)),
+    (2048, 3, 256, dict(fwd_bn=128, fwd_pair=1, wgrad_bn=256, bwd_persistent=256)),
+    (2048, 4, 200, dict(fwd_bn=128, fwd_pair=1, wgrad_bn=256, bwd_persistent=256)),   # padding rows in the second batch tile
     (1024, 3, 256, dict(fwd_bn=64, fwd_pair=1, wgrad_bn=256)),
     (1024, 4, 128, dict(fwd_bn=32, fwd_pair=0, wgrad_bn=256)),
     (512, 4, 64, dict(fwd_bn=32, fwd_pair=0, wgrad_bn=128)),
@@ -88,3 +89,38 @@ def test_benchmark_shape_training_iterations_follow_the_oracle():
         assert abs(lg - lq) <= 3e-2 * abs(lq), (it, lg, lq)
     for name, a, b in zip(orc.NAMES, g.params(), q.params()):
         assert frob_rel(a, b) < 3e-2, name
+
+
+def test_persistent_bptt_agrees_with_the_per_timestep_kernels():
+    """The persistent BPTT recurrence (tc_recur.cu) against the launch-per-timestep kernels (LSTM_BWD_RECUR=0) on the same
+    window over 12 timesteps at config 4's width: both contract the same bf16 operands, so only the fp32 summation order of the
+    split-K partials differs."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    code = r"""
+import sys, numpy as np
+import eigen_lstm_b200 as el
+M, N, S, B = 256, 2048, 13, 256
+g = el.LSTM(M, N, S, B, dtype=el.BF16)
+g.init_params(3, 0.01, 1.0)
+rng = np.random.default_rng(0)
+g.set_state(rng.normal(0, 0.3, (N, B)).astype(np.float32), rng.normal(0, 0.3, (N, B)).astype(np.float32))
+x = rng.integers(0, M, (S, B)).astype(np.int32); t = rng.integers(0, M, (S, B)).astype(np.int32)
+loss = g.forward(x, t); g.backward()
+np.savez(sys.argv[1], loss=loss, v=np.array([g.variant()["bwd_persistent"]]), dg1=g.activation("dg", 1), dg7=g.activation("dg", 7),
+         **{n: a for n, a in zip(["W", "U", "b", "Why", "by"], g.grads())})
+"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = []
+    with tempfile.TemporaryDirectory() as d:
+        for i, env in enumerate(({}, {"LSTM_BWD_RECUR": "0"})):
+            path = os.path.join(d, f"r{i}.npz")
+            subprocess.run([sys.executable, "-c", code, path], check=True, cwd=root, env=dict(os.environ, **env), timeout=300)
+            out.append(dict(np.load(path)))
+    a, b = out
+    assert int(a["v"][0]) == 256 and int(b["v"][0]) == 0
+    assert a["loss"] == b["loss"]                          # the forward pass is the same code
+    for k in ("dg1", "dg7", "W", "U", "b", "Why", "by"):
+        assert frob_rel(a[k], b[k]) < 3e-3, k             # dg is rounded to bf16 every timestep: summation-order noise x 12 steps
