@@ -255,6 +255,24 @@ void launch_state_to_f32(const __nv_bfloat16* Hbf_slot, float* h, int B, int N, 
   launch_bf16_to_f32(Hbf_slot, h, (size_t)B * N, st);
 }
 
+// blocked copy of U for the persistent forward recurrence (tc_recur.cu): one contiguous [bn][64] block per (tile, k-block)
+__global__ void k_block_fwd_weights(const float* __restrict__ U, __nv_bfloat16* __restrict__ Wb, int N, int bn, size_t total) {
+  const int N4 = 4 * N, nkb = N / 64;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx & 63);
+    const size_t q = idx >> 6;
+    const int row = (int)(q % bn);
+    const size_t q2 = q / bn;
+    const int kb = (int)(q2 % nkb), tile = (int)(q2 / nkb);
+    const int rp = tile * bn + row;                          // unit-major gate row r' = 4*unit + gate
+    const int k = kb * 64 + c;
+    Wb[idx] = __float2bfloat16_rn(U[(size_t)k * N4 + (size_t)(rp & 3) * N + (rp >> 2)]);
+  }
+}
+void launch_block_fwd_weights(const float* U, __nv_bfloat16* Wb, int N, int bn, cudaStream_t st) {
+  k_block_fwd_weights<<<148 * 8, 256, 0, st>>>(U, Wb, N, bn, (size_t)4 * N * N);
+}
+
 // blocked copy of the BPTT weights (tc_recur.cu): one contiguous [bnj][64] block per (tile, k-block)
 __global__ void k_block_bwd_weights(const float* __restrict__ U, const float* __restrict__ Why, __nv_bfloat16* __restrict__ Wb,
                                     int N, int M, int bnj, size_t total) {

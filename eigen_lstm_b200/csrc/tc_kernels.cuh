@@ -74,6 +74,21 @@ struct BwdPersistArgs {
   int writer_fence;
 };
 
+// persistent forward recurrence (tc_recur.cu): all T timesteps in one launch
+struct FwdRecurArgs {
+  int B, Bp, N, M, T;
+  const int* xs;               // [S][B] input bytes; timestep t reads row t
+  const float* Wp;             // [M][4N r']
+  const float* bp;             // [4N r']
+  float* Cs;                   // [(T+1)][B][N]: slot 0 read once, slot t written by timestep t
+  float* Gp;                   // [T][B][4N r']
+  __nv_bfloat16* Hbf;          // [(T+1)][Bp][N]: slot t-1 read (TMA), slot t written by timestep t
+  __nv_bfloat16* ZT_h0;        // ZT + M*ldz: the h rows; timestep t writes columns [t*Bp, (t+1)*Bp)
+  long ldz;
+  unsigned int* gbar;          // [2][8] per-batch-half arrival counters (zeroed by the launcher)
+  long long* dbg;
+};
+
 // persistent BPTT recurrence (tc_recur.cu): all T timesteps in one launch, cta_group::2 pairs + KS-way split-K
 struct BwdRecurArgs {
   int B, Bp, N, M, T;
@@ -156,6 +171,11 @@ bool launch_bwd_persist(int BN, const CUtensorMap& tmdG, const CUtensorMap& tmUk
                         const BwdPersistArgs& a, cudaStream_t st);
 // persistent BPTT recurrence: bwd_recur_bnj() = hidden units per tile (256 | 128) if this shape runs persistently, else 0;
 // tmWb = the blocked weight copy [N/bnj][4N/64 + M/64][bnj][64] as a 2D map with a box of bnj/2 rows
+int fwd_recur_bn(int N, int Bp, int M);
+// tmWb = blocked U [4N/bn][N/64][bn][64] as a 2D map with a box of bn/2 rows; tmH box = 128 rows
+bool launch_fwd_recur(int bn, const CUtensorMap& tmH, const CUtensorMap& tmWb, const FwdRecurArgs& a, cudaStream_t st);
+// Wb[(tile*N/64 + kb)*bn + row][c] = U(r' = tile*bn + row, k = kb*64 + c)   (r' = 4*unit + gate)
+void launch_block_fwd_weights(const float* U, __nv_bfloat16* Wb, int N, int bn, cudaStream_t st);
 int bwd_recur_bnj(int N, int Bp, int M);
 size_t bwd_recur_red_floats(int N, int bnj);
 bool launch_bwd_recur(int bnj, const CUtensorMap& tmdG, const CUtensorMap& tmWb, const CUtensorMap& tmdY, const BwdRecurArgs& a,

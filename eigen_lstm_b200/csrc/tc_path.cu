@@ -13,6 +13,9 @@ using bf16 = __nv_bfloat16;
 
 struct Bf16State {
   int Bp = 0, N4 = 0, RZ = 0, BN2 = 0, BN5 = 0;
+  int bn2r = 0;                   // persistent forward recurrence (tc_recur.cu): gate columns per tile, 0 = per-timestep kernels
+  bf16* Wb2 = nullptr;            // its blocked copy of U
+  CUtensorMap tmWb2;
   int bnj5 = 0;                   // persistent BPTT recurrence (tc_recur.cu): hidden units per tile, 0 = per-timestep kernels
   bf16* Wb5 = nullptr;            // its blocked weight copy
   float* red5 = nullptr;
@@ -106,6 +109,8 @@ int tc_create(lstm_ctx* ctx) {
   s->xcnt_bytes = (size_t)(N / s->BN5) * (Bp / 128) * sizeof(unsigned int);
   TC_ALLOC(s->xcnt, s->xcnt_bytes);
   if (getenv("LSTM_TC_DEBUG")) TC_ALLOC(s->dbg, 32 * sizeof(long long));
+  s->bn2r = tc::fwd_recur_bn(N, s->Bp, M);
+  if (s->bn2r) TC_ALLOC(s->Wb2, N4 * N * sizeof(bf16));
   s->bnj5 = tc::bwd_recur_bnj(N, s->Bp, M);
   if (s->bnj5) {
     TC_ALLOC(s->Wb5, (size_t)N * (N4 + M) * sizeof(bf16));
@@ -136,6 +141,7 @@ int tc_create(lstm_ctx* ctx) {
   ok &= make_tmap(&s->tmdGT, s->dGT, N4, s->LDT, 128);
   ok &= make_tmap(&s->tmZT, s->ZT, s->RZ, s->LDZ, 128);
   ok &= make_tmap(&s->tmZT256, s->ZT, s->RZ, s->LDZ, 256);
+  if (s->bn2r) ok &= make_tmap(&s->tmWb2, s->Wb2, (uint64_t)N4 * (N / 64), 64, (uint32_t)s->bn2r / 2);
   if (s->bnj5) ok &= make_tmap(&s->tmWb5, s->Wb5, (uint64_t)N * ((N4 + M) / 64), 64, (uint32_t)s->bnj5 / 2);
   if (!ok) return lstm_fail(ctx, LSTM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   return LSTM_OK;
@@ -145,7 +151,7 @@ void tc_destroy(lstm_ctx* ctx) {
   Bf16State* s = ctx->tc;
   if (!s) return;
   void* bufs[] = {s->Hbf, s->Urk, s->Ukr, s->Wmn, s->Wnm, s->dYbf, s->dYT, s->dGbf, s->dGT, s->ZT, s->Wp, s->bp, s->Gp,
-                  s->dcnext, s->scratch, s->red, s->dbg, s->gbar, s->xcnt, s->Wb5, s->red5};
+                  s->dcnext, s->scratch, s->red, s->dbg, s->gbar, s->xcnt, s->Wb5, s->red5, s->Wb2};
   for (void* b : bufs) if (b) cudaFree(b);
   delete s;
   ctx->tc = nullptr;
@@ -162,6 +168,10 @@ int tc_params_changed(lstm_ctx* ctx) {
   tc::launch_transpose_cast(ctx->p(LSTM_WHY), s->Wmn, N, M, 0, ctx->st);       // Wmn[m][n]
   tc::launch_cast_bf16(ctx->p(LSTM_WHY), s->Wnm, (size_t)M * N, ctx->st);      // Wnm[n][m]
   LSTM_LAUNCHED(6);
+  if (s->bn2r) {
+    tc::launch_block_fwd_weights(ctx->p(LSTM_U), s->Wb2, N, s->bn2r, ctx->st);
+    LSTM_LAUNCHED(1);
+  }
   if (s->bnj5) {
     tc::launch_block_bwd_weights(ctx->p(LSTM_U), ctx->p(LSTM_WHY), s->Wb5, N, M, s->bnj5, ctx->st);
     LSTM_LAUNCHED(1);
@@ -202,7 +212,15 @@ int tc_forward(lstm_ctx* ctx) {
   tc::launch_build_xt(ctx->xs + B, s->ZT, s->LDZ, M, T, B, s->Bp, ctx->st);
   LSTM_LAUNCHED(1);
   bool persistent = false;
-  if (tc::fwd_persist_enabled() && !ctx->profiling) {   // experimental: the whole recurrence in one persistent launch
+  if (s->bn2r) {                                         // the whole forward recurrence in one persistent launch (tc_recur.cu)
+    tc::FwdRecurArgs pa;
+    pa.B = B; pa.Bp = s->Bp; pa.N = N; pa.M = M; pa.T = T;
+    pa.xs = ctx->xs; pa.Wp = s->Wp; pa.bp = s->bp; pa.Cs = ctx->Cs; pa.Gp = s->Gp; pa.Hbf = s->Hbf;
+    pa.ZT_h0 = s->ZT + (size_t)M * s->LDZ; pa.ldz = s->LDZ; pa.gbar = s->gbar; pa.dbg = s->dbg;
+    persistent = tc::launch_fwd_recur(s->bn2r, s->tmH, s->tmWb2, pa, ctx->st);
+    if (persistent) LSTM_LAUNCHED(1);
+  }
+  if (!persistent && tc::fwd_persist_enabled() && !ctx->profiling) {   // experimental: the whole recurrence in one persistent launch
     tc::FwdPersistArgs pa;
     pa.B = B; pa.Bp = s->Bp; pa.N = N; pa.M = M; pa.T = T;
     pa.xs = ctx->xs; pa.Wp = s->Wp; pa.bp = s->bp; pa.Cs = ctx->Cs; pa.Gp = s->Gp; pa.Hbf = s->Hbf;
@@ -311,7 +329,7 @@ void tc_variant(lstm_ctx* ctx, int out[8]) {
   out[2] = s->BN5;
   out[3] = tc::bwd_pair(s->Bp) ? (tc::bwd_flag_exchange(s->Bp) ? 2 : 1) : 0;
   out[4] = (ctx->M + ctx->N + 1 >= 1024) ? 256 : 128;
-  out[5] = tc::fwd_persist_enabled() ? 1 : 0;
+  out[5] = s->bn2r ? s->bn2r : (tc::fwd_persist_enabled() ? 1 : 0);
   out[6] = s->bnj5 ? s->bnj5 : (tc::bwd_persist_enabled() ? 1 : 0);
 }
 

@@ -76,6 +76,256 @@ __device__ __forceinline__ void counters_wait(const unsigned int* slots, int n, 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Forward recurrence (K2) of a whole window as one persistent kernel.
+//   R/lstm.cc:173-192   for t = 1 .. S-1:  g = W x(t) + U h(t-1) + b;  gates;  c(t) = tanh(i u + f c(t-1));  h(t) = o c(t)
+// 4N/BN gate-column tiles, each computed for all 256 streams by a cta_group::2 pair (one M = 256 MMA per k-step; each CTA
+// stages its own h tile and half of the U tile).  The U tiles of the NEXT timestep's first k-blocks are prefetched during the
+// epilogue; h(t) travels through global memory (generic stores -> fence.proxy.async -> red.release.gpu on the batch half's
+// arrival counters -> producers acquire-poll -> fence.proxy.async -> TMA); c(t) stays in the registers of the thread that owns
+// the (stream, unit) pair; the gate stash, c(t) and the h^T rows for K6 are stored after h(t) has been announced.
+// U is read from a blocked copy (Wb2[tile][k-block][BN rows][64]): every TMA box is one contiguous 8 KB run.
+// ------------------------------------------------------------------------------------------------------------------
+template <int BN>
+struct FwdRecurCfg {
+  static constexpr int STAGES = BN == 128 ? 5 : 8;
+  static constexpr int UT = BN / 4;
+  static constexpr int ACC_LD = BN + 4;
+  static constexpr int ACC_BYTES = 128 * ACC_LD * 4;
+  static constexpr int HT_BYTES = UT * R_HT_LD * 2;
+  static constexpr int X_BYTES = 128 * 4;
+  static constexpr int EPI_BYTES = ACC_BYTES + HT_BYTES + X_BYTES;
+  static constexpr int SMEM_BYTES = PairCfg<BN, STAGES>::TILE_BYTES + 1024 + 256 + (EPI_BYTES + 127) / 128 * 128;
+};
+
+// grid (2 * n_tiles), cluster (2,1,1): blockIdx.x & 1 = pair member = batch half
+template <int BN>
+__global__ void __launch_bounds__(R_CTA_THREADS, 1)
+k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmWb, const FwdRecurArgs a) {
+  using F = FwdRecurCfg<BN>;
+  using PC = PairCfg<BN, F::STAGES>;
+  constexpr int STAGES = F::STAGES, UT = F::UT, RG = R_EPI_THREADS / UT, ROWS = 128 / RG, ACC_LD = F::ACC_LD;
+  extern __shared__ uint8_t smem_raw[];
+  TileCtx c = pair_prologue<BN, STAGES>(smem_raw);
+  uint64_t* tmem_free = c.accum_full + 2;
+  if (threadIdx.x == 0) { mbar_init(tmem_free, 2); fence_barrier_init(); }
+  __syncthreads();
+  cluster_sync_all();
+  const uint32_t rank = cluster_ctarank();
+  const int nb = (int)(blockIdx.x >> 1);
+  const int mb = (int)rank;
+  const int n_tiles = (int)(gridDim.x >> 1);
+  const int nkb = a.N / BK;
+  const unsigned int per_slot = (unsigned int)(n_tiles / R_SLOTS);
+  unsigned int* my_slots = a.gbar + (size_t)mb * R_SLOTS;
+  const int N = a.N, N4 = 4 * a.N, B = a.B;
+  const int wrow0 = nb * nkb * BN + (int)rank * (BN / 2);    // + kb * BN
+  constexpr int DBG_T = 4;
+  long long* dbg = (a.dbg && blockIdx.x == 0 && a.T > DBG_T) ? a.dbg : nullptr;
+
+  if (c.warp == 0) {
+    // ---------------- producer ----------------
+    if (elect_one()) { tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmWb); }
+    __syncwarp();
+    const int pre = nkb < STAGES ? nkb : STAGES;
+    int g = 0;
+    for (int t = 1; t <= a.T; t++) {
+      const int a_row = (t - 1) * a.Bp + mb * BM;
+      for (int kb = 0; kb < pre; kb++) {                     // weights first: they do not depend on h(t-1)
+        const int st = (g + kb) % STAGES;
+        const uint32_t ph = (uint32_t)((g + kb) / STAGES) & 1u;
+        mbar_wait(&c.empty[st], ph ^ 1u);
+        if (elect_one()) {
+          uint8_t* bdst = c.tiles + (size_t)st * PC::STAGE_BYTES + A_TILE_BYTES;
+          if (rank == 0) mbar_expect_tx(&c.full[st], 2u * (uint32_t)PC::STAGE_BYTES);
+          tma_load_2d_pair_hint(bdst, &tmWb, &c.full[st], 0, wrow0 + kb * BN, L2_EVICT_LAST);
+        }
+        __syncwarp();
+      }
+      if (t > 1) {                                           // h(t-1) of this batch half is complete in global memory
+        if (dbg && c.lane == 0 && (t == DBG_T || t == DBG_T + 1)) dbg[t == DBG_T ? 0 : 8] = clock64();
+        counters_wait(my_slots, R_SLOTS, (unsigned int)(t - 1) * per_slot, c.lane);
+        fence_proxy_async_global();
+        if (dbg && c.lane == 0 && t == DBG_T) dbg[1] = clock64();
+      }
+      for (int kb = 0; kb < nkb; kb++) {
+        const int st = (g + kb) % STAGES;
+        const uint32_t ph = (uint32_t)((g + kb) / STAGES) & 1u;
+        if (kb >= pre) mbar_wait(&c.empty[st], ph ^ 1u);
+        if (elect_one()) {
+          uint8_t* adst = c.tiles + (size_t)st * PC::STAGE_BYTES;
+          if (kb >= pre) {
+            if (rank == 0) mbar_expect_tx(&c.full[st], 2u * (uint32_t)PC::STAGE_BYTES);
+            tma_load_2d_pair_hint(adst + A_TILE_BYTES, &tmWb, &c.full[st], 0, wrow0 + kb * BN, L2_EVICT_LAST);
+          }
+          tma_load_2d_pair(adst, &tmH, &c.full[st], kb * BK, a_row);
+        }
+        __syncwarp();
+      }
+      g += nkb;
+    }
+  } else if (c.warp == 1) {
+    // ---------------- MMA issuer (leader CTA of the pair) ----------------
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
+      const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(c.tiles));
+      const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(c.tiles) + A_TILE_BYTES);
+      int g = 0;
+      for (int t = 1; t <= a.T; t++) {
+        if (t > 1) {
+          mbar_wait_cluster(tmem_free, (uint32_t)(t - 2) & 1u);
+          tcgen05_after_sync();
+        }
+        for (int kb = 0; kb < nkb; kb++) {
+          const int st = (g + kb) % STAGES;
+          const uint32_t ph = (uint32_t)((g + kb) / STAGES) & 1u;
+          mbar_wait(&c.full[st], ph);
+          if (dbg && c.lane == 0 && t == DBG_T && kb == 0) dbg[2] = clock64();
+          tcgen05_after_sync();
+          if (elect_one()) {
+            const uint64_t soff = (uint64_t)((uint32_t)st * (uint32_t)(PC::STAGE_BYTES >> 4));
+#pragma unroll
+            for (int k = 0; k < BK / 16; k++)
+              umma_bf16_pair(c.tmem_d, a_desc0 + soff + 2 * k, b_desc0 + soff + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+            umma_commit_pair(&c.empty[st], (uint16_t)0x3);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit_pair(c.accum_full, (uint16_t)0x3);
+        __syncwarp();
+        if (dbg && c.lane == 0 && t == DBG_T) dbg[3] = clock64();
+        g += nkb;
+      }
+    }
+  } else {
+    // ---------------- epilogue: LSTM math, lane = hidden unit ----------------
+    float* acc = reinterpret_cast<float*>(c.epi);
+    __nv_bfloat16* hT = reinterpret_cast<__nv_bfloat16*>(c.epi + F::ACC_BYTES);
+    int* sx = reinterpret_cast<int*>(c.epi + F::ACC_BYTES + F::HT_BYTES);
+    const int e = threadIdx.x - 64;
+    const int l = e % UT, rg = e / UT;
+    const int j = nb * UT + l;
+    const int rp = 4 * j;
+    const float4 bias = *reinterpret_cast<const float4*>(a.bp + rp);
+    float cpv[ROWS];                                         // c(t-1) of this thread's (stream, unit) pairs: register-resident
+#pragma unroll
+    for (int q = 0; q < ROWS; q++) {
+      const int b = mb * BM + rg + RG * q;
+      cpv[q] = b < B ? a.Cs[(size_t)b * N + j] : 0.f;        // slot 0 = carried-in state
+    }
+    for (int t = 1; t <= a.T; t++) {
+      const int* x_t = a.xs + (size_t)t * B;
+      float* c_out = a.Cs + (size_t)t * B * N;
+      float* Gp_t = a.Gp + (size_t)(t - 1) * B * N4;
+      __nv_bfloat16* Hbf_t = a.Hbf + (size_t)t * a.Bp * N;
+      __nv_bfloat16* ZT_h = a.ZT_h0 + (size_t)t * a.Bp;
+      if (e < 128) {
+        const int b = mb * BM + e;
+        sx[e] = (b < B) ? x_t[b] : -2;                       // -2 = padding row, -1 = all-zero input column
+      }
+      named_bar_sync(1, R_EPI_THREADS);
+      float4 w[ROWS];
+      int xv[ROWS];
+#pragma unroll
+      for (int q = 0; q < ROWS; q++) {                       // W*x for one-hot x = a row gather; in flight during the contraction
+        const int x = sx[rg + RG * q];
+        xv[q] = x;
+        w[q] = bias;
+        if (x >= 0) {
+          const float4 wr = __ldg(reinterpret_cast<const float4*>(a.Wp + (size_t)x * N4 + rp));
+          w[q] = make_float4(wr.x + bias.x, wr.y + bias.y, wr.z + bias.z, wr.w + bias.w);
+        }
+      }
+      if (c.warp < 6) {                                      // TMEM (lane = stream) -> shared memory tile
+        const int quarter = c.warp & 3;
+        const int row = quarter * 32 + c.lane;
+        mbar_wait(c.accum_full, (uint32_t)(t - 1) & 1u);
+        if (dbg && e == 0 && t == DBG_T) dbg[4] = clock64();
+        tcgen05_after_sync();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          float v[32];
+          tmem_ld32(c.tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+          float4* dst = reinterpret_cast<float4*>(acc + (size_t)row * ACC_LD + c0);
+#pragma unroll
+          for (int u = 0; u < 8; u++) dst[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+        }
+        tcgen05_before_sync();
+      }
+      named_bar_sync(1, R_EPI_THREADS);
+      if (dbg && e == 0 && t == DBG_T) dbg[5] = clock64();
+      if (e == 0) mbar_arrive_remote(tmem_free, 0);          // this CTA's half of the accumulator is drained
+      // Only h(t) is on the critical path of the other CTAs: it is stored FIRST, fenced and announced; the gate stash and
+      // c(t) (registers until then) follow after the arrival.
+#pragma unroll
+      for (int q = 0; q < ROWS; q++) {
+        const int r = rg + RG * q;
+        float hval = 0.f;
+        if (xv[q] >= -1) {
+          const int b = mb * BM + r;
+          const float4 pre = *reinterpret_cast<const float4*>(acc + (size_t)r * ACC_LD + 4 * l);
+          const float gi = sigmoid_fast(pre.x + w[q].x);
+          const float go = sigmoid_fast(pre.y + w[q].y);
+          const float gf = sigmoid_fast(pre.z + w[q].z);
+          const float gu = tanh_fast(pre.w + w[q].w);
+          const float cc = tanh_fast(gi * gu + gf * cpv[q]);   // the carried cell value is the tanh'd one (R/lstm.cc:185-189)
+          hval = go * cc;
+          cpv[q] = cc;
+          w[q] = make_float4(gi, go, gf, gu);                  // the W row is dead: its registers carry the activated gates
+          Hbf_t[(size_t)b * N + j] = __float2bfloat16_rn(hval);
+        }
+        hT[l * R_HT_LD + r] = __float2bfloat16_rn(hval);
+      }
+      fence_proxy_async_global();                            // h(t) is read by other CTAs' TMA loads
+      named_bar_sync(1, R_EPI_THREADS);
+      if (e == 0) red_release_gpu_add(my_slots + (nb % R_SLOTS), 1u);   // release: cumulative over the barrier-ordered stores
+      if (dbg && e == 0 && t == DBG_T) dbg[6] = clock64();
+#pragma unroll
+      for (int q = 0; q < ROWS; q++) {
+        if (xv[q] >= -1) {
+          const int b = mb * BM + rg + RG * q;
+          __stcs(reinterpret_cast<float4*>(Gp_t + (size_t)b * N4 + rp), w[q]);   // streamed: read once, in BPTT
+          c_out[(size_t)b * N + j] = cpv[q];
+        }
+      }
+      {                                                      // h^T rows of ZT (K6 operand): off the critical path
+        const int w4 = e >> 5, lane = e & 31;
+        for (int u = w4; u < UT; u += R_EPI_WARPS) {
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(hT + u * R_HT_LD);
+          uint32_t* dst = reinterpret_cast<uint32_t*>(ZT_h + (size_t)(nb * UT + u) * a.ldz + mb * BM);
+          __stcs(dst + lane, src[lane]);
+          __stcs(dst + lane + 32, src[lane + 32]);
+        }
+      }
+      if (dbg && e == 0 && t == DBG_T) dbg[7] = clock64();
+    }
+  }
+  pair_epilogue_end<BN, STAGES>(c);
+}
+
+template <int BN>
+bool launch_fwd_recur_t(const CUtensorMap& tmH, const CUtensorMap& tmWb, const FwdRecurArgs& a, cudaStream_t st) {
+  using F = FwdRecurCfg<BN>;
+  const int n_tiles = 4 * a.N / BN;
+  auto kernel = k_fwd_recur<BN>;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES) != cudaSuccess) { cudaGetLastError(); return false; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * n_tiles, 1, 1);
+  cfg.blockDim = dim3(R_CTA_THREADS);
+  cfg.dynamicSmemBytes = (size_t)F::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int max_clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (max_clusters < n_tiles) return false;                  // every CTA must be resident: the grid barrier spins
+  if (cudaMemsetAsync(a.gbar, 0, 2 * R_SLOTS * sizeof(unsigned int), st) != cudaSuccess) { cudaGetLastError(); return false; }
+  return cudaLaunchKernelEx(&cfg, kernel, tmH, tmWb, a) == cudaSuccess;
+}
+
 template <int BNJ, int KS>
 struct BwdRecurCfg {
   static constexpr int STAGES = BNJ == 256 ? 4 : 5;
@@ -384,6 +634,24 @@ bool launch_bwd_recur_t(const CUtensorMap& tmdG, const CUtensorMap& tmWb, const 
 
 }  // namespace
 
+// Gate columns per tile (128 | 64) if this shape runs the forward recurrence persistently, else 0: one pair of batch tiles,
+// 4N/BN pairs <= 74 and a multiple of 8 (barrier counters).  LSTM_FWD_RECUR=0 forces the per-timestep kernels.
+int fwd_recur_bn(int N, int Bp, int M) {
+  if (Bp != 256 || M != 256) return 0;
+  static const int force = getenv("LSTM_FWD_RECUR") ? atoi(getenv("LSTM_FWD_RECUR")) : -1;
+  if (force == 0) return 0;
+  for (int bn : {128, 64}) {
+    const int pairs = 4 * N / bn;
+    if ((4 * N) % bn == 0 && pairs <= 74 && pairs % R_SLOTS == 0) return bn;
+  }
+  return 0;
+}
+bool launch_fwd_recur(int bn, const CUtensorMap& tmH, const CUtensorMap& tmWb, const FwdRecurArgs& a, cudaStream_t st) {
+  if (bn == 128) return launch_fwd_recur_t<128>(tmH, tmWb, a, st);
+  if (bn == 64) return launch_fwd_recur_t<64>(tmH, tmWb, a, st);
+  return false;
+}
+
 // Which <BNJ, KS> instantiation (if any) runs this shape persistently: 0 = none (per-timestep kernels), else BNJ.
 // Needs one pair of batch tiles (Bp == 256), N/BNJ * KS pairs <= 74 and (N/BNJ * KS) % 8 == 0 for the barrier counters.
 int bwd_recur_bnj(int N, int Bp, int M) {
@@ -395,9 +663,11 @@ int bwd_recur_bnj(int N, int Bp, int M) {
     const int pairs = (N / bnj) * ks;
     return N % bnj == 0 && nkbu % ks == 0 && pairs <= 74 && pairs % R_SLOTS == 0;
   };
-  if (force == 128) return fits(128, 4) ? 128 : 0;
-  if (fits(256, 8)) return 256;
+  // measured at N = 2048 (profiles/r02d_*): <128, 4> 12.9 us per timestep, <256, 8> 16.8 us — the 8-way exchange moves 14 MB
+  // through L2 per timestep instead of 6 MB and that costs more than the smaller operand tiles save
+  if (force == 256) return fits(256, 8) ? 256 : 0;
   if (fits(128, 4)) return 128;
+  if (fits(256, 8)) return 256;
   return 0;
 }
 size_t bwd_recur_red_floats(int N, int bnj) {

@@ -296,8 +296,16 @@ __device__ __forceinline__ void pair_mainloop(const TileCtx& c, const KSeg& s0, 
   }
 }
 
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float tanh_fast(float x) { return 1.0f - __fdividef(2.0f, __expf(2.0f * x) + 1.0f); }
+// Gate nonlinearities of the bf16 path: ONE MUFU operation each (tanh.approx.f32, max. relative error 2^-11 — a quarter of the
+// rounding h(t) gets when it is stored as bf16).  The exp + reciprocal forms cost two MUFU operations per activation, and with
+// five activations per (stream, unit) the 16 MUFU lanes of an SM bounded the epilogue of the timestep kernels (2.6 k cycles per
+// 128 x 32 tile).  LSTM_F32 contexts use expf / tanhf like the reference (kernels_f32.cu).
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(tanh_fast(0.5f * x), 0.5f, 0.5f); }
 
 
 template <typename K>
