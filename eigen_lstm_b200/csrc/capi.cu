@@ -170,11 +170,13 @@ extern "C" int lstm_create(lstm_ctx** out, int M, int N, int S, int B, int devic
   CREATE_CUDA(cudaMemsetAsync(ctx->tg, 0xff, (size_t)S * B * sizeof(int), ctx->st));
   ctx->loss_cap = 1024;
   CREATE_CUDA(cudaMalloc(&ctx->d_loss, ctx->loss_cap * sizeof(double)));
-  CREATE_CUDA(cudaMallocHost(&ctx->h_loss_pinned, sizeof(double)));
+  CREATE_CUDA(cudaMallocHost(&ctx->h_loss_ring, lstm_ctx::LOSS_RING * sizeof(double)));
   CREATE_CUDA(cudaMalloc(&ctx->d_iter, sizeof(unsigned long long)));
   CREATE_CUDA(cudaMemsetAsync(ctx->d_iter, 0, sizeof(unsigned long long), ctx->st));
-  CREATE_CUDA(cudaMallocHost(&ctx->h_xs_pinned, (size_t)S * B * sizeof(int32_t)));
-  CREATE_CUDA(cudaMallocHost(&ctx->h_tg_pinned, (size_t)S * B * sizeof(int32_t)));
+  for (int k = 0; k < 2; k++) {
+    CREATE_CUDA(cudaMallocHost(&ctx->h_win[k], 2 * (size_t)S * B * sizeof(int32_t)));
+    CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_win[k], cudaEventDisableTiming));
+  }
   CREATE_CUDA(cudaMalloc(&ctx->pos0, (size_t)B * sizeof(unsigned long long)));
   CREATE_CUDA(cudaMalloc(&ctx->vcount, sizeof(unsigned long long)));
   CREATE_CUDA(cudaMemsetAsync(ctx->vcount, 0, sizeof(unsigned long long), ctx->st));
@@ -204,9 +206,11 @@ extern "C" int lstm_destroy(lstm_ctx* ctx) {
   void* bufs[] = {ctx->params, ctx->grads, ctx->mem, ctx->Hs, ctx->Cs, ctx->Gs, ctx->dY, ctx->dHy, ctx->dG,
                   ctx->dcnext, ctx->surp, ctx->xs, ctx->tg, ctx->d_loss, ctx->text, ctx->pos0, ctx->vcount, ctx->logit_shift};
   for (void* b : bufs) if (b) cudaFree(b);
-  if (ctx->h_loss_pinned) cudaFreeHost(ctx->h_loss_pinned);
-  if (ctx->h_xs_pinned) cudaFreeHost(ctx->h_xs_pinned);
-  if (ctx->h_tg_pinned) cudaFreeHost(ctx->h_tg_pinned);
+  if (ctx->h_loss_ring) cudaFreeHost(ctx->h_loss_ring);
+  for (int k = 0; k < 2; k++) {
+    if (ctx->h_win[k]) cudaFreeHost(ctx->h_win[k]);
+    if (ctx->ev_win[k]) cudaEventDestroy(ctx->ev_win[k]);
+  }
   if (ctx->d_iter) cudaFree(ctx->d_iter);
   for (auto& g : ctx->graph) free_iter_graph(g);
   for (int i = 0; i < 2; i++) {
@@ -225,6 +229,8 @@ extern "C" int lstm_sync(lstm_ctx* ctx) {
   LSTM_CUDA(cudaSetDevice(ctx->device));
   LSTM_CUDA(cudaStreamSynchronize(ctx->st));
   LSTM_CUDA(cudaStreamSynchronize(ctx->comm_st));
+  for (auto& pl : ctx->pending_loss) *pl.second = ctx->h_loss_ring[pl.first];   // losses requested by lstm_train_step
+  ctx->pending_loss.clear();
   return LSTM_OK;
 }
 
@@ -515,45 +521,49 @@ static int finish_profile(lstm_ctx* ctx) {
   return LSTM_OK;
 }
 
-// loss of the most recent forward
-static int fetch_loss(lstm_ctx* ctx, double* out) {
+// loss of the most recent forward: device ring -> pinned ring now (stream-ordered), pinned ring -> *out at the next lstm_sync
+static int queue_loss(lstm_ctx* ctx, double* out) {
+  if ((int)ctx->pending_loss.size() == lstm_ctx::LOSS_RING) {
+    int rc = lstm_sync(ctx);
+    if (rc) return rc;
+  }
+  const int k = (int)ctx->pending_loss.size();
   const size_t slot = (size_t)((ctx->fwd_count - 1) % ctx->loss_cap);
-  LSTM_CUDA(cudaMemcpyAsync(ctx->h_loss_pinned, ctx->d_loss + slot, sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
-  LSTM_CUDA(cudaStreamSynchronize(ctx->st));
-  *out = *ctx->h_loss_pinned;
+  LSTM_CUDA(cudaMemcpyAsync(ctx->h_loss_ring + k, ctx->d_loss + slot, sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+  ctx->pending_loss.emplace_back(k, out);
   return LSTM_OK;
 }
+static int fetch_loss(lstm_ctx* ctx, double* out) {
+  int rc = queue_loss(ctx, out);
+  return rc ? rc : lstm_sync(ctx);
+}
 
+// Stage the caller's window in the pinned buffer that is not in flight and copy it to the device (asynchronously: the caller's
+// arrays may be reused as soon as this returns).
 static int upload_window(lstm_ctx* ctx, const int32_t* x_idx, const int32_t* t_idx) {
-  const size_t bytes = (size_t)ctx->S * ctx->B * sizeof(int);
+  const size_t n = (size_t)ctx->S * ctx->B, bytes = n * sizeof(int);
   if (!x_idx || !t_idx) return lstm_fail(ctx, LSTM_ERR_ARG, "x_idx / t_idx is NULL");
-  for (size_t i = 0; i < (size_t)ctx->S * ctx->B; i++)
+  for (size_t i = 0; i < n; i++)
     if (x_idx[i] < -1 || x_idx[i] >= ctx->M || t_idx[i] < -1 || t_idx[i] >= ctx->M)
       return lstm_fail(ctx, LSTM_ERR_ARG, "window index outside [-1, M)");
-  // staged through the context's pinned buffers: the copies below are then true async DMA and can live in a graph
-  LSTM_CUDA(cudaStreamSynchronize(ctx->st));   // the previous step's DMA has read the staging buffers
-  memcpy(ctx->h_xs_pinned, x_idx, bytes);
-  memcpy(ctx->h_tg_pinned, t_idx, bytes);
-  return LSTM_OK;
-}
-
-static int window_h2d(lstm_ctx* ctx) {
-  const size_t bytes = (size_t)ctx->S * ctx->B * sizeof(int);
-  LSTM_CUDA(cudaMemcpyAsync(ctx->xs, ctx->h_xs_pinned, bytes, cudaMemcpyHostToDevice, ctx->st));
-  LSTM_CUDA(cudaMemcpyAsync(ctx->tg, ctx->h_tg_pinned, bytes, cudaMemcpyHostToDevice, ctx->st));
+  const int k = ctx->win_k;
+  ctx->win_k ^= 1;
+  LSTM_CUDA(cudaEventSynchronize(ctx->ev_win[k]));   // the copy issued two steps ago has read this buffer (usually long done)
+  memcpy(ctx->h_win[k], x_idx, bytes);
+  memcpy(ctx->h_win[k] + n, t_idx, bytes);
+  LSTM_CUDA(cudaMemcpyAsync(ctx->xs, ctx->h_win[k], bytes, cudaMemcpyHostToDevice, ctx->st));
+  LSTM_CUDA(cudaMemcpyAsync(ctx->tg, ctx->h_win[k] + n, bytes, cudaMemcpyHostToDevice, ctx->st));
+  LSTM_CUDA(cudaEventRecord(ctx->ev_win[k], ctx->st));
   return LSTM_OK;
 }
 
 // One full training iteration on the context's stream.  mode 0: window built on the device from the loaded text;
-// mode 1: window copied from the pinned staging buffers.
+// mode 1: the window is already on its way (upload_window).
 static int iteration_body(lstm_ctx* ctx, int mode, int stride, float lr) {
   int rc;
   if (mode == 0) {
     launch_window_advance(ctx->text, ctx->text_len, ctx->pos0, ctx->vcount, stride, ctx->S, ctx->B, ctx->xs, ctx->tg, ctx->st);
     LSTM_LAUNCHED(1);
-  } else {
-    rc = window_h2d(ctx);
-    if (rc) return rc;
   }
   rc = forward_device(ctx);
   if (rc) return rc;
@@ -643,8 +653,6 @@ extern "C" int lstm_forward(lstm_ctx* ctx, const int32_t* x_idx, const int32_t* 
   PROF(0);
   int rc = upload_window(ctx, x_idx, t_idx);
   if (rc) return rc;
-  rc = window_h2d(ctx);
-  if (rc) return rc;
   rc = forward_device(ctx);
   if (rc) return rc;
   ctx->fwd_count++;
@@ -697,7 +705,7 @@ extern "C" int lstm_train_step(lstm_ctx* ctx, const int32_t* x_idx, const int32_
   if (rc) return rc;
   rc = finish_profile(ctx);
   if (rc) return rc;
-  if (loss_out) return fetch_loss(ctx, loss_out);
+  if (loss_out) return queue_loss(ctx, loss_out);   // delivered at the next lstm_sync: the step itself never blocks
   return LSTM_OK;
 }
 
@@ -845,8 +853,9 @@ extern "C" int lstm_eval_bpc(lstm_ctx* ctx, const uint8_t* bytes, size_t n, doub
 
 extern "C" int lstm_sample(lstm_ctx* ctx, uint64_t seed, const float* h0, const float* c0, uint8_t* out, size_t n,
                            int greedy) {
-  if (!ctx || !out) return LSTM_ERR_ARG;
+  if (!ctx) return LSTM_ERR_ARG;
   if (n == 0) return LSTM_OK;
+  if (!out) return LSTM_ERR_ARG;
   LSTM_CUDA(cudaSetDevice(ctx->device));
   // R/lstm.cc:309-311,326: mt19937 + uniform_real_distribution<double>(0,1), narrowed to float
   std::vector<float> u(n);

@@ -43,8 +43,15 @@ struct lstm_ctx {
     int stride = 0; float lr = 0.f; float clip = 0.f; long launches = 0; int warm = 0;
   } graph[2];
   IterGraph* seg_capture = nullptr;      // non-null while run_iteration captures a segmented graph
-  int32_t *h_xs_pinned = nullptr, *h_tg_pinned = nullptr;
-  double* h_loss_pinned = nullptr;
+  // lstm_train_step / lstm_forward stage the caller's windows through TWO pinned buffers ([x | t], 2*S*B ints each) so that a
+  // step never waits for the previous step's DMA; ev_win[k] marks the last copy that read buffer k.
+  int32_t* h_win[2] = {nullptr, nullptr};
+  cudaEvent_t ev_win[2] = {nullptr, nullptr};
+  int win_k = 0;
+  // losses requested through loss_out travel device -> pinned ring -> caller's double at the next synchronisation
+  static constexpr int LOSS_RING = 256;
+  double* h_loss_ring = nullptr;
+  std::vector<std::pair<int, double*>> pending_loss;
   // device text pipeline
   uint8_t* text = nullptr;
   size_t text_len = 0;

@@ -64,6 +64,14 @@ int main(int argc, char** argv) {
   double test_every_seconds = 0;
   // the reference's self-test (OV/lstm_eigen_class_batch/lstm.cc:286-318): numerical vs analytic gradients, then exit
   bool gradcheck = false;
+  // additions of the last snapshot (OV/lstm_eigen_class_CUDA/lstm.cc): lr = 0 while the window warms up (:364-367: the first
+  // 50*S iterations there), the "[Epoch e/E] ... (eta h m s) loss = ... GFlOP/s" progress line (:239-268), a NaN loss is kept
+  // out of the running sums (cu_lstm.h:203-215); and of the class_batch snapshot: last-timestep ln loss report, global-max
+  // softmax shift (lstm.cc:308-319, lstm.h:175).  --clip is the north-star's fused gradient clipping (0 = off = the reference).
+  long lr_warmup = 0;
+  bool eta_progress = false;
+  double clip = 0.0;
+  int loss_mode = 0, softmax_shift = 0;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
     auto next = [&]() -> const char* { return (i + 1 < argc) ? argv[++i] : ""; };
@@ -86,10 +94,16 @@ int main(int argc, char** argv) {
     else if (a == "--load") load_prefix = next();
     else if (a == "--save") save_prefix = next();
     else if (a == "--gradcheck") gradcheck = true;
+    else if (a == "--lr-warmup") lr_warmup = atol(next());
+    else if (a == "--progress") eta_progress = std::string(next()) == "eta";
+    else if (a == "--clip") clip = atof(next());
+    else if (a == "--loss") loss_mode = std::string(next()) == "last-ln" ? 1 : 0;
+    else if (a == "--softmax-shift") softmax_shift = std::string(next()) == "global" ? 1 : 0;
     else {
       std::cerr << "usage: lstm [--file F|DIR]... [--hidden N] [--seq S] [--batch B] [--epochs E] [--lr LR] [--seed K] [--stride K]\n"
                    "            [--bf16] [--device D] [--sample N] [--forget-bias X] [--state-std X] [--max-iters K]\n"
-                   "            [--load PREFIX] [--save PREFIX] [--train-percent P --test-every SECONDS] [--gradcheck]\n";
+                   "            [--load PREFIX] [--save PREFIX] [--train-percent P --test-every SECONDS] [--gradcheck]\n"
+                   "            [--lr-warmup ITERS] [--progress percent|eta] [--clip X] [--loss log2-all|last-ln] [--softmax-shift none|global]\n";
       return 2;
     }
   }
@@ -126,6 +140,9 @@ int main(int argc, char** argv) {
     return 1;
   }
   CK(lstm_init_params(ctx, seed, 0.01f, forget_bias));              // :113-119
+  if (clip > 0) CK(lstm_set_option(ctx, LSTM_OPT_CLIP, clip));
+  if (loss_mode) CK(lstm_set_option(ctx, LSTM_OPT_LOSS_MODE, loss_mode));
+  if (softmax_shift) CK(lstm_set_option(ctx, LSTM_OPT_SOFTMAX_SHIFT, softmax_shift));
   if (!load_prefix.empty() && lstm_load_text_ckpt(ctx, load_prefix.c_str()) != 0)
     std::cout << lstm_last_error(ctx) << std::endl;                  // the reference prints and keeps the random init
   // first train_percent % for training, the rest held out (class_CUDA/lstm.cc:73-86)
@@ -183,7 +200,8 @@ int main(int argc, char** argv) {
   const double flops_per_epoch = (double)S * (4.0 * N * M * 2 + 4.0 * N * N * 2) * (double)length;   // :140
   const size_t iters_per_epoch = (length - S + stride - 1) / stride;
   std::vector<double> losses(100);
-  long total_iters = 0;
+  long total_iters = 0, nan_iters = 0;
+  const double flops_per_iteration = (double)(S - 1) * (double)B * (22.0 * N * M + 24.0 * N * N);
 
   // Seeding follows the ORDER in which the reference constructs its generators, the k-th one seeded seed + k
   // (the test build of the reference program, tests/golden/make_ref_run.py, is given the same schedule): W, U, Why
@@ -219,9 +237,15 @@ int main(int argc, char** argv) {
       if (chunk == 0) chunk = 100 / stride ? 100 / stride : 1;
       if (chunk > iters_per_epoch - done) chunk = iters_per_epoch - done;
       if (max_iters >= 0 && total_iters + (long)chunk >= max_iters) { chunk = (size_t)(max_iters - total_iters); stop = true; }
+      if (total_iters < lr_warmup && total_iters + (long)chunk > lr_warmup) { chunk = (size_t)(lr_warmup - total_iters); stop = false; }
+      const float lr_now = total_iters < lr_warmup ? 0.f : learning_rate;   // class_CUDA/lstm.cc:364-367
       if (chunk > losses.size()) losses.resize(chunk);
-      if (chunk > 0) CK(lstm_train_text(ctx, (int)chunk, stride, learning_rate, losses.data()));
-      for (size_t k = 0; k < chunk; k++) { epoch_loss += losses[k]; window_loss += losses[k]; }
+      const auto chunk_t0 = std::chrono::steady_clock::now();
+      if (chunk > 0) CK(lstm_train_text(ctx, (int)chunk, stride, lr_now, losses.data()));
+      for (size_t k = 0; k < chunk; k++) {
+        if (std::isnan(losses[k])) { nan_iters++; continue; }          // cu_lstm.h:210: a NaN never reaches the running sums
+        epoch_loss += losses[k]; window_loss += losses[k];
+      }
       window_iters += chunk;
       done += chunk;
       if (test_every_seconds > 0 && testdata.size() > 1) {
@@ -254,7 +278,18 @@ int main(int argc, char** argv) {
       }
       total_iters += (long)chunk;
       const size_t i = S + done * stride;
-      if ((i % 100 == 0 && i < length) || stride > 1)   // the reference's loop ends at i = length - 1 (:151): no print at i = length
+      if (eta_progress && chunk > 0) {                  // class_CUDA/lstm.cc:239-268
+        const double chunk_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - chunk_t0).count();
+        size_t eta_sec = (size_t)(chunk_time / (double)chunk * (double)(iters_per_epoch - done));
+        const size_t eta_hours = eta_sec / 3600, eta_min = (eta_sec % 3600) / 60;
+        eta_sec = eta_sec % 60;
+        const double gflops_per_sec = (double)chunk * flops_per_iteration / 1073741824.0 / chunk_time;
+        std::cout << std::setw(15) << "[Epoch " << e + 1 << "/" << epochs << "]" << std::fixed << std::setw(10) << std::setprecision(2)
+                  << 100.0f * (float)i / (float)length << "%     (eta " << std::setw(2) << eta_hours << " h " << std::setfill('0')
+                  << std::setw(2) << eta_min << " m " << std::setfill('0') << std::setw(2) << eta_sec << " s)" << std::setfill(' ')
+                  << std::setw(12) << std::setprecision(6) << "loss = " << epoch_loss / ((double)done * (double)(S - 1))
+                  << std::setw(9) << std::setprecision(2) << gflops_per_sec << " GFlOP/s\r" << std::flush;
+      } else if ((i % 100 == 0 && i < length) || stride > 1)   // the reference's loop ends at i = length - 1 (:151): no print at i = length
         std::cout << std::fixed << std::setw(7) << std::setprecision(2) << 100.0f * (float)i / (float)length << "%\r" << std::flush;
     }
     CK(lstm_sync(ctx));
@@ -279,6 +314,7 @@ int main(int argc, char** argv) {
     std::cout << std::endl << std::endl << "************ Generated text |";
     for (uint8_t ch : text) std::cout << (char)ch;
     std::cout << "| Generated text END ************" << std::endl;
+    if (nan_iters) std::cout << nan_iters << " iteration(s) with a NaN loss were left out of the averages" << std::endl;
     if (!save_prefix.empty()) CK(lstm_save_text_ckpt(ctx, save_prefix.c_str()));
     if (stop) break;
   }

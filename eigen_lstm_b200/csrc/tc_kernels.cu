@@ -111,7 +111,11 @@ k_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   const int gsize = min(a.tiles_m - first_m, GROUP);
   const int tm = first_m + (pid % per_group) % gsize;
   const int tn = (pid % per_group) / gsize;
-  const KSeg s0{&tmA, &tmB, tm * BM, a.b_row0 + tn * K6_BN, a.a_k0, a.b_k0, a.nkb};
+  // split-K (blockIdx.y): every split contracts its own nkb k-blocks into its own partial output (deterministic: the partials are
+  // summed in a fixed order by k_sum_splits)
+  const int split = blockIdx.y;
+  float* C = a.C + (size_t)split * a.split_stride;
+  const KSeg s0{&tmA, &tmB, tm * BM, a.b_row0 + tn * K6_BN, a.a_k0 + split * a.nkb * BK, a.b_k0 + split * a.nkb * BK, a.nkb};
   const KSeg s1{&tmA, &tmB, 0, 0, 0, 0, 0};
   tile_mainloop<K6_BN, K6_STAGES>(c, s0, s1);
   if (c.warp >= 2) {
@@ -127,7 +131,7 @@ k_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
         for (int i = 0; i < 32; i++) {
           const int col = tn * K6_BN + c0 + i;
-          if (col < a.cols) a.C[(size_t)col * a.ldc + row] = v[i];
+          if (col < a.cols) C[(size_t)col * a.ldc + row] = v[i];
         }
       }
     }
@@ -146,13 +150,31 @@ void launch_logits(const CUtensorMap& tmH, const CUtensorMap& tmWmn, const Logit
 
 // bn = 128 or 256 = tile width; tmB must have a box of bn rows and a.tiles_n = ceil(cols / bn)
 void launch_gemm_nt(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st) {
+  const dim3 grid(a.tiles_m * a.tiles_n, a.splits > 1 ? a.splits : 1);
   if (bn == 256) {
     set_smem(k_gemm_nt<256>, Cfg<256, 4>::SMEM_BYTES);
-    k_gemm_nt<256><<<a.tiles_m * a.tiles_n, 192, Cfg<256, 4>::SMEM_BYTES, st>>>(tmA, tmB, a);
+    k_gemm_nt<256><<<grid, 192, Cfg<256, 4>::SMEM_BYTES, st>>>(tmA, tmB, a);
   } else {
     set_smem(k_gemm_nt<128>, Cfg<128, 6>::SMEM_BYTES);
-    k_gemm_nt<128><<<a.tiles_m * a.tiles_n, 192, Cfg<128, 6>::SMEM_BYTES, st>>>(tmA, tmB, a);
+    k_gemm_nt<128><<<grid, 192, Cfg<128, 6>::SMEM_BYTES, st>>>(tmA, tmB, a);
   }
+}
+
+// out[i] = parts[0][i] + parts[1][i] + ... in that order (split-K partials of k_gemm_nt)
+__global__ void k_sum_splits(const float* __restrict__ parts, float* __restrict__ out, size_t n4, size_t stride4, int splits) {
+  const float4* p = reinterpret_cast<const float4*>(parts);
+  float4* o = reinterpret_cast<float4*>(out);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 acc = p[i];
+    for (int s = 1; s < splits; s++) {
+      const float4 x = p[i + (size_t)s * stride4];
+      acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+    }
+    o[i] = acc;
+  }
+}
+void launch_sum_splits(const float* parts, float* out, size_t n, size_t stride, int splits, cudaStream_t st) {
+  k_sum_splits<<<148 * 4, 256, 0, st>>>(parts, out, n / 4, stride / 4, splits);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -253,6 +275,57 @@ void launch_state_to_bf16(const float* h, __nv_bfloat16* Hbf_slot, __nv_bfloat16
 }
 void launch_state_to_f32(const __nv_bfloat16* Hbf_slot, float* h, int B, int N, cudaStream_t st) {
   launch_bf16_to_f32(Hbf_slot, h, (size_t)B * N, st);
+}
+
+// All bf16 operand copies of U in ONE pass over the fp32 master (read once, coalesced; every write a 128-byte row segment):
+// one CTA transposes the tile [64 k] x [16 units x 4 gates] through shared memory.
+//   Urk [4N r'][N k]   and its blocked form Wb2[(tile*N/64 + kb)*bn2 + row][64]   (r' = 4*unit + gate; K2 operands)
+//   Ukr [N k][4N r']   and its blocked form Wb5[(tile*NKBG + kbg)*bn5 + row][64]  (K5 operands; NKBG = 4N/64 + M/64)
+// Null outputs are skipped.  grid (N/16, N/64), 256 threads.
+__global__ void __launch_bounds__(256) k_refresh_u(const float* __restrict__ U, __nv_bfloat16* __restrict__ Urk,
+                                                   __nv_bfloat16* __restrict__ Ukr, __nv_bfloat16* __restrict__ Wb2, int bn2,
+                                                   __nv_bfloat16* __restrict__ Wb5, int bn5, int nkbg, int N) {
+  __shared__ float tile[64][65];                             // [k][r' local]
+  const int N4 = 4 * N;
+  const int j0 = blockIdx.x * 16, kb = blockIdx.y, k0 = kb * 64;
+  const int rp0 = 4 * j0;                                    // a multiple of 64: one k-block of the r' axis
+  for (int idx = threadIdx.x; idx < 64 * 64; idx += 256) {
+    const int u = idx & 15, g = (idx >> 4) & 3, k = idx >> 6;
+    tile[k][4 * u + g] = U[(size_t)(k0 + k) * N4 + (size_t)g * N + j0 + u];   // 16 consecutive floats per (k, gate)
+  }
+  __syncthreads();
+  // rows = r', 64 consecutive k each (Urk / Wb2)
+  for (int idx = threadIdx.x; idx < 64 * 32; idx += 256) {
+    const int c2 = idx & 31, r = idx >> 5;
+    const __nv_bfloat162 v = __floats2bfloat162_rn(tile[2 * c2][r], tile[2 * c2 + 1][r]);
+    const int rp = rp0 + r;
+    if (Urk) *reinterpret_cast<__nv_bfloat162*>(Urk + (size_t)rp * N + k0 + 2 * c2) = v;
+    if (Wb2) *reinterpret_cast<__nv_bfloat162*>(Wb2 + (((size_t)(rp / bn2) * (N / 64) + kb) * bn2 + rp % bn2) * 64 + 2 * c2) = v;
+  }
+  // rows = k, 64 consecutive r' each (Ukr / Wb5)
+  for (int idx = threadIdx.x; idx < 64 * 32; idx += 256) {
+    const int c2 = idx & 31, kk = idx >> 5;
+    const __nv_bfloat162 v = __floats2bfloat162_rn(tile[kk][2 * c2], tile[kk][2 * c2 + 1]);
+    const int k = k0 + kk;
+    if (Ukr) *reinterpret_cast<__nv_bfloat162*>(Ukr + (size_t)k * N4 + rp0 + 2 * c2) = v;
+    if (Wb5) *reinterpret_cast<__nv_bfloat162*>(Wb5 + (((size_t)(k / bn5) * nkbg + rp0 / 64) * bn5 + k % bn5) * 64 + 2 * c2) = v;
+  }
+}
+void launch_refresh_u(const float* U, __nv_bfloat16* Urk, __nv_bfloat16* Ukr, __nv_bfloat16* Wb2, int bn2, __nv_bfloat16* Wb5,
+                      int bn5, int M, int N, cudaStream_t st) {
+  k_refresh_u<<<dim3(N / 16, N / 64), 256, 0, st>>>(U, Urk, Ukr, Wb2, bn2 ? bn2 : 64, Wb5, bn5 ? bn5 : 64, (4 * N + M) / 64, N);
+}
+// the Why k-blocks of the blocked BPTT weight copy: Wb5[(tile*NKBG + 4N/64 + mkb)*bn5 + row][c] = Why(m = mkb*64 + c, j = tile*bn5 + row)
+__global__ void k_block_why(const float* __restrict__ Why, __nv_bfloat16* __restrict__ Wb5, int N, int M, int bn5) {
+  const int nkbu = 4 * N / 64, nkbg = nkbu + M / 64;
+  const size_t total = (size_t)N * M;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(idx % M), j = (int)(idx / M);
+    Wb5[(((size_t)(j / bn5) * nkbg + nkbu + m / 64) * bn5 + j % bn5) * 64 + (m & 63)] = __float2bfloat16_rn(Why[idx]);
+  }
+}
+void launch_block_why(const float* Why, __nv_bfloat16* Wb5, int N, int M, int bn5, cudaStream_t st) {
+  k_block_why<<<148 * 2, 256, 0, st>>>(Why, Wb5, N, M, bn5);
 }
 
 // blocked copy of U for the persistent forward recurrence (tc_recur.cu): one contiguous [bn][64] block per (tile, k-block)

@@ -146,6 +146,8 @@ struct GemmArgs {
   float* C;                    // C[col*ldc + row]
   long ldc;
   int tiles_m, tiles_n;
+  int splits;                  // split-K: nkb is the k-blocks PER split; split s writes to C + s * split_stride (1 = off)
+  size_t split_stride;
 };
 
 // K2 can run in clusters of cn x cm CTAs that share operand tiles by TMA multicast (cn CTAs along the gate-column
@@ -190,6 +192,12 @@ void launch_bwd_step(int BN, const CUtensorMap& tmdG, const CUtensorMap& tmUkr, 
 // K6: C = A * B^T, both K-major bf16, fp32 out, 128 x bn tiles (bn = 128 | 256; tmB box = bn rows)
 void launch_gemm_nt(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st);
 
+// every bf16 operand copy of U from ONE pass over the fp32 master (null outputs skipped); N % 64 == 0
+void launch_refresh_u(const float* U, __nv_bfloat16* Urk, __nv_bfloat16* Ukr, __nv_bfloat16* Wb2, int bn2, __nv_bfloat16* Wb5,
+                      int bn5, int M, int N, cudaStream_t st);
+void launch_block_why(const float* Why, __nv_bfloat16* Wb5, int N, int M, int bn5, cudaStream_t st);
+// out[i] = sum over the splits of parts[s * stride + i], fixed order; n and stride multiples of 4
+void launch_sum_splits(const float* parts, float* out, size_t n, size_t stride, int splits, cudaStream_t st);
 // parameter / state conversion kernels
 void launch_permute_rows_f32(const float* in, float* out, int rows, int N, cudaStream_t st);           // out[k][4j+g] = in[k][gN+j]
 void launch_permute_rows_bf16(const float* in, __nv_bfloat16* out, int rows, int N, cudaStream_t st);  // same, cast

@@ -19,6 +19,7 @@ struct Bf16State {
   int bnj5 = 0;                   // persistent BPTT recurrence (tc_recur.cu): hidden units per tile, 0 = per-timestep kernels
   bf16* Wb5 = nullptr;            // its blocked weight copy
   float* red5 = nullptr;
+  float* kc_parts = nullptr;      // split-K partials of the dWhy|dby GEMM
   CUtensorMap tmWb5;
   long LDZ = 0, LDT = 0;
   bf16 *Hbf = nullptr, *Urk = nullptr, *Ukr = nullptr, *Wmn = nullptr, *Wnm = nullptr;
@@ -105,10 +106,11 @@ int tc_create(lstm_ctx* ctx) {
   TC_ALLOC(s->red, (size_t)(N / s->BN5) * (Bp / 128) * 16 * 128 * (s->BN5 / 4) * sizeof(float));   // K5 split-K exchange
   s->scratch_elems = (size_t)B * N4;
   TC_ALLOC(s->scratch, s->scratch_elems * sizeof(float));
-  TC_ALLOC(s->gbar, (size_t)(Bp / 128) * 8 * 32 * sizeof(unsigned int));
+  TC_ALLOC(s->gbar, std::max<size_t>((size_t)(Bp / 128) * 8 * 32, 2 * 256) * sizeof(unsigned int));   // persistent kernels: 2 x 256 flags
   s->xcnt_bytes = (size_t)(N / s->BN5) * (Bp / 128) * sizeof(unsigned int);
   TC_ALLOC(s->xcnt, s->xcnt_bytes);
   if (getenv("LSTM_TC_DEBUG")) TC_ALLOC(s->dbg, 32 * sizeof(long long));
+  TC_ALLOC(s->kc_parts, 8 * (ctx->P - ctx->off[LSTM_WHY]) * sizeof(float));
   s->bn2r = tc::fwd_recur_bn(N, s->Bp, M);
   if (s->bn2r) TC_ALLOC(s->Wb2, N4 * N * sizeof(bf16));
   s->bnj5 = tc::bwd_recur_bnj(N, s->Bp, M);
@@ -151,7 +153,7 @@ void tc_destroy(lstm_ctx* ctx) {
   Bf16State* s = ctx->tc;
   if (!s) return;
   void* bufs[] = {s->Hbf, s->Urk, s->Ukr, s->Wmn, s->Wnm, s->dYbf, s->dYT, s->dGbf, s->dGT, s->ZT, s->Wp, s->bp, s->Gp,
-                  s->dcnext, s->scratch, s->red, s->dbg, s->gbar, s->xcnt, s->Wb5, s->red5, s->Wb2};
+                  s->dcnext, s->scratch, s->red, s->dbg, s->gbar, s->xcnt, s->Wb5, s->red5, s->Wb2, s->kc_parts};
   for (void* b : bufs) if (b) cudaFree(b);
   delete s;
   ctx->tc = nullptr;
@@ -161,21 +163,17 @@ void tc_destroy(lstm_ctx* ctx) {
 int tc_params_changed(lstm_ctx* ctx) {
   Bf16State* s = ctx->tc;
   const int M = ctx->M, N = ctx->N;
-  tc::launch_transpose_cast(ctx->p(LSTM_U), s->Urk, N, s->N4, 1, ctx->st);     // Urk[r'][k]
-  tc::launch_permute_rows_bf16(ctx->p(LSTM_U), s->Ukr, N, N, ctx->st);          // Ukr[k][r']
+  // Every bf16 copy of U from one pass over the fp32 master.  The row-major copies feed the per-timestep kernels only: a context
+  // whose shape runs a recurrence persistently (tc_recur.cu) reads the blocked copy instead and skips the other.
+  tc::launch_refresh_u(ctx->p(LSTM_U), s->bn2r ? nullptr : s->Urk, s->bnj5 ? nullptr : s->Ukr, s->Wb2, s->bn2r, s->Wb5, s->bnj5, M, N,
+                       ctx->st);
   tc::launch_permute_rows_f32(ctx->p(LSTM_W), s->Wp, M, N, ctx->st);            // Wp[m][r']
   tc::launch_permute_rows_f32(ctx->p(LSTM_B), s->bp, 1, N, ctx->st);
   tc::launch_transpose_cast(ctx->p(LSTM_WHY), s->Wmn, N, M, 0, ctx->st);       // Wmn[m][n]
-  tc::launch_cast_bf16(ctx->p(LSTM_WHY), s->Wnm, (size_t)M * N, ctx->st);      // Wnm[n][m]
-  LSTM_LAUNCHED(6);
-  if (s->bn2r) {
-    tc::launch_block_fwd_weights(ctx->p(LSTM_U), s->Wb2, N, s->bn2r, ctx->st);
-    LSTM_LAUNCHED(1);
-  }
-  if (s->bnj5) {
-    tc::launch_block_bwd_weights(ctx->p(LSTM_U), ctx->p(LSTM_WHY), s->Wb5, N, M, s->bnj5, ctx->st);
-    LSTM_LAUNCHED(1);
-  }
+  LSTM_LAUNCHED(4);
+  if (s->bnj5) tc::launch_block_why(ctx->p(LSTM_WHY), s->Wb5, N, M, s->bnj5, ctx->st);
+  else tc::launch_cast_bf16(ctx->p(LSTM_WHY), s->Wnm, (size_t)M * N, ctx->st);  // Wnm[n][m]
+  LSTM_LAUNCHED(1);
   return LSTM_OK;
 }
 
@@ -264,8 +262,21 @@ int tc_backward(lstm_ctx* ctx) {
     tc::GemmArgs g;
     g.rows = M; g.cols = N + 1; g.nkb = (int)(s->LDT / 64); g.a_k0 = 0; g.b_k0 = s->Bp; g.b_row0 = M;
     g.C = ctx->g(LSTM_WHY); g.ldc = M; g.tiles_m = M / 128; g.tiles_n = (N + 1 + 127) / 128;
-    tc::launch_gemm_nt(128, s->tmdYT, s->tmZT, g, ctx->st);
-    LSTM_LAUNCHED(1);
+    g.splits = 1; g.split_stride = 0;
+    // few output tiles and a long K: split K over enough CTAs to fill the SMs, partials summed in a fixed order
+    const int tiles = g.tiles_m * g.tiles_n;
+    int splits = 1;
+    while (splits < 8 && tiles * splits * 2 <= 148 && g.nkb % (splits * 2) == 0) splits *= 2;
+    const size_t out_n = ctx->P - ctx->off[LSTM_WHY];        // [Why | by] incl. alignment padding: a multiple of 4 floats
+    if (splits > 1 && s->kc_parts) {
+      g.nkb /= splits; g.splits = splits; g.split_stride = out_n; g.C = s->kc_parts;
+      tc::launch_gemm_nt(128, s->tmdYT, s->tmZT, g, ctx->st);
+      tc::launch_sum_splits(s->kc_parts, ctx->g(LSTM_WHY), out_n, out_n, splits, ctx->st);
+      LSTM_LAUNCHED(2);
+    } else {
+      tc::launch_gemm_nt(128, s->tmdYT, s->tmZT, g, ctx->st);
+      LSTM_LAUNCHED(1);
+    }
   }
   PROF(4);
   int rc = lstm_allreduce_bucket(ctx, 1);
@@ -315,6 +326,7 @@ int tc_backward(lstm_ctx* ctx) {
     g.rows = (int)N4; g.cols = M + N + 1; g.nkb = (int)(s->LDT / 64); g.a_k0 = 0; g.b_k0 = 0; g.b_row0 = 0;
     const int bn = (M + N + 1 >= 1024) ? 256 : 128;   // wide tiles once there are enough of them to fill the SMs
     g.C = ctx->g(LSTM_W); g.ldc = (long)N4; g.tiles_m = (int)N4 / 128; g.tiles_n = (M + N + 1 + bn - 1) / bn;
+    g.splits = 1; g.split_stride = 0;
     tc::launch_gemm_nt(bn, bn == 256 ? s->tmdGT : s->tmdGT, bn == 256 ? s->tmZT256 : s->tmZT, g, ctx->st);
     LSTM_LAUNCHED(1);
   }

@@ -538,8 +538,8 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
       if (w == 1) counters_wait(xcnt, 1, (unsigned int)KS * (unsigned int)(s + 1), lane);
       named_bar_sync(1, R_EPI_THREADS);                      // every reader is ordered after the acquire
       if (dbg && e == 0 && s == DBG_S) dbg[6] = clock64();
-      // 3. reduce: float4 position p = (u, row); sum over the KS sources in a fixed order
-#pragma unroll 1
+      // 3. reduce: float4 position p = (u, row); sum over the KS sources in a fixed order (both positions' loads in flight at once)
+#pragma unroll
       for (int p = e; p < 8 * 128; p += R_EPI_THREADS) {
         const int u = p >> 7, row = p & 127;
         float4 pv[KS];

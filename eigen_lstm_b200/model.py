@@ -160,7 +160,16 @@ class LSTM:
         x, t = self._win(x_idx), self._win(t_idx)
         loss = C.c_double()
         self._ck(self.lib.lstm_train_step(self.ctx, _ptr(x), _ptr(t), stride, lr, C.byref(loss) if want_loss else None))
+        if want_loss:
+            self.sync()                  # the step is asynchronous: its loss arrives with the next synchronisation
         return loss.value if want_loss else None
+
+    def train_step_async(self, x_idx, t_idx, losses, i, stride=1, lr=0.1):
+        """lstm_train_step without waiting: losses (float64 numpy array that outlives the next sync()) gets the step's loss
+        in losses[i] when sync() is called."""
+        x, t = self._win(x_idx), self._win(t_idx)
+        assert losses.dtype == np.float64 and losses.flags["C_CONTIGUOUS"]
+        self._ck(self.lib.lstm_train_step(self.ctx, _ptr(x), _ptr(t), stride, lr, C.c_void_p(losses.ctypes.data + 8 * i)))
 
     # ---- device text pipeline ----
     def load_text(self, data):

@@ -103,7 +103,10 @@ int lstm_adagrad(lstm_ctx* ctx, float lr, double eps, float clip);
  * (tests/test_oracle_vs_reference_source.py replays that program this way). */
 int lstm_carry_state(lstm_ctx* ctx, int stride);
 /* forward + backward + (data-parallel gradient allreduce) + adagrad + carry(stride) in one call: the window
- * starts from the state in slot 0 (lstm_set_state / the previous step's carry) and leaves h(stride),c(stride) there */
+ * starts from the state in slot 0 (lstm_set_state / the previous step's carry) and leaves h(stride),c(stride) there.
+ * ASYNCHRONOUS: x_idx / t_idx are copied into pinned staging before the call returns (the caller may reuse them at once);
+ * *loss_out (optional; must stay valid) is written at the next lstm_sync() — or any other call that synchronises the
+ * context — so that consecutive steps never wait for one another. */
 int lstm_train_step(lstm_ctx* ctx, const int32_t* x_idx, const int32_t* t_idx, int stride, float lr,
                     double* loss_out);
 

@@ -1,0 +1,29 @@
+#!/bin/bash
+# round 2, call f: v2 of the persistent recurrences (per-producer flags instead of a grid barrier, staggered k order, K5 merged math)
+OUT=gpurun_out
+mkdir -p $OUT
+B="python bench.py --steps 5 --warmup 3 --no-cpu-baseline"
+line() {
+  python - "$1" <<'PY'
+import json, sys
+try:
+    d = json.load(open(sys.argv[1]))
+    u = d["us_per_recurrent_timestep"]
+    print(f'{d["value"]:12.0f} chars/s {d["ms_per_step"]:8.3f} ms/step  fwd {u["forward"]:6.2f} us  bwd {u["backward"]:6.2f} us  '
+          f'loss {d["final_loss_bits_per_char"]!r}  launches {d["gpu_launches"]}')
+except Exception as e:
+    print("FAILED:", e)
+PY
+}
+timeout 600 python -m pytest tests/test_gpu_bench_variants.py tests/test_gpu_parity_bf16.py -x -q 2>&1 | tail -15 | tee $OUT/r02f_pytest.txt
+for V in "LSTM_X=0" "LSTM_BWD_RECUR=256"; do
+  F=$OUT/r02f_bench_$(echo $V | tr ' =' '__').json
+  env $V timeout 120 $B > $F 2> ${F%.json}.err
+  echo -n "   $V: "; line $F; tail -2 ${F%.json}.err
+done
+LSTM_TC_DEBUG=1 timeout 100 python scripts/recur_clocks.py cfg4 2>&1 | tail -26 | tee $OUT/r02f_clocks.txt
+python - <<'PY'
+import json
+d = json.load(open("gpurun_out/r02f_bench_LSTM_X_0.json"))
+print(d["phases_ms_last_step"]); print(d["e2e"])
+PY

@@ -11,6 +11,10 @@ Outputs (tests/golden/):
                     logged_test_bpc = column 4 of models/enwik5_test.txt:1 (3.24396)
   alice29_head.bin  first 8192 bytes of R/alice29.txt (config-1 loss-trace parity input)
   enwik6_head.bin   first 65536 bytes of R/enwik6.txt (batched-config parity input)
+  enwik5_test_{W,U,Why,b,by}.txt   the checkpoint files themselves, byte for byte (590 KB): the product's own reader
+                    (lstm_load_text_ckpt / `lstm --load`) must parse what the reference's save_to_disk wrote (io.h:16-32)
+  enwik6.txt        R/enwik6.txt in full (10^6 bytes): the corpus of BASELINE config 2 and the stand-in for the missing
+                    enwik7 of config 3 (bf16-vs-fp32 bits-per-char comparison, scripts/bpc_bf16_vs_f32.py)
   enwik6_hist.npy   byte histogram of R/enwik6.txt (int64[256]) for the synthetic bench corpus
 """
 import os
@@ -37,6 +41,11 @@ def main():
     open(f"{OUT}/alice29_head.bin", "wb").write(open(f"{R}/alice29.txt", "rb").read()[:8192])
     e6 = open(f"{R}/enwik6.txt", "rb").read()
     open(f"{OUT}/enwik6_head.bin", "wb").write(e6[:65536])
+    import shutil
+    for name in ["W", "U", "Why", "b", "by"]:
+        shutil.copyfile(f"{MD}/enwik5_test_{name}.txt", f"{OUT}/enwik5_test_{name}.txt")
+        os.chmod(f"{OUT}/enwik5_test_{name}.txt", 0o644)
+    open(f"{OUT}/enwik6.txt", "wb").write(e6)
     np.save(f"{OUT}/enwik6_hist.npy", np.bincount(np.frombuffer(e6, dtype=np.uint8), minlength=256).astype(np.int64))
     print("logged", logged, "test bytes", test_bytes.size)
 

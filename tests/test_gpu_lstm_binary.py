@@ -9,6 +9,7 @@ import json
 import os
 import re
 import subprocess
+import tempfile
 
 import pytest
 
@@ -80,3 +81,49 @@ def test_lstm_binary_heldout_eval_results_log_and_checkpoint_roundtrip(tmp_path,
     assert m, out2.stdout.decode(errors="replace")
     # the checkpoint was written at the LAST evaluation or at the end of the epoch (later): at least as good as the last row
     assert float(m.group(1)) < rows[-1, 3] + 0.3        # (an unloaded, untrained model scores 8.0)
+
+
+def test_reference_text_checkpoint_through_the_product_reader(golden_dir):
+    """the reference's own checkpoint files models/enwik5_test_{W,U,Why,b,by}.txt (written by its
+    Parameters::save_to_disk, OV/lstm_eigen_class_CUDA/io.h:16-32), committed byte for byte under tests/golden/, are parsed by
+    lstm_load_text_ckpt — not by numpy — and evaluated on the GPU with the test() recipe: the reference logged 3.24396."""
+    import numpy as np
+    import eigen_lstm_b200 as el
+    z = np.load(os.path.join(golden_dir, "enwik5_test.npz"))
+    g = el.LSTM(256, 32, 3, 1)
+    g.load_from_disk(os.path.join(golden_dir, "enwik5_test"))
+    bpc = g.test(z["test_bytes"].tobytes())
+    assert abs(bpc - float(z["logged_test_bpc"])) < 2e-4, bpc
+    for name, got in zip(["W", "U", "b", "Why", "by"], g.params()):
+        assert np.array_equal(got, z[name].reshape(got.shape)), name      # same numbers numpy parsed from the same files
+    # and through the drop-in binary: `lstm --load` + a held-out evaluation prints the same test error
+    with tempfile.TemporaryDirectory() as d:
+        corpus = os.path.join(d, "enwik5_like.txt")
+        text = open(os.path.join(golden_dir, "enwik6.txt"), "rb").read()[:100000]
+        open(corpus, "wb").write(text)
+        out = subprocess.run([BIN, "--file", corpus, "--hidden", "32", "--seq", "25", "--batch", "16", "--lr", "0", "--epochs", "1",
+                              "--max-iters", "300", "--train-percent", "99", "--test-every", "0.001", "--sample", "0", "--seed", "1",
+                              "--load", os.path.join(golden_dir, "enwik5_test")], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stderr
+        errs = [float(l.split("Test error: ")[1]) for l in out.stdout.splitlines() if "Test error: " in l]
+        assert errs and abs(errs[0] - 3.24396) < 2e-4, out.stdout[-400:]
+
+
+def test_last_snapshot_workflow_flags(golden_dir):
+    """lr = 0 while the window warms up (OV/lstm_eigen_class_CUDA/lstm.cc:364-367), the eta progress line (:239-268), --clip and the
+    class_batch loss report through the binary."""
+    with tempfile.TemporaryDirectory() as d:
+        corpus = os.path.join(d, "c.txt")
+        open(corpus, "wb").write(open(os.path.join(golden_dir, "enwik6_head.bin"), "rb").read()[:20000])
+        base = [BIN, "--file", corpus, "--hidden", "32", "--seq", "8", "--batch", "4", "--epochs", "1", "--sample", "0", "--seed", "3",
+                "--stride", "7", "--max-iters", "400"]
+        a = subprocess.run(base + ["--save", os.path.join(d, "a"), "--lr-warmup", "400"], capture_output=True, text=True, timeout=120)
+        b = subprocess.run(base + ["--save", os.path.join(d, "b"), "--lr", "0"], capture_output=True, text=True, timeout=120)
+        assert a.returncode == 0 and b.returncode == 0, a.stderr + b.stderr
+        for n in ("W", "U", "Why", "b", "by"):                               # 400 warm-up iterations = 400 iterations at lr 0
+            assert open(os.path.join(d, f"a_{n}.txt")).read() == open(os.path.join(d, f"b_{n}.txt")).read(), n
+        c = subprocess.run(base + ["--progress", "eta", "--clip", "0.5", "--loss", "last-ln", "--softmax-shift", "global"],
+                           capture_output=True, text=True, timeout=120)
+        assert c.returncode == 0, c.stderr
+        import re
+        assert re.search(r"\[Epoch 1/1\]\s+\d+\.\d\d%\s+\(eta\s+\d+ h \d\d m \d\d s\)\s+loss = \d+\.\d{6}\s+\d+\.\d\d GFlOP/s", c.stdout), c.stdout[:300]
