@@ -40,6 +40,8 @@ WORKLOADS = {
     "cfg3": dict(N=1024, B=128, S=101, desc="char-LSTM H=1024, batch 128, seq 100"),
     "cfg2": dict(N=512, B=64, S=101, desc="class_batch-style char-LSTM H=512, batch 64, seq 100"),
     "cfg1": dict(N=64, B=1, S=3, desc="lstm.cc default char-LSTM H=64, batch 1, S=3"),
+    # BASELINE.json configs[4]: a different metric (sampled chars/s); handled by bench_sampling()
+    "cfg5": dict(N=1024, B=1, S=3, desc="latency-bound sampling: 1M chars at batch 1 from an H=1024 model (persistent recurrent kernel)"),
 }
 M = 256
 LR = 0.002   # Adagrad's first steps move every weight by +-lr whatever the gradient size; 0.1 (R/lstm.cc:59) saturates a 2048-wide net
@@ -108,85 +110,187 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (port of the reference's algorithm) on host cores, bounded sample
 # -------------------------------------------------------------------------------------------------
-def blas_threads():
-    """Threads numpy's BLAS will use (threadpoolctl when present, else the core count)."""
+def host_threads():
+    """Threads the CPU arm uses: every core the process may run on — set EXPLICITLY, so that the number does not depend on how
+    the process was launched (torch.distributed.run exports OMP_NUM_THREADS=1 to its workers)."""
     try:
-        from threadpoolctl import threadpool_info
-        n = [d.get("num_threads", 0) for d in threadpool_info() if d.get("user_api") == "blas"]
-        if n:
-            return int(max(n))
+        return len(os.sched_getaffinity(0))
     except Exception:
-        pass
-    return os.cpu_count() or 1
+        return os.cpu_count() or 1
 
 
-def cpu_arm_blas(cfg, text, target_seconds, steps=1, warmup=0):
-    """Large configurations: the structure of OV/lstm_eigen_BLAS/lstm.cc (every contraction a multi-threaded BLAS GEMM,
-    dense one-hot products) on numpy's OpenBLAS — oracle/oracle_blas.py — over ALL B streams and a bounded number of
-    timesteps."""
+def cpu_arm_torch(cfg, text, target_seconds, steps=1, warmup=0):
+    """Large configurations: the structure of OV/lstm_eigen_BLAS/lstm.cc (every contraction one multi-threaded BLAS GEMM with
+    dense one-hot inputs, like the reference; element-wise work between them) on torch's CPU backend — oracle/oracle_torch.py —
+    with all B streams.  A full window is COMPOSED from separately timed parts, T * t_timestep + t_adagrad: the per-timestep cost
+    is measured over a bounded number of timesteps, the Adagrad sweep once, and one sweep is charged per window of T timesteps
+    exactly as in the real iteration."""
     from oracle import oracle as orc
-    from oracle import oracle_blas as ob
+    from oracle import oracle_torch as ot
     N, S, B = cfg["N"], cfg["S"], cfg["B"]
+    T = S - 1
+    th = host_threads()
     params = orc.init_params(M, N, seed=0, sd=0.01)
-
-    def make(Tw):
-        q = ob.BlasOracle(M, N, Tw + 1, B)
-        q.set_params(params)
-        return q, [Tw + 1 + i * 1000 for i in range(B)]
-
-    q, pos = make(2)                                   # probe: cost of one timestep of B streams (+ one Adagrad sweep)
-    q.train_windows(text, pos, 1, 2, LR)
-    _, secs = q.train_windows(text, pos, 1, 2, LR)
-    Ts = int(max(2, min(S - 1, target_seconds / max(secs / 2, 1e-9))))
-    del q
-    q, pos = make(Ts)
-    for _ in range(warmup):
-        q.train_windows(text, pos, 1, Ts, LR)
-    t = []
-    for _ in range(steps):
-        _, secs = q.train_windows(text, pos, 1, Ts, LR)
-        t.append(secs)
-    secs = sum(t) / len(t)
-    th = blas_threads()
-    return dict(value=B * Ts / secs, unit="chars/s", cores=th, kind="port",
-                sample=f"{B} streams x {Ts} timesteps of the same N={N} model per step (full workload: {B} x {S - 1}), "
-                       f"oracle/oracle_blas.py: the lstm_eigen_BLAS structure (every contraction a BLAS sgemm, dense one-hot "
-                       f"products like the reference) on numpy's OpenBLAS, {th} threads"), secs
+    t_step, t_ada, th = ot.time_parts(M, N, B, 2, params, text, threads=th)          # probe
+    Ts = int(max(2, min(T, target_seconds / max(t_step, 1e-9))))
+    vals = []
+    for _ in range(max(1, steps)):
+        t_step, t_ada, th = ot.time_parts(M, N, B, Ts, params, text, threads=th)
+        vals.append((t_step, t_ada))
+    t_step = sum(v[0] for v in vals) / len(vals)
+    t_ada = sum(v[1] for v in vals) / len(vals)
+    window_s = T * t_step + t_ada
+    fl = flops_per_charstep(N)["dense"] * B
+    return dict(value=B * T / window_s, unit="chars/s", cores=th, kind="port",
+                gflops_dense=fl / t_step / 1e9, seconds_per_timestep=t_step, seconds_per_adagrad_sweep=t_ada,
+                sample=f"{B} streams x {Ts} timesteps timed (forward + BPTT), one Adagrad sweep timed separately; a full window "
+                       f"composed as {T} x t_timestep + t_adagrad.  oracle/oracle_torch.py: the lstm_eigen_BLAS structure (every "
+                       f"contraction one BLAS sgemm, dense one-hot products like the reference, multi-threaded element-wise math) "
+                       f"on torch's CPU backend, {th} threads set explicitly"), window_s
 
 
 def cpu_arm(cfg, text, target_seconds, steps=1, warmup=0):
     from oracle import oracle as orc
     N, S = cfg["N"], cfg["S"]
     if cfg["B"] * N >= 4096 and not os.environ.get("BENCH_CPU_PORT"):
-        return cpu_arm_blas(cfg, text, target_seconds, steps, warmup)   # GEMM throughput decides: use the best BLAS present
-    threads = os.cpu_count() or 1
-    if cfg["B"] * N < 4096:
-        threads = 1                                   # tiny models: fork/join costs more than the loops (the reference is 1 thread)
-    Bs = min(cfg["B"], threads)                       # one stream per host thread
-    # probe: a short window to find the per-char-step cost, then size the sample
-    Tp = min(S - 1, 4)
-    o = orc.Oracle(M, N, Tp + 1, Bs, "f32", mt=True, threads=threads)
+        return cpu_arm_torch(cfg, text, target_seconds, steps, warmup)   # GEMM throughput decides: use the best BLAS present
+    threads = 1                                       # tiny models: fork/join costs more than the loops (the reference is 1 thread)
+    Bs = min(cfg["B"], threads)
+    # the reference's own default (config 1): the single-thread C++ port compiled with the reference's flags, full windows
+    iters = 2000
+    o = orc.Oracle(M, N, S, Bs, "f32", mt=False, threads=1)
     o.set_options(dense_onehot=1)                     # the reference multiplies the one-hot densely (R/lstm.cc:176,251)
     o.set_params(orc.init_params(M, N, seed=0, sd=0.01))
-    o.set_positions([Tp + 1 + i * 1000 for i in range(Bs)])
-    _, secs = o.train(text, 1, stride=Tp, lr=0.1)
-    per_cs = secs / (Bs * Tp)
-    Ts = int(max(2, min(S - 1, target_seconds / max(per_cs * Bs, 1e-9))))
-    del o
-    o = orc.Oracle(M, N, Ts + 1, Bs, "f32", mt=True, threads=threads)
-    o.set_options(dense_onehot=1)
-    o.set_params(orc.init_params(M, N, seed=0, sd=0.01))
-    o.set_positions([Ts + 1 + i * 1000 for i in range(Bs)])
-    for _ in range(warmup):
-        o.train(text, 1, stride=Ts, lr=0.1)
+    o.set_positions([S + i * 1000 for i in range(Bs)])
+    _, secs = o.train(text, iters, stride=S - 1, lr=0.1)
+    iters = int(max(200, min(2_000_000, iters * target_seconds / max(secs, 1e-9))))
     t = []
-    for _ in range(steps):
-        _, secs = o.train(text, 1, stride=Ts, lr=0.1)
-        t.append(secs)
-    secs = sum(t) / len(t)
-    return dict(value=Bs * Ts / secs, unit="chars/s", cores=o.threads, kind="port",
-                sample=f"{Bs} streams x {Ts} timesteps of the same N={N} model per step (full workload: {cfg['B']} x {S - 1}), "
-                       f"oracle/liblstm_oracle_mt.so, dense one-hot products like the reference, {o.threads} host threads"), secs
+    for _ in range(max(1, steps)):
+        _, secs = o.train(text, iters, stride=S - 1, lr=0.1)
+        t.append(secs / iters)
+    per_iter = sum(t) / len(t)
+    return dict(value=Bs * (S - 1) / per_iter, unit="chars/s", cores=1, kind="port",
+                gflops_dense=flops_per_charstep(N)["dense"] * Bs * (S - 1) / per_iter / 1e9,
+                sample=f"{iters} full training iterations (window of {S - 1} timesteps, forward + BPTT + Adagrad) of the N={N} model, "
+                       f"oracle/liblstm_oracle.so: the scalar port compiled like R/Makefile (g++ -O3, one thread, dense one-hot "
+                       f"products like the reference)"), per_iter
+
+
+def dp_check(el, dist, rank, world, local_rank, net, dtype_code):
+    """Correctness of the data-parallel path, run before the timed region on every multi-GPU bench (the records then carry it):
+      (1) `world` contexts with b streams each == ONE context with world*b streams (fp32: the exact same sums up to order),
+          on a small shape, after 4 full training iterations incl. graph capture and replay;
+      (2) at the BENCH shape: the gradients the library allreduced itself == the sum over ranks of the gradients of a second,
+          communicator-less context fed the same local window (summed here with torch.distributed);
+      (3) replicas bit-identical (min == max over ranks of every parameter) — checked again after the timed region."""
+    import torch
+    from eigen_lstm_b200 import dp
+    out = {}
+    dev = torch.device("cuda", local_rank)
+    # (1) small-shape equivalence
+    Ms, Ns, Ss, Bs, chunk = 256, 64, 6, 4, 700
+    text = synthetic_text(chunk * Bs * world + 64, seed=3).tobytes()
+    g = el.LSTM(Ms, Ns, Ss, Bs, device=local_rank, dtype=el.F32)
+    g.dp_init(rank, world, dp.broadcast_unique_id(dist, el.dp_unique_id, rank))
+    g.init_params(7, 0.05, 1.0)
+    g.load_text(text); g.set_positions(dp.stream_positions(Bs * world, rank, world, Ss, chunk))
+    g.train_text(4, stride=Ss - 1, lr=0.01)
+    flat = np.concatenate([p.ravel(order="F") for p in g.params()])
+    err = 0.0
+    if rank == 0:
+        one = el.LSTM(Ms, Ns, Ss, Bs * world, device=local_rank, dtype=el.F32)
+        one.init_params(7, 0.05, 1.0)
+        one.load_text(text); one.set_positions(dp.stream_positions(Bs * world, 0, 1, Ss, chunk))
+        one.train_text(4, stride=Ss - 1, lr=0.01)
+        ref = np.concatenate([p.ravel(order="F") for p in one.params()])
+        err = float(np.max(np.abs(flat - ref)) / np.max(np.abs(ref)))
+        one.close()
+    out["f32_vs_one_gpu_with_concatenated_batch_max_rel_err"] = err
+    t = torch.from_numpy(flat).to(dev)
+    lo, hi = t.clone(), t.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    out["small_replicas_identical"] = bool(torch.equal(lo, hi))
+    g.close()
+    # (2) bench shape: library allreduce vs torch.distributed sum of local gradients (one forward + backward, no update)
+    M_, N_, S_, B_ = net.M, net.N, net.S, net.B
+    x, tg = net.window()
+    if (x[1:] < 0).any():                      # the window has not been built yet: advance once
+        net.train_text(1, stride=S_ - 1, lr=0.0, want_losses=False)
+        x, tg = net.window()
+    h0, c0 = net.get_state()
+    net.forward(x, tg); net.backward(); net.sync()
+    got = [a.copy() for a in net.grads()]
+    loc = el.LSTM(M_, N_, S_, B_, device=local_rank, dtype=dtype_code)
+    loc.set_params(net.params()); loc.set_state(h0, c0)
+    loc.forward(x, tg); loc.backward()
+    worst = 0.0
+    for a, b in zip(got, loc.grads()):
+        tb = torch.from_numpy(np.ascontiguousarray(b)).to(dev)
+        dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+        want = tb.cpu().numpy()
+        worst = max(worst, float(np.max(np.abs(a - want)) / max(float(np.max(np.abs(want))), 1e-30)))
+    loc.close()
+    net.set_state(h0, c0)
+    tw = torch.tensor([worst], device=dev, dtype=torch.float64)
+    dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+    out["bench_shape_allreduced_grads_vs_sum_of_local_grads_max_rel_err"] = float(tw.item())
+    out["ok"] = bool(out["small_replicas_identical"] and out["bench_shape_allreduced_grads_vs_sum_of_local_grads_max_rel_err"] < 1e-4
+                     and (rank != 0 or err < 2e-4))
+    return out
+
+
+def replicas_identical(dist, net, local_rank):
+    import torch
+    flat = np.concatenate([p.ravel(order="F") for p in net.params()])
+    t = torch.from_numpy(flat).to(torch.device("cuda", local_rank))
+    lo, hi = t.clone(), t.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    return bool(torch.equal(lo, hi))
+
+
+def bench_sampling(args, cfg):
+    """BASELINE.json configs[4]: generate characters at batch 1 from an H=1024 model with the persistent batch-1 kernel (K9),
+    and the companion held-out evaluation (test()).  One JSON line; the metric here is SAMPLED chars/s."""
+    import torch
+    import eigen_lstm_b200 as el
+    N = cfg["N"]
+    n = 1_000_000
+    net = el.LSTM(M, N, 3, 1, device=0, dtype=el.F32)
+    net.init_params(seed=0, std=0.05, forget_bias=0.0)
+    stream = torch.cuda.ExternalStream(net.stream(), device=torch.device("cuda", 0))
+    net.sample(20000, seed=1)                                    # warm-up
+    sampler = ClockSampler(0)
+    t = []
+    for k in range(max(1, args.steps)):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        out = net.sample(n, seed=2 + k)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t.append(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    ms = sum(t) / len(t)
+    text = synthetic_text(200_001, seed=5).tobytes()
+    net.test(text[:20000])
+    w0 = time.perf_counter(); bpc = net.test(text); ev_s = time.perf_counter() - w0
+    pk = peaks()
+    U_bytes = 4.0 * N * N * 4                                    # fp32 U resident in shared memory, read once per character
+    line = {"metric": "sampled chars/sec at batch 1 (persistent recurrent kernel)", "value": n / (ms * 1e-3), "unit": "chars/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"cfg5: {cfg['desc']}", "N": N, "M": M, "chars_per_step": n,
+                       "l2": "weights are resident in shared memory; per-step traffic is h(t) only"},
+            "us_per_sampled_char": ms * 1e3 / n, "us_per_evaluated_char": ev_s * 1e6 / (len(text) - 1), "eval_bits_per_char": bpc,
+            "e2e": {"value": n / (ms * 1e-3), "unit": "chars/s", "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": n,
+                    "api": "lstm_sample: host uniforms -> device, sampled bytes -> host, inside the timed region"},
+            "gpu_launches": int(args.steps), "clocks": clocks,
+            "roofline": {"bound": "latency", "kernel": "k_recur_persist (one grid barrier pair per character)",
+                         "achieved": U_bytes * n / (ms * 1e-3) / 1e9, "peak": None, "unit": "GB/s (shared-memory weight reads)",
+                         "frac": None, "traffic": None,
+                         "note": "serial GEMV chain: bounded by two grid-wide barriers per character, not by bandwidth; reported in us/char"},
+            "sampled_text_head": bytes(out[:60]).decode("latin1")}
+    print(json.dumps(line), flush=True)
+    return 0
 
 
 def main():
@@ -199,6 +303,7 @@ def main():
     ap.add_argument("--dtype", default="auto", choices=["auto", "bf16", "f32"])
     ap.add_argument("--cpu-seconds", type=float, default=None, help="CPU work per sample (default 12 s for cpu_baseline; --impl reference sizes it from --steps)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-f32", action="store_true", help="skip the fp32-path measurement of the same workload")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     cfg = WORKLOADS[args.workload]
@@ -212,11 +317,13 @@ def main():
               "global_batch": B * world, "parallelism": f"dp{world}",
               "flops_per_charstep_dense": fl["dense"], "flops_per_charstep_alg": fl["alg"]}
 
+    if args.workload == "cfg5" and args.impl != "reference":
+        return bench_sampling(args, cfg) if rank == 0 else 0
     if args.impl == "reference":
         if rank != 0:
             return 0
         text = synthetic_text(1 << 20)
-        per_step = args.cpu_seconds if args.cpu_seconds else max(2.0, min(20.0, 90.0 / (args.steps + args.warmup)))
+        per_step = args.cpu_seconds if args.cpu_seconds else max(2.0, min(20.0, 90.0 / (args.steps + 1)))
         cb, secs = cpu_arm(cfg, text.tobytes(), per_step, steps=args.steps, warmup=args.warmup)
         line = {"impl": "reference", "metric": "training chars/sec (fwd+BPTT+Adagrad)", "value": cb["value"], "unit": "chars/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs * 1e3,
@@ -224,8 +331,9 @@ def main():
                 "config": config, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "chars/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "note": "R/lstm.cc and OV/lstm_eigen_BLAS need Eigen / OpenBLAS, which are not installed (no network): the CPU arm is "
-                        "the oracle's port of the algorithm on the best BLAS present, all host threads (the reference sources "
-                        "compiled against oracle/eigen_shim pin the oracle's semantics but are not a timing baseline)"}
+                        "the oracle's port of the algorithm on the best BLAS present (torch CPU), all host threads set explicitly "
+                        "(same count at every N); the reference sources compiled against oracle/eigen_shim pin the oracle's "
+                        "semantics but are not a timing baseline"}
         print(json.dumps(line), flush=True)
         return 0
 
@@ -258,6 +366,12 @@ def main():
     net.load_text(text.tobytes())
     net.set_positions([S + (rank * B + b) * chunk for b in range(B)])
     stream = torch.cuda.ExternalStream(net.stream(), device=torch.device("cuda", local_rank))
+    dpc = None
+    if world > 1:
+        dpc = dp_check(el, dist, rank, world, local_rank, net, el.BF16 if dtype == "bf16" else el.F32)
+        net.init_params(seed=0, std=0.01, forget_bias=1.0)
+        net.reset_state(0, 0.0)
+        net.set_positions([S + (rank * B + b) * chunk for b in range(B)])
 
     def barrier():
         if world > 1:
@@ -306,20 +420,25 @@ def main():
     for _ in range(3):
         pos += T; host_window(pos); net.train_step(xn, tn, stride=T, lr=LR)
     barrier()
+    e2e_losses = np.zeros(args.steps, dtype=np.float64)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         pos += T
-        host_window(pos)
-        net.train_step(xn, tn, stride=T, lr=LR, want_loss=True)
+        host_window(pos)                                          # the step's inputs are produced on the host ...
+        net.train_step_async(xn, tn, e2e_losses, i, stride=T, lr=LR)   # ... copied in, and the step's loss is copied out, every step
+    net.sync()                                                    # all K losses are on the host when the clock stops
     barrier()
     e2e_s = time.perf_counter() - t0
+    assert np.all(np.isfinite(e2e_losses)) and np.all(e2e_losses > 0), e2e_losses
     if world > 1:
         tm = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         e2e_s = float(tm.item())
     e2e = {"value": B * T * world * args.steps / e2e_s, "unit": "chars/s", "h2d_bytes_per_step": int(2 * S * B * 4),
            "d2h_bytes_per_step": 8, "ms_per_step": e2e_s * 1e3 / args.steps,
-           "api": "lstm_train_step (host int32 windows in pinned memory -> device, loss -> host, every step)"}
+           "api": "lstm_train_step (host int32 windows -> pinned staging -> device, loss -> host, every step; steps are "
+                  "asynchronous, the clock stops after lstm_sync has delivered all losses)"}
+    same = replicas_identical(dist, net, local_rank) if world > 1 else None
 
     if rank != 0:
         if world > 1:
@@ -376,6 +495,28 @@ def main():
                                   "frac_of_peak_alg": e2e_tf / (pk["tf_sustained"] * world)},
             "final_loss_bits_per_char": float(losses[-1] / T) if len(losses) else None, "learning_rate": LR,
             "launch_mode": "one CUDA graph per training iteration (timed region); plain stream launches for the profiled iteration"}
+    if dpc is not None:
+        dpc["replicas_identical_after_timed_region"] = same
+        dpc["ok"] = bool(dpc["ok"] and same)
+        line["dp_check"] = dpc
+    if world == 1 and dtype == "bf16" and not args.no_f32:
+        # the same configuration on the fp32 path (SIMT FFMA, the reference's arithmetic): same-precision throughput
+        net.close()
+        f = el.LSTM(M, N, S, B, device=local_rank, dtype=el.F32)
+        f.init_params(seed=0, std=0.01, forget_bias=1.0); f.reset_state(0, 0.0)
+        f.load_text(text.tobytes()); f.set_positions([S + b * chunk for b in range(B)])
+        fs = torch.cuda.ExternalStream(f.stream(), device=torch.device("cuda", local_rank))
+        f.train_text(2, stride=T, lr=LR, want_losses=False); f.sync()
+        k = 3
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(fs); f.train_text(k, stride=T, lr=LR, want_losses=False); e1.record(fs)
+        torch.cuda.synchronize()
+        fms = e0.elapsed_time(e1) / k
+        line["f32"] = {"value": B * T / (fms * 1e-3), "unit": "chars/s", "ms_per_step": fms, "steps": k,
+                       "tflops_dense": fl["dense"] * B * T / (fms * 1e-3) / 1e12,
+                       "note": "same workload on the LSTM_F32 path (every contraction fp32 SIMT FFMA, the reference's rounding): "
+                               "the same-precision number; the headline `value` is the bf16-GEMM / fp32-accumulate path"}
+        f.close()
     if not args.no_cpu_baseline and world == 1:
         cb, _ = cpu_arm(cfg, text.tobytes()[: 1 << 20], args.cpu_seconds or 12.0)
         line["cpu_baseline"] = cb

@@ -138,7 +138,7 @@ extern "C" int lstm_create(lstm_ctx** out, int M, int N, int S, int B, int devic
   } while (0)
   CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
   CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->comm_st, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < lstm_ctx::NBUCKET; i++) {
     CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_bucket[i], cudaEventDisableTiming));
     CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_comm[i], cudaEventDisableTiming));
   }
@@ -213,7 +213,7 @@ extern "C" int lstm_destroy(lstm_ctx* ctx) {
   }
   if (ctx->d_iter) cudaFree(ctx->d_iter);
   for (auto& g : ctx->graph) free_iter_graph(g);
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < lstm_ctx::NBUCKET; i++) {
     if (ctx->ev_bucket[i]) cudaEventDestroy(ctx->ev_bucket[i]);
     if (ctx->ev_comm[i]) cudaEventDestroy(ctx->ev_comm[i]);
   }
@@ -442,8 +442,11 @@ int lstm_allreduce_bucket(lstm_ctx* ctx, int bucket) {
   // bucket 0 = [W,U,b], bucket 1 = [Why,by]; both contiguous in the flat gradient vector.
   if (ctx->world <= 1) return LSTM_OK;
   if (ctx->seg_capture) return cut_segment(ctx, bucket);   // capture pass: the graph ends here, NCCL runs between replays
-  float* ptr = bucket == 0 ? ctx->g(LSTM_W) : ctx->g(LSTM_WHY);
-  const size_t cnt = bucket == 0 ? ctx->off[LSTM_WHY] : ctx->P - ctx->off[LSTM_WHY];
+  // K6a may be launched as two column panels of the column-major [W|U|b] matrix = two contiguous ranges of the flat gradient
+  // vector: the leading panel (bucket 2) is summed while the second one is still being computed
+  const size_t split = ctx->panel_split;
+  float* ptr = bucket == 1 ? ctx->g(LSTM_WHY) : (bucket == 2 ? ctx->g(LSTM_W) : ctx->g(LSTM_W) + split);
+  const size_t cnt = bucket == 1 ? ctx->P - ctx->off[LSTM_WHY] : (bucket == 2 ? split : ctx->off[LSTM_WHY] - split);
   LSTM_CUDA(cudaEventRecord(ctx->ev_bucket[bucket], ctx->st));
   LSTM_CUDA(cudaStreamWaitEvent(ctx->comm_st, ctx->ev_bucket[bucket], 0));
   LSTM_NCCL(g_nccl.AllReduce(ptr, ptr, cnt, ncclFloat, ncclSum, ctx->comm, ctx->comm_st));
@@ -493,8 +496,7 @@ static int backward_device(lstm_ctx* ctx) {
 
 static int adagrad_device(lstm_ctx* ctx, float lr, double eps, float clip) {
   if (ctx->world > 1 && !ctx->seg_capture) {   // segmented replay issues these waits itself, before the last segment
-    LSTM_CUDA(cudaStreamWaitEvent(ctx->st, ctx->ev_comm[0], 0));
-    LSTM_CUDA(cudaStreamWaitEvent(ctx->st, ctx->ev_comm[1], 0));
+    for (int i = 0; i < lstm_ctx::NBUCKET; i++) LSTM_CUDA(cudaStreamWaitEvent(ctx->st, ctx->ev_comm[i], 0));
   }
   PROF(7);
   launch_adagrad_f32(ctx->params, ctx->grads, ctx->mem, ctx->P, lr, eps, clip, ctx->st);
@@ -632,8 +634,7 @@ static int run_iteration(lstm_ctx* ctx, int mode, int stride, float lr) {
   } else {
     for (size_t i = 0; i < g.segs.size(); i++) {
       if (i + 1 == g.segs.size() && i > 0) {                  // Adagrad reads the summed gradients
-        LSTM_CUDA(cudaStreamWaitEvent(ctx->st, ctx->ev_comm[0], 0));
-        LSTM_CUDA(cudaStreamWaitEvent(ctx->st, ctx->ev_comm[1], 0));
+        for (int b = 0; b < lstm_ctx::NBUCKET; b++) LSTM_CUDA(cudaStreamWaitEvent(ctx->st, ctx->ev_comm[b], 0));
       }
       LSTM_CUDA(cudaGraphLaunch(g.segs[i], ctx->st));
       if (g.seg_bucket[i] >= 0) {
@@ -666,8 +667,7 @@ extern "C" int lstm_backward(lstm_ctx* ctx) {
   int rc = backward_device(ctx);
   if (rc) return rc;
   if (ctx->world > 1) {  // standalone backward: make the summed gradients visible to the caller
-    LSTM_CUDA(cudaStreamWaitEvent(ctx->st, ctx->ev_comm[0], 0));
-    LSTM_CUDA(cudaStreamWaitEvent(ctx->st, ctx->ev_comm[1], 0));
+    for (int i = 0; i < lstm_ctx::NBUCKET; i++) LSTM_CUDA(cudaStreamWaitEvent(ctx->st, ctx->ev_comm[i], 0));
   }
   return LSTM_OK;
 }

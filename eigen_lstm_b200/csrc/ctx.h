@@ -15,7 +15,9 @@ struct Bf16State;  // bf16 tensor-core path state (tc_path.cu)
 struct lstm_ctx {
   int M = 0, N = 0, S = 0, B = 0, T = 0, device = 0, dtype = 0;
   cudaStream_t st = nullptr, comm_st = nullptr;
-  cudaEvent_t ev_bucket[2] = {nullptr, nullptr}, ev_comm[2] = {nullptr, nullptr};
+  static constexpr int NBUCKET = 4;   // 0 = [W|U|b] (or its tail panel), 1 = [Why|by], 2 = leading column panel of [W|U|b]
+  cudaEvent_t ev_bucket[NBUCKET] = {}, ev_comm[NBUCKET] = {};
+  size_t panel_split = 0;             // floats of [W|U|b] summed as bucket 2 (0 = none): set by the path that launches K6a in two panels
   // flat parameter / gradient / Adagrad-memory vectors, tensor order W,U,b,Why,by (column-major each)
   size_t P = 0, off[5] = {0, 0, 0, 0, 0}, sz[5] = {0, 0, 0, 0, 0};
   float *params = nullptr, *grads = nullptr, *mem = nullptr;
@@ -113,5 +115,6 @@ int tc_state_to_f32(lstm_ctx* ctx);    // bf16 h(0) -> Hs slot 0
 int tc_carry(lstm_ctx* ctx, int stride);
 int tc_debug_read(lstm_ctx* ctx, long long out[32]);
 void tc_variant(lstm_ctx* ctx, int out[8]);   // which kernel instantiations this context's shape selects
-// sum gradient bucket (0 = [W,U,b], 1 = [Why,by]) over the data-parallel ranks on the communication stream
+// sum gradient bucket (0 = [W,U,b] from ctx->panel_split on, 1 = [Why,by], 2 = the first panel_split floats of [W,U,b]) over
+// the data-parallel ranks on the communication stream
 int lstm_allreduce_bucket(lstm_ctx* ctx, int bucket);

@@ -567,17 +567,20 @@ void launch_recur_b1_f32(const float* W, const float* U, const float* bias, cons
 // double-buffered global vector and one grid-wide barrier; sampling needs the full softmax, i.e. a second
 // barrier; evaluation defers the softmax normalisation to the end (per-step partial sums) and needs one.
 // ------------------------------------------------------------------------------------------------
+// One arriving thread (release: cumulative over the __syncthreads-ordered stores of the CTA) and one polling WARP per CTA:
+// scripts/gridbar_bench.cu measures 1.17 us per barrier over 128 co-resident CTAs for this scheme against 4.4 us for
+// atomicAdd + last-arriver flag.  Bounded: a protocol bug must not hang the GPU.
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
+  if (threadIdx.x < 32) {
+    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
     const long long t0 = clock64();
-    unsigned int v;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-      if (clock64() - t0 > 4000000000LL) __trap();   // a protocol bug must not hang the GPU
-    } while ((int)(v - target) < 0);
+    for (;;) {
+      unsigned int v = target;
+      if (threadIdx.x == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (__all_sync(0xffffffffu, (int)(v - target) >= 0)) break;
+      if (clock64() - t0 > 4000000000LL) __trap();
+    }
   }
   __syncthreads();
 }

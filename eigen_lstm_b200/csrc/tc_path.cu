@@ -327,8 +327,25 @@ int tc_backward(lstm_ctx* ctx) {
     const int bn = (M + N + 1 >= 1024) ? 256 : 128;   // wide tiles once there are enough of them to fill the SMs
     g.C = ctx->g(LSTM_W); g.ldc = (long)N4; g.tiles_m = (int)N4 / 128; g.tiles_n = (M + N + 1 + bn - 1) / bn;
     g.splits = 1; g.split_stride = 0;
-    tc::launch_gemm_nt(bn, bn == 256 ? s->tmdGT : s->tmdGT, bn == 256 ? s->tmZT256 : s->tmZT, g, ctx->st);
-    LSTM_LAUNCHED(1);
+    // Data parallel: two column panels (6 + 4 tile columns of 256 at N = 2048: 2.6 + 1.7 waves, the same five tile times as one
+    // launch of 4.3 waves); the leading panel's allreduce then runs under the second panel's GEMM.
+    const int lead = g.tiles_n >= 10 ? (g.tiles_n * 6) / 10 : 0;
+    ctx->panel_split = 0;
+    if (ctx->world > 1 && lead > 0) {
+      tc::GemmArgs g1 = g, g2 = g;
+      g1.tiles_n = lead; g1.cols = lead * bn;
+      g2.tiles_n = g.tiles_n - lead; g2.cols = g.cols - lead * bn; g2.b_row0 = lead * bn; g2.C = g.C + (size_t)lead * bn * g.ldc;
+      ctx->panel_split = (size_t)lead * bn * (size_t)N4;
+      tc::launch_gemm_nt(bn, s->tmdGT, bn == 256 ? s->tmZT256 : s->tmZT, g1, ctx->st);
+      LSTM_LAUNCHED(1);
+      int rc2 = lstm_allreduce_bucket(ctx, 2);
+      if (rc2) return rc2;
+      tc::launch_gemm_nt(bn, s->tmdGT, bn == 256 ? s->tmZT256 : s->tmZT, g2, ctx->st);
+      LSTM_LAUNCHED(1);
+    } else {
+      tc::launch_gemm_nt(bn, s->tmdGT, bn == 256 ? s->tmZT256 : s->tmZT, g, ctx->st);
+      LSTM_LAUNCHED(1);
+    }
   }
   PROF(6);
   return lstm_allreduce_bucket(ctx, 0);

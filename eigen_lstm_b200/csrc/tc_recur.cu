@@ -86,16 +86,25 @@ __device__ __forceinline__ void counters_wait(const unsigned int* slots, int n, 
 // the (stream, unit) pair; the gate stash, c(t) and the h^T rows for K6 are stored after h(t) has been announced.
 // U is read from a blocked copy (Wb2[tile][k-block][BN rows][64]): every TMA box is one contiguous 8 KB run.
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int SMEM_LIMIT = 227 * 1024;   // opt-in dynamic shared memory per CTA on sm_100
+
 template <int BN>
 struct FwdRecurCfg {
-  static constexpr int STAGES = BN == 128 ? 5 : 8;
+  static constexpr int STAGES = BN == 128 ? 4 : 6;
   static constexpr int UT = BN / 4;
   static constexpr int ACC_LD = BN + 4;
   static constexpr int ACC_BYTES = 128 * ACC_LD * 4;
   static constexpr int HT_BYTES = UT * R_HT_LD * 2;
   static constexpr int X_BYTES = 128 * 4;
-  static constexpr int EPI_BYTES = ACC_BYTES + HT_BYTES + X_BYTES;
-  static constexpr int SMEM_BYTES = PairCfg<BN, STAGES>::TILE_BYTES + 1024 + 256 + (EPI_BYTES + 127) / 128 * 128;
+  static constexpr int EPI_BYTES = (ACC_BYTES + HT_BYTES + X_BYTES + 127) / 128 * 128;
+  static constexpr int FIXED_BYTES = PairCfg<BN, STAGES>::TILE_BYTES + 1024 + 256 + EPI_BYTES + 1024;
+  // Recurrent weights RESIDENT in shared memory: whatever is left after the operand ring and the epilogue tiles holds the
+  // first RES k-blocks of this CTA's U half-tile for the whole window (loaded once); only the remaining k-blocks are streamed
+  // from L2 every timestep.  (U in bf16 is 33.5 MB at N = 2048, the SMs have 33.6 MB of shared memory in total: full residency
+  // is impossible there; at N <= 1024 the whole tile fits.)
+  static constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
+  static constexpr int RES = (SMEM_LIMIT - FIXED_BYTES) / B_HALF_BYTES;
+  static constexpr int SMEM_BYTES = FIXED_BYTES + RES * B_HALF_BYTES;
 };
 
 // grid (2 * n_tiles), cluster (2,1,1): blockIdx.x & 1 = pair member = batch half
@@ -108,9 +117,15 @@ k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUt
   extern __shared__ uint8_t smem_raw[];
   TileCtx c = pair_prologue<BN, STAGES>(smem_raw);
   uint64_t* tmem_free = c.accum_full + 2;
-  if (threadIdx.x == 0) { mbar_init(tmem_free, 2); fence_barrier_init(); }
+  uint64_t* res_full = c.accum_full + 3;                     // (leader) both CTAs' resident U k-blocks have landed
+  if (threadIdx.x == 0) { mbar_init(tmem_free, 2); mbar_init(res_full, 1); fence_barrier_init(); }
   __syncthreads();
   cluster_sync_all();
+  uint8_t* res;                                              // resident U k-blocks: [nres][BN/2 rows][128 B], 1024-byte aligned
+  {
+    const uint32_t e0 = smem_u32(c.epi) + (uint32_t)F::EPI_BYTES;
+    res = c.epi + F::EPI_BYTES + (((e0 + 1023u) & ~1023u) - e0);
+  }
   const uint32_t rank = cluster_ctarank();
   const int nb = (int)(blockIdx.x >> 1);
   const int mb = (int)rank;
@@ -120,6 +135,7 @@ k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUt
   unsigned int* my_slots = a.gbar + (size_t)mb * R_SLOTS;
   const int N = a.N, N4 = 4 * a.N, B = a.B;
   const int wrow0 = nb * nkb * BN + (int)rank * (BN / 2);    // + kb * BN
+  const int nres = F::RES < nkb ? F::RES : nkb;              // k-blocks [0, nres) of U never leave shared memory
   constexpr int DBG_T = 4;
   long long* dbg = (a.dbg && blockIdx.x == 0 && a.T > DBG_T) ? a.dbg : nullptr;
 
@@ -127,18 +143,24 @@ k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUt
     // ---------------- producer ----------------
     if (elect_one()) { tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmWb); }
     __syncwarp();
+    if (elect_one()) {                                       // once: the resident k-blocks
+      if (rank == 0) mbar_expect_tx(res_full, 2u * (uint32_t)nres * (uint32_t)F::B_HALF_BYTES);
+      for (int kb = 0; kb < nres; kb++)
+        tma_load_2d_pair(res + (size_t)kb * F::B_HALF_BYTES, &tmWb, res_full, 0, wrow0 + kb * BN);
+    }
+    __syncwarp();
     const int pre = nkb < STAGES ? nkb : STAGES;
     int g = 0;
     for (int t = 1; t <= a.T; t++) {
       const int a_row = (t - 1) * a.Bp + mb * BM;
-      for (int kb = 0; kb < pre; kb++) {                     // weights first: they do not depend on h(t-1)
+      for (int kb = 0; kb < pre; kb++) {                     // streamed weights first: they do not depend on h(t-1)
         const int st = (g + kb) % STAGES;
         const uint32_t ph = (uint32_t)((g + kb) / STAGES) & 1u;
         mbar_wait(&c.empty[st], ph ^ 1u);
         if (elect_one()) {
           uint8_t* bdst = c.tiles + (size_t)st * PC::STAGE_BYTES + A_TILE_BYTES;
-          if (rank == 0) mbar_expect_tx(&c.full[st], 2u * (uint32_t)PC::STAGE_BYTES);
-          tma_load_2d_pair_hint(bdst, &tmWb, &c.full[st], 0, wrow0 + kb * BN, L2_EVICT_LAST);
+          if (rank == 0) mbar_expect_tx(&c.full[st], 2u * (uint32_t)(kb < nres ? A_TILE_BYTES : PC::STAGE_BYTES));
+          if (kb >= nres) tma_load_2d_pair_hint(bdst, &tmWb, &c.full[st], 0, wrow0 + kb * BN, L2_EVICT_LAST);
         }
         __syncwarp();
       }
@@ -155,8 +177,8 @@ k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUt
         if (elect_one()) {
           uint8_t* adst = c.tiles + (size_t)st * PC::STAGE_BYTES;
           if (kb >= pre) {
-            if (rank == 0) mbar_expect_tx(&c.full[st], 2u * (uint32_t)PC::STAGE_BYTES);
-            tma_load_2d_pair_hint(adst + A_TILE_BYTES, &tmWb, &c.full[st], 0, wrow0 + kb * BN, L2_EVICT_LAST);
+            if (rank == 0) mbar_expect_tx(&c.full[st], 2u * (uint32_t)(kb < nres ? A_TILE_BYTES : PC::STAGE_BYTES));
+            if (kb >= nres) tma_load_2d_pair_hint(adst + A_TILE_BYTES, &tmWb, &c.full[st], 0, wrow0 + kb * BN, L2_EVICT_LAST);
           }
           tma_load_2d_pair(adst, &tmH, &c.full[st], kb * BK, a_row);
         }
@@ -170,6 +192,8 @@ k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUt
       constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
       const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(c.tiles));
       const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(c.tiles) + A_TILE_BYTES);
+      const uint64_t r_desc0 = make_smem_desc_sw128(smem_u32(res));
+      mbar_wait(res_full, 0);                                // the resident k-blocks of both CTAs are in shared memory
       int g = 0;
       for (int t = 1; t <= a.T; t++) {
         if (t > 1) {
@@ -184,9 +208,10 @@ k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUt
           tcgen05_after_sync();
           if (elect_one()) {
             const uint64_t soff = (uint64_t)((uint32_t)st * (uint32_t)(PC::STAGE_BYTES >> 4));
+            const uint64_t bd = kb < nres ? r_desc0 + (uint64_t)((uint32_t)kb * (uint32_t)(F::B_HALF_BYTES >> 4)) : b_desc0 + soff;
 #pragma unroll
             for (int k = 0; k < BK / 16; k++)
-              umma_bf16_pair(c.tmem_d, a_desc0 + soff + 2 * k, b_desc0 + soff + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+              umma_bf16_pair(c.tmem_d, a_desc0 + soff + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb | k) != 0));
             umma_commit_pair(&c.empty[st], (uint16_t)0x3);
           }
           __syncwarp();

@@ -169,7 +169,8 @@ class LSTM:
         in losses[i] when sync() is called."""
         x, t = self._win(x_idx), self._win(t_idx)
         assert losses.dtype == np.float64 and losses.flags["C_CONTIGUOUS"]
-        self._ck(self.lib.lstm_train_step(self.ctx, _ptr(x), _ptr(t), stride, lr, C.c_void_p(losses.ctypes.data + 8 * i)))
+        slot = C.cast(C.c_void_p(losses.ctypes.data + 8 * i), C.POINTER(C.c_double))
+        self._ck(self.lib.lstm_train_step(self.ctx, _ptr(x), _ptr(t), stride, lr, slot))
 
     # ---- device text pipeline ----
     def load_text(self, data):

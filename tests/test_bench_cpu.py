@@ -46,11 +46,24 @@ def test_non_rank0_reference_arm_exits_quietly():
     assert out.returncode == 0 and out.stdout.strip() == ""
 
 
-def test_reference_arm_uses_the_blas_port_for_large_configurations():
+def test_reference_arm_uses_the_multithreaded_blas_port_for_large_configurations():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg2",
                           "--steps", "1", "--warmup", "3", "--cpu-seconds", "0.5"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-500:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     cb = line["cpu_baseline"]
     assert line["impl"] == "reference" and line["value"] > 0 and cb["value"] == line["value"]
-    assert cb["kind"] == "port" and "oracle_blas" in cb["sample"] and "64 streams" in cb["sample"] and cb["cores"] >= 1
+    assert cb["kind"] == "port" and "oracle_torch" in cb["sample"] and "64 streams" in cb["sample"] and cb["cores"] >= 1
+    # a full window is composed from separately timed parts: T x t_timestep + one Adagrad sweep
+    assert abs(cb["value"] - 64 * 100 / (100 * cb["seconds_per_timestep"] + cb["seconds_per_adagrad_sweep"])) < 1e-6 * cb["value"]
+    assert cb["gflops_dense"] > 0
+
+
+def test_reference_arm_thread_count_does_not_depend_on_the_launcher():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the CPU arm sets its thread count explicitly."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg2", "--gpus", "2",
+                          "--steps", "1", "--warmup", "3", "--cpu-seconds", "0.3"], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-500:]
+    cb = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+    assert cb["cores"] == len(os.sched_getaffinity(0))

@@ -46,3 +46,30 @@ def test_blas_oracle_train_windows_runs_and_learns(enwik6):
     losses, secs = q.train_windows(enwik6[:20000], [9 + 900 * b for b in range(8)], 60, 8, 0.1)
     assert secs > 0 and np.all(np.isfinite(losses))
     assert losses[-10:].mean() < 0.8 * losses[:3].mean()      # 8 bits/char at the start, falling
+
+
+def test_torch_oracle_matches_the_blas_oracle(enwik6):
+    """oracle/oracle_torch.py (bench.py's multi-threaded CPU arm) against oracle_blas.py: same statements, same numbers."""
+    from oracle import oracle_torch as ot
+    M, N, S, B = 256, 24, 6, 5
+    params = orc.init_params(M, N, seed=11, sd=0.08, forget_bias=1.0)
+    q = ob.BlasOracle(M, N, S, B); q.set_params(params)
+    p = ot.TorchOracle(M, N, S, B, threads=2); p.set_params(params)
+    rng = np.random.default_rng(0)
+    h0 = rng.normal(0, 0.1, (N, B)).astype(np.float32); c0 = rng.normal(0, 0.1, (N, B)).astype(np.float32)
+    q.h[0][...] = h0; q.c[0][...] = c0
+    import torch
+    p.h[0] = torch.from_numpy(h0.copy()); p.c[0] = torch.from_numpy(c0.copy())
+    d = np.frombuffer(enwik6, dtype=np.uint8)
+    for it in range(4):
+        idx = (100 * np.arange(B))[None, :] + it * (S - 1) + np.arange(S)[:, None]
+        x, t = d[idx].astype(np.int64), d[idx + 1].astype(np.int64)
+        q.set_window(x, t); p.set_window(x, t)
+        lq, lp = q.forward(), p.forward()
+        assert abs(lq - lp) <= 2e-6 * abs(lq), (it, lq, lp)
+        q.backward(); p.backward()
+        for gq, gp in zip(q.grads, p.grads):
+            assert rel_err(gp.numpy(), gq) < 2e-5
+        q.adagrad(0.1); p.adagrad(0.1); q.carry(S - 1); p.carry(S - 1)
+    step, ada, th = ot.time_parts(M, N, B, 3, params, enwik6[:5000], threads=2)
+    assert step > 0 and ada > 0 and th == 2
