@@ -582,17 +582,15 @@ static int iteration_body(lstm_ctx* ctx, int mode, int stride, float lr) {
 // Data parallel: NCCL is kept OUT of the graphs (capturing the allreduce on the side stream into the iteration graph
 // hung at 4 and 8 ranks on B200 / NCCL 2.28).  The iteration is captured as segments cut at each gradient bucket
 // (lstm_allreduce_bucket -> cut_segment); a replay launches segment, eager allreduce on the communication stream,
-// next segment, ..., and joins the communication stream before the last segment (Adagrad).  LSTM_DP_GRAPH=0 falls
-// back to plain stream launches.
+// next segment, ..., and joins the communication stream before the last segment (Adagrad).
 static int run_iteration(lstm_ctx* ctx, int mode, int stride, float lr) {
-  static const bool no_graph = getenv("LSTM_NO_GRAPH") != nullptr;
-  static const bool dp_graph = !(getenv("LSTM_DP_GRAPH") && atoi(getenv("LSTM_DP_GRAPH")) == 0);
+  static const bool no_graph = getenv("LSTM_NO_GRAPH") != nullptr;   // diagnostics (per-kernel profiling): plain stream launches
   lstm_ctx::IterGraph& g = ctx->graph[mode];
   const bool dp = ctx->world > 1;
   if ((g.exec || !g.segs.empty()) && (g.stride != stride || g.lr != lr)) free_iter_graph(g);
   // the host mirrors of the device counters (fwd_count ~ *d_iter, iteration) move only once the iteration is enqueued
   struct Bump { lstm_ctx* c; bool ok = false; ~Bump() { if (ok) { c->fwd_count++; c->iteration++; } } } bump{ctx};
-  if (ctx->profiling || no_graph || (dp && !dp_graph)) {
+  if (ctx->profiling || no_graph) {
     PROF(0);
     int rc = iteration_body(ctx, mode, stride, lr);
     bump.ok = rc == LSTM_OK;
@@ -789,10 +787,7 @@ extern "C" int lstm_train_text(lstm_ctx* ctx, int iters, int stride, float lr, d
 // ------------------------------------------------------------------------------------------------
 // Batch-1 recurrences run on the persistent multi-CTA kernel (K9) when the model is big enough to need more than one
 // SM; tiny models (the reference's N = 64 default) stay on the single-CTA kernel, which has no grid barriers.
-static bool use_persistent(const lstm_ctx* ctx) {
-  static const bool off = getenv("LSTM_NO_PERSIST") != nullptr;
-  return !off && ctx->N >= 128;
-}
+static bool use_persistent(const lstm_ctx* ctx) { return ctx->N >= 128; }
 
 struct ScopedFree {
   std::vector<void*> p;

@@ -328,50 +328,6 @@ void launch_block_why(const float* Why, __nv_bfloat16* Wb5, int N, int M, int bn
   k_block_why<<<148 * 2, 256, 0, st>>>(Why, Wb5, N, M, bn5);
 }
 
-// blocked copy of U for the persistent forward recurrence (tc_recur.cu): one contiguous [bn][64] block per (tile, k-block)
-__global__ void k_block_fwd_weights(const float* __restrict__ U, __nv_bfloat16* __restrict__ Wb, int N, int bn, size_t total) {
-  const int N4 = 4 * N, nkb = N / 64;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(idx & 63);
-    const size_t q = idx >> 6;
-    const int row = (int)(q % bn);
-    const size_t q2 = q / bn;
-    const int kb = (int)(q2 % nkb), tile = (int)(q2 / nkb);
-    const int rp = tile * bn + row;                          // unit-major gate row r' = 4*unit + gate
-    const int k = kb * 64 + c;
-    Wb[idx] = __float2bfloat16_rn(U[(size_t)k * N4 + (size_t)(rp & 3) * N + (rp >> 2)]);
-  }
-}
-void launch_block_fwd_weights(const float* U, __nv_bfloat16* Wb, int N, int bn, cudaStream_t st) {
-  k_block_fwd_weights<<<148 * 8, 256, 0, st>>>(U, Wb, N, bn, (size_t)4 * N * N);
-}
-
-// blocked copy of the BPTT weights (tc_recur.cu): one contiguous [bnj][64] block per (tile, k-block)
-__global__ void k_block_bwd_weights(const float* __restrict__ U, const float* __restrict__ Why, __nv_bfloat16* __restrict__ Wb,
-                                    int N, int M, int bnj, size_t total) {
-  const int N4 = 4 * N, nkbu = N4 / 64, nkbg = nkbu + M / 64;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(idx & 63);
-    const size_t q = idx >> 6;
-    const int row = (int)(q % bnj);
-    const size_t q2 = q / bnj;
-    const int kbg = (int)(q2 % nkbg), tile = (int)(q2 / nkbg);
-    const int j = tile * bnj + row;
-    float v;
-    if (kbg < nkbu) {
-      const int rp = kbg * 64 + c;                           // unit-major gate row r' = 4*unit + gate
-      v = U[(size_t)j * N4 + (size_t)(rp & 3) * N + (rp >> 2)];
-    } else {
-      v = Why[(size_t)j * M + (kbg - nkbu) * 64 + c];
-    }
-    Wb[idx] = __float2bfloat16_rn(v);
-  }
-}
-void launch_block_bwd_weights(const float* U, const float* Why, __nv_bfloat16* Wb, int N, int M, int bnj, cudaStream_t st) {
-  const size_t total = (size_t)N * (4 * (size_t)N + M);
-  k_block_bwd_weights<<<148 * 8, 256, 0, st>>>(U, Why, Wb, N, M, bnj, total);
-}
-
 template <typename T>
 __global__ void k_unpermute(const T* __restrict__ in, float* __restrict__ out, int N) {
   const int N4 = 4 * N;

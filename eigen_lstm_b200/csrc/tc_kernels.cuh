@@ -38,40 +38,6 @@ struct FwdStepArgs {
   __nv_bfloat16* ZT_h;         // ZT + M*ldz + t*Bp : h rows of this slot
   long ldz;                    // ZT leading dimension (columns)
   long long* dbg;              // optional: clock64 stamps of CTA (0,0) for diagnostics (NULL = off)
-  const void* pin; size_t pin_bytes;   // recurrent weights (Urk): L2-persisting access window of this launch
-  int early_b;                 // weight tiles of the pipeline fill are issued before griddepcontrol.wait (set by the launcher)
-  int l2hint;                  // bit 0: weight loads evict_last, bit 1: activation loads evict_first (set by the launcher)
-};
-
-// persistent forward recurrence (tc_persist.cu, experimental): all T timesteps in one launch
-struct FwdPersistArgs {
-  int B, Bp, N, M, T;
-  const int* xs;               // [S][B] input bytes; timestep t reads row t
-  const float* Wp;             // [M][4N r']
-  const float* bp;             // [4N r']
-  float* Cs;                   // [(T+1)][B][N]: slot 0 read once, slot t written by timestep t
-  float* Gp;                   // [T][B][4N r']
-  __nv_bfloat16* Hbf;          // [(T+1)][Bp][N]: slot t-1 read (TMA), slot t written by timestep t
-  __nv_bfloat16* ZT_h0;        // ZT + M*ldz: the h rows; timestep t writes columns [t*Bp, (t+1)*Bp)
-  long ldz;
-  unsigned int* bar;           // [Bp/128][8][32] words for the grid barrier's arrival counters (zeroed by the launcher)
-  int bar_stride;              // words between two counters: 1 (one sector) or 32 (one 128-byte line each); set by the launcher
-  int writer_fence;            // 1 every writer thread executes fence.proxy.async.global, 2 only the announcing thread, 0 none
-  long long* dbg;              // optional clock64 stamps of CTA (0,0) around one timestep (NULL = off)
-};
-
-// persistent BPTT recurrence (tc_persist.cu, experimental): all T timesteps in one launch
-struct BwdPersistArgs {
-  int B, Bp, N, M, T;
-  const float* Gp;             // [T][B][4N r'] activated gates
-  const float* Cs;             // [(T+1)][B][N]
-  __nv_bfloat16* dGbf;         // [T][Bp][4N r']: slot t (= dg(t+1)) read by TMA, slot t-1 written by timestep t
-  __nv_bfloat16* dGT;          // [4N][T*Bp]: timestep t writes columns [(t-1)*Bp, t*Bp)
-  long ldg;
-  float* red;                  // split-K exchange scratch (same layout as BwdStepArgs::red)
-  unsigned int* bar;           // grid-barrier arrival counters (same buffer as the forward variant; zeroed by the launcher)
-  int bar_stride;
-  int writer_fence;
 };
 
 // persistent forward recurrence (tc_recur.cu): all T timesteps in one launch
@@ -126,16 +92,6 @@ struct BwdStepArgs {
   long ldg;                    // dGT leading dimension (columns)
   float* red;                  // split-K exchange scratch: [tiles][4 dst][4 src][128][BN/4] fp32 (L2-resident)
   long long* dbg;              // optional: clock64 stamps of CTA (0,0,0) for diagnostics (NULL = off)
-  const void* pin; size_t pin_bytes;   // recurrent weights (Ukr): L2-persisting access window of this launch
-  int early_b;                 // see FwdStepArgs
-  int l2hint;
-  // LSTM_BWD_PAIR=2 (experimental): cta_group::2 pairs in clusters of 2 only; the four split-K ranks of a tile are then
-  // different clusters and exchange their partial sums through `red` ordered by a per-tile arrival counter
-  // (red.release.gpu / ld.acquire.gpu) instead of the cluster barrier.  xcnt[tile] is zeroed once per iteration and
-  // reaches 4 * epoch when the four ranks of this launch have written (epoch = 1 for the first BPTT step, 2 for the next ...)
-  int flag_exchange;
-  int epoch;
-  unsigned int* xcnt;
 };
 
 struct GemmArgs {
@@ -150,43 +106,24 @@ struct GemmArgs {
   size_t split_stride;
 };
 
-// K2 can run in clusters of cn x cm CTAs that share operand tiles by TMA multicast (cn CTAs along the gate-column
-// tiles share the h tile, cm CTAs along the batch tiles share the U tile): its h map then needs a box of 128/cn rows,
-// its U map one of BN/cm rows.  Measured on B200 (profiles/): multicast clusters are SLOWER than independent CTAs
-// for this kernel (lock-step stage reuse across the cluster), so the default is 1 x 1; LSTM_FWD_CN / LSTM_FWD_CM
-// override it for experiments.
-int fwd_cluster_n(int n_tiles);
-int fwd_cluster_m(int Bp);
-// K2 runs as cta_group::2 CTA pairs over the two batch tiles when Bp/128 is even (LSTM_PAIR=0 disables; K5 only with
-// LSTM_BWD_PAIR=1): each CTA then stages only half of the weight tile, so the weight maps need boxes of BN/2 rows.
+// K2 runs as cta_group::2 CTA pairs over the batch tiles when Bp/128 is even: each CTA then stages only half of the weight tile,
+// so the weight map needs a box of BN/2 rows.
 bool step_pair(int Bp);
-bool bwd_pair(int Bp);
-bool bwd_flag_exchange(int Bp);   // LSTM_BWD_PAIR=2: pair clusters of 2 + counter-ordered split-K exchange (experimental)
-int bwd_box_rows(int BN, int Bp);
 // K2: one recurrent timestep.  BN in {32, 64, 128} gate columns per CTA.
 void launch_fwd_step(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st);
-// experimental persistent variant of K2 (LSTM_PERSIST_FWD=1): returns false if the shape cannot run persistently
-bool fwd_persist_enabled();
-bool launch_fwd_persist(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdPersistArgs& a, cudaStream_t st);
-bool bwd_persist_enabled();
-bool launch_bwd_persist(int BN, const CUtensorMap& tmdG, const CUtensorMap& tmUkr, const CUtensorMap& tmdY, const CUtensorMap& tmWnm,
-                        const BwdPersistArgs& a, cudaStream_t st);
-// persistent BPTT recurrence: bwd_recur_bnj() = hidden units per tile (256 | 128) if this shape runs persistently, else 0;
-// tmWb = the blocked weight copy [N/bnj][4N/64 + M/64][bnj][64] as a 2D map with a box of bnj/2 rows
 int fwd_recur_bn(int N, int Bp, int M);
-// tmWb = blocked U [4N/bn][N/64][bn][64] as a 2D map with a box of bn/2 rows; tmH box = 128 rows
+// tmWb = blocked U, Wb2[(tile*N/64 + kb)*bn + row][c] = U(r' = tile*bn + row, k = kb*64 + c) (r' = 4*unit + gate), as a 2D map
+// with a box of bn/2 rows; tmH box = 128 rows
 bool launch_fwd_recur(int bn, const CUtensorMap& tmH, const CUtensorMap& tmWb, const FwdRecurArgs& a, cudaStream_t st);
-// Wb[(tile*N/64 + kb)*bn + row][c] = U(r' = tile*bn + row, k = kb*64 + c)   (r' = 4*unit + gate)
-void launch_block_fwd_weights(const float* U, __nv_bfloat16* Wb, int N, int bn, cudaStream_t st);
+// tmWb = blocked BPTT weights, Wb5[(tile*NKBG + kbg)*bnj + row][c]: kbg < 4N/64: U(r' = kbg*64 + c, j = tile*bnj + row), else
+// Why(m = (kbg - 4N/64)*64 + c, j); NKBG = 4N/64 + M/64; box of bnj/2 rows
 int bwd_recur_bnj(int N, int Bp, int M);
 size_t bwd_recur_red_floats(int N, int bnj);
 bool launch_bwd_recur(int bnj, const CUtensorMap& tmdG, const CUtensorMap& tmWb, const CUtensorMap& tmdY, const BwdRecurArgs& a,
                       cudaStream_t st);
-// Wb[(tile*NKBG + kbg)*bnj + row][c]: kbg < 4N/64: U(r' = kbg*64 + c, j = tile*bnj + row), else Why(m = (kbg - 4N/64)*64 + c, j)
-void launch_block_bwd_weights(const float* U, const float* Why, __nv_bfloat16* Wb, int N, int M, int bnj, cudaStream_t st);
 // K3: logits + softmax + loss + dy for all timesteps
 void launch_logits(const CUtensorMap& tmH, const CUtensorMap& tmWmn, const LogitsArgs& a, cudaStream_t st);
-// K5: one BPTT timestep.  BN in {32, 64, 128} hidden units per CTA.
+// K5: one BPTT timestep.  BN in {32, 64, 128} hidden units per tile (4 split-K CTAs each).
 void launch_bwd_step(int BN, const CUtensorMap& tmdG, const CUtensorMap& tmUkr, const CUtensorMap& tmdY,
                      const CUtensorMap& tmWnm, const BwdStepArgs& a, cudaStream_t st);
 // K6: C = A * B^T, both K-major bf16, fp32 out, 128 x bn tiles (bn = 128 | 256; tmB box = bn rows)

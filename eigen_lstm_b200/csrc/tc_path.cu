@@ -25,12 +25,12 @@ struct Bf16State {
   bf16 *Hbf = nullptr, *Urk = nullptr, *Ukr = nullptr, *Wmn = nullptr, *Wnm = nullptr;
   bf16 *dYbf = nullptr, *dYT = nullptr, *dGbf = nullptr, *dGT = nullptr, *ZT = nullptr;
   float *Wp = nullptr, *bp = nullptr, *Gp = nullptr, *dcnext = nullptr, *scratch = nullptr, *red = nullptr;
-  unsigned int* gbar = nullptr;   // grid-barrier arrival counters of the experimental persistent recurrence
-  unsigned int* xcnt = nullptr;   // per-tile arrival counters of K5's counter-ordered split-K exchange (LSTM_BWD_PAIR=2)
+  unsigned int* gbar = nullptr;   // arrival counters of the persistent recurrences' grid barriers
+  unsigned int* xcnt = nullptr;   // per-tile arrival counters of the persistent BPTT recurrence's split-K exchange
   size_t xcnt_bytes = 0;
   long long* dbg = nullptr;   // [32] kernel-internal clock stamps (LSTM_TC_DEBUG=1)
-  size_t scratch_elems = 0, pin_bytes = 0;
-  CUtensorMap tmH, tmH2, tmUrk, tmUkr, tmWmn, tmWnm, tmdY, tmdYT, tmdG, tmdGT, tmZT, tmZT256;
+  size_t scratch_elems = 0;
+  CUtensorMap tmH, tmUrk, tmUkr, tmWmn, tmWnm, tmdY, tmdYT, tmdG, tmdGT, tmZT, tmZT256;
 };
 
 namespace {
@@ -121,22 +121,12 @@ int tc_create(lstm_ctx* ctx) {
   }
   tc::launch_fill_bf16(s->ZT + (size_t)(M + N) * s->LDZ, 1.0f, (size_t)s->LDZ, ctx->st);  // the ones row (db, dby)
   LSTM_LAUNCHED(1);
-  {  // let the recurrent weight operand (one of Urk / Ukr at a time) persist in L2 across the timestep kernels
-    cudaDeviceProp prop;
-    cudaGetDeviceProperties(&prop, ctx->device);
-    const size_t want = N4 * N * sizeof(bf16);
-    const size_t lim = std::min((size_t)prop.persistingL2CacheMaxSize, want + (want >> 2));
-    if (lim > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lim) == cudaSuccess)
-      s->pin_bytes = std::min(want, (size_t)prop.accessPolicyMaxWindowSize);
-    cudaGetLastError();
-  }
   bool ok = true;
   ok &= make_tmap(&s->tmH, s->Hbf, (uint64_t)(T + 1) * Bp, N, 128);
-  ok &= make_tmap(&s->tmH2, s->Hbf, (uint64_t)(T + 1) * Bp, N, 128 / tc::fwd_cluster_n(s->N4 / s->BN2));            // K2: multicast slices
-  ok &= make_tmap(&s->tmUrk, s->Urk, N4, N, s->BN2 / tc::fwd_cluster_m(s->Bp));
-  ok &= make_tmap(&s->tmUkr, s->Ukr, N, N4, tc::bwd_box_rows(s->BN5, s->Bp));
+  ok &= make_tmap(&s->tmUrk, s->Urk, N4, N, tc::step_pair(s->Bp) ? s->BN2 / 2 : s->BN2);   // pairs stage half of the U tile each
+  ok &= make_tmap(&s->tmUkr, s->Ukr, N, N4, s->BN5);
   ok &= make_tmap(&s->tmWmn, s->Wmn, M, N, 256);
-  ok &= make_tmap(&s->tmWnm, s->Wnm, N, M, tc::bwd_box_rows(s->BN5, s->Bp));
+  ok &= make_tmap(&s->tmWnm, s->Wnm, N, M, s->BN5);
   ok &= make_tmap(&s->tmdY, s->dYbf, (uint64_t)T * Bp, M, 128);
   ok &= make_tmap(&s->tmdYT, s->dYT, M, s->LDT, 128);
   ok &= make_tmap(&s->tmdG, s->dGbf, (uint64_t)T * Bp, N4, 128);
@@ -218,14 +208,6 @@ int tc_forward(lstm_ctx* ctx) {
     persistent = tc::launch_fwd_recur(s->bn2r, s->tmH, s->tmWb2, pa, ctx->st);
     if (persistent) LSTM_LAUNCHED(1);
   }
-  if (!persistent && tc::fwd_persist_enabled() && !ctx->profiling) {   // experimental: the whole recurrence in one persistent launch
-    tc::FwdPersistArgs pa;
-    pa.B = B; pa.Bp = s->Bp; pa.N = N; pa.M = M; pa.T = T;
-    pa.xs = ctx->xs; pa.Wp = s->Wp; pa.bp = s->bp; pa.Cs = ctx->Cs; pa.Gp = s->Gp; pa.Hbf = s->Hbf;
-    pa.ZT_h0 = s->ZT + (size_t)M * s->LDZ; pa.ldz = s->LDZ; pa.bar = s->gbar; pa.bar_stride = 1; pa.dbg = s->dbg;
-    persistent = tc::launch_fwd_persist(s->BN2, s->tmH2, s->tmUrk, pa, ctx->st);
-    if (persistent) LSTM_LAUNCHED(1);
-  }
   for (int t = 1; t <= T && !persistent; t++) {
     tc::FwdStepArgs a;
     a.B = B; a.Bp = s->Bp; a.N = N; a.M = M;
@@ -238,8 +220,7 @@ int tc_forward(lstm_ctx* ctx) {
     a.ZT_h = s->ZT + (size_t)M * s->LDZ + (size_t)t * Bp;
     a.ldz = s->LDZ;
     a.dbg = s->dbg;
-    a.pin = s->Urk; a.pin_bytes = s->pin_bytes;
-    tc::launch_fwd_step(s->BN2, s->tmH2, s->tmUrk, a, ctx->st);
+    tc::launch_fwd_step(s->BN2, s->tmH, s->tmUrk, a, ctx->st);
   }
   if (!persistent) LSTM_LAUNCHED(T);
   PROF(2);
@@ -281,7 +262,6 @@ int tc_backward(lstm_ctx* ctx) {
   PROF(4);
   int rc = lstm_allreduce_bucket(ctx, 1);
   if (rc) return rc;
-  if (tc::bwd_flag_exchange(s->Bp)) LSTM_CUDA(cudaMemsetAsync(s->xcnt, 0, s->xcnt_bytes, ctx->st));
   bool persistent = false;
   if (s->bnj5) {                                         // the whole BPTT recurrence in one persistent launch (tc_recur.cu)
     tc::BwdRecurArgs pa;
@@ -289,14 +269,6 @@ int tc_backward(lstm_ctx* ctx) {
     pa.Gp = s->Gp; pa.Cs = ctx->Cs; pa.dGbf = s->dGbf; pa.dGT = s->dGT; pa.ldg = s->LDT; pa.red = s->red5;
     pa.xcnt = s->xcnt; pa.gbar = s->gbar; pa.dbg = s->dbg ? s->dbg + 16 : nullptr;
     persistent = tc::launch_bwd_recur(s->bnj5, s->tmdG, s->tmWb5, s->tmdY, pa, ctx->st);
-    if (persistent) LSTM_LAUNCHED(1);
-  }
-  if (!persistent && tc::bwd_persist_enabled() && !ctx->profiling) {   // experimental: the whole BPTT recurrence in one persistent launch
-    tc::BwdPersistArgs pa;
-    pa.B = B; pa.Bp = s->Bp; pa.N = N; pa.M = M; pa.T = T;
-    pa.Gp = s->Gp; pa.Cs = ctx->Cs; pa.dGbf = s->dGbf; pa.dGT = s->dGT; pa.ldg = s->LDT; pa.red = s->red;
-    pa.bar = s->gbar; pa.bar_stride = 1; pa.writer_fence = 1;
-    persistent = tc::launch_bwd_persist(s->BN5, s->tmdG, s->tmUkr, s->tmdY, s->tmWnm, pa, ctx->st);
     if (persistent) LSTM_LAUNCHED(1);
   }
   for (int t = T; t >= 1 && !persistent; t--) {
@@ -312,9 +284,7 @@ int tc_backward(lstm_ctx* ctx) {
     a.dGT_t = s->dGT + (size_t)(t - 1) * Bp;
     a.ldg = s->LDT;
     a.red = s->red;
-    a.xcnt = s->xcnt; a.epoch = T - t + 1; a.flag_exchange = 0;
     a.dbg = s->dbg ? s->dbg + 16 : nullptr;
-    a.pin = s->Ukr; a.pin_bytes = s->pin_bytes;
     tc::launch_bwd_step(s->BN5, s->tmdG, s->tmUkr, s->tmdY, s->tmWnm, a, ctx->st);
   }
   if (!persistent) LSTM_LAUNCHED(T);
@@ -356,10 +326,10 @@ void tc_variant(lstm_ctx* ctx, int out[8]) {
   out[0] = s->BN2;
   out[1] = tc::step_pair(s->Bp) ? 1 : 0;
   out[2] = s->BN5;
-  out[3] = tc::bwd_pair(s->Bp) ? (tc::bwd_flag_exchange(s->Bp) ? 2 : 1) : 0;
+  out[3] = 0;
   out[4] = (ctx->M + ctx->N + 1 >= 1024) ? 256 : 128;
-  out[5] = s->bn2r ? s->bn2r : (tc::fwd_persist_enabled() ? 1 : 0);
-  out[6] = s->bnj5 ? s->bnj5 : (tc::bwd_persist_enabled() ? 1 : 0);
+  out[5] = s->bn2r;
+  out[6] = s->bnj5;
 }
 
 int tc_debug_read(lstm_ctx* ctx, long long out[32]) {

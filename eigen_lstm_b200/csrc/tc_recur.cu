@@ -90,9 +90,14 @@ constexpr int SMEM_LIMIT = 227 * 1024;   // opt-in dynamic shared memory per CTA
 
 template <int BN>
 struct FwdRecurCfg {
-  static constexpr int STAGES = BN == 128 ? 4 : 6;
-  static constexpr int UT = BN / 4;
-  static constexpr int ACC_LD = BN + 4;
+  // The mainloop is bound by bytes in flight (L2 latency under load ~1.7 k cycles): ring depth comes first.  The accumulator is
+  // therefore drained in CHUNKS of 64 gate columns (16 hidden units) through a 35 KB staging tile instead of a 67 KB one, which
+  // pays for a sixth stage.
+  static constexpr int STAGES = 6;
+  static constexpr int UT = BN / 4;                        // hidden units per tile
+  static constexpr int CW = 64;                            // gate columns per drain chunk
+  static constexpr int CH = BN / CW;                       // chunks
+  static constexpr int ACC_LD = CW + 4;
   static constexpr int ACC_BYTES = 128 * ACC_LD * 4;
   static constexpr int HT_BYTES = UT * R_HT_LD * 2;
   static constexpr int X_BYTES = 128 * 4;
@@ -113,7 +118,8 @@ __global__ void __launch_bounds__(R_CTA_THREADS, 1)
 k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmWb, const FwdRecurArgs a) {
   using F = FwdRecurCfg<BN>;
   using PC = PairCfg<BN, F::STAGES>;
-  constexpr int STAGES = F::STAGES, UT = F::UT, RG = R_EPI_THREADS / UT, ROWS = 128 / RG, ACC_LD = F::ACC_LD;
+  constexpr int STAGES = F::STAGES, UT = F::UT, ACC_LD = F::ACC_LD, CH = F::CH;
+  constexpr int UC = F::CW / 4, RG = R_EPI_THREADS / UC, RPC = 128 / RG;   // per chunk: 16 units x 32 row groups, 4 rows per thread
   extern __shared__ uint8_t smem_raw[];
   TileCtx c = pair_prologue<BN, STAGES>(smem_raw);
   uint64_t* tmem_free = c.accum_full + 2;
@@ -228,15 +234,18 @@ k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUt
     __nv_bfloat16* hT = reinterpret_cast<__nv_bfloat16*>(c.epi + F::ACC_BYTES);
     int* sx = reinterpret_cast<int*>(c.epi + F::ACC_BYTES + F::HT_BYTES);
     const int e = threadIdx.x - 64;
-    const int l = e % UT, rg = e / UT;
-    const int j = nb * UT + l;
-    const int rp = 4 * j;
-    const float4 bias = *reinterpret_cast<const float4*>(a.bp + rp);
-    float cpv[ROWS];                                         // c(t-1) of this thread's (stream, unit) pairs: register-resident
+    const int l2 = e % UC, rg = e / UC;                      // unit inside a chunk, row group
+    float cpv[CH][RPC];                                      // c(t-1) of this thread's (stream, unit) pairs: register-resident
+    float4 bias[CH];
 #pragma unroll
-    for (int q = 0; q < ROWS; q++) {
-      const int b = mb * BM + rg + RG * q;
-      cpv[q] = b < B ? a.Cs[(size_t)b * N + j] : 0.f;        // slot 0 = carried-in state
+    for (int ch = 0; ch < CH; ch++) {
+      const int j = nb * UT + ch * UC + l2;
+      bias[ch] = *reinterpret_cast<const float4*>(a.bp + 4 * j);
+#pragma unroll
+      for (int q = 0; q < RPC; q++) {
+        const int b = mb * BM + rg + RG * q;
+        cpv[ch][q] = b < B ? a.Cs[(size_t)b * N + j] : 0.f;  // slot 0 = carried-in state
+      }
     }
     for (int t = 1; t <= a.T; t++) {
       const int* x_t = a.xs + (size_t)t * B;
@@ -249,68 +258,85 @@ k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUt
         sx[e] = (b < B) ? x_t[b] : -2;                       // -2 = padding row, -1 = all-zero input column
       }
       named_bar_sync(1, R_EPI_THREADS);
-      float4 w[ROWS];
-      int xv[ROWS];
+      float4 w[CH][RPC];
+      int xv[RPC];
 #pragma unroll
-      for (int q = 0; q < ROWS; q++) {                       // W*x for one-hot x = a row gather; in flight during the contraction
+      for (int q = 0; q < RPC; q++) {                        // W*x for one-hot x = a row gather; in flight during the contraction
         const int x = sx[rg + RG * q];
         xv[q] = x;
-        w[q] = bias;
-        if (x >= 0) {
-          const float4 wr = __ldg(reinterpret_cast<const float4*>(a.Wp + (size_t)x * N4 + rp));
-          w[q] = make_float4(wr.x + bias.x, wr.y + bias.y, wr.z + bias.z, wr.w + bias.w);
+#pragma unroll
+        for (int ch = 0; ch < CH; ch++) {
+          w[ch][q] = bias[ch];
+          if (x >= 0) {
+            const float4 wr = __ldg(reinterpret_cast<const float4*>(a.Wp + (size_t)x * N4 + 4 * (nb * UT + ch * UC + l2)));
+            w[ch][q] = make_float4(wr.x + bias[ch].x, wr.y + bias[ch].y, wr.z + bias[ch].z, wr.w + bias[ch].w);
+          }
         }
       }
-      if (c.warp < 6) {                                      // TMEM (lane = stream) -> shared memory tile
-        const int quarter = c.warp & 3;
-        const int row = quarter * 32 + c.lane;
-        mbar_wait(c.accum_full, (uint32_t)(t - 1) & 1u);
-        if (dbg && e == 0 && t == DBG_T) dbg[4] = clock64();
-        tcgen05_after_sync();
+      // Only h(t) is on the critical path of the other CTAs: it is computed and stored chunk by chunk, fenced and announced; the
+      // gate stash and c(t) (registers until then) follow after the arrival.
+#pragma unroll
+      for (int ch = 0; ch < CH; ch++) {
+        if (c.warp < 6) {                                    // TMEM (lane = stream) -> shared memory, 64 gate columns
+          const int quarter = c.warp & 3;
+          const int row = quarter * 32 + c.lane;
+          if (ch == 0) {
+            mbar_wait(c.accum_full, (uint32_t)(t - 1) & 1u);
+            if (dbg && e == 0 && t == DBG_T) dbg[4] = clock64();
+            tcgen05_after_sync();
+          }
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          float v[32];
-          tmem_ld32(c.tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-          float4* dst = reinterpret_cast<float4*>(acc + (size_t)row * ACC_LD + c0);
+          for (int c0 = 0; c0 < F::CW; c0 += 32) {
+            float v[32];
+            tmem_ld32(c.tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(ch * F::CW + c0), v);
+            float4* dst = reinterpret_cast<float4*>(acc + (size_t)row * ACC_LD + c0);
 #pragma unroll
-          for (int u = 0; u < 8; u++) dst[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+            for (int u = 0; u < 8; u++) dst[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+          }
+          if (ch == CH - 1) tcgen05_before_sync();
         }
-        tcgen05_before_sync();
-      }
-      named_bar_sync(1, R_EPI_THREADS);
-      if (dbg && e == 0 && t == DBG_T) dbg[5] = clock64();
-      if (e == 0) mbar_arrive_remote(tmem_free, 0);          // this CTA's half of the accumulator is drained
-      // Only h(t) is on the critical path of the other CTAs: it is stored FIRST, fenced and announced; the gate stash and
-      // c(t) (registers until then) follow after the arrival.
+        named_bar_sync(1, R_EPI_THREADS);
+        if (ch == CH - 1) {
+          if (dbg && e == 0 && t == DBG_T) dbg[5] = clock64();
+          if (e == 0) mbar_arrive_remote(tmem_free, 0);      // this CTA's half of the accumulator is drained
+        }
+        const int l = ch * UC + l2;                          // unit inside the tile
+        const int j = nb * UT + l;
 #pragma unroll
-      for (int q = 0; q < ROWS; q++) {
-        const int r = rg + RG * q;
-        float hval = 0.f;
-        if (xv[q] >= -1) {
-          const int b = mb * BM + r;
-          const float4 pre = *reinterpret_cast<const float4*>(acc + (size_t)r * ACC_LD + 4 * l);
-          const float gi = sigmoid_fast(pre.x + w[q].x);
-          const float go = sigmoid_fast(pre.y + w[q].y);
-          const float gf = sigmoid_fast(pre.z + w[q].z);
-          const float gu = tanh_fast(pre.w + w[q].w);
-          const float cc = tanh_fast(gi * gu + gf * cpv[q]);   // the carried cell value is the tanh'd one (R/lstm.cc:185-189)
-          hval = go * cc;
-          cpv[q] = cc;
-          w[q] = make_float4(gi, go, gf, gu);                  // the W row is dead: its registers carry the activated gates
-          Hbf_t[(size_t)b * N + j] = __float2bfloat16_rn(hval);
+        for (int q = 0; q < RPC; q++) {
+          const int r = rg + RG * q;
+          float hval = 0.f;
+          if (xv[q] >= -1) {
+            const int b = mb * BM + r;
+            const float4 pre = *reinterpret_cast<const float4*>(acc + (size_t)r * ACC_LD + 4 * l2);
+            const float gi = sigmoid_fast(pre.x + w[ch][q].x);
+            const float go = sigmoid_fast(pre.y + w[ch][q].y);
+            const float gf = sigmoid_fast(pre.z + w[ch][q].z);
+            const float gu = tanh_fast(pre.w + w[ch][q].w);
+            const float cc = tanh_fast(gi * gu + gf * cpv[ch][q]);   // the carried cell value is the tanh'd one (R/lstm.cc:185-189)
+            hval = go * cc;
+            cpv[ch][q] = cc;
+            w[ch][q] = make_float4(gi, go, gf, gu);          // the W row is dead: its registers carry the activated gates
+            Hbf_t[(size_t)b * N + j] = __float2bfloat16_rn(hval);
+          }
+          hT[l * R_HT_LD + r] = __float2bfloat16_rn(hval);
         }
-        hT[l * R_HT_LD + r] = __float2bfloat16_rn(hval);
+        if (ch < CH - 1) named_bar_sync(1, R_EPI_THREADS);   // the staging tile is rewritten by the next chunk's drain
       }
       fence_proxy_async_global();                            // h(t) is read by other CTAs' TMA loads
       named_bar_sync(1, R_EPI_THREADS);
       if (e == 0) red_release_gpu_add(my_slots + (nb % R_SLOTS), 1u);   // release: cumulative over the barrier-ordered stores
       if (dbg && e == 0 && t == DBG_T) dbg[6] = clock64();
 #pragma unroll
-      for (int q = 0; q < ROWS; q++) {
-        if (xv[q] >= -1) {
-          const int b = mb * BM + rg + RG * q;
-          __stcs(reinterpret_cast<float4*>(Gp_t + (size_t)b * N4 + rp), w[q]);   // streamed: read once, in BPTT
-          c_out[(size_t)b * N + j] = cpv[q];
+      for (int ch = 0; ch < CH; ch++) {
+        const int j = nb * UT + ch * UC + l2;
+#pragma unroll
+        for (int q = 0; q < RPC; q++) {
+          if (xv[q] >= -1) {
+            const int b = mb * BM + rg + RG * q;
+            __stcs(reinterpret_cast<float4*>(Gp_t + (size_t)b * N4 + 4 * j), w[ch][q]);   // streamed: read once, in BPTT
+            c_out[(size_t)b * N + j] = cpv[ch][q];
+          }
         }
       }
       {                                                      // h^T rows of ZT (K6 operand): off the critical path
@@ -353,16 +379,19 @@ bool launch_fwd_recur_t(const CUtensorMap& tmH, const CUtensorMap& tmWb, const F
 
 template <int BNJ, int KS>
 struct BwdRecurCfg {
-  static constexpr int STAGES = BNJ == 256 ? 4 : 5;
+  static constexpr int STAGES = BNJ == 256 ? 4 : 6;        // ring depth first (see FwdRecurCfg)
   static constexpr int UO = BNJ / KS;                      // hidden units finalised by each CTA
   static_assert(UO == 32, "the epilogue maps one warp lane to each of the 32 hidden units a CTA finalises");
   using PC = PairCfg<BNJ, STAGES>;
   static constexpr int DH_LD = UO + 4;                     // fp32 row pitch of the dh tile (16-byte aligned rows)
   static constexpr int DH_BYTES = 128 * DH_LD * 4;
   static constexpr int GT_BYTES = 4 * UO * R_HT_LD * 2;    // dg^T staging [gate*UO + unit][row]
-  static constexpr int ST_BYTES = 128 * UO * 8;            // per (stream, unit): dcnext and c(t), carried across timesteps
-  static constexpr int EPI_BYTES = DH_BYTES + GT_BYTES + ST_BYTES;
-  static constexpr int SMEM_BYTES = PC::TILE_BYTES + 1024 + 256 + (EPI_BYTES + 127) / 128 * 128;
+  static constexpr int ST_BYTES = 128 * UO * 4;            // per (stream, unit): dcnext, carried across timesteps
+  static constexpr int EPI_BYTES = (DH_BYTES + GT_BYTES + ST_BYTES + 127) / 128 * 128;
+  static constexpr int FIXED_BYTES = PC::TILE_BYTES + 1024 + 256 + EPI_BYTES + 1024;
+  static constexpr int B_HALF_BYTES = (BNJ / 2) * BK * 2;
+  static constexpr int RES = (SMEM_LIMIT - FIXED_BYTES) / B_HALF_BYTES;   // resident U^T k-blocks, see FwdRecurCfg
+  static constexpr int SMEM_BYTES = FIXED_BYTES + RES * B_HALF_BYTES;
   static constexpr int CHUNKS_PER_WARP = KS / 4;           // 32-column slices each drain warp moves
 };
 
@@ -377,9 +406,15 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
   extern __shared__ uint8_t smem_raw[];
   TileCtx c = pair_prologue<BNJ, STAGES>(smem_raw);
   uint64_t* tmem_free = c.accum_full + 2;                    // (leader) both CTAs have read the accumulator out of TMEM
-  if (threadIdx.x == 0) { mbar_init(tmem_free, 2); fence_barrier_init(); }
+  uint64_t* res_full = c.accum_full + 3;                     // (leader) both CTAs' resident weight k-blocks have landed
+  if (threadIdx.x == 0) { mbar_init(tmem_free, 2); mbar_init(res_full, 1); fence_barrier_init(); }
   __syncthreads();
   cluster_sync_all();
+  uint8_t* res;                                              // resident U^T k-blocks: [nres][BNJ/2 rows][128 B], 1024-byte aligned
+  {
+    const uint32_t e0 = smem_u32(c.epi) + (uint32_t)F::EPI_BYTES;
+    res = c.epi + F::EPI_BYTES + (((e0 + 1023u) & ~1023u) - e0);
+  }
   const uint32_t rank = cluster_ctarank();                   // pair member = batch half
   const int mb = (int)rank;
   const int pairi = (int)(blockIdx.x >> 1);
@@ -387,6 +422,7 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
   const int N = a.N, N4 = 4 * a.N, B = a.B, T = a.T;
   const int nkbu = N4 / BK / KS;                             // U k-blocks per rank and timestep
   const int nkbw = (ks < a.M / BK) ? 1 : 0;                  // one Why k-block for the first M/64 ranks
+  const int nres = F::RES < nkbu ? F::RES : nkbu;            // this rank's first nres U k-blocks never leave shared memory
   const int NKBG = N4 / BK + a.M / BK;                       // k-blocks per tile in the blocked weight copy
   const int wrow0 = jt * NKBG * BNJ + (int)rank * (BNJ / 2); // + kbg * BNJ
   const int tile = jt * 2 + mb;
@@ -401,25 +437,32 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
     // ---------------- producer ----------------
     if (elect_one()) { tma_prefetch_desc(&tmdG); tma_prefetch_desc(&tmWb); tma_prefetch_desc(&tmdY); }
     __syncwarp();
+    if (elect_one()) {                                       // once: the resident k-blocks
+      if (rank == 0 && nres > 0) mbar_expect_tx(res_full, 2u * (uint32_t)nres * (uint32_t)F::B_HALF_BYTES);
+      for (int iu = 0; iu < nres; iu++)
+        tma_load_2d_pair(res + (size_t)iu * F::B_HALF_BYTES, &tmWb, res_full, 0, wrow0 + (ks * nkbu + iu) * BNJ);
+    }
+    __syncwarp();
     int g = 0;                                               // k-blocks issued so far (ring position)
     for (int s = 0; s < T; s++) {
       const int t = T - s;
       const int nu = s == 0 ? 0 : nkbu;                      // dg(T+1) = 0: the first timestep has no U part
       const int total = nkbw + nu;
-      // Phase A: everything of this timestep that no other CTA produces: the dy / Why k-block completely, and the weight
-      // tiles of the first U k-blocks (as many as fit in the ring)
+      // Phase A: everything of this timestep that no other CTA produces: the dy / Why k-block completely, and the streamed
+      // weight tiles of the first U k-blocks (as many as fit in the ring)
       const int pre = total < STAGES ? total : STAGES;
       for (int i = 0; i < pre; i++) {
         const int st = (g + i) % STAGES;
         const uint32_t ph = (uint32_t)((g + i) / STAGES) & 1u;
+        const bool resident = i >= nkbw && i - nkbw < nres;
         mbar_wait(&c.empty[st], ph ^ 1u);
         if (elect_one()) {
           uint8_t* adst = c.tiles + (size_t)st * PC::STAGE_BYTES;
-          if (rank == 0) mbar_expect_tx(&c.full[st], 2u * (uint32_t)PC::STAGE_BYTES);
+          if (rank == 0) mbar_expect_tx(&c.full[st], 2u * (uint32_t)(resident ? A_TILE_BYTES : PC::STAGE_BYTES));
           if (i < nkbw) {
             tma_load_2d_pair_hint(adst + A_TILE_BYTES, &tmWb, &c.full[st], 0, wrow0 + (N4 / BK + ks) * BNJ, L2_EVICT_LAST);
             tma_load_2d_pair(adst, &tmdY, &c.full[st], ks * BK, (t - 1) * a.Bp + mb * BM);
-          } else {
+          } else if (!resident) {
             const int kbg = ks * nkbu + (i - nkbw);
             tma_load_2d_pair_hint(adst + A_TILE_BYTES, &tmWb, &c.full[st], 0, wrow0 + kbg * BNJ, L2_EVICT_LAST);
           }
@@ -436,12 +479,13 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
         const int st = (g + i) % STAGES;
         const uint32_t ph = (uint32_t)((g + i) / STAGES) & 1u;
         const int kbg = ks * nkbu + (i - nkbw);
+        const bool resident = i - nkbw < nres;
         if (i >= pre) mbar_wait(&c.empty[st], ph ^ 1u);
         if (elect_one()) {
           uint8_t* adst = c.tiles + (size_t)st * PC::STAGE_BYTES;
           if (i >= pre) {
-            if (rank == 0) mbar_expect_tx(&c.full[st], 2u * (uint32_t)PC::STAGE_BYTES);
-            tma_load_2d_pair_hint(adst + A_TILE_BYTES, &tmWb, &c.full[st], 0, wrow0 + kbg * BNJ, L2_EVICT_LAST);
+            if (rank == 0) mbar_expect_tx(&c.full[st], 2u * (uint32_t)(resident ? A_TILE_BYTES : PC::STAGE_BYTES));
+            if (!resident) tma_load_2d_pair_hint(adst + A_TILE_BYTES, &tmWb, &c.full[st], 0, wrow0 + kbg * BNJ, L2_EVICT_LAST);
           }
           tma_load_2d_pair(adst, &tmdG, &c.full[st], kbg * BK, t * a.Bp + mb * BM);
         }
@@ -455,6 +499,8 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
       constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BNJ);
       const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(c.tiles));
       const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(c.tiles) + A_TILE_BYTES);
+      const uint64_t r_desc0 = make_smem_desc_sw128(smem_u32(res));
+      if (nres > 0) mbar_wait(res_full, 0);                  // the resident k-blocks of both CTAs are in shared memory
       int g = 0, used = 0;                                   // used = timesteps that produced an accumulator so far
       for (int s = 0; s < T; s++) {
         const int total = nkbw + (s == 0 ? 0 : nkbu);
@@ -471,9 +517,11 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
           tcgen05_after_sync();
           if (elect_one()) {
             const uint64_t soff = (uint64_t)((uint32_t)st * (uint32_t)(PC::STAGE_BYTES >> 4));
+            const bool resident = i >= nkbw && i - nkbw < nres;
+            const uint64_t bd = resident ? r_desc0 + (uint64_t)((uint32_t)(i - nkbw) * (uint32_t)(F::B_HALF_BYTES >> 4)) : b_desc0 + soff;
 #pragma unroll
             for (int k = 0; k < BK / 16; k++)
-              umma_bf16_pair(c.tmem_d, a_desc0 + soff + 2 * k, b_desc0 + soff + 2 * k, idesc, (uint32_t)((i | k) != 0));
+              umma_bf16_pair(c.tmem_d, a_desc0 + soff + 2 * k, bd + 2 * k, idesc, (uint32_t)((i | k) != 0));
             umma_commit_pair(&c.empty[st], (uint16_t)0x3);
           }
           __syncwarp();
@@ -495,19 +543,17 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
     const int cgrp = w >> 2;                                 // which of the four column groups of this quarter's warps
     const int l = e % UO, rg = e / UO;
     const int j = jt * BNJ + ks * UO + l;                    // the hidden unit this thread finalises
-    // dcnext and c(t) of this thread's (stream, unit) pairs live in shared memory for the whole window: [q][thread] float2
-    float2* carry = reinterpret_cast<float2*>(c.epi + F::DH_BYTES + F::GT_BYTES);
+    // dcnext of this thread's (stream, unit) pairs lives in shared memory for the whole window: [q][thread]
+    float* carry = reinterpret_cast<float*>(c.epi + F::DH_BYTES + F::GT_BYTES);
 #pragma unroll
-    for (int q = 0; q < ROWS; q++) {
-      const int b = mb * BM + rg + RG * q;
-      carry[q * R_EPI_THREADS + e] = make_float2(0.f, b < B ? a.Cs[((size_t)T * B + b) * N + j] : 0.f);   // (dcnext = 0, c(T))
-    }
+    for (int q = 0; q < ROWS; q++) carry[q * R_EPI_THREADS + e] = 0.f;
     int used = 0;
     for (int s = 0; s < T; s++) {
       const int t = T - s;
       const bool has_acc = nkbw + (s == 0 ? 0 : nkbu) > 0;
       const float* Gp_t = a.Gp + (size_t)(t - 1) * B * N4;
       const float* c_prev = a.Cs + (size_t)(t - 1) * B * N;
+      const float* c_cur = a.Cs + (size_t)t * B * N;
       __nv_bfloat16* dGbf_t = a.dGbf + (size_t)(t - 1) * a.Bp * N4;
       __nv_bfloat16* dGT_t = a.dGT + (size_t)(t - 1) * a.Bp;
       // 1. drain: TMEM (lane = stream) -> KS slices of 32 hidden units
@@ -549,15 +595,16 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
       }
       // operands of the gate math that no timestep of this launch produces: in flight while the exchange is awaited
       float4 gv[ROWS];
-      float cpp[ROWS];
+      float cpp[ROWS], ctt[ROWS];
 #pragma unroll
       for (int q = 0; q < ROWS; q++) {
         const int b = mb * BM + rg + RG * q;
         gv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        cpp[q] = 0.f;
+        cpp[q] = ctt[q] = 0.f;
         if (b < B) {
           gv[q] = __ldcs(reinterpret_cast<const float4*>(Gp_t + (size_t)b * N4 + 4 * (size_t)j));   // i o f u (last use)
           cpp[q] = c_prev[(size_t)b * N + j];
+          ctt[q] = c_cur[(size_t)b * N + j];
         }
       }
       if (w == 1) counters_wait(xcnt, 1, (unsigned int)KS * (unsigned int)(s + 1), lane);
@@ -591,14 +638,13 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
         if (b < B) {
           const float dhv = dh[(size_t)r * DH_LD + l];
           const float4 gg = gv[q];
-          const float2 cr = carry[q * R_EPI_THREADS + e];                      // (dcnext, c(t))
-          const float ct = cr.y;
-          const float dc = (dhv * gg.y + cr.x) * (1.0f - ct * ct);             // :233-235
+          const float ct = ctt[q];
+          const float dc = (dhv * gg.y + carry[q * R_EPI_THREADS + e]) * (1.0f - ct * ct);   // :233-235
           d_o = dhv * ct * (gg.y * (1.0f - gg.y));                             // :238,244
           d_i = dc * gg.w * (gg.x * (1.0f - gg.x));                            // :239,244
           d_f = dc * cpp[q] * (gg.z * (1.0f - gg.z));                          // :240,244
           d_u = dc * gg.x * (1.0f - gg.w * gg.w);                              // :241,247
-          carry[q * R_EPI_THREADS + e] = make_float2(dc * gg.z, cpp[q]);       // :256; c(t-1) is the next timestep's c(t)
+          carry[q * R_EPI_THREADS + e] = dc * gg.z;                            // :256
           uint2 pk;
           pk.x = pack_bf16x2(d_i, d_o);
           pk.y = pack_bf16x2(d_f, d_u);

@@ -7,6 +7,10 @@
 //   k_fwd_step  R/lstm.cc:176-192   g = W x + U h(t-1) + b, gates, c = tanh(i u + f c(t-1)), h = o c
 //   k_bwd_step  R/lstm.cc:228-256   dh = Why^T dy + U^T dg(t+1), gate gradients, dcnext
 //
+// These are the GENERAL kernels (any B, N % 64 == 0), one launch per timestep, linked by programmatic dependent launch inside
+// the iteration's CUDA graph.  Shapes with one pair of batch tiles and N <= 2048 run both recurrences as persistent kernels
+// instead (tc_recur.cu).
+//
 // K5's output (B x N) is 4x smaller than K2's (B x 4N) for the same flops, so its K range
 // (4N + M) is split over a cluster of 4 CTAs; the partial accumulators are reduce-scattered (each CTA
 // finalises a quarter of the tile's hidden units).  The exchange goes through an L2-resident global
@@ -42,10 +46,9 @@ struct FwdCfg {
   static constexpr int SMEM_BYTES = PAIR ? PairCfg<BN, STAGES>::TILE_BYTES + 1024 + 256 + (EPI_BYTES + 127) / 128 * 128 : C::SMEM_BYTES;
 };
 
-// CN x CM cluster: the CN CTAs along x share the h tile, the CM CTAs along y share the U tile (TMA multicast).
-// PAIR: the two batch tiles of one gate-column tile form a cta_group::2 pair (cluster 1 x 2): one M = 256 MMA,
+// PAIR: the two batch tiles of one gate-column tile form a cta_group::2 pair (cluster 2 x 1): one M = 256 MMA,
 // each CTA stages its own h tile and half of the U tile.
-template <int BN, int CN, int CM, bool PAIR = false>
+template <int BN, bool PAIR = false>
 __global__ void __launch_bounds__(CTA_THREADS, 1)
 k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmU, const FwdStepArgs a) {
   using F = FwdCfg<BN, PAIR>;
@@ -54,19 +57,11 @@ k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUte
   const long long t_entry = clock64();
   TileCtx c;
   if constexpr (PAIR) c = pair_prologue<BN, STAGES>(smem_raw);
-  else c = tile_prologue<BN, STAGES, CN, CM>(smem_raw);
+  else c = tile_prologue<BN, STAGES>(smem_raw);
   pdl_launch_dependents();   // the next timestep's CTAs may take SMs as ours drain; they block in pdl_wait()
-  // early_b: the U tiles of the pipeline fill (weights: no predecessor writes them) go in flight before the wait; the
-  // producer warp and the epilogue warps then wait on their own (tc_tile.cuh).  Otherwise: wait here, all threads.
-  const bool early = a.early_b != 0 && CN * CM == 1;
-  if (early) {
-    if (c.warp == 0 && elect_one()) { tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmU); }
-  } else {
-    pdl_wait();              // everything below reads what the previous timestep's kernel wrote
-  }
+  pdl_wait();                // everything below reads what the previous timestep's kernel wrote
   c.dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0) ? a.dbg : nullptr;
-  if (a.l2hint & 1) c.hint_b = L2_EVICT_LAST;
-  if (a.l2hint & 2) c.hint_a = L2_EVICT_FIRST;
+  c.hint_b = L2_EVICT_LAST;  // U is re-read by every timestep: keep it in L2 ahead of the streamed stash
   const bool stamp = c.dbg && threadIdx.x == 64;
   if (stamp) { c.dbg[0] = t_entry; c.dbg[4] = clock64(); }
   float* acc = reinterpret_cast<float*>(c.epi);
@@ -77,10 +72,9 @@ k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUte
   const int mb = PAIR ? (int)(blockIdx.y * 2 + (blockIdx.x & 1)) : (int)blockIdx.y;
   const KSeg s0{&tmH, &tmU, a.a_row0 + mb * BM, nb * BN, 0, 0, a.N / BK};
   const KSeg s1{&tmH, &tmU, 0, 0, 0, 0, 0};
-  if constexpr (PAIR) pair_mainloop<BN, STAGES>(c, s0, s1, cluster_ctarank(), (uint16_t)0x3, early);
-  else tile_mainloop<BN, STAGES, CN, CM>(c, s0, s1, (int)(blockIdx.x % CN), (int)(blockIdx.y % CM), early);
+  if constexpr (PAIR) pair_mainloop<BN, STAGES>(c, s0, s1, cluster_ctarank(), (uint16_t)0x3);
+  else tile_mainloop<BN, STAGES>(c, s0, s1);
   if (c.warp >= 2) {
-    if (early) pdl_wait();                                 // c(t-1) below is the previous timestep kernel's output
     const int e = threadIdx.x - 64;                        // 0..EPI_THREADS-1
     const int N = a.N, N4 = 4 * a.N;
     const int l = e % UT, rg = e / UT;                     // phase-2 mapping: lane = hidden unit
@@ -162,23 +156,14 @@ k_fwd_step(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUte
     }
   }
   if constexpr (PAIR) pair_epilogue_end<BN, STAGES>(c);
-  else tile_epilogue_end<BN, STAGES, CN, CM>(c);
+  else tile_epilogue_end<BN, STAGES>(c);
   if (stamp) c.dbg[8] = clock64();
 }
 
-static bool use_pdl() {
-  static const bool on = getenv("LSTM_NO_PDL") == nullptr;
-  return on;
-}
-static bool use_l2pin() {
-  static const bool on = getenv("LSTM_NO_L2PIN") == nullptr;
-  return on;
-}
-// `pin`/`pin_bytes`: the recurrent weight operand of this launch.  It is re-read by every timestep kernel, so its L2
-// lines are marked persisting (and everything else streaming on a miss) to survive the per-step activation traffic.
+// cluster launch with programmatic stream serialization (PDL): the successor's CTAs are resident and past their prologue when
+// the predecessor grid drains
 template <typename Kern, typename... Args>
-static void launch_cluster(Kern kernel, dim3 grid, dim3 cluster, int smem, cudaStream_t st, const void* pin, size_t pin_bytes,
-                           Args... args) {
+static void launch_cluster(Kern kernel, dim3 grid, dim3 cluster, int smem, cudaStream_t st, Args... args) {
   set_smem(kernel, smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -192,78 +177,25 @@ static void launch_cluster(Kern kernel, dim3 grid, dim3 cluster, int smem, cudaS
   attr[0].val.clusterDim.z = cluster.z;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
-  int na = use_pdl() ? 2 : 1;
-  cudaLaunchAttribute all[3];
-  all[0] = attr[0];
-  all[1] = attr[1];
-  if (pin && pin_bytes && use_l2pin()) {
-    all[na].id = cudaLaunchAttributeAccessPolicyWindow;
-    all[na].val.accessPolicyWindow.base_ptr = const_cast<void*>(pin);
-    all[na].val.accessPolicyWindow.num_bytes = pin_bytes;
-    all[na].val.accessPolicyWindow.hitRatio = 1.0f;
-    all[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    all[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    na++;
-  }
-  cfg.attrs = all;
-  cfg.numAttrs = na;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
   cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
-// LSTM_EARLY_B=1: issue the weight tiles of the pipeline fill before griddepcontrol.wait (needs PDL; see tc_tile.cuh)
-static int early_b() {
-  static const int on = env_int("LSTM_EARLY_B", 0) != 0 && use_pdl();
-  return on;
-}
-// timestep-kernel launch shape: CTA pairs (cta_group::2) when there is an even number of batch tiles, unless
-// LSTM_PAIR=0; LSTM_FWD_CN / LSTM_FWD_CM select the (slower) multicast-cluster experiment instead.
-bool step_pair(int Bp) {
-  return env_int("LSTM_PAIR", 1) != 0 && (Bp / 128) % 2 == 0 && env_int("LSTM_FWD_CN", 1) == 1 && env_int("LSTM_FWD_CM", 1) == 1;
-}
-// K5 as pairs needs clusters of 2 x 1 x 4 = 8 CTAs; 16 of those do not all become co-resident on a B200 (GPCs of
-// 16-20 SMs, some with fewer usable): measured 37.5 us per step instead of 20.1.  Off unless LSTM_BWD_PAIR=1.
-bool bwd_pair(int Bp) { return step_pair(Bp) && env_int("LSTM_BWD_PAIR", 0) != 0; }
-// LSTM_BWD_PAIR=2: pairs in clusters of 2 + split-K exchange through a global arrival counter (BwdStepArgs::flag_exchange)
-bool bwd_flag_exchange(int Bp) { return bwd_pair(Bp) && env_int("LSTM_BWD_PAIR", 0) == 2; }
-int bwd_box_rows(int BN, int Bp) { return bwd_pair(Bp) ? BN / 2 : BN; }
-int fwd_cluster_n(int n_tiles) {
-  const int cn = env_int("LSTM_FWD_CN", 1);
-  return (cn == 2 || cn == 4) && n_tiles % cn == 0 ? cn : 1;
-}
-int fwd_cluster_m(int Bp) {
-  if (step_pair(Bp)) return 2;                       // a pair stages half of the U tile per CTA: same box as CM = 2
-  const int cm = env_int("LSTM_FWD_CM", 1);
-  return cm == 2 && (Bp / 128) % 2 == 0 ? 2 : 1;
-}
+// K2 runs as cta_group::2 CTA pairs over the batch tiles when there is an even number of them: each CTA then stages only half
+// of the weight tile, so the weight map needs a box of BN/2 rows.
+bool step_pair(int Bp) { return (Bp / 128) % 2 == 0; }
 
-template <int BN, int CN>
-static void launch_fwd_cn(int CM, dim3 grid, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st) {
-  using F = FwdCfg<BN>;
-  if (CM == 2) launch_cluster(k_fwd_step<BN, CN, 2>, grid, dim3(CN, 2, 1), F::C::SMEM_BYTES, st, a.pin, a.pin_bytes, tmH, tmUrk, a);
-  else launch_cluster(k_fwd_step<BN, CN, 1>, grid, dim3(CN, 1, 1), F::C::SMEM_BYTES, st, a.pin, a.pin_bytes, tmH, tmUrk, a);
-}
 template <int BN>
 static void launch_fwd_t(const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st) {
   dim3 grid(4 * a.N / BN, a.Bp / BM);
-  if (step_pair(a.Bp)) {
-    launch_cluster(k_fwd_step<BN, 1, 1, true>, dim3(2 * grid.x, grid.y / 2), dim3(2, 1, 1), FwdCfg<BN, true>::SMEM_BYTES, st,
-                   a.pin, a.pin_bytes, tmH, tmUrk, a);
-    return;
-  }
-  const int CN = fwd_cluster_n((int)grid.x), CM = fwd_cluster_m(a.Bp);
-  if (CN == 4) launch_fwd_cn<BN, 4>(CM, grid, tmH, tmUrk, a, st);
-  else if (CN == 2) launch_fwd_cn<BN, 2>(CM, grid, tmH, tmUrk, a, st);
-  else launch_fwd_cn<BN, 1>(CM, grid, tmH, tmUrk, a, st);
+  if (step_pair(a.Bp))
+    launch_cluster(k_fwd_step<BN, true>, dim3(2 * grid.x, grid.y / 2), dim3(2, 1, 1), FwdCfg<BN, true>::SMEM_BYTES, st, tmH, tmUrk, a);
+  else
+    launch_cluster(k_fwd_step<BN, false>, grid, dim3(1, 1, 1), FwdCfg<BN>::C::SMEM_BYTES, st, tmH, tmUrk, a);
 }
-// tmH must have a box of 128/fwd_cluster_n rows and tmUrk one of BN/fwd_cluster_m rows
-void launch_fwd_step(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a0, cudaStream_t st) {
-  FwdStepArgs a = a0;
-  a.early_b = early_b();
-  a.l2hint = env_int("LSTM_L2HINT", 0);
+// tmH must have a box of 128 rows and tmUrk one of BN rows (BN/2 when step_pair(Bp))
+void launch_fwd_step(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st) {
   if (BN == 128) launch_fwd_t<128>(tmH, tmUrk, a, st);
   else if (BN == 64) launch_fwd_t<64>(tmH, tmUrk, a, st);
   else launch_fwd_t<32>(tmH, tmUrk, a, st);
@@ -275,52 +207,36 @@ void launch_fwd_step(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, c
 // grid (N/BN, Bp/128, 4), cluster (1,1,4)
 // ------------------------------------------------------------------------------------------------
 constexpr int SPLIT = 4;
-template <int BN, bool PAIR = false>
+template <int BN>
 struct BwdCfg {
-  static constexpr int STAGES = PAIR ? (BN == 128 ? 5 : 8) : (BN == 128 ? 4 : (BN == 64 ? 6 : 8));   // 5 stages: no faster
+  static constexpr int STAGES = BN == 128 ? 4 : (BN == 64 ? 6 : 8);
   static constexpr int UO = BN / SPLIT;                    // hidden units finalised by each CTA of the cluster
   static constexpr int RV_LD = UO + 4;                     // fp32 row pitch of this CTA's own partial slice
   static constexpr int RV_BYTES = 128 * RV_LD * 4;         // [row][UO]
   static constexpr int GT_BYTES = 4 * UO * HT_LD * 2;      // dg^T staging [gate*UO + unit][row]
   static constexpr int EPI_BYTES = RV_BYTES + GT_BYTES;
   using C = Cfg<BN, STAGES, EPI_BYTES>;
-  static constexpr int SMEM_BYTES = PAIR ? PairCfg<BN, STAGES>::TILE_BYTES + 1024 + 256 + (EPI_BYTES + 127) / 128 * 128 : C::SMEM_BYTES;
 };
 
-// PAIR: cluster (2,1,4) — x = the two batch tiles of a cta_group::2 pair, z = the 4 split-K ranks
-template <int BN, bool PAIR = false>
+template <int BN>
 __global__ void __launch_bounds__(CTA_THREADS, 1)
 k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUtensorMap tmU,
            const __grid_constant__ CUtensorMap tmdY, const __grid_constant__ CUtensorMap tmW, const BwdStepArgs a) {
-  using F = BwdCfg<BN, PAIR>;
+  using F = BwdCfg<BN>;
   constexpr int STAGES = F::STAGES, UO = F::UO, RG = EPI_THREADS / UO, ROWS = 128 / RG, RV_LD = F::RV_LD;
   extern __shared__ uint8_t smem_raw[];
   const long long t_entry = clock64();
-  TileCtx c;
-  if constexpr (PAIR) c = pair_prologue<BN, STAGES>(smem_raw);
-  else c = tile_prologue<BN, STAGES>(smem_raw);
+  TileCtx c = tile_prologue<BN, STAGES>(smem_raw);
   pdl_launch_dependents();
-  const bool early = a.early_b != 0;                         // see k_fwd_step
-  if (early) {
-    if (c.warp == 0 && elect_one()) {
-      tma_prefetch_desc(&tmdG); tma_prefetch_desc(&tmU); tma_prefetch_desc(&tmdY); tma_prefetch_desc(&tmW);
-    }
-  } else {
-    pdl_wait();
-  }
+  pdl_wait();
   c.dbg = (a.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? a.dbg : nullptr;
-  if (a.l2hint & 1) c.hint_b = L2_EVICT_LAST;
-  if (a.l2hint & 2) c.hint_a = L2_EVICT_FIRST;
+  c.hint_b = L2_EVICT_LAST;  // U^T / Why^T are re-read by every timestep (measured: -0.9 us per step at N = 2048)
   const bool stamp = c.dbg && threadIdx.x == 64;
   if (stamp) { c.dbg[0] = t_entry; c.dbg[4] = clock64(); }
   float* recv = reinterpret_cast<float*>(c.epi);
   __nv_bfloat16* gT = reinterpret_cast<__nv_bfloat16*>(c.epi + F::RV_BYTES);
-  const int nb = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int mb = PAIR ? (int)(blockIdx.y * 2 + (blockIdx.x & 1)) : (int)blockIdx.y;
-  const uint32_t crank = cluster_ctarank();                  // PAIR: x (pair member) + 2 * z (split-K rank)
-  // flagx: clusters of 2 (just the pair); the split-K rank is blockIdx.z and the exchange is ordered by a global counter
-  const bool flagx = PAIR && a.flag_exchange != 0;
-  const uint32_t rank = PAIR ? (flagx ? (uint32_t)blockIdx.z : crank >> 1) : crank;   // split-K rank
+  const int nb = (int)blockIdx.x, mb = (int)blockIdx.y;
+  const uint32_t rank = cluster_ctarank();                   // split-K rank
   float* red_tile = a.red + (size_t)(mb * (a.N / BN) + nb) * (SPLIT * SPLIT * 128 * UO);
   // this CTA's quarter of the concatenated K range [0, nkb0) ++ [0, nkb1)
   const int nkb0 = a.first ? 0 : (4 * a.N) / BK, nkb1 = a.M / BK;
@@ -330,14 +246,12 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
   const int lo1 = max(lo, nkb0) - nkb0, hi1 = max(hi, nkb0) - nkb0;
   const KSeg s0{&tmdG, &tmU, a.dg_row0 + mb * BM, nb * BN, lo0 * BK, lo0 * BK, hi0 - lo0};
   const KSeg s1{&tmdY, &tmW, a.dy_row0 + mb * BM, nb * BN, lo1 * BK, lo1 * BK, hi1 - lo1};
-  if constexpr (PAIR) pair_mainloop<BN, STAGES>(c, s0, s1, crank & 1u, (uint16_t)(flagx ? 0x3u : 0x3u << (2 * rank)), early);
-  else tile_mainloop<BN, STAGES>(c, s0, s1, 0, 0, early);
+  tile_mainloop<BN, STAGES>(c, s0, s1);
   const int e = threadIdx.x - 64;
   const int N = a.N, N4 = 4 * a.N;
   const int l = e >= 0 ? e % UO : 0, rg = e >= 0 ? e / UO : 0;
   const int j = nb * BN + (int)rank * UO + l;              // the hidden unit this thread finalises
   if (c.warp >= 2) {
-    if (early) pdl_wait();                                 // dcnext and the exchange scratch belong to the previous step until now
 #pragma unroll
     for (int i = 0; i < ROWS; i++) {                       // warm L2 for phase 2
       const int b = mb * BM + rg + RG * i;
@@ -366,24 +280,7 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
       }
     }
   }
-  if (flagx) {
-    // the four ranks of this tile sit in four different clusters: announce our slices, wait for the other three
-    unsigned int* cnt = a.xcnt + (size_t)(mb * (a.N / BN) + nb);
-    if (c.warp >= 2 && c.warp < 6) named_bar_sync(2, 128);   // the four writer warps have issued their stores
-    if (threadIdx.x == 64) red_release_gpu_add(cnt, 1u);     // release: cumulative over the stores ordered by the barrier
-    if (c.warp == 6) {
-      const unsigned int target = (unsigned int)SPLIT * (unsigned int)a.epoch;
-      const long long t0 = clock64();
-      for (;;) {
-        const unsigned int v = c.lane == 0 ? ld_acquire_gpu(cnt) : target;
-        if (__all_sync(0xffffffffu, (int)(v - target) >= 0)) break;
-        if (clock64() - t0 > 4000000000LL) __trap();         // bounded: a protocol error must not hang the GPU
-      }
-    }
-    if (c.warp >= 2) named_bar_sync(1, EPI_THREADS);         // every reader is ordered after the acquire
-  } else {
-    cluster_sync_all();                                    // all partial slices are written (cluster-scope release/acquire)
-  }
+  cluster_sync_all();                                      // all partial slices are written (cluster-scope release/acquire)
   if (stamp) c.dbg[6] = clock64();
   if (c.warp >= 2) {
     // phase 2: lane = hidden unit; batches of RB rows with all global loads issued up front (latency-bound phase)
@@ -454,8 +351,7 @@ k_bwd_step(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUt
       }
     }
   }
-  if constexpr (PAIR) pair_epilogue_end<BN, STAGES>(c);
-  else tile_epilogue_end<BN, STAGES>(c);
+  tile_epilogue_end<BN, STAGES>(c);
   if (stamp) c.dbg[8] = clock64();
 }
 
@@ -463,20 +359,10 @@ template <int BN>
 static void launch_bwd_t(const CUtensorMap& tmdG, const CUtensorMap& tmUkr, const CUtensorMap& tmdY,
                          const CUtensorMap& tmWnm, const BwdStepArgs& a, cudaStream_t st) {
   using F = BwdCfg<BN>;
-  dim3 grid(a.N / BN, a.Bp / BM, SPLIT);
-  if (bwd_pair(a.Bp)) {   // tmUkr / tmWnm boxes are BN/2 rows in this mode (bwd_box_rows)
-    launch_cluster(k_bwd_step<BN, true>, dim3(2 * grid.x, grid.y / 2, SPLIT), dim3(2, 1, a.flag_exchange ? 1 : SPLIT),
-                   BwdCfg<BN, true>::SMEM_BYTES, st, a.pin, a.pin_bytes, tmdG, tmUkr, tmdY, tmWnm, a);
-    return;
-  }
-  launch_cluster(k_bwd_step<BN>, grid, dim3(1, 1, SPLIT), F::C::SMEM_BYTES, st, a.pin, a.pin_bytes, tmdG, tmUkr, tmdY, tmWnm, a);
+  launch_cluster(k_bwd_step<BN>, dim3(a.N / BN, a.Bp / BM, SPLIT), dim3(1, 1, SPLIT), F::C::SMEM_BYTES, st, tmdG, tmUkr, tmdY, tmWnm, a);
 }
 void launch_bwd_step(int BN, const CUtensorMap& tmdG, const CUtensorMap& tmUkr, const CUtensorMap& tmdY,
-                     const CUtensorMap& tmWnm, const BwdStepArgs& a0, cudaStream_t st) {
-  BwdStepArgs a = a0;
-  a.early_b = early_b();
-  a.l2hint = env_int("LSTM_L2HINT", 0);
-  a.flag_exchange = (bwd_flag_exchange(a.Bp) && a.xcnt) ? 1 : 0;
+                     const CUtensorMap& tmWnm, const BwdStepArgs& a, cudaStream_t st) {
   if (BN == 128) launch_bwd_t<128>(tmdG, tmUkr, tmdY, tmWnm, a, st);
   else if (BN == 64) launch_bwd_t<64>(tmdG, tmUkr, tmdY, tmWnm, a, st);
   else launch_bwd_t<32>(tmdG, tmUkr, tmdY, tmWnm, a, st);

@@ -44,9 +44,7 @@ __device__ __forceinline__ void tma_ld_pair(void* dst, const CUtensorMap* tm, ui
 }
 
 // Common prologue: carve shared memory, init barriers, allocate TMEM.
-// CN x CM = thread-block cluster sharing operand tiles by TMA multicast (tile_mainloop): a stage of this CTA is
-// written by CN + CM - 1 CTAs' loads, so that many consumers must release it.
-template <int BN, int STAGES, int CN = 1, int CM = 1>
+template <int BN, int STAGES>
 __device__ __forceinline__ TileCtx tile_prologue(uint8_t* raw) {
   using C = Cfg<BN, STAGES>;
   TileCtx c;
@@ -64,88 +62,51 @@ __device__ __forceinline__ TileCtx tile_prologue(uint8_t* raw) {
   c.warp = threadIdx.x >> 5;
   c.lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) { mbar_init(&c.full[s], 1); mbar_init(&c.empty[s], CN + CM - 1); }
+    for (int s = 0; s < STAGES; s++) { mbar_init(&c.full[s], 1); mbar_init(&c.empty[s], 1); }
     mbar_init(c.accum_full, 1);
     fence_barrier_init();
   }
   if (c.warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_slot);
   tcgen05_before_sync();
   __syncthreads();
-  if (CN * CM > 1) cluster_sync_all();                     // peers' barriers are initialised before any multicast lands
   tcgen05_after_sync();
   c.tmem_d = *tmem_slot;
   return c;
 }
 
-template <int BN, int STAGES, int CN = 1, int CM = 1>
+template <int BN, int STAGES>
 __device__ __forceinline__ void tile_epilogue_end(const TileCtx& c) {
   tcgen05_before_sync();
   __syncthreads();
-  if (CN * CM > 1) cluster_sync_all();                     // no peer may still multicast into / signal an exited CTA
   if (c.warp == 1) {
     __syncwarp();
     tmem_dealloc<Cfg<BN, STAGES>::TMEM_COLS>(c.tmem_d);
   }
 }
 
-// Producer (warp 0, one lane) and MMA issuer (warp 1, one lane) of one output tile.
-// With a CN x CM cluster (cluster rank = xr + yr*CN): the A tile (128 rows) is common to the CN CTAs of a cluster
-// row and the B tile (BN rows) to the CM CTAs of a cluster column; every CTA loads a 1/CN (1/CM) row slice and
-// multicasts it, so each operand byte crosses L2 -> SM once per cluster instead of once per CTA.
-//
-// early_b (timestep kernels under programmatic dependent launch, CN = CM = 1): the B operand is a WEIGHT matrix that no
-// predecessor grid writes, so the producer puts the B tiles of the first STAGES k-blocks in flight BEFORE
-// griddepcontrol.wait and only the A tiles (h / dg of the previous timestep) after it: the weight fetch (HBM or L2) of
-// the pipeline fill overlaps the predecessor's tail.  In this mode the producer warp executes the wait itself; every
-// other thread that reads the predecessor's output must call pdl_wait() on its own.
-template <int BN, int STAGES, int CN = 1, int CM = 1>
-__device__ __forceinline__ void tile_mainloop(const TileCtx& c, const KSeg& s0, const KSeg& s1, int xr = 0, int yr = 0,
-                                              bool early_b = false) {
+// Producer (warp 0) and MMA issuer (warp 1) of one output tile.
+// Both role loops run WARP-UNIFORM (all 32 lanes take the loop and the waits) with the single-thread instructions under
+// elect.sync: issued from a divergent `if (lane == 0)` region, every UTMALDG / UTCHMMA / UTCBAR gets wrapped by ptxas in a
+// vote-and-branch loop, and the MMA issue thread — not the tensor pipe or the operand delivery — became the bottleneck
+// (~530 cycles per k-block regardless of tile size).
+template <int BN, int STAGES>
+__device__ __forceinline__ void tile_mainloop(const TileCtx& c, const KSeg& s0, const KSeg& s1) {
   using C = Cfg<BN, STAGES>;
-  constexpr int A_ROWS = BM / CN, B_ROWS = BN / CM;
-  static_assert(A_ROWS % 8 == 0 && B_ROWS % 8 == 0, "multicast slices must be whole 8-row swizzle atoms");
   const int total = s0.nkb + s1.nkb;
-  uint16_t mask_a = 0, mask_b = 0;
-  for (int i = 0; i < CN; i++) mask_a |= (uint16_t)(1u << (yr * CN + i));
-  for (int j = 0; j < CM; j++) mask_b |= (uint16_t)(1u << (j * CN + xr));
-  // Both role loops run WARP-UNIFORM (all 32 lanes take the loop and the waits) with the single-thread instructions
-  // under elect.sync: issued from a divergent `if (lane == 0)` region, every UTMALDG / UTCHMMA / UTCBAR gets wrapped
-  // by ptxas in a vote-and-branch loop, and the MMA issue thread — not the tensor pipe or the operand delivery —
-  // became the bottleneck (~530 cycles per k-block regardless of tile size).
   if (c.warp == 0) {
-    int pre = 0;
-    if (CN * CM == 1 && early_b) {
-      pre = total < STAGES ? total : STAGES;
-      for (int kb = 0; kb < pre; kb++) {        // fresh stages: no empty-wait needed
-        if (elect_one()) {
-          const bool first = kb < s0.nkb;
-          const KSeg& s = first ? s0 : s1;
-          const int k = first ? kb : kb - s0.nkb;
-          uint8_t* b = c.tiles + (size_t)kb * C::STAGE_BYTES + A_TILE_BYTES;
-          mbar_expect_tx(&c.full[kb], (uint32_t)C::STAGE_BYTES);   // armed once for both operands of the stage
-          tma_ld(b, s.tb, &c.full[kb], s.b_k0 + k * BK, s.b_row, c.hint_b);
-        }
-        __syncwarp();
-      }
-      pdl_wait();
-    }
     for (int kb = 0; kb < total; kb++) {
       const int st = kb % STAGES;
       const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-      if (kb >= pre) mbar_wait(&c.empty[st], ph ^ 1u);
+      mbar_wait(&c.empty[st], ph ^ 1u);
       if (elect_one()) {
         const bool first = kb < s0.nkb;
         const KSeg& s = first ? s0 : s1;
         const int k = first ? kb : kb - s0.nkb;
         uint8_t* a = c.tiles + (size_t)st * C::STAGE_BYTES;
         uint8_t* b = a + A_TILE_BYTES;
-        if (kb >= pre) mbar_expect_tx(&c.full[st], (uint32_t)C::STAGE_BYTES);
-        if (CN == 1) tma_ld(a, s.ta, &c.full[st], s.a_k0 + k * BK, s.a_row, c.hint_a);
-        else tma_load_2d_mc(a + xr * A_ROWS * 128, s.ta, &c.full[st], s.a_k0 + k * BK, s.a_row + xr * A_ROWS, mask_a);
-        if (kb >= pre) {
-          if (CM == 1) tma_ld(b, s.tb, &c.full[st], s.b_k0 + k * BK, s.b_row, c.hint_b);
-          else tma_load_2d_mc(b + yr * B_ROWS * 128, s.tb, &c.full[st], s.b_k0 + k * BK, s.b_row + yr * B_ROWS, mask_b);
-        }
+        mbar_expect_tx(&c.full[st], (uint32_t)C::STAGE_BYTES);
+        tma_ld(a, s.ta, &c.full[st], s.a_k0 + k * BK, s.a_row, c.hint_a);
+        tma_ld(b, s.tb, &c.full[st], s.b_k0 + k * BK, s.b_row, c.hint_b);
       }
       __syncwarp();
     }
@@ -165,9 +126,7 @@ __device__ __forceinline__ void tile_mainloop(const TileCtx& c, const KSeg& s0, 
 #pragma unroll
         for (int k = 0; k < BK / 16; k++)   // UMMA_K = 16 bf16 = 32 bytes inside the swizzled row
           umma_bf16(c.tmem_d, a_desc0 + soff + 2 * k, b_desc0 + soff + 2 * k, idesc, (uint32_t)((kb | k) != 0));
-        // frees the stage once these MMAs have read it — in every CTA whose loads write into this CTA's stage
-        if (CN * CM == 1) umma_commit(&c.empty[st]);
-        else umma_commit_mc(&c.empty[st], (uint16_t)(mask_a | mask_b));
+        umma_commit(&c.empty[st]);          // frees the stage once these MMAs have read it
       }
       __syncwarp();
     }
@@ -233,40 +192,23 @@ __device__ __forceinline__ void pair_epilogue_end(const TileCtx& c) {
 // s.a_row = this CTA's own 128 A rows; s.b_row = first row of the pair's BN-row B tile (each CTA loads rows
 // [b_row + rank*BN/2, +BN/2)).  rank = cluster rank within the pair (0 = leader).
 template <int BN, int STAGES>
-__device__ __forceinline__ void pair_mainloop(const TileCtx& c, const KSeg& s0, const KSeg& s1, uint32_t rank, uint16_t pair_mask,
-                                              bool early_b = false) {
+__device__ __forceinline__ void pair_mainloop(const TileCtx& c, const KSeg& s0, const KSeg& s1, uint32_t rank, uint16_t pair_mask) {
   using C = PairCfg<BN, STAGES>;
   const int total = s0.nkb + s1.nkb;
   if (c.warp == 0) {
-    int pre = 0;
-    if (early_b) {                                // see tile_mainloop: weight tiles in flight before griddepcontrol.wait
-      pre = total < STAGES ? total : STAGES;
-      for (int kb = 0; kb < pre; kb++) {
-        if (elect_one()) {
-          const bool first = kb < s0.nkb;
-          const KSeg& s = first ? s0 : s1;
-          const int k = first ? kb : kb - s0.nkb;
-          uint8_t* b = c.tiles + (size_t)kb * C::STAGE_BYTES + A_TILE_BYTES;
-          if (rank == 0) mbar_expect_tx(&c.full[kb], 2u * (uint32_t)C::STAGE_BYTES);
-          tma_ld_pair(b, s.tb, &c.full[kb], s.b_k0 + k * BK, s.b_row + (int)rank * (BN / 2), c.hint_b);
-        }
-        __syncwarp();
-      }
-      pdl_wait();
-    }
     for (int kb = 0; kb < total; kb++) {
       const int st = kb % STAGES;
       const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-      if (kb >= pre) mbar_wait(&c.empty[st], ph ^ 1u);
+      mbar_wait(&c.empty[st], ph ^ 1u);
       if (elect_one()) {
         const bool first = kb < s0.nkb;
         const KSeg& s = first ? s0 : s1;
         const int k = first ? kb : kb - s0.nkb;
         uint8_t* a = c.tiles + (size_t)st * C::STAGE_BYTES;
         uint8_t* b = a + A_TILE_BYTES;
-        if (rank == 0 && kb >= pre) mbar_expect_tx(&c.full[st], 2u * (uint32_t)C::STAGE_BYTES);   // both CTAs' bytes land on the leader's barrier
+        if (rank == 0) mbar_expect_tx(&c.full[st], 2u * (uint32_t)C::STAGE_BYTES);   // both CTAs' bytes land on the leader's barrier
         tma_ld_pair(a, s.ta, &c.full[st], s.a_k0 + k * BK, s.a_row, c.hint_a);
-        if (kb >= pre) tma_ld_pair(b, s.tb, &c.full[st], s.b_k0 + k * BK, s.b_row + (int)rank * (BN / 2), c.hint_b);
+        tma_ld_pair(b, s.tb, &c.full[st], s.b_k0 + k * BK, s.b_row + (int)rank * (BN / 2), c.hint_b);
       }
       __syncwarp();
     }

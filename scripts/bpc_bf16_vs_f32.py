@@ -1,9 +1,9 @@
 """North-star check: the bf16-GEMM / fp32-accumulate path reaches a final bits-per-char within 0.01 of the fp32 path
 (same text, seed, initial weights, schedule).  Runs on one B200:  python scripts/bpc_bf16_vs_f32.py [N B S iters lr]
 
-Text: the committed 64 KiB head of enwik6 (tests/golden/enwik6_head.bin; the GPU box has no /root/reference);
-first 90 % for training with B streams, last 10 % held out and scored with the reference's test() recipe
-(OV/lstm_eigen_class_CUDA/lstm.cc:661-720)."""
+Text: the committed enwik6 (tests/golden/enwik6.txt, 10^6 bytes: BASELINE config 2's corpus and the stand-in for config 3's
+missing enwik7); first 95 % for training with B streams, last 5 % held out (OV/lstm_eigen_class_batch/lstm.cc:55-59) and scored
+with the reference's test() recipe (OV/lstm_eigen_class_CUDA/lstm.cc:661-720).  BPC_TEXT=head uses the 64 KiB head instead."""
 import json
 import os
 import sys
@@ -18,8 +18,9 @@ N, B, S, iters, lr = 256, 32, 51, 1500, 0.02
 if len(sys.argv) > 1:
     N, B, S, iters = [int(v) for v in sys.argv[1:5]]
     lr = float(sys.argv[5])
-text = open(os.path.join(ROOT, "tests", "golden", "enwik6_head.bin"), "rb").read()
-cut = len(text) * 9 // 10
+head = os.environ.get("BPC_TEXT") == "head"
+text = open(os.path.join(ROOT, "tests", "golden", "enwik6_head.bin" if head else "enwik6.txt"), "rb").read()
+cut = len(text) * (90 if head else 95) // 100
 train, held = text[:cut], text[cut:]
 pos = [S + (len(train) - 2 * S) * b // B for b in range(B)]
 res = {}
@@ -43,8 +44,9 @@ for name, dt in (("f32", el.F32), ("bf16", el.BF16), ("f32_ulp", el.F32)):
 res["abs_diff_heldout"] = abs(res["f32"]["heldout_bpc"] - res["bf16"]["heldout_bpc"])
 res["abs_diff_train"] = abs(res["f32"]["train_bpc_curve"][-1] - res["bf16"]["train_bpc_curve"][-1])
 res["noise_floor_heldout_f32_vs_f32_plus_1ulp"] = abs(res["f32"]["heldout_bpc"] - res["f32_ulp"]["heldout_bpc"])
-res["config"] = dict(N=N, B=B, S=S, iters=iters, lr=lr, text="enwik6 head 64 KiB, 90/10 split")
+res["config"] = dict(N=N, B=B, S=S, iters=iters, lr=lr, text="enwik6 head 64 KiB, 90/10 split" if head else "enwik6 (10^6 bytes), 95/5 split",
+                     variant=g.variant())
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(res, open(os.path.join(ROOT, "gpurun_out", "bpc_bf16_vs_f32.json"), "w"), indent=1)
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", os.environ.get("BPC_OUT", "bpc_bf16_vs_f32.json")), "w"), indent=1)
 print("held-out |bf16 - f32| =", res["abs_diff_heldout"], " train |diff| =", res["abs_diff_train"],
       " noise floor |f32 - f32(+1ulp)| =", res["noise_floor_heldout_f32_vs_f32_plus_1ulp"])

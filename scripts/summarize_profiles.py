@@ -34,9 +34,10 @@ def launches():
         a[1] += v
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(OUT, f"{tag}_launches.md"), "w") as f:
-        f.write(f"# {tag}: ncu launch list of one training iteration (config 4: N=2048, B=256, T=256, bf16)\n\n"
-                "`ncu --metrics gpu__time_duration.sum --clock-control none` over `bench.py --workload cfg4 --steps 1` "
-                "(LSTM_NO_GRAPH=1: same kernels as plain launches).  Times are cold-cache and serialised — compare SHARES.\n\n"
+        f.write(f"# {tag}: ncu launch list of the bench command (config 4: N=2048, B=256, T=256, bf16; every training iteration it runs)\n\n"
+                "`ncu --metrics gpu__time_duration.sum --clock-control none` over `bench.py --workload cfg4 --steps 1 --warmup 3` "
+                "(LSTM_NO_GRAPH=1: same kernels as plain launches; the first lines are the one-time parameter set-up).  "
+                "Times are cold-cache and serialised — compare SHARES.\n\n"
                 "| kernel | launches | total ms | avg µs | share |\n|---|---:|---:|---:|---:|\n")
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{k}` | {v[0]} | {v[1] / 1e3:.3f} | {v[1] / v[0]:.2f} | {100 * v[1] / tot:.1f} % |\n")

@@ -145,6 +145,25 @@ def test_cfg1_free_running_divergence_is_intrinsic(alice):
     assert abs(got[-200:].mean() - ref[-200:].mean()) < 0.15 * ref[-200:].mean()
 
 
+def test_cfg1_free_running_1000_iterations_at_a_non_chaotic_learning_rate(alice):
+    """The same 1000 FREE-RUNNING iterations at the reference's shape (N=64, S=3, B=1, alice29) with lr = 1e-3 instead of 0.1:
+    Adagrad's first steps then move a weight by 1e-3 against an N(0, 0.01) init, the trajectory is no longer chaotic, and the
+    GPU path must stay within 1e-4 relative of the oracle's per-iteration loss with NO resynchronisation — which rules out a slow
+    systematic drift that the resynchronised test above could not see."""
+    import eigen_lstm_b200 as el
+    M, N, S, B, params, h0, c0 = _cfg1_setup(alice)
+    o = orc.Oracle(M, N, S, B, "f32")
+    o.set_params(params); o.set_state("h", 1, h0); o.set_state("c", 1, c0)   # its first carry moves slot 1 -> 0
+    ref, _ = o.train(alice, 1000, stride=1, lr=1e-3)
+    g = el.LSTM(M, N, S, B)
+    g.set_params(params); g.set_state(h0, c0); g.load_text(alice)
+    got = g.train_text(1000, stride=1, lr=1e-3)
+    rel = np.abs(got - ref) / np.abs(ref)
+    assert rel.max() < 1e-4, (int(rel.argmax()), float(rel.max()))
+    for name, a, b in zip(orc.NAMES, g.params(), o.params()):
+        assert rel_err(a, b) < 1e-4, name
+
+
 def test_cfg1_device_pipeline_equals_host_windows(alice):
     """lstm_train_text (windows built by the K10 kernel) == lstm_train_step with host-built windows."""
     import eigen_lstm_b200 as el
