@@ -112,6 +112,7 @@ bool step_pair(int Bp);
 // K2: one recurrent timestep.  BN in {32, 64, 128} gate columns per CTA.
 void launch_fwd_step(int BN, const CUtensorMap& tmH, const CUtensorMap& tmUrk, const FwdStepArgs& a, cudaStream_t st);
 int fwd_recur_bn(int N, int Bp, int M);
+int fwd_recur_box_rows(int bn, int Bp);   // rows of the blocked-U TMA box: bn/2 for pairs (Bp = 256), bn for single CTAs (Bp = 128)
 // tmWb = blocked U, Wb2[(tile*N/64 + kb)*bn + row][c] = U(r' = tile*bn + row, k = kb*64 + c) (r' = 4*unit + gate), as a 2D map
 // with a box of bn/2 rows; tmH box = 128 rows
 bool launch_fwd_recur(int bn, const CUtensorMap& tmH, const CUtensorMap& tmWb, const FwdRecurArgs& a, cudaStream_t st);
@@ -119,6 +120,7 @@ bool launch_fwd_recur(int bn, const CUtensorMap& tmH, const CUtensorMap& tmWb, c
 // Why(m = (kbg - 4N/64)*64 + c, j); NKBG = 4N/64 + M/64; box of bnj/2 rows
 int bwd_recur_bnj(int N, int Bp, int M);
 size_t bwd_recur_red_floats(int N, int bnj);
+int bwd_recur_box_rows(int bnj, int Bp);
 bool launch_bwd_recur(int bnj, const CUtensorMap& tmdG, const CUtensorMap& tmWb, const CUtensorMap& tmdY, const BwdRecurArgs& a,
                       cudaStream_t st);
 // K3: logits + softmax + loss + dy for all timesteps

@@ -107,7 +107,7 @@ int tc_create(lstm_ctx* ctx) {
   s->scratch_elems = (size_t)B * N4;
   TC_ALLOC(s->scratch, s->scratch_elems * sizeof(float));
   TC_ALLOC(s->gbar, std::max<size_t>((size_t)(Bp / 128) * 8 * 32, 2 * 256) * sizeof(unsigned int));   // persistent kernels: 2 x 256 flags
-  s->xcnt_bytes = (size_t)(N / s->BN5) * (Bp / 128) * sizeof(unsigned int);
+  s->xcnt_bytes = std::max<size_t>((size_t)(N / s->BN5) * (Bp / 128), (size_t)(N / 32) * 2) * sizeof(unsigned int);
   TC_ALLOC(s->xcnt, s->xcnt_bytes);
   if (getenv("LSTM_TC_DEBUG")) TC_ALLOC(s->dbg, 32 * sizeof(long long));
   TC_ALLOC(s->kc_parts, 8 * (ctx->P - ctx->off[LSTM_WHY]) * sizeof(float));
@@ -133,8 +133,8 @@ int tc_create(lstm_ctx* ctx) {
   ok &= make_tmap(&s->tmdGT, s->dGT, N4, s->LDT, 128);
   ok &= make_tmap(&s->tmZT, s->ZT, s->RZ, s->LDZ, 128);
   ok &= make_tmap(&s->tmZT256, s->ZT, s->RZ, s->LDZ, 256);
-  if (s->bn2r) ok &= make_tmap(&s->tmWb2, s->Wb2, (uint64_t)N4 * (N / 64), 64, (uint32_t)s->bn2r / 2);
-  if (s->bnj5) ok &= make_tmap(&s->tmWb5, s->Wb5, (uint64_t)N * ((N4 + M) / 64), 64, (uint32_t)s->bnj5 / 2);
+  if (s->bn2r) ok &= make_tmap(&s->tmWb2, s->Wb2, (uint64_t)N4 * (N / 64), 64, (uint32_t)tc::fwd_recur_box_rows(s->bn2r, s->Bp));
+  if (s->bnj5) ok &= make_tmap(&s->tmWb5, s->Wb5, (uint64_t)N * ((N4 + M) / 64), 64, (uint32_t)tc::bwd_recur_box_rows(s->bnj5, s->Bp));
   if (!ok) return lstm_fail(ctx, LSTM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   return LSTM_OK;
 }

@@ -76,6 +76,32 @@ __device__ __forceinline__ void counters_wait(const unsigned int* slots, int n, 
   }
 }
 
+// PAIR = true: two batch tiles (128 < B <= 256) as a cta_group::2 pair; PAIR = false: one batch tile (B <= 128), cta_group::1.
+template <bool PAIR> __device__ __forceinline__ void r_tma(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  if constexpr (PAIR) tma_load_2d_pair(dst, tm, bar, c0, c1);
+  else tma_load_2d(dst, tm, bar, c0, c1);
+}
+template <bool PAIR> __device__ __forceinline__ void r_tma_w(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  if constexpr (PAIR) tma_load_2d_pair_hint(dst, tm, bar, c0, c1, L2_EVICT_LAST);   // weights: re-read every timestep
+  else tma_load_2d_hint(dst, tm, bar, c0, c1, L2_EVICT_LAST);
+}
+template <bool PAIR> __device__ __forceinline__ void r_mma(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+  if constexpr (PAIR) umma_bf16_pair(d, ad, bd, idesc, acc);
+  else umma_bf16(d, ad, bd, idesc, acc);
+}
+template <bool PAIR> __device__ __forceinline__ void r_commit(uint64_t* bar) {
+  if constexpr (PAIR) umma_commit_pair(bar, (uint16_t)0x3);
+  else umma_commit(bar);
+}
+template <int BN, int STAGES, bool PAIR> __device__ __forceinline__ TileCtx r_prologue(uint8_t* raw) {
+  if constexpr (PAIR) return pair_prologue<BN, STAGES>(raw);
+  else return tile_prologue<BN, STAGES>(raw);
+}
+template <int BN, int STAGES, bool PAIR> __device__ __forceinline__ void r_epilogue_end(const TileCtx& c) {
+  if constexpr (PAIR) pair_epilogue_end<BN, STAGES>(c);
+  else tile_epilogue_end<BN, STAGES>(c);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Forward recurrence (K2) of a whole window as one persistent kernel.
 //   R/lstm.cc:173-192   for t = 1 .. S-1:  g = W x(t) + U h(t-1) + b;  gates;  c(t) = tanh(i u + f c(t-1));  h(t) = o c(t)
@@ -88,59 +114,63 @@ __device__ __forceinline__ void counters_wait(const unsigned int* slots, int n, 
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int SMEM_LIMIT = 227 * 1024;   // opt-in dynamic shared memory per CTA on sm_100
 
-template <int BN>
+template <int BN, bool PAIR>
 struct FwdRecurCfg {
   // The mainloop is bound by bytes in flight (L2 latency under load ~1.7 k cycles): ring depth comes first.  The accumulator is
   // therefore drained in CHUNKS of 64 gate columns (16 hidden units) through a 35 KB staging tile instead of a 67 KB one, which
   // pays for a sixth stage.
   static constexpr int STAGES = 6;
   static constexpr int UT = BN / 4;                        // hidden units per tile
-  static constexpr int CW = 64;                            // gate columns per drain chunk
+  static constexpr int CW = BN < 64 ? BN : 64;             // gate columns per drain chunk
   static constexpr int CH = BN / CW;                       // chunks
   static constexpr int ACC_LD = CW + 4;
   static constexpr int ACC_BYTES = 128 * ACC_LD * 4;
   static constexpr int HT_BYTES = UT * R_HT_LD * 2;
   static constexpr int X_BYTES = 128 * 4;
-  static constexpr int EPI_BYTES = (ACC_BYTES + HT_BYTES + X_BYTES + 127) / 128 * 128;
-  static constexpr int FIXED_BYTES = PairCfg<BN, STAGES>::TILE_BYTES + 1024 + 256 + EPI_BYTES + 1024;
+  static constexpr int CC_BYTES = 128 * UT * 4;            // c(t-1) of the tile's (stream, unit) pairs, carried across timesteps
+  static constexpr int EPI_BYTES = (ACC_BYTES + HT_BYTES + X_BYTES + CC_BYTES + 127) / 128 * 128;
+  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;        // weight-tile rows staged by each CTA
+  static constexpr int B_HALF_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_HALF_BYTES;
+  static constexpr int FIXED_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES + 1024;
   // Recurrent weights RESIDENT in shared memory: whatever is left after the operand ring and the epilogue tiles holds the
   // first RES k-blocks of this CTA's U half-tile for the whole window (loaded once); only the remaining k-blocks are streamed
   // from L2 every timestep.  (U in bf16 is 33.5 MB at N = 2048, the SMs have 33.6 MB of shared memory in total: full residency
   // is impossible there; at N <= 1024 the whole tile fits.)
-  static constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
   static constexpr int RES = (SMEM_LIMIT - FIXED_BYTES) / B_HALF_BYTES;
   static constexpr int SMEM_BYTES = FIXED_BYTES + RES * B_HALF_BYTES;
 };
 
-// grid (2 * n_tiles), cluster (2,1,1): blockIdx.x & 1 = pair member = batch half
-template <int BN>
+// PAIR: grid (2 * n_tiles), cluster (2,1,1): blockIdx.x & 1 = pair member = batch half.  Otherwise grid (n_tiles).
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(R_CTA_THREADS, 1)
 k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmWb, const FwdRecurArgs a) {
-  using F = FwdRecurCfg<BN>;
-  using PC = PairCfg<BN, F::STAGES>;
+  using F = FwdRecurCfg<BN, PAIR>;
+  constexpr uint32_t NCTA = PAIR ? 2u : 1u;                  // CTAs whose loads complete on the (leader's) full barrier
   constexpr int STAGES = F::STAGES, UT = F::UT, ACC_LD = F::ACC_LD, CH = F::CH;
   constexpr int UC = F::CW / 4, RG = R_EPI_THREADS / UC, RPC = 128 / RG;   // per chunk: 16 units x 32 row groups, 4 rows per thread
   extern __shared__ uint8_t smem_raw[];
-  TileCtx c = pair_prologue<BN, STAGES>(smem_raw);
+  TileCtx c = r_prologue<BN, STAGES, PAIR>(smem_raw);
+  c.epi = c.tiles + STAGES * F::STAGE_BYTES + 256;
   uint64_t* tmem_free = c.accum_full + 2;
-  uint64_t* res_full = c.accum_full + 3;                     // (leader) both CTAs' resident U k-blocks have landed
-  if (threadIdx.x == 0) { mbar_init(tmem_free, 2); mbar_init(res_full, 1); fence_barrier_init(); }
+  uint64_t* res_full = c.accum_full + 3;                     // (leader) the CTAs' resident U k-blocks have landed
+  if (threadIdx.x == 0) { mbar_init(tmem_free, NCTA); mbar_init(res_full, 1); fence_barrier_init(); }
   __syncthreads();
-  cluster_sync_all();
-  uint8_t* res;                                              // resident U k-blocks: [nres][BN/2 rows][128 B], 1024-byte aligned
+  if constexpr (PAIR) cluster_sync_all();
+  uint8_t* res;                                              // resident U k-blocks: [nres][B_ROWS][128 B], 1024-byte aligned
   {
     const uint32_t e0 = smem_u32(c.epi) + (uint32_t)F::EPI_BYTES;
     res = c.epi + F::EPI_BYTES + (((e0 + 1023u) & ~1023u) - e0);
   }
-  const uint32_t rank = cluster_ctarank();
-  const int nb = (int)(blockIdx.x >> 1);
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int nb = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int mb = (int)rank;
-  const int n_tiles = (int)(gridDim.x >> 1);
+  const int n_tiles = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int nkb = a.N / BK;
   const unsigned int per_slot = (unsigned int)(n_tiles / R_SLOTS);
   unsigned int* my_slots = a.gbar + (size_t)mb * R_SLOTS;
   const int N = a.N, N4 = 4 * a.N, B = a.B;
-  const int wrow0 = nb * nkb * BN + (int)rank * (BN / 2);    // + kb * BN
+  const int wrow0 = nb * nkb * BN + (int)rank * F::B_ROWS;   // + kb * BN
   const int nres = F::RES < nkb ? F::RES : nkb;              // k-blocks [0, nres) of U never leave shared memory
   constexpr int DBG_T = 4;
   long long* dbg = (a.dbg && blockIdx.x == 0 && a.T > DBG_T) ? a.dbg : nullptr;
@@ -150,9 +180,9 @@ k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUt
     if (elect_one()) { tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmWb); }
     __syncwarp();
     if (elect_one()) {                                       // once: the resident k-blocks
-      if (rank == 0) mbar_expect_tx(res_full, 2u * (uint32_t)nres * (uint32_t)F::B_HALF_BYTES);
+      if (rank == 0) mbar_expect_tx(res_full, NCTA * (uint32_t)nres * (uint32_t)F::B_HALF_BYTES);
       for (int kb = 0; kb < nres; kb++)
-        tma_load_2d_pair(res + (size_t)kb * F::B_HALF_BYTES, &tmWb, res_full, 0, wrow0 + kb * BN);
+        r_tma<PAIR>(res + (size_t)kb * F::B_HALF_BYTES, &tmWb, res_full, 0, wrow0 + kb * BN);
     }
     __syncwarp();
     const int pre = nkb < STAGES ? nkb : STAGES;
@@ -164,9 +194,9 @@ k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUt
         const uint32_t ph = (uint32_t)((g + kb) / STAGES) & 1u;
         mbar_wait(&c.empty[st], ph ^ 1u);
         if (elect_one()) {
-          uint8_t* bdst = c.tiles + (size_t)st * PC::STAGE_BYTES + A_TILE_BYTES;
-          if (rank == 0) mbar_expect_tx(&c.full[st], 2u * (uint32_t)(kb < nres ? A_TILE_BYTES : PC::STAGE_BYTES));
-          if (kb >= nres) tma_load_2d_pair_hint(bdst, &tmWb, &c.full[st], 0, wrow0 + kb * BN, L2_EVICT_LAST);
+          uint8_t* bdst = c.tiles + (size_t)st * F::STAGE_BYTES + A_TILE_BYTES;
+          if (rank == 0) mbar_expect_tx(&c.full[st], NCTA * (uint32_t)(kb < nres ? A_TILE_BYTES : F::STAGE_BYTES));
+          if (kb >= nres) r_tma_w<PAIR>(bdst, &tmWb, &c.full[st], 0, wrow0 + kb * BN);
         }
         __syncwarp();
       }
@@ -181,12 +211,12 @@ k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUt
         const uint32_t ph = (uint32_t)((g + kb) / STAGES) & 1u;
         if (kb >= pre) mbar_wait(&c.empty[st], ph ^ 1u);
         if (elect_one()) {
-          uint8_t* adst = c.tiles + (size_t)st * PC::STAGE_BYTES;
+          uint8_t* adst = c.tiles + (size_t)st * F::STAGE_BYTES;
           if (kb >= pre) {
-            if (rank == 0) mbar_expect_tx(&c.full[st], 2u * (uint32_t)(kb < nres ? A_TILE_BYTES : PC::STAGE_BYTES));
-            if (kb >= nres) tma_load_2d_pair_hint(adst + A_TILE_BYTES, &tmWb, &c.full[st], 0, wrow0 + kb * BN, L2_EVICT_LAST);
+            if (rank == 0) mbar_expect_tx(&c.full[st], NCTA * (uint32_t)(kb < nres ? A_TILE_BYTES : F::STAGE_BYTES));
+            if (kb >= nres) r_tma_w<PAIR>(adst + A_TILE_BYTES, &tmWb, &c.full[st], 0, wrow0 + kb * BN);
           }
-          tma_load_2d_pair(adst, &tmH, &c.full[st], kb * BK, a_row);
+          r_tma<PAIR>(adst, &tmH, &c.full[st], kb * BK, a_row);
         }
         __syncwarp();
       }
@@ -195,7 +225,7 @@ k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUt
   } else if (c.warp == 1) {
     // ---------------- MMA issuer (leader CTA of the pair) ----------------
     if (rank == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, BN);
       const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(c.tiles));
       const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(c.tiles) + A_TILE_BYTES);
       const uint64_t r_desc0 = make_smem_desc_sw128(smem_u32(res));
@@ -213,16 +243,16 @@ k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUt
           if (dbg && c.lane == 0 && t == DBG_T && kb == 0) dbg[2] = clock64();
           tcgen05_after_sync();
           if (elect_one()) {
-            const uint64_t soff = (uint64_t)((uint32_t)st * (uint32_t)(PC::STAGE_BYTES >> 4));
+            const uint64_t soff = (uint64_t)((uint32_t)st * (uint32_t)(F::STAGE_BYTES >> 4));
             const uint64_t bd = kb < nres ? r_desc0 + (uint64_t)((uint32_t)kb * (uint32_t)(F::B_HALF_BYTES >> 4)) : b_desc0 + soff;
 #pragma unroll
             for (int k = 0; k < BK / 16; k++)
-              umma_bf16_pair(c.tmem_d, a_desc0 + soff + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb | k) != 0));
-            umma_commit_pair(&c.empty[st], (uint16_t)0x3);
+              r_mma<PAIR>(c.tmem_d, a_desc0 + soff + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+            r_commit<PAIR>(&c.empty[st]);
           }
           __syncwarp();
         }
-        if (elect_one()) umma_commit_pair(c.accum_full, (uint16_t)0x3);
+        if (elect_one()) r_commit<PAIR>(c.accum_full);
         __syncwarp();
         if (dbg && c.lane == 0 && t == DBG_T) dbg[3] = clock64();
         g += nkb;
@@ -235,16 +265,16 @@ k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUt
     int* sx = reinterpret_cast<int*>(c.epi + F::ACC_BYTES + F::HT_BYTES);
     const int e = threadIdx.x - 64;
     const int l2 = e % UC, rg = e / UC;                      // unit inside a chunk, row group
-    float cpv[CH][RPC];                                      // c(t-1) of this thread's (stream, unit) pairs: register-resident
-    float4 bias[CH];
+    // c(t-1) of this thread's (stream, unit) pairs never leaves the SM: [ch][q][thread] in shared memory (registers are the
+    // scarce resource of this 576-thread CTA: 96 per thread)
+    float* cc_s = reinterpret_cast<float*>(c.epi + F::ACC_BYTES + F::HT_BYTES + F::X_BYTES);
 #pragma unroll
     for (int ch = 0; ch < CH; ch++) {
       const int j = nb * UT + ch * UC + l2;
-      bias[ch] = *reinterpret_cast<const float4*>(a.bp + 4 * j);
 #pragma unroll
       for (int q = 0; q < RPC; q++) {
         const int b = mb * BM + rg + RG * q;
-        cpv[ch][q] = b < B ? a.Cs[(size_t)b * N + j] : 0.f;  // slot 0 = carried-in state
+        cc_s[(ch * RPC + q) * R_EPI_THREADS + e] = b < B ? a.Cs[(size_t)b * N + j] : 0.f;  // slot 0 = carried-in state
       }
     }
     for (int t = 1; t <= a.T; t++) {
@@ -259,17 +289,16 @@ k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUt
       }
       named_bar_sync(1, R_EPI_THREADS);
       float4 w[CH][RPC];
-      int xv[RPC];
 #pragma unroll
-      for (int q = 0; q < RPC; q++) {                        // W*x for one-hot x = a row gather; in flight during the contraction
-        const int x = sx[rg + RG * q];
-        xv[q] = x;
+      for (int ch = 0; ch < CH; ch++) {                      // W*x for one-hot x = a row gather; in flight during the contraction
+        const float4 bias = __ldg(reinterpret_cast<const float4*>(a.bp + 4 * (nb * UT + ch * UC + l2)));
 #pragma unroll
-        for (int ch = 0; ch < CH; ch++) {
-          w[ch][q] = bias[ch];
+        for (int q = 0; q < RPC; q++) {
+          const int x = sx[rg + RG * q];
+          w[ch][q] = bias;
           if (x >= 0) {
             const float4 wr = __ldg(reinterpret_cast<const float4*>(a.Wp + (size_t)x * N4 + 4 * (nb * UT + ch * UC + l2)));
-            w[ch][q] = make_float4(wr.x + bias[ch].x, wr.y + bias[ch].y, wr.z + bias[ch].z, wr.w + bias[ch].w);
+            w[ch][q] = make_float4(wr.x + bias.x, wr.y + bias.y, wr.z + bias.z, wr.w + bias.w);
           }
         }
       }
@@ -285,6 +314,7 @@ k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUt
             if (dbg && e == 0 && t == DBG_T) dbg[4] = clock64();
             tcgen05_after_sync();
           }
+          static_assert(F::CW % 32 == 0, "drain chunks are moved 32 columns at a time");
 #pragma unroll 1
           for (int c0 = 0; c0 < F::CW; c0 += 32) {
             float v[32];
@@ -298,7 +328,7 @@ k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUt
         named_bar_sync(1, R_EPI_THREADS);
         if (ch == CH - 1) {
           if (dbg && e == 0 && t == DBG_T) dbg[5] = clock64();
-          if (e == 0) mbar_arrive_remote(tmem_free, 0);      // this CTA's half of the accumulator is drained
+          if (e == 0) { if constexpr (PAIR) mbar_arrive_remote(tmem_free, 0); else mbar_arrive(tmem_free); }   // accumulator drained
         }
         const int l = ch * UC + l2;                          // unit inside the tile
         const int j = nb * UT + l;
@@ -306,16 +336,17 @@ k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUt
         for (int q = 0; q < RPC; q++) {
           const int r = rg + RG * q;
           float hval = 0.f;
-          if (xv[q] >= -1) {
+          if (sx[r] >= -1) {
             const int b = mb * BM + r;
             const float4 pre = *reinterpret_cast<const float4*>(acc + (size_t)r * ACC_LD + 4 * l2);
             const float gi = sigmoid_fast(pre.x + w[ch][q].x);
             const float go = sigmoid_fast(pre.y + w[ch][q].y);
             const float gf = sigmoid_fast(pre.z + w[ch][q].z);
             const float gu = tanh_fast(pre.w + w[ch][q].w);
-            const float cc = tanh_fast(gi * gu + gf * cpv[ch][q]);   // the carried cell value is the tanh'd one (R/lstm.cc:185-189)
+            float* ccp = cc_s + (ch * RPC + q) * R_EPI_THREADS + e;
+            const float cc = tanh_fast(gi * gu + gf * *ccp);   // the carried cell value is the tanh'd one (R/lstm.cc:185-189)
             hval = go * cc;
-            cpv[ch][q] = cc;
+            *ccp = cc;
             w[ch][q] = make_float4(gi, go, gf, gu);          // the W row is dead: its registers carry the activated gates
             Hbf_t[(size_t)b * N + j] = __float2bfloat16_rn(hval);
           }
@@ -332,10 +363,10 @@ k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUt
         const int j = nb * UT + ch * UC + l2;
 #pragma unroll
         for (int q = 0; q < RPC; q++) {
-          if (xv[q] >= -1) {
+          if (sx[rg + RG * q] >= -1) {
             const int b = mb * BM + rg + RG * q;
             __stcs(reinterpret_cast<float4*>(Gp_t + (size_t)b * N4 + 4 * j), w[ch][q]);   // streamed: read once, in BPTT
-            c_out[(size_t)b * N + j] = cpv[ch][q];
+            c_out[(size_t)b * N + j] = cc_s[(ch * RPC + q) * R_EPI_THREADS + e];
           }
         }
       }
@@ -351,23 +382,23 @@ k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUt
       if (dbg && e == 0 && t == DBG_T) dbg[7] = clock64();
     }
   }
-  pair_epilogue_end<BN, STAGES>(c);
+  r_epilogue_end<BN, STAGES, PAIR>(c);
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 bool launch_fwd_recur_t(const CUtensorMap& tmH, const CUtensorMap& tmWb, const FwdRecurArgs& a, cudaStream_t st) {
-  using F = FwdRecurCfg<BN>;
+  using F = FwdRecurCfg<BN, PAIR>;
   const int n_tiles = 4 * a.N / BN;
-  auto kernel = k_fwd_recur<BN>;
+  auto kernel = k_fwd_recur<BN, PAIR>;
   if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES) != cudaSuccess) { cudaGetLastError(); return false; }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * n_tiles, 1, 1);
+  cfg.gridDim = dim3((PAIR ? 2 : 1) * n_tiles, 1, 1);
   cfg.blockDim = dim3(R_CTA_THREADS);
   cfg.dynamicSmemBytes = (size_t)F::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int max_clusters = 0;
@@ -377,59 +408,64 @@ bool launch_fwd_recur_t(const CUtensorMap& tmH, const CUtensorMap& tmWb, const F
   return cudaLaunchKernelEx(&cfg, kernel, tmH, tmWb, a) == cudaSuccess;
 }
 
-template <int BNJ, int KS>
+template <int BNJ, int KS, bool PAIR>
 struct BwdRecurCfg {
   static constexpr int STAGES = BNJ == 256 ? 4 : 6;        // ring depth first (see FwdRecurCfg)
   static constexpr int UO = BNJ / KS;                      // hidden units finalised by each CTA
-  static_assert(UO == 32, "the epilogue maps one warp lane to each of the 32 hidden units a CTA finalises");
-  using PC = PairCfg<BNJ, STAGES>;
+  static_assert(UO == 8 || UO == 16 || UO == 32, "one tcgen05.ld of 8, 16 or 32 columns per exchanged slice");
+  static_assert(KS % 4 == 0, "four drain warps per TMEM lane quarter share the KS slices");
+  static constexpr int B_ROWS = PAIR ? BNJ / 2 : BNJ;      // weight-tile rows staged by each CTA
+  static constexpr int B_HALF_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_TILE_BYTES + B_HALF_BYTES;
   static constexpr int DH_LD = UO + 4;                     // fp32 row pitch of the dh tile (16-byte aligned rows)
   static constexpr int DH_BYTES = 128 * DH_LD * 4;
   static constexpr int GT_BYTES = 4 * UO * R_HT_LD * 2;    // dg^T staging [gate*UO + unit][row]
   static constexpr int ST_BYTES = 128 * UO * 4;            // per (stream, unit): dcnext, carried across timesteps
   static constexpr int EPI_BYTES = (DH_BYTES + GT_BYTES + ST_BYTES + 127) / 128 * 128;
-  static constexpr int FIXED_BYTES = PC::TILE_BYTES + 1024 + 256 + EPI_BYTES + 1024;
-  static constexpr int B_HALF_BYTES = (BNJ / 2) * BK * 2;
+  static constexpr int FIXED_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_BYTES + 1024;
   static constexpr int RES = (SMEM_LIMIT - FIXED_BYTES) / B_HALF_BYTES;   // resident U^T k-blocks, see FwdRecurCfg
   static constexpr int SMEM_BYTES = FIXED_BYTES + RES * B_HALF_BYTES;
-  static constexpr int CHUNKS_PER_WARP = KS / 4;           // 32-column slices each drain warp moves
+  static constexpr int CHUNKS_PER_WARP = KS / 4;           // UO-column slices each drain warp moves
+  static constexpr int U4 = UO / 4;                        // float4 groups per slice row
+  static constexpr size_t RED_TILE_FLOATS = (size_t)KS * KS * U4 * 128 * 4;   // [dst][src][u][row][4]
 };
 
-// grid (2 * JT * KS), cluster (2,1,1): blockIdx.x & 1 = pair member = batch half
-template <int BNJ, int KS>
+// PAIR: grid (2 * JT * KS), cluster (2,1,1): blockIdx.x & 1 = pair member = batch half.  Otherwise grid (JT * KS), one batch tile.
+template <int BNJ, int KS, bool PAIR>
 __global__ void __launch_bounds__(R_CTA_THREADS, 1)
 k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CUtensorMap tmWb,
             const __grid_constant__ CUtensorMap tmdY, const BwdRecurArgs a) {
-  using F = BwdRecurCfg<BNJ, KS>;
-  using PC = typename F::PC;
-  constexpr int STAGES = F::STAGES, UO = F::UO, RG = R_EPI_THREADS / UO, ROWS = 128 / RG, DH_LD = F::DH_LD;
+  using F = BwdRecurCfg<BNJ, KS, PAIR>;
+  constexpr int STAGES = F::STAGES, UO = F::UO, RG = R_EPI_THREADS / UO, ROWS = 128 / RG, DH_LD = F::DH_LD, U4 = F::U4;
+  constexpr uint32_t NCTA = PAIR ? 2u : 1u;
   extern __shared__ uint8_t smem_raw[];
-  TileCtx c = pair_prologue<BNJ, STAGES>(smem_raw);
-  uint64_t* tmem_free = c.accum_full + 2;                    // (leader) both CTAs have read the accumulator out of TMEM
-  uint64_t* res_full = c.accum_full + 3;                     // (leader) both CTAs' resident weight k-blocks have landed
-  if (threadIdx.x == 0) { mbar_init(tmem_free, 2); mbar_init(res_full, 1); fence_barrier_init(); }
+  TileCtx c = r_prologue<BNJ, STAGES, PAIR>(smem_raw);
+  c.epi = c.tiles + STAGES * F::STAGE_BYTES + 256;
+  uint64_t* tmem_free = c.accum_full + 2;                    // (leader) the CTAs have read the accumulator out of TMEM
+  uint64_t* res_full = c.accum_full + 3;                     // (leader) the CTAs' resident weight k-blocks have landed
+  if (threadIdx.x == 0) { mbar_init(tmem_free, NCTA); mbar_init(res_full, 1); fence_barrier_init(); }
   __syncthreads();
-  cluster_sync_all();
+  if constexpr (PAIR) cluster_sync_all();
   uint8_t* res;                                              // resident U^T k-blocks: [nres][BNJ/2 rows][128 B], 1024-byte aligned
   {
     const uint32_t e0 = smem_u32(c.epi) + (uint32_t)F::EPI_BYTES;
     res = c.epi + F::EPI_BYTES + (((e0 + 1023u) & ~1023u) - e0);
   }
-  const uint32_t rank = cluster_ctarank();                   // pair member = batch half
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;       // pair member = batch half
   const int mb = (int)rank;
-  const int pairi = (int)(blockIdx.x >> 1);
+  const int pairi = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int jt = pairi / KS, ks = pairi - jt * KS;
   const int N = a.N, N4 = 4 * a.N, B = a.B, T = a.T;
   const int nkbu = N4 / BK / KS;                             // U k-blocks per rank and timestep
   const int nkbw = (ks < a.M / BK) ? 1 : 0;                  // one Why k-block for the first M/64 ranks
   const int nres = F::RES < nkbu ? F::RES : nkbu;            // this rank's first nres U k-blocks never leave shared memory
   const int NKBG = N4 / BK + a.M / BK;                       // k-blocks per tile in the blocked weight copy
-  const int wrow0 = jt * NKBG * BNJ + (int)rank * (BNJ / 2); // + kbg * BNJ
+  const int wrow0 = jt * NKBG * BNJ + (int)rank * F::B_ROWS; // + kbg * BNJ
   const int tile = jt * 2 + mb;
   unsigned int* my_slots = a.gbar + (size_t)mb * R_SLOTS;
   unsigned int* xcnt = a.xcnt + tile;
-  const unsigned int per_slot = (unsigned int)(gridDim.x / 2 / R_SLOTS);   // arrivals per counter and timestep
-  float* red_tile = a.red + (size_t)tile * KS * KS * 8 * 128 * 4;          // [dst][src][u][row][4]
+  const unsigned int per_slot = (unsigned int)(gridDim.x / NCTA / R_SLOTS);   // arrivals per counter and timestep
+  float* red_tile = a.red + (size_t)tile * F::RED_TILE_FLOATS;             // [dst][src][u][row][4]
   long long* dbg = (a.dbg && blockIdx.x == 0) ? a.dbg : nullptr;
   constexpr int DBG_S = 4;                                   // the timestep (0-based from the end of the window) that is stamped
 
@@ -438,9 +474,9 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
     if (elect_one()) { tma_prefetch_desc(&tmdG); tma_prefetch_desc(&tmWb); tma_prefetch_desc(&tmdY); }
     __syncwarp();
     if (elect_one()) {                                       // once: the resident k-blocks
-      if (rank == 0 && nres > 0) mbar_expect_tx(res_full, 2u * (uint32_t)nres * (uint32_t)F::B_HALF_BYTES);
+      if (rank == 0 && nres > 0) mbar_expect_tx(res_full, NCTA * (uint32_t)nres * (uint32_t)F::B_HALF_BYTES);
       for (int iu = 0; iu < nres; iu++)
-        tma_load_2d_pair(res + (size_t)iu * F::B_HALF_BYTES, &tmWb, res_full, 0, wrow0 + (ks * nkbu + iu) * BNJ);
+        r_tma<PAIR>(res + (size_t)iu * F::B_HALF_BYTES, &tmWb, res_full, 0, wrow0 + (ks * nkbu + iu) * BNJ);
     }
     __syncwarp();
     int g = 0;                                               // k-blocks issued so far (ring position)
@@ -457,14 +493,14 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
         const bool resident = i >= nkbw && i - nkbw < nres;
         mbar_wait(&c.empty[st], ph ^ 1u);
         if (elect_one()) {
-          uint8_t* adst = c.tiles + (size_t)st * PC::STAGE_BYTES;
-          if (rank == 0) mbar_expect_tx(&c.full[st], 2u * (uint32_t)(resident ? A_TILE_BYTES : PC::STAGE_BYTES));
+          uint8_t* adst = c.tiles + (size_t)st * F::STAGE_BYTES;
+          if (rank == 0) mbar_expect_tx(&c.full[st], NCTA * (uint32_t)(resident ? A_TILE_BYTES : F::STAGE_BYTES));
           if (i < nkbw) {
-            tma_load_2d_pair_hint(adst + A_TILE_BYTES, &tmWb, &c.full[st], 0, wrow0 + (N4 / BK + ks) * BNJ, L2_EVICT_LAST);
-            tma_load_2d_pair(adst, &tmdY, &c.full[st], ks * BK, (t - 1) * a.Bp + mb * BM);
+            r_tma_w<PAIR>(adst + A_TILE_BYTES, &tmWb, &c.full[st], 0, wrow0 + (N4 / BK + ks) * BNJ);
+            r_tma<PAIR>(adst, &tmdY, &c.full[st], ks * BK, (t - 1) * a.Bp + mb * BM);
           } else if (!resident) {
             const int kbg = ks * nkbu + (i - nkbw);
-            tma_load_2d_pair_hint(adst + A_TILE_BYTES, &tmWb, &c.full[st], 0, wrow0 + kbg * BNJ, L2_EVICT_LAST);
+            r_tma_w<PAIR>(adst + A_TILE_BYTES, &tmWb, &c.full[st], 0, wrow0 + kbg * BNJ);
           }
         }
         __syncwarp();
@@ -482,12 +518,12 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
         const bool resident = i - nkbw < nres;
         if (i >= pre) mbar_wait(&c.empty[st], ph ^ 1u);
         if (elect_one()) {
-          uint8_t* adst = c.tiles + (size_t)st * PC::STAGE_BYTES;
+          uint8_t* adst = c.tiles + (size_t)st * F::STAGE_BYTES;
           if (i >= pre) {
-            if (rank == 0) mbar_expect_tx(&c.full[st], 2u * (uint32_t)(resident ? A_TILE_BYTES : PC::STAGE_BYTES));
-            if (!resident) tma_load_2d_pair_hint(adst + A_TILE_BYTES, &tmWb, &c.full[st], 0, wrow0 + kbg * BNJ, L2_EVICT_LAST);
+            if (rank == 0) mbar_expect_tx(&c.full[st], NCTA * (uint32_t)(resident ? A_TILE_BYTES : F::STAGE_BYTES));
+            if (!resident) r_tma_w<PAIR>(adst + A_TILE_BYTES, &tmWb, &c.full[st], 0, wrow0 + kbg * BNJ);
           }
-          tma_load_2d_pair(adst, &tmdG, &c.full[st], kbg * BK, t * a.Bp + mb * BM);
+          r_tma<PAIR>(adst, &tmdG, &c.full[st], kbg * BK, t * a.Bp + mb * BM);
         }
         __syncwarp();
       }
@@ -496,7 +532,7 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
   } else if (c.warp == 1) {
     // ---------------- MMA issuer (leader CTA of the pair) ----------------
     if (rank == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BNJ);
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, BNJ);
       const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(c.tiles));
       const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(c.tiles) + A_TILE_BYTES);
       const uint64_t r_desc0 = make_smem_desc_sw128(smem_u32(res));
@@ -516,17 +552,17 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
           if (dbg && c.lane == 0 && s == DBG_S && i == nkbw) dbg[2] = clock64();
           tcgen05_after_sync();
           if (elect_one()) {
-            const uint64_t soff = (uint64_t)((uint32_t)st * (uint32_t)(PC::STAGE_BYTES >> 4));
+            const uint64_t soff = (uint64_t)((uint32_t)st * (uint32_t)(F::STAGE_BYTES >> 4));
             const bool resident = i >= nkbw && i - nkbw < nres;
             const uint64_t bd = resident ? r_desc0 + (uint64_t)((uint32_t)(i - nkbw) * (uint32_t)(F::B_HALF_BYTES >> 4)) : b_desc0 + soff;
 #pragma unroll
             for (int k = 0; k < BK / 16; k++)
-              umma_bf16_pair(c.tmem_d, a_desc0 + soff + 2 * k, bd + 2 * k, idesc, (uint32_t)((i | k) != 0));
-            umma_commit_pair(&c.empty[st], (uint16_t)0x3);
+              r_mma<PAIR>(c.tmem_d, a_desc0 + soff + 2 * k, bd + 2 * k, idesc, (uint32_t)((i | k) != 0));
+            r_commit<PAIR>(&c.empty[st]);
           }
           __syncwarp();
         }
-        if (elect_one()) umma_commit_pair(c.accum_full, (uint16_t)0x3);
+        if (elect_one()) r_commit<PAIR>(c.accum_full);
         __syncwarp();
         if (dbg && c.lane == 0 && s == DBG_S) dbg[3] = clock64();
         g += total;
@@ -566,22 +602,22 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
         }
 #pragma unroll 1
         for (int ch = 0; ch < F::CHUNKS_PER_WARP; ch++) {
-          const int d = cgrp * F::CHUNKS_PER_WARP + ch;      // destination rank of this 32-column slice
-          float v[32];
+          const int d = cgrp * F::CHUNKS_PER_WARP + ch;      // destination rank of this UO-column slice
+          float v[UO];
           if (has_acc) {
-            tmem_ld32(c.tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(d * UO), v);
+            tmem_ldw<UO>(c.tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(d * UO), v);
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; i++) v[i] = 0.f;
+            for (int i = 0; i < UO; i++) v[i] = 0.f;
           }
           if (d == ks) {
             float4* dst = reinterpret_cast<float4*>(dh + (size_t)row * DH_LD);
 #pragma unroll
-            for (int u = 0; u < 8; u++) dst[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+            for (int u = 0; u < U4; u++) dst[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
           } else {
-            float4* dst = reinterpret_cast<float4*>(red_tile + ((size_t)(d * KS + ks) * 8 * 128 + row) * 4);
+            float4* dst = reinterpret_cast<float4*>(red_tile + ((size_t)(d * KS + ks) * U4 * 128 + row) * 4);
 #pragma unroll
-            for (int u = 0; u < 8; u++) dst[(size_t)u * 128] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+            for (int u = 0; u < U4; u++) dst[(size_t)u * 128] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
           }
         }
         if (has_acc) tcgen05_before_sync();
@@ -591,7 +627,7 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
       // 2. exchange: announce our slices, free the accumulator, wait for the other ranks
       if (e == 0) {
         red_release_gpu_add(xcnt, 1u);                       // release: cumulative over the barrier-ordered stores
-        if (has_acc) mbar_arrive_remote(tmem_free, 0);
+        if (has_acc) { if constexpr (PAIR) mbar_arrive_remote(tmem_free, 0); else mbar_arrive(tmem_free); }
       }
       // operands of the gate math that no timestep of this launch produces: in flight while the exchange is awaited
       float4 gv[ROWS];
@@ -612,12 +648,12 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
       if (dbg && e == 0 && s == DBG_S) dbg[6] = clock64();
       // 3. reduce: float4 position p = (u, row); sum over the KS sources in a fixed order (both positions' loads in flight at once)
 #pragma unroll
-      for (int p = e; p < 8 * 128; p += R_EPI_THREADS) {
+      for (int p = e; p < U4 * 128; p += R_EPI_THREADS) {
         const int u = p >> 7, row = p & 127;
         float4 pv[KS];
 #pragma unroll
         for (int sr = 0; sr < KS; sr++)
-          if (sr != ks) pv[sr] = __ldcg(reinterpret_cast<const float4*>(red_tile + ((size_t)(ks * KS + sr) * 8 * 128 + (size_t)u * 128 + row) * 4));
+          if (sr != ks) pv[sr] = __ldcg(reinterpret_cast<const float4*>(red_tile + ((size_t)(ks * KS + sr) * U4 * 128 + (size_t)u * 128 + row) * 4));
         float4* own = reinterpret_cast<float4*>(dh + (size_t)row * DH_LD + 4 * u);
         const float4 o = *own;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -674,27 +710,27 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
       if (has_acc) used++;
     }
   }
-  pair_epilogue_end<BNJ, STAGES>(c);
+  r_epilogue_end<BNJ, STAGES, PAIR>(c);
 }
 
-template <int BNJ, int KS>
+template <int BNJ, int KS, bool PAIR>
 bool launch_bwd_recur_t(const CUtensorMap& tmdG, const CUtensorMap& tmWb, const CUtensorMap& tmdY, const BwdRecurArgs& a,
                         cudaStream_t st) {
-  using F = BwdRecurCfg<BNJ, KS>;
+  using F = BwdRecurCfg<BNJ, KS, PAIR>;
   const int JT = a.N / BNJ;
-  auto kernel = k_bwd_recur<BNJ, KS>;
+  auto kernel = k_bwd_recur<BNJ, KS, PAIR>;
   if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM_BYTES) != cudaSuccess) { cudaGetLastError(); return false; }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * JT * KS, 1, 1);
+  cfg.gridDim = dim3((PAIR ? 2 : 1) * JT * KS, 1, 1);
   cfg.blockDim = dim3(R_CTA_THREADS);
   cfg.dynamicSmemBytes = (size_t)F::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  // every CTA must be resident at once (the grid barrier spins): refuse unless all pairs fit on an idle GPU
+  // every CTA must be resident at once (the grid barrier spins): refuse unless all of them fit on an idle GPU
   int max_clusters = 0;
   if (cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return false; }
   if (max_clusters < JT * KS) return false;
@@ -705,50 +741,77 @@ bool launch_bwd_recur_t(const CUtensorMap& tmdG, const CUtensorMap& tmWb, const 
 
 }  // namespace
 
-// Gate columns per tile (128 | 64) if this shape runs the forward recurrence persistently, else 0: one pair of batch tiles,
-// 4N/BN pairs <= 74 and a multiple of 8 (barrier counters).  LSTM_FWD_RECUR=0 forces the per-timestep kernels.
+// Shape policy of the persistent recurrences.  One launch must hold every CTA (co-resident, <= 148) and the barrier counters
+// want a multiple of 8 CTAs per batch half:
+//   128 < B <= 256 (Bp = 256): cta_group::2 pairs, one per tile, each CTA one batch half;
+//   B <= 128       (Bp = 128): cta_group::1, one CTA per tile (small models: U fully resident in shared memory).
+// Returns the tile width (gate columns / hidden units per tile), 0 = run the per-timestep kernels.
 int fwd_recur_bn(int N, int Bp, int M) {
-  if (Bp != 256 || M != 256) return 0;
+  if ((Bp != 256 && Bp != 128) || M != 256) return 0;
   static const int force = getenv("LSTM_FWD_RECUR") ? atoi(getenv("LSTM_FWD_RECUR")) : -1;
   if (force == 0) return 0;
-  for (int bn : {128, 64}) {
-    const int pairs = 4 * N / bn;
-    if ((4 * N) % bn == 0 && pairs <= 74 && pairs % R_SLOTS == 0) return bn;
+  if (Bp == 256) {
+    for (int bn : {128, 64}) {
+      const int tiles = 4 * N / bn;
+      if ((4 * N) % bn == 0 && tiles <= 74 && tiles % R_SLOTS == 0) return bn;
+    }
+    return 0;
+  }
+  for (int bn : {32, 64}) {                                  // one batch tile: narrow tiles, so that more SMs share the timestep
+    const int tiles = 4 * N / bn;
+    if ((4 * N) % bn == 0 && tiles <= 148 && tiles % R_SLOTS == 0) return bn;
   }
   return 0;
 }
 bool launch_fwd_recur(int bn, const CUtensorMap& tmH, const CUtensorMap& tmWb, const FwdRecurArgs& a, cudaStream_t st) {
-  if (bn == 128) return launch_fwd_recur_t<128>(tmH, tmWb, a, st);
-  if (bn == 64) return launch_fwd_recur_t<64>(tmH, tmWb, a, st);
+  if (a.Bp == 256) {
+    if (bn == 128) return launch_fwd_recur_t<128, true>(tmH, tmWb, a, st);
+    if (bn == 64) return launch_fwd_recur_t<64, true>(tmH, tmWb, a, st);
+  } else if (a.Bp == 128) {
+    if (bn == 64) return launch_fwd_recur_t<64, false>(tmH, tmWb, a, st);
+    if (bn == 32) return launch_fwd_recur_t<32, false>(tmH, tmWb, a, st);
+  }
   return false;
 }
+int fwd_recur_box_rows(int bn, int Bp) { return Bp == 256 ? bn / 2 : bn; }
 
-// Which <BNJ, KS> instantiation (if any) runs this shape persistently: 0 = none (per-timestep kernels), else BNJ.
-// Needs one pair of batch tiles (Bp == 256), N/BNJ * KS pairs <= 74 and (N/BNJ * KS) % 8 == 0 for the barrier counters.
+// BPTT: tile = BNJ hidden units, KS split-K ranks, each rank finalises BNJ/KS units.
+//   Bp = 256: <128, 4> pairs (measured at N = 2048, profiles/r02d_*: 12.9 us per timestep against 16.8 us for <256, 8>, whose 8-way
+//             exchange moves 14 MB through L2 per timestep instead of 6 MB); LSTM_BWD_RECUR=256 selects the latter for tests;
+//   Bp = 128: <64, 4> or <32, 4> single CTAs, whichever yields 64..148 CTAs.
 int bwd_recur_bnj(int N, int Bp, int M) {
-  if (Bp != 256 || M != 256) return 0;
+  if ((Bp != 256 && Bp != 128) || M != 256) return 0;
   static const int force = getenv("LSTM_BWD_RECUR") ? atoi(getenv("LSTM_BWD_RECUR")) : -1;
   if (force == 0) return 0;
   const int nkbu = 4 * N / BK;
   auto fits = [&](int bnj, int ks) {
-    const int pairs = (N / bnj) * ks;
-    return N % bnj == 0 && nkbu % ks == 0 && pairs <= 74 && pairs % R_SLOTS == 0;
+    const int ctas = (N / bnj) * ks;                         // per batch half
+    return N % bnj == 0 && nkbu % ks == 0 && ctas <= (Bp == 256 ? 74 : 148) && ctas % R_SLOTS == 0;
   };
-  // measured at N = 2048 (profiles/r02d_*): <128, 4> 12.9 us per timestep, <256, 8> 16.8 us — the 8-way exchange moves 14 MB
-  // through L2 per timestep instead of 6 MB and that costs more than the smaller operand tiles save
-  if (force == 256) return fits(256, 8) ? 256 : 0;
-  if (fits(128, 4)) return 128;
-  if (fits(256, 8)) return 256;
+  if (Bp == 256) {
+    if (force == 256) return fits(256, 8) ? 256 : 0;
+    if (fits(128, 4)) return 128;
+    if (fits(256, 8)) return 256;
+    return 0;
+  }
+  if (fits(32, 4)) return 32;
+  if (fits(64, 4)) return 64;
   return 0;
 }
 size_t bwd_recur_red_floats(int N, int bnj) {
   const int ks = bnj == 256 ? 8 : 4;
-  return (size_t)(N / bnj) * 2 * ks * ks * 8 * 128 * 4;
+  return (size_t)(N / bnj) * 2 * ks * ks * (bnj / ks / 4) * 128 * 4;
 }
+int bwd_recur_box_rows(int bnj, int Bp) { return Bp == 256 ? bnj / 2 : bnj; }
 bool launch_bwd_recur(int bnj, const CUtensorMap& tmdG, const CUtensorMap& tmWb, const CUtensorMap& tmdY, const BwdRecurArgs& a,
                       cudaStream_t st) {
-  if (bnj == 256) return launch_bwd_recur_t<256, 8>(tmdG, tmWb, tmdY, a, st);
-  if (bnj == 128) return launch_bwd_recur_t<128, 4>(tmdG, tmWb, tmdY, a, st);
+  if (a.Bp == 256) {
+    if (bnj == 256) return launch_bwd_recur_t<256, 8, true>(tmdG, tmWb, tmdY, a, st);
+    if (bnj == 128) return launch_bwd_recur_t<128, 4, true>(tmdG, tmWb, tmdY, a, st);
+  } else if (a.Bp == 128) {
+    if (bnj == 64) return launch_bwd_recur_t<64, 4, false>(tmdG, tmWb, tmdY, a, st);
+    if (bnj == 32) return launch_bwd_recur_t<32, 4, false>(tmdG, tmWb, tmdY, a, st);
+  }
   return false;
 }
 

@@ -26,9 +26,12 @@ def frob_rel(a, b):
 CASES = [
     (2048, 3, 256, dict(fwd_bn=128, fwd_pair=1, wgrad_bn=256, bwd_persistent=128, fwd_persistent=128)),
     (2048, 4, 200, dict(fwd_bn=128, fwd_pair=1, wgrad_bn=256, bwd_persistent=128, fwd_persistent=128)),   # padding rows in the second batch tile
-    (1024, 3, 256, dict(fwd_bn=64, fwd_pair=1, wgrad_bn=256)),
-    (1024, 4, 128, dict(fwd_bn=32, fwd_pair=0, wgrad_bn=256)),
-    (512, 4, 64, dict(fwd_bn=32, fwd_pair=0, wgrad_bn=128)),
+    (1024, 3, 256, dict(wgrad_bn=256, fwd_persistent=128, bwd_persistent=128)),
+    (1024, 4, 128, dict(wgrad_bn=256, fwd_persistent=32, bwd_persistent=32)),     # config 3: one batch tile, U resident
+    (512, 4, 64, dict(wgrad_bn=128, fwd_persistent=32, bwd_persistent=32)),       # config 2
+    (2048, 3, 100, dict(wgrad_bn=256, fwd_persistent=64, bwd_persistent=64)),
+    (1024, 3, 384, dict(fwd_bn=32, fwd_pair=0, wgrad_bn=256, fwd_persistent=0, bwd_persistent=0)),   # three batch tiles: per-timestep kernels
+    (1024, 3, 512, dict(fwd_bn=64, fwd_pair=1, wgrad_bn=256, fwd_persistent=0, bwd_persistent=0)),   # ... as cta_group::2 pairs
 ]
 
 
@@ -91,10 +94,11 @@ def test_benchmark_shape_training_iterations_follow_the_oracle():
         assert frob_rel(a, b) < 3e-2, name
 
 
-def test_persistent_recurrences_agree_with_the_per_timestep_kernels():
+@pytest.mark.parametrize("N,S,B,want_persistent", [(2048, 13, 256, 128), (1024, 13, 128, 32), (512, 9, 64, 32)])
+def test_persistent_recurrences_agree_with_the_per_timestep_kernels(N, S, B, want_persistent):
     """The persistent recurrences (tc_recur.cu) against the launch-per-timestep kernels (LSTM_*_RECUR=0) on the same
-    window over 12 timesteps at config 4's width: both contract the same bf16 operands, so only the fp32 summation order of the
-    split-K partials differs."""
+    window over S-1 timesteps at the widths and batches of configs 4, 3 and 2: both contract the same bf16 operands, so only the
+    fp32 summation order of the split-K partials differs."""
     import os
     import subprocess
     import sys
@@ -102,27 +106,36 @@ def test_persistent_recurrences_agree_with_the_per_timestep_kernels():
     code = r"""
 import sys, numpy as np
 import eigen_lstm_b200 as el
-M, N, S, B = 256, 2048, 13, 256
+M, N, S, B = 256, int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
 g = el.LSTM(M, N, S, B, dtype=el.BF16)
 g.init_params(3, 0.01, 1.0)
 rng = np.random.default_rng(0)
 g.set_state(rng.normal(0, 0.3, (N, B)).astype(np.float32), rng.normal(0, 0.3, (N, B)).astype(np.float32))
 x = rng.integers(0, M, (S, B)).astype(np.int32); t = rng.integers(0, M, (S, B)).astype(np.int32)
 loss = g.forward(x, t); g.backward()
-np.savez(sys.argv[1], loss=loss, v=np.array([g.variant()["bwd_persistent"]]), dg1=g.activation("dg", 1), dg7=g.activation("dg", 7),
-         **{n: a for n, a in zip(["W", "U", "b", "Why", "by"], g.grads())})
+v = g.variant()
+np.savez(sys.argv[1], loss=loss, v=np.array([v["fwd_persistent"], v["bwd_persistent"]]), dg1=g.activation("dg", 1), dg7=g.activation("dg", 7),
+         h5=g.activation("h", 5), **{n: a for n, a in zip(["W", "U", "b", "Why", "by"], g.grads())})
 """
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    envs = [{}, {"LSTM_BWD_RECUR": "0", "LSTM_FWD_RECUR": "0"}]
+    if B > 128:
+        envs.append({"LSTM_BWD_RECUR": "256"})
     out = []
     with tempfile.TemporaryDirectory() as d:
-        for i, env in enumerate(({}, {"LSTM_BWD_RECUR": "0", "LSTM_FWD_RECUR": "0"}, {"LSTM_BWD_RECUR": "256"})):
+        for i, env in enumerate(envs):
             path = os.path.join(d, f"r{i}.npz")
-            subprocess.run([sys.executable, "-c", code, path], check=True, cwd=root, env=dict(os.environ, **env), timeout=300)
+            subprocess.run([sys.executable, "-c", code, path, str(N), str(S), str(B)], check=True, cwd=root, env=dict(os.environ, **env),
+                           timeout=300)
             out.append(dict(np.load(path)))
-    a, b, c = out
-    assert int(a["v"][0]) == 128 and int(b["v"][0]) == 0 and int(c["v"][0]) == 256
-    assert a["loss"] == c["loss"]                          # same forward kernel
+    a, b = out[0], out[1]
+    assert list(a["v"]) == [want_persistent, want_persistent] and list(b["v"]) == [0, 0]
     assert abs(a["loss"] - b["loss"]) < 1e-5 * abs(b["loss"])   # persistent vs per-timestep forward: same bf16 operands, other fp32 order
+    assert frob_rel(a["h5"], b["h5"]) < 2e-3
     for k in ("dg1", "dg7", "W", "U", "b", "Why", "by"):
         assert frob_rel(a[k], b[k]) < 3e-3, k             # dg is rounded to bf16 every timestep: summation-order noise x 12 steps
-        assert frob_rel(c[k], b[k]) < 3e-3, k
+    if B > 128:
+        c = out[2]
+        assert int(c["v"][1]) == 256 and a["loss"] == c["loss"]   # same forward kernel
+        for k in ("dg1", "dg7", "W", "U", "b", "Why", "by"):
+            assert frob_rel(c[k], b[k]) < 3e-3, k
