@@ -589,6 +589,7 @@ struct RecurArgs {
   const float *W, *U, *bias, *Why, *by;   // fp32 masters, column-major like the reference
   int M, N, mode;                          // mode 0 eval, 1 sample, 2 greedy
   int UPC, rows_resident;                  // hidden units per CTA; 1 if this CTA's U rows live in smem
+  int w_resident;                          // 1 if this CTA's W rows ([4*UPC][M]) live in smem too
   const uint8_t* text; size_t n;
   const float* uniforms; const float *h0, *c0;
   uint8_t* out;
@@ -609,7 +610,8 @@ __global__ void __launch_bounds__(256, 1) k_recur_persist(const RecurArgs a) {
   float* sU = sh + N;                                  // [R][N+1] resident rows of U (pitch N+1: conflict-free)
   const int UP = N + 1;
   float* sWhy = sU + (a.rows_resident ? (size_t)R * UP : 0);   // [MPC][N+1]
-  float* sg = sWhy + (size_t)MPC * UP;                 // [R] gate pre-activations
+  float* sW = sWhy + (size_t)MPC * UP;                 // [R][M] resident rows of W: the one-hot product W x is one smem read per row
+  float* sg = sW + (a.w_resident ? (size_t)R * M : 0); // [R] gate pre-activations
   float* sc = sg + R;                                  // [UPC] cell state of the owned units
   float* se = sc + UPC;                                // [M] exp(y) of the current step
   __shared__ float s_sum;
@@ -626,6 +628,12 @@ __global__ void __launch_bounds__(256, 1) k_recur_persist(const RecurArgs a) {
     const int mm = idx / N, k = idx - mm * N, m = g * MPC + mm;
     sWhy[(size_t)mm * UP + k] = (m < M) ? a.Why[(size_t)k * M + m] : 0.f;
   }
+  if (a.w_resident)
+    for (int idx = tid; idx < R * M; idx += blockDim.x) {
+      const int r = idx / M, m = idx - r * M;
+      const int u = r >> 2, gate = r & 3, j = j0 + u;
+      sW[idx] = (j < N) ? a.W[(size_t)m * N4 + (size_t)gate * N + j] : 0.f;
+    }
   for (int u = tid; u < UPC; u += blockDim.x) sc[u] = (a.c0 && j0 + u < N) ? a.c0[j0 + u] : 0.f;
   if (g == 0)
     for (int k = tid; k < N; k += blockDim.x) a.hbuf[k] = a.h0 ? a.h0[k] : 0.f;
@@ -644,7 +652,9 @@ __global__ void __launch_bounds__(256, 1) k_recur_persist(const RecurArgs a) {
   // 8 lanes per gate row (4 rows per warp and pass; every lane runs the shuffles): dot(U_row, h) + W[x][row] + b[row];
   // then the cell update for the owned units
   const int warp = tid >> 5, lane = tid & 31, lane8 = lane & 7, nwarps = blockDim.x >> 5;
-  auto cell = [&](int x, int buf_out) {
+  // U h for the owned gate rows: 8 lanes per row (4 rows per warp and pass; every lane runs the shuffles).  Does NOT depend on
+  // the input byte, so when sampling it runs BEFORE the byte is drawn, off the critical path.
+  auto matvec = [&]() {
     for (int base = warp * 4; base < R; base += nwarps * 4) {
       const int r = base + (lane >> 3);
       const int u = r >> 2, gate = r & 3, j = j0 + u;
@@ -662,10 +672,17 @@ __global__ void __launch_bounds__(256, 1) k_recur_persist(const RecurArgs a) {
       acc += __shfl_xor_sync(0xffffffffu, acc, 4);
       acc += __shfl_xor_sync(0xffffffffu, acc, 2);
       acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      if (lane8 == 0 && ok) {
+      if (lane8 == 0 && ok) sg[r] = acc;
+    }
+  };
+  // g = W[:, x] + U h + b (R/lstm.cc:176), gates, cell update for the owned units; needs a __syncthreads() after matvec()
+  auto finish = [&](int x, int buf_out) {
+    for (int r = tid; r < R; r += blockDim.x) {
+      const int u = r >> 2, gate = r & 3, j = j0 + u;
+      if (j < N) {
         const size_t row = (size_t)gate * N + j;
-        const float wx = (x >= 0) ? a.W[(size_t)x * N4 + row] : 0.f;
-        const float pre = __fadd_rn(__fadd_rn(wx, acc), a.bias[row]);
+        const float wx = (x >= 0) ? (a.w_resident ? sW[(size_t)r * M + x] : a.W[(size_t)x * N4 + row]) : 0.f;
+        const float pre = __fadd_rn(__fadd_rn(wx, sg[r]), a.bias[row]);
         sg[r] = (gate < 3) ? logistic_f(pre) : tanhf(pre);
       }
     }
@@ -701,35 +718,43 @@ __global__ void __launch_bounds__(256, 1) k_recur_persist(const RecurArgs a) {
   };
 
   if (a.mode == 0) {
-    // evaluation: step on text[i], then score text[i+1]; ONE barrier per character
+    // evaluation: ONE phase and ONE barrier per character.  With h(i) in shared memory a phase scores text[i] against the
+    // output of the previous step (logits of h(i), normalisation deferred) AND steps on text[i] (cell) — the two do not depend on
+    // each other.
     float* my_e = se;          // [MPC]
     float* my_y = se + MPC;    // [MPC]
-    for (size_t i = 0; i + 1 < a.n; i++) {
+    for (size_t i = 0; i < a.n; i++) {
       const int buf = (int)(i & 1);
       load_h(buf);
-      cell((int)a.text[i], buf ^ 1);
-      grid_barrier(a.bar, ++epoch * G);
-      load_h(buf ^ 1);
-      logits(my_e, my_y);
-      if (tid == 0) {
-        float s = 0.f;
-        const int tgt = (int)a.text[i + 1];
-        for (int mm = 0; mm < MPC; mm++) {
-          const int m = g * MPC + mm;
-          if (m < M) { s += my_e[mm]; if (m == tgt) a.y_tgt[i] = my_y[mm]; }
+      if (i > 0) {
+        logits(my_e, my_y);
+        if (tid == 0) {
+          float s = 0.f;
+          const int tgt = (int)a.text[i];
+          for (int mm = 0; mm < MPC; mm++) {
+            const int m = g * MPC + mm;
+            if (m < M) { s += my_e[mm]; if (m == tgt) a.y_tgt[i - 1] = my_y[mm]; }
+          }
+          a.sum_part[(i - 1) * G + g] = s;
         }
-        a.sum_part[i * G + g] = s;
       }
-      __syncthreads();
+      if (i + 1 < a.n) {
+        matvec();
+        __syncthreads();
+        finish((int)a.text[i], buf ^ 1);
+        grid_barrier(a.bar, ++epoch * G);
+      }
     }
   } else {
-    // sampling: p from the current h, draw, emit, step on the drawn byte; TWO barriers per character
+    // sampling: p from the current h, draw, emit, step on the drawn byte; TWO barriers per character.  U h — the expensive part
+    // of the step — does not depend on the drawn byte: it is computed next to the logits, before the first barrier.
     for (size_t i = 0; i < a.n; i++) {
       const int buf = (int)(i & 1);
       load_h(buf);
       logits(se, nullptr);                                           // se[0..MPC) = owned exp(y)
       for (int mm = tid; mm < MPC; mm += blockDim.x)
         if (g * MPC + mm < M) a.ebuf[(size_t)buf * M + g * MPC + mm] = se[mm];
+      matvec();
       grid_barrier(a.bar, ++epoch * G);
       for (int m = tid; m < M; m += blockDim.x) se[m] = __ldcg(a.ebuf + (size_t)buf * M + m);
       __syncthreads();
@@ -763,7 +788,7 @@ __global__ void __launch_bounds__(256, 1) k_recur_persist(const RecurArgs a) {
         if (g == 0) a.out[i] = (uint8_t)index;
       }
       __syncthreads();
-      cell(s_index, buf ^ 1);
+      finish(s_index, buf ^ 1);
       grid_barrier(a.bar, ++epoch * G);
     }
   }
@@ -774,9 +799,10 @@ __global__ void __launch_bounds__(256, 1) k_recur_persist(const RecurArgs a) {
 }
 
 // host side: sizes, cooperative launch.  Returns cudaSuccess or the launch error.
-size_t recur_persist_smem(int M, int N, int G, int UPC, int resident) {
+size_t recur_persist_smem(int M, int N, int G, int UPC, int resident, int w_resident) {
   const int MPC = (M + G - 1) / G;
-  return sizeof(float) * ((size_t)N + (resident ? (size_t)4 * UPC * (N + 1) : 0) + (size_t)MPC * (N + 1) + 4 * UPC + UPC + M + 2 * MPC + 64);
+  return sizeof(float) * ((size_t)N + (resident ? (size_t)4 * UPC * (N + 1) : 0) + (size_t)MPC * (N + 1) +
+                          (w_resident ? (size_t)4 * UPC * M : 0) + 4 * UPC + UPC + M + 2 * MPC + 64);
 }
 
 cudaError_t launch_recur_persist(const float* W, const float* U, const float* bias, const float* Why, const float* by, int M,
@@ -787,12 +813,13 @@ cudaError_t launch_recur_persist(const float* W, const float* U, const float* bi
   while (G > 1 && (N + G - 1) / G * (G - 1) >= N) G--;       // no CTA without units
   if (N % 128 == 0 && num_sms >= 128) G = 128;                // even split: 128 CTAs x N/128 units
   const int UPC = (N + G - 1) / G;
-  int resident = 1;
-  size_t smem = recur_persist_smem(M, N, G, UPC, 1);
-  if (smem > 227 * 1024) { resident = 0; smem = recur_persist_smem(M, N, G, UPC, 0); }
+  int resident = 1, w_resident = 1;
+  size_t smem = recur_persist_smem(M, N, G, UPC, 1, 1);
+  if (smem > 227 * 1024) { w_resident = 0; smem = recur_persist_smem(M, N, G, UPC, 1, 0); }
+  if (smem > 227 * 1024) { resident = 0; smem = recur_persist_smem(M, N, G, UPC, 0, 0); }
   RecurArgs a;
   a.W = W; a.U = U; a.bias = bias; a.Why = Why; a.by = by; a.M = M; a.N = N; a.mode = mode;
-  a.UPC = UPC; a.rows_resident = resident; a.text = text; a.n = n; a.uniforms = uniforms; a.h0 = h0; a.c0 = c0;
+  a.UPC = UPC; a.rows_resident = resident; a.w_resident = w_resident; a.text = text; a.n = n; a.uniforms = uniforms; a.h0 = h0; a.c0 = c0;
   a.out = out; a.hbuf = hbuf; a.ebuf = ebuf; a.sum_part = sum_part; a.y_tgt = y_tgt; a.c_out = c_out; a.bar = bar;
   cudaError_t e = cudaFuncSetAttribute(k_recur_persist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

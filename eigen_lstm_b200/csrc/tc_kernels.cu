@@ -16,78 +16,147 @@ namespace tc {
 
 // ------------------------------------------------------------------------------------------------
 // K3: logits for all (t,b) rows + fused softmax / loss / dy.  D[(s,b)][m] = sum_n h[(s+1,b)][n] Why[m][n]
-// One CTA per 128 rows; each epilogue thread owns one (t,b) row with all M = 256 logits in TMEM.
+// PERSISTENT: one CTA per SM loops over the 128-row tiles; the accumulator is DOUBLE-BUFFERED in TMEM (2 x 256 columns) so that
+// the softmax epilogue of tile i (each epilogue thread owns one (t,b) row with all M = 256 logits) runs under the contraction
+// of tile i+1.
 // ------------------------------------------------------------------------------------------------
 constexpr int K3_BN = 256, K3_STAGES = 4;
 __global__ void __launch_bounds__(192, 1)
 k_logits(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmW, const LogitsArgs a) {
+  using C = Cfg<K3_BN, K3_STAGES>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ float s_by[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) s_by[i] = i < a.M ? a.by[i] : -1e30f;
-  TileCtx c = tile_prologue<K3_BN, K3_STAGES>(smem_raw);
-  const int row0 = blockIdx.x * BM;                      // row in (slot s, padded b) space
-  const KSeg s0{&tmH, &tmW, row0 + a.Bp, 0, 0, 0, a.N / BK};   // h of slot s+1
-  const KSeg s1{&tmH, &tmW, 0, 0, 0, 0, 0};
-  tile_mainloop<K3_BN, K3_STAGES>(c, s0, s1);
-  if (c.warp >= 2) {
-    const int quarter = c.warp & 3;
-    const int q = row0 + quarter * 32 + c.lane;
-    const int s = q / a.Bp, b = q - s * a.Bp;
-    const bool valid = b < a.B;
-    const int k = valid ? a.tg[(size_t)s * a.B + b] : -1;
-    const uint32_t taddr = c.tmem_d + ((uint32_t)(quarter * 32) << 16);
-    constexpr float LOG2E = 1.4426950408889634f;
-    mbar_wait(c.accum_full, 0);
-    tcgen05_after_sync();
-    float mx = -1e30f;
-#pragma unroll 1
-    for (int c0 = 0; c0 < K3_BN; c0 += 32) {
-      float v[32];
-      tmem_ld32(taddr + c0, v);
-#pragma unroll
-      for (int i = 0; i < 32; i++) mx = fmaxf(mx, v[i] + s_by[c0 + i]);
-    }
-    float sum = 0.f, yk = 0.f;
-#pragma unroll 1
-    for (int c0 = 0; c0 < K3_BN; c0 += 32) {
-      float v[32];
-      tmem_ld32(taddr + c0, v);
-#pragma unroll
-      for (int i = 0; i < 32; i++) {
-        const float y = v[i] + s_by[c0 + i];
-        sum += exp2f((y - mx) * LOG2E);
-        if (c0 + i == k) yk = y;
+  // prologue (tile_prologue with two accumulators): barriers full/empty per stage, acc_full/acc_empty per accumulator
+  const uint32_t base = smem_u32(smem_raw);
+  uint8_t* tiles = smem_raw + (((base + 1023u) & ~1023u) - base);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + C::TILE_BYTES);
+  uint64_t *full = bars, *empty = bars + K3_STAGES, *acc_full = bars + 2 * K3_STAGES, *acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < K3_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tcgen05_before_sync();
+  __syncthreads();
+  tcgen05_after_sync();
+  const uint32_t tmem_d = *tmem_slot;
+  const int n_tiles = a.T * a.Bp / BM;
+  const int nkb = a.N / BK;
+  if (warp == 0) {
+    int g = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int row0 = tile * BM;                          // row in (slot s, padded b) space; h of slot s+1
+      for (int kb = 0; kb < nkb; kb++, g++) {
+        const int st = g % K3_STAGES;
+        mbar_wait(&empty[st], ((uint32_t)(g / K3_STAGES) & 1u) ^ 1u);
+        if (elect_one()) {
+          uint8_t* sa = tiles + (size_t)st * C::STAGE_BYTES;
+          mbar_expect_tx(&full[st], (uint32_t)C::STAGE_BYTES);
+          tma_load_2d(sa, &tmH, &full[st], kb * BK, row0 + a.Bp);
+          tma_load_2d_hint(sa + A_TILE_BYTES, &tmW, &full[st], kb * BK, 0, L2_EVICT_LAST);
+        }
+        __syncwarp();
       }
     }
-    const float inv = __fdividef(1.0f, sum);
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc_bf16(BM, K3_BN);
+    const uint64_t a_desc0 = make_smem_desc_sw128(smem_u32(tiles));
+    const uint64_t b_desc0 = make_smem_desc_sw128(smem_u32(tiles) + A_TILE_BYTES);
+    int g = 0, it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+      const int slot = it & 1;
+      mbar_wait(&acc_empty[slot], ((uint32_t)(it >> 1) & 1u) ^ 1u);   // the epilogue has read this accumulator's previous tile
+      tcgen05_after_sync();
+      for (int kb = 0; kb < nkb; kb++, g++) {
+        const int st = g % K3_STAGES;
+        mbar_wait(&full[st], (uint32_t)(g / K3_STAGES) & 1u);
+        tcgen05_after_sync();
+        if (elect_one()) {
+          const uint64_t soff = (uint64_t)((uint32_t)st * (uint32_t)(C::STAGE_BYTES >> 4));
+#pragma unroll
+          for (int k = 0; k < BK / 16; k++)
+            umma_bf16(tmem_d + (uint32_t)(slot * K3_BN), a_desc0 + soff + 2 * k, b_desc0 + soff + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+          umma_commit(&empty[st]);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&acc_full[slot]);
+      __syncwarp();
+    }
+  } else {
+    const int quarter = warp & 3;
+    constexpr float LOG2E = 1.4426950408889634f;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+      const int slot = it & 1;
+      const int q = tile * BM + quarter * 32 + lane;
+      const int s = q / a.Bp, b = q - s * a.Bp;
+      const bool valid = b < a.B;
+      const int k = valid ? a.tg[(size_t)s * a.B + b] : -1;
+      const uint32_t taddr = tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * K3_BN);
+      mbar_wait(&acc_full[slot], (uint32_t)(it >> 1) & 1u);
+      tcgen05_after_sync();
+      float mx = -1e30f;
 #pragma unroll 1
-    for (int c0 = 0; c0 < K3_BN; c0 += 32) {
-      float v[32];
-      tmem_ld32(taddr + c0, v);
-      if (valid) {
-        float dy[32];
+      for (int c0 = 0; c0 < K3_BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(taddr + c0, v);
+#pragma unroll
+        for (int i = 0; i < 32; i++) mx = fmaxf(mx, v[i] + s_by[c0 + i]);
+      }
+      float sum = 0.f, yk = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < K3_BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(taddr + c0, v);
 #pragma unroll
         for (int i = 0; i < 32; i++) {
-          const float p = exp2f((v[i] + s_by[c0 + i] - mx) * LOG2E) * inv;
-          dy[i] = (c0 + i == k) ? p - 1.0f : p;          // dy = probs - target (R/lstm.cc:225)
+          const float y = v[i] + s_by[c0 + i];
+          sum += exp2f((y - mx) * LOG2E);
+          if (c0 + i == k) yk = y;
         }
-        uint4* row = reinterpret_cast<uint4*>(a.dYbf + (size_t)q * a.M + c0);
-#pragma unroll
-        for (int w = 0; w < 4; w++) {
-          uint4 o;
-          o.x = pack_bf16x2(dy[8 * w + 0], dy[8 * w + 1]); o.y = pack_bf16x2(dy[8 * w + 2], dy[8 * w + 3]);
-          o.z = pack_bf16x2(dy[8 * w + 4], dy[8 * w + 5]); o.w = pack_bf16x2(dy[8 * w + 6], dy[8 * w + 7]);
-          if (c0 + 8 * w < a.M) row[w] = o;
-        }
-        const size_t ldt = (size_t)a.T * a.Bp;
-#pragma unroll
-        for (int i = 0; i < 32; i++)
-          if (c0 + i < a.M) a.dYT[(size_t)(c0 + i) * ldt + q] = __float2bfloat16_rn(dy[i]);
       }
+      const float inv = __fdividef(1.0f, sum);
+#pragma unroll 1
+      for (int c0 = 0; c0 < K3_BN; c0 += 32) {
+        float v[32];
+        tmem_ld32(taddr + c0, v);
+        if (valid) {
+          float dy[32];
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            const float p = exp2f((v[i] + s_by[c0 + i] - mx) * LOG2E) * inv;
+            dy[i] = (c0 + i == k) ? p - 1.0f : p;          // dy = probs - target (R/lstm.cc:225)
+          }
+          uint4* row = reinterpret_cast<uint4*>(a.dYbf + (size_t)q * a.M + c0);
+#pragma unroll
+          for (int w = 0; w < 4; w++) {
+            uint4 o;
+            o.x = pack_bf16x2(dy[8 * w + 0], dy[8 * w + 1]); o.y = pack_bf16x2(dy[8 * w + 2], dy[8 * w + 3]);
+            o.z = pack_bf16x2(dy[8 * w + 4], dy[8 * w + 5]); o.w = pack_bf16x2(dy[8 * w + 6], dy[8 * w + 7]);
+            if (c0 + 8 * w < a.M) row[w] = o;
+          }
+          const size_t ldt = (size_t)a.T * a.Bp;
+#pragma unroll
+          for (int i = 0; i < 32; i++)
+            if (c0 + i < a.M) a.dYT[(size_t)(c0 + i) * ldt + q] = __float2bfloat16_rn(dy[i]);
+        }
+      }
+      tcgen05_before_sync();
+      mbar_arrive(&acc_empty[slot]);                       // this thread's TMEM lane of the accumulator is free again
+      if (valid) a.surp[(size_t)s * a.B + b] = (k >= 0) ? -((yk - mx) * LOG2E - log2f(sum)) : 0.f;  // -log2 p[k]
     }
-    if (valid) a.surp[(size_t)s * a.B + b] = (k >= 0) ? -((yk - mx) * LOG2E - log2f(sum)) : 0.f;  // -log2 p[k]
   }
-  tile_epilogue_end<K3_BN, K3_STAGES>(c);
+  tcgen05_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc<512>(tmem_d);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -144,8 +213,11 @@ k_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 // ------------------------------------------------------------------------------------------------
 
 void launch_logits(const CUtensorMap& tmH, const CUtensorMap& tmWmn, const LogitsArgs& a, cudaStream_t st) {
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int tiles = a.T * a.Bp / BM;
   set_smem(k_logits, Cfg<K3_BN, K3_STAGES>::SMEM_BYTES);
-  k_logits<<<a.T * a.Bp / BM, 192, Cfg<K3_BN, K3_STAGES>::SMEM_BYTES, st>>>(tmH, tmWmn, a);
+  k_logits<<<tiles < sms ? tiles : sms, 192, Cfg<K3_BN, K3_STAGES>::SMEM_BYTES, st>>>(tmH, tmWmn, a);
 }
 
 // bn = 128 or 256 = tile width; tmB must have a box of bn rows and a.tiles_n = ceil(cols / bn)

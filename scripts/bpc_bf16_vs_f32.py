@@ -18,6 +18,12 @@ N, B, S, iters, lr = 256, 32, 51, 1500, 0.02
 if len(sys.argv) > 1:
     N, B, S, iters = [int(v) for v in sys.argv[1:5]]
     lr = float(sys.argv[5])
+# BPC_MEM0=c: Adagrad memory initialised to c instead of 0 (an "initial accumulator value", same for every run).  With m = 0 the
+# first update of EVERY weight is +-lr whatever the size of its gradient (d / sqrt(d^2)), i.e. a sign function of gradients that
+# are mostly noise: a 1-ulp perturbation of the weights then moves the held-out bits/char by 0.1-0.3 after 3000 iterations
+# (profiles/r02*_bpc_*lr*.json), which buries any bf16-vs-fp32 effect.  With m0 > 0 small gradients give small steps and the
+# comparison measures precision instead of chaos.
+mem0 = float(os.environ.get("BPC_MEM0", "0"))
 head = os.environ.get("BPC_TEXT") == "head"
 text = open(os.path.join(ROOT, "tests", "golden", "enwik6_head.bin" if head else "enwik6.txt"), "rb").read()
 cut = len(text) * (90 if head else 95) // 100
@@ -33,6 +39,9 @@ for name, dt in (("f32", el.F32), ("bf16", el.BF16), ("f32_ulp", el.F32)):
         for w in range(5):
             p = g.get(0, w)
             g.set(0, w, (p * (1.0 + 1.2e-7 * rng.choice([-1.0, 1.0], p.shape))).astype(np.float32))
+    if mem0 > 0:
+        for w in range(5):
+            g.set(2, w, np.full(g.shape(w), mem0, dtype=np.float32))
     g.load_text(train)
     g.set_positions(pos)
     curve = []
@@ -44,7 +53,7 @@ for name, dt in (("f32", el.F32), ("bf16", el.BF16), ("f32_ulp", el.F32)):
 res["abs_diff_heldout"] = abs(res["f32"]["heldout_bpc"] - res["bf16"]["heldout_bpc"])
 res["abs_diff_train"] = abs(res["f32"]["train_bpc_curve"][-1] - res["bf16"]["train_bpc_curve"][-1])
 res["noise_floor_heldout_f32_vs_f32_plus_1ulp"] = abs(res["f32"]["heldout_bpc"] - res["f32_ulp"]["heldout_bpc"])
-res["config"] = dict(N=N, B=B, S=S, iters=iters, lr=lr, text="enwik6 head 64 KiB, 90/10 split" if head else "enwik6 (10^6 bytes), 95/5 split",
+res["config"] = dict(N=N, B=B, S=S, iters=iters, lr=lr, adagrad_mem0=mem0, text="enwik6 head 64 KiB, 90/10 split" if head else "enwik6 (10^6 bytes), 95/5 split",
                      variant=g.variant())
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", os.environ.get("BPC_OUT", "bpc_bf16_vs_f32.json")), "w"), indent=1)

@@ -30,8 +30,9 @@ CASES = [
     (1024, 4, 128, dict(wgrad_bn=256, fwd_persistent=32, bwd_persistent=32)),     # config 3: one batch tile, U resident
     (512, 4, 64, dict(wgrad_bn=128, fwd_persistent=32, bwd_persistent=32)),       # config 2
     (2048, 3, 100, dict(wgrad_bn=256, fwd_persistent=64, bwd_persistent=64)),
-    (1024, 3, 384, dict(fwd_bn=32, fwd_pair=0, wgrad_bn=256, fwd_persistent=0, bwd_persistent=0)),   # three batch tiles: per-timestep kernels
-    (1024, 3, 512, dict(fwd_bn=64, fwd_pair=1, wgrad_bn=256, fwd_persistent=0, bwd_persistent=0)),   # ... as cta_group::2 pairs
+    (1024, 3, 384, dict(fwd_bn=128, fwd_pair=0, wgrad_bn=256, fwd_persistent=0, bwd_persistent=0)),   # three batch tiles: per-timestep kernels
+    (1024, 3, 512, dict(fwd_bn=128, fwd_pair=1, wgrad_bn=256, fwd_persistent=0, bwd_persistent=0)),
+    (512, 3, 512, dict(fwd_bn=64, fwd_pair=1, bwd_bn=64, wgrad_bn=128, fwd_persistent=0, bwd_persistent=0)),   # ... as cta_group::2 pairs
 ]
 
 

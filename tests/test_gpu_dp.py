@@ -13,8 +13,10 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, dtype, out):
+def _worker(rank, world, port, dtype, no_graph, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    if no_graph:
+        os.environ["LSTM_NO_GRAPH"] = "1"      # plain stream launches instead of the segmented graph replay (read at first use)
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(rank)
@@ -46,13 +48,14 @@ def _worker(rank, world, port, dtype, out):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("no_graph", [0, 1])
 @pytest.mark.parametrize("dtype", [0, 1])
-def test_two_gpus_equal_one_gpu_with_the_concatenated_batch(dtype):
+def test_two_gpus_equal_one_gpu_with_the_concatenated_batch(dtype, no_graph):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     import torch.multiprocessing as mp
     mgr = mp.Manager(); out = mgr.dict()
-    mp.spawn(_worker, args=(2, _free_port(), dtype, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), dtype, no_graph, out), nprocs=2, join=True)
     assert out["replicas_identical"]
     assert out["err"] < (2e-4 if dtype == 0 else 2e-2), out["err"]
