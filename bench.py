@@ -394,6 +394,7 @@ def main():
     clocks = sampler.stop() if sampler else None
     # one more, profiled iteration (plain stream launches with CUDA events between the phases): the live
     # per-kernel durations behind `roofline` and `us_per_recurrent_timestep`
+    net_variant = net.variant()
     net.set_profiling(True)
     losses = net.train_text(2, stride=T, lr=LR, want_losses=True)
     phases = net.phase_ms()
@@ -454,19 +455,31 @@ def main():
     bwd_flops = 2.0 * N * (4 * N + (M if dtype == "bf16" else 0)) * B   # U^T*dg (+ Why^T*dy folded into K5's K range)
     dom = "fwd" if phases["fwd_recurrence"] >= phases["bwd_recurrence"] else "bwd"
     dom_us, dom_flops = (fwd_us, fwd_flops) if dom == "fwd" else (bwd_us, bwd_flops)
-    dom_kernel = {"fwd": "k_fwd_step", "bwd": "k_bwd_step"}[dom] if dtype == "bf16" else {"fwd": "k_step_fwd_f32", "bwd": "k_step_bwd_f32"}[dom]
+    var = net_variant if dtype == "bf16" else {}
+    persistent = bool(var.get("fwd_persistent" if dom == "fwd" else "bwd_persistent"))
+    if dtype != "bf16":
+        dom_kernel = {"fwd": "k_step_fwd_f32", "bwd": "k_step_bwd_f32"}[dom]
+    elif persistent:
+        dom_kernel = {"fwd": "k_fwd_recur", "bwd": "k_bwd_recur"}[dom]
+    else:
+        dom_kernel = {"fwd": "k_fwd_step", "bwd": "k_bwd_step"}[dom]
+    # one LAUNCH of the dominant kernel: the whole recurrence of a window (T timesteps) for the persistent kernels, one timestep
+    # for the per-timestep ones; flops, duration and ncu's DRAM traffic are all per launch
+    per_launch = T if persistent else 1
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     if dtype == "bf16" and args.workload == "cfg4" and os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(dom_kernel, {}).get("dram_bytes_per_launch")
     achieved = dom_flops / (dom_us * 1e-6) / 1e12 if dom_us > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": f"{dom_kernel} (one recurrent timestep, {'tcgen05 bf16' if dtype == 'bf16' else 'SIMT fp32'})",
+    roofline = {"bound": "tensor",
+                "kernel": f"{dom_kernel} ({'all ' + str(T) + ' timesteps of a window in one persistent launch' if persistent else 'one recurrent timestep'}, "
+                          f"{'tcgen05 bf16' if dtype == 'bf16' else 'SIMT fp32'})",
                 "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
-                "traffic": traffic, "traffic_source": "ncu --set full dram__bytes_read+write per launch (profiles/r01e_kernels.md)" if traffic else None,
+                "traffic": traffic, "traffic_source": "ncu --set full dram__bytes_read+write per launch (profiles/r02_kernels.md)" if traffic else None,
                 "peak_source": f"{pk['src']} sustained bf16 (kernel timed inside a long step)",
-                "flops_per_launch": dom_flops, "us_per_launch": dom_us,
-                "note": "operand bytes per launch (U 33.5 MB + h/dg) exceed what the tensor pipe can be fed at: the step is bound by "
-                        "L2->SM operand delivery, see DESIGN.md section 5"}
+                "flops_per_launch": dom_flops * per_launch, "us_per_launch": dom_us * per_launch, "us_per_timestep": dom_us,
+                "note": "the recurrence is a serial chain per timestep (contraction -> exchange -> gate math -> publish): the tensor "
+                        "pipe idles during the hand-offs, see DESIGN.md section 5 for the measured anatomy"}
     BT = B * T
     wg_flops = 2.0 * 4 * N * (M + N + 1) * BT               # dW|dU|db as one GEMM (bf16 path)
     pre_flops = 2.0 * M * (N + 1) * BT                      # dWhy|dby
@@ -494,6 +507,7 @@ def main():
             "end_to_end_tflops": {"alg": e2e_tf, "dense": fl["dense"] * value / 1e12,
                                   "frac_of_peak_alg": e2e_tf / (pk["tf_sustained"] * world)},
             "final_loss_bits_per_char": float(losses[-1] / T) if len(losses) else None, "learning_rate": LR,
+            "kernel_variant": net_variant,
             "launch_mode": "one CUDA graph per training iteration (timed region); plain stream launches for the profiled iteration"}
     if dpc is not None:
         dpc["replicas_identical_after_timed_region"] = same

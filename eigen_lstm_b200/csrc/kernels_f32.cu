@@ -570,10 +570,12 @@ void launch_recur_b1_f32(const float* W, const float* U, const float* bias, cons
 // One arriving thread (release: cumulative over the __syncthreads-ordered stores of the CTA) and one polling WARP per CTA:
 // scripts/gridbar_bench.cu measures 1.17 us per barrier over 128 co-resident CTAs for this scheme against 4.4 us for
 // atomicAdd + last-arriver flag.  Bounded: a protocol bug must not hang the GPU.
-__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+__device__ __forceinline__ void grid_arrive(unsigned int* counter) {
   __syncthreads();
+  if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+}
+__device__ __forceinline__ void grid_wait(unsigned int* counter, unsigned int target) {
   if (threadIdx.x < 32) {
-    if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
     const long long t0 = clock64();
     for (;;) {
       unsigned int v = target;
@@ -584,6 +586,12 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   }
   __syncthreads();
 }
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  grid_arrive(counter);
+  grid_wait(counter, target);
+}
+
+__host__ __device__ inline int recur_pitch(int N) { return (N + 31) / 32 * 32 + 8; }
 
 struct RecurArgs {
   const float *W, *U, *bias, *Why, *by;   // fp32 masters, column-major like the reference
@@ -608,8 +616,10 @@ __global__ void __launch_bounds__(256, 1) k_recur_persist(const RecurArgs a) {
   const int MPC = (M + G - 1) / G;                    // logit rows owned by this CTA
   float* sh = sm;                                      // [N]   h(t)
   float* sU = sh + N;                                  // [R][N+1] resident rows of U (pitch N+1: conflict-free)
-  const int UP = N + 1;
-  float* sWhy = sU + (a.rows_resident ? (size_t)R * UP : 0);   // [MPC][N+1]
+  // row pitch of the resident rows: == 8 (mod 32) words, so that the 4 rows x 8 lanes of a warp pass hit 32 distinct banks
+  // (pitch N + 1 made rows r and lanes l with equal r + l collide: up to 4-way conflicts on every load of the matvec)
+  const int UP = recur_pitch(N);
+  float* sWhy = sU + (a.rows_resident ? (size_t)R * UP : 0);   // [MPC][UP]
   float* sW = sWhy + (size_t)MPC * UP;                 // [R][M] resident rows of W: the one-hot product W x is one smem read per row
   float* sg = sW + (a.w_resident ? (size_t)R * M : 0); // [R] gate pre-activations
   float* sc = sg + R;                                  // [UPC] cell state of the owned units
@@ -754,8 +764,9 @@ __global__ void __launch_bounds__(256, 1) k_recur_persist(const RecurArgs a) {
       logits(se, nullptr);                                           // se[0..MPC) = owned exp(y)
       for (int mm = tid; mm < MPC; mm += blockDim.x)
         if (g * MPC + mm < M) a.ebuf[(size_t)buf * M + g * MPC + mm] = se[mm];
+      grid_arrive(a.bar);                                            // split barrier: U h is computed while the other CTAs arrive
       matvec();
-      grid_barrier(a.bar, ++epoch * G);
+      grid_wait(a.bar, ++epoch * G);
       for (int m = tid; m < M; m += blockDim.x) se[m] = __ldcg(a.ebuf + (size_t)buf * M + m);
       __syncthreads();
       if (tid < 32) {                                                // same reduction shape as the 1-CTA kernel
@@ -777,11 +788,20 @@ __global__ void __launch_bounds__(256, 1) k_recur_persist(const RecurArgs a) {
           float best = se[0];
           for (int q = 1; q < M; q++) if (se[q] > best) { best = se[q]; index = q; }
         } else {
+          // sequential cdf, first r < cdf (R/lstm.cc:321-338): the fp32 adds keep the reference's order; eight probabilities
+          // are loaded per round so that the shared-memory latency is paid once per eight dependent adds instead of per add
           const float r = a.uniforms[i];
           float cdf = 0.f;
-          for (int q = 0; q < M; q++) {                              // sequential cdf, first r < cdf  (R/lstm.cc:321-338)
-            cdf = (q == 0) ? se[0] : __fadd_rn(cdf, se[q]);
-            if (r < cdf) { index = q; break; }
+          bool found = false;
+          for (int q0 = 0; q0 < M && !found; q0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = (q0 + k < M) ? se[q0 + k] : 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              cdf = (q0 + k == 0) ? v[0] : __fadd_rn(cdf, v[k]);
+              if (!found && q0 + k < M && r < cdf) { index = q0 + k; found = true; }
+            }
           }
         }
         s_index = index;
@@ -801,7 +821,8 @@ __global__ void __launch_bounds__(256, 1) k_recur_persist(const RecurArgs a) {
 // host side: sizes, cooperative launch.  Returns cudaSuccess or the launch error.
 size_t recur_persist_smem(int M, int N, int G, int UPC, int resident, int w_resident) {
   const int MPC = (M + G - 1) / G;
-  return sizeof(float) * ((size_t)N + (resident ? (size_t)4 * UPC * (N + 1) : 0) + (size_t)MPC * (N + 1) +
+  const size_t UP = (size_t)recur_pitch(N);
+  return sizeof(float) * ((size_t)N + (resident ? (size_t)4 * UPC * UP : 0) + (size_t)MPC * UP +
                           (w_resident ? (size_t)4 * UPC * M : 0) + 4 * UPC + UPC + M + 2 * MPC + 64);
 }
 

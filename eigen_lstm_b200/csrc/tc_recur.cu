@@ -627,6 +627,7 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
       // 2. exchange: announce our slices, free the accumulator, wait for the other ranks
       if (e == 0) {
         red_release_gpu_add(xcnt, 1u);                       // release: cumulative over the barrier-ordered stores
+        if (dbg && s == DBG_S) dbg[9] = clock64();
         if (has_acc) { if constexpr (PAIR) mbar_arrive_remote(tmem_free, 0); else mbar_arrive(tmem_free); }
       }
       // operands of the gate math that no timestep of this launch produces: in flight while the exchange is awaited
@@ -643,7 +644,10 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
           ctt[q] = c_cur[(size_t)b * N + j];
         }
       }
-      if (w == 1) counters_wait(xcnt, 1, (unsigned int)KS * (unsigned int)(s + 1), lane);
+      if (w == 1) {
+        counters_wait(xcnt, 1, (unsigned int)KS * (unsigned int)(s + 1), lane);
+        if (dbg && lane == 0 && s == DBG_S) dbg[10] = clock64();
+      }
       named_bar_sync(1, R_EPI_THREADS);                      // every reader is ordered after the acquire
       if (dbg && e == 0 && s == DBG_S) dbg[6] = clock64();
       // 3. reduce: float4 position p = (u, row); sum over the KS sources in a fixed order (both positions' loads in flight at once)
@@ -665,6 +669,7 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
         *own = acc;
       }
       named_bar_sync(1, R_EPI_THREADS);
+      if (dbg && e == 0 && s == DBG_S) dbg[11] = clock64();
       // 4. gate gradients, lane = hidden unit (R/lstm.cc:233-256)
 #pragma unroll
       for (int q = 0; q < ROWS; q++) {
@@ -691,6 +696,7 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
         gT[(2 * UO + l) * R_HT_LD + r] = __float2bfloat16_rn(d_f);
         gT[(3 * UO + l) * R_HT_LD + r] = __float2bfloat16_rn(d_u);
       }
+      if (dbg && e == 0 && s == DBG_S) dbg[12] = clock64();
       fence_proxy_async_global();                            // dg(t) is read by other CTAs' TMA loads
       named_bar_sync(1, R_EPI_THREADS);
       if (e == 0) red_release_gpu_add(my_slots + (pairi % R_SLOTS), 1u);

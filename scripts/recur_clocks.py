@@ -31,3 +31,6 @@ for title, o in (("forward recurrence", 0), ("BPTT recurrence", 16)):
     for n, v in zip(names, d):
         print(f"  {v:8d} cycles  {n}")
     print(f"  timestep period: {d[8]} cycles = {d[8] / 1.965e3:.2f} us at 1965 MHz")
+    if o == 16:
+        x = out[o + 9:o + 13] - out[o]
+        print(f"  BPTT detail: exchange release done {x[0]}, exchange poll done {x[1]}, partials summed {x[2]}, gate math + stores issued {x[3]}")
