@@ -115,14 +115,15 @@ int fwd_recur_bn(int N, int Bp, int M);
 int fwd_recur_box_rows(int bn, int Bp);   // rows of the blocked-U TMA box: bn/2 for pairs (Bp = 256), bn for single CTAs (Bp = 128)
 // tmWb = blocked U, Wb2[(tile*N/64 + kb)*bn + row][c] = U(r' = tile*bn + row, k = kb*64 + c) (r' = 4*unit + gate), as a 2D map
 // with a box of bn/2 rows; tmH box = 128 rows
-bool launch_fwd_recur(int bn, const CUtensorMap& tmH, const CUtensorMap& tmWb, const FwdRecurArgs& a, cudaStream_t st);
+// dry = true: launch nothing, only answer whether all CTAs would be co-resident on this device
+bool launch_fwd_recur(int bn, const CUtensorMap& tmH, const CUtensorMap& tmWb, const FwdRecurArgs& a, cudaStream_t st, bool dry = false);
 // tmWb = blocked BPTT weights, Wb5[(tile*NKBG + kbg)*bnj + row][c]: kbg < 4N/64: U(r' = kbg*64 + c, j = tile*bnj + row), else
 // Why(m = (kbg - 4N/64)*64 + c, j); NKBG = 4N/64 + M/64; box of bnj/2 rows
 int bwd_recur_bnj(int N, int Bp, int M);
 size_t bwd_recur_red_floats(int N, int bnj);
 int bwd_recur_box_rows(int bnj, int Bp);
 bool launch_bwd_recur(int bnj, const CUtensorMap& tmdG, const CUtensorMap& tmWb, const CUtensorMap& tmdY, const BwdRecurArgs& a,
-                      cudaStream_t st);
+                      cudaStream_t st, bool dry = false);
 // K3: logits + softmax + loss + dy for all timesteps
 void launch_logits(const CUtensorMap& tmH, const CUtensorMap& tmWmn, const LogitsArgs& a, cudaStream_t st);
 // K5: one BPTT timestep.  BN in {32, 64, 128} hidden units per tile (4 split-K CTAs each).

@@ -111,9 +111,19 @@ int tc_create(lstm_ctx* ctx) {
   TC_ALLOC(s->xcnt, s->xcnt_bytes);
   if (getenv("LSTM_TC_DEBUG")) TC_ALLOC(s->dbg, 32 * sizeof(long long));
   TC_ALLOC(s->kc_parts, 8 * (ctx->P - ctx->off[LSTM_WHY]) * sizeof(float));
+  // Persistent recurrences: the shape policy proposes a tile width, the occupancy query decides (every CTA of the launch must be
+  // co-resident on THIS device).  Decided once, here: the operand copies that are kept fresh depend on it (tc_params_changed),
+  // and a launch that fails later is an error, never a silent switch to kernels whose operands were not refreshed.
   s->bn2r = tc::fwd_recur_bn(N, s->Bp, M);
-  if (s->bn2r) TC_ALLOC(s->Wb2, N4 * N * sizeof(bf16));
   s->bnj5 = tc::bwd_recur_bnj(N, s->Bp, M);
+  {
+    tc::FwdRecurArgs fa = {}; fa.B = B; fa.Bp = s->Bp; fa.N = N; fa.M = M; fa.T = T;
+    tc::BwdRecurArgs ba = {}; ba.B = B; ba.Bp = s->Bp; ba.N = N; ba.M = M; ba.T = T;
+    CUtensorMap none = {};
+    if (s->bn2r && !tc::launch_fwd_recur(s->bn2r, none, none, fa, ctx->st, true)) s->bn2r = 0;
+    if (s->bnj5 && !tc::launch_bwd_recur(s->bnj5, none, none, none, ba, ctx->st, true)) s->bnj5 = 0;
+  }
+  if (s->bn2r) TC_ALLOC(s->Wb2, N4 * N * sizeof(bf16));
   if (s->bnj5) {
     TC_ALLOC(s->Wb5, (size_t)N * (N4 + M) * sizeof(bf16));
     TC_ALLOC(s->red5, tc::bwd_recur_red_floats(N, s->bnj5) * sizeof(float));
@@ -206,7 +216,8 @@ int tc_forward(lstm_ctx* ctx) {
     pa.xs = ctx->xs; pa.Wp = s->Wp; pa.bp = s->bp; pa.Cs = ctx->Cs; pa.Gp = s->Gp; pa.Hbf = s->Hbf;
     pa.ZT_h0 = s->ZT + (size_t)M * s->LDZ; pa.ldz = s->LDZ; pa.gbar = s->gbar; pa.dbg = s->dbg;
     persistent = tc::launch_fwd_recur(s->bn2r, s->tmH, s->tmWb2, pa, ctx->st);
-    if (persistent) LSTM_LAUNCHED(1);
+    if (!persistent) return lstm_fail(ctx, LSTM_ERR_CUDA, "the persistent forward recurrence could not be launched");
+    LSTM_LAUNCHED(1);
   }
   for (int t = 1; t <= T && !persistent; t++) {
     tc::FwdStepArgs a;
@@ -260,7 +271,10 @@ int tc_backward(lstm_ctx* ctx) {
     }
   }
   PROF(4);
-  int rc = lstm_allreduce_bucket(ctx, 1);
+  // The [Why|by] bucket (2 MB) is summed under the BPTT recurrence when that is a chain of per-timestep launches; a PERSISTENT
+  // recurrence needs all of its CTAs co-resident, so NCCL's CTAs must not sit on its SMs: the bucket then goes out right after
+  // the recurrence and hides under the weight-gradient GEMM instead.
+  int rc = s->bnj5 ? 0 : lstm_allreduce_bucket(ctx, 1);
   if (rc) return rc;
   bool persistent = false;
   if (s->bnj5) {                                         // the whole BPTT recurrence in one persistent launch (tc_recur.cu)
@@ -269,7 +283,8 @@ int tc_backward(lstm_ctx* ctx) {
     pa.Gp = s->Gp; pa.Cs = ctx->Cs; pa.dGbf = s->dGbf; pa.dGT = s->dGT; pa.ldg = s->LDT; pa.red = s->red5;
     pa.xcnt = s->xcnt; pa.gbar = s->gbar; pa.dbg = s->dbg ? s->dbg + 16 : nullptr;
     persistent = tc::launch_bwd_recur(s->bnj5, s->tmdG, s->tmWb5, s->tmdY, pa, ctx->st);
-    if (persistent) LSTM_LAUNCHED(1);
+    if (!persistent) return lstm_fail(ctx, LSTM_ERR_CUDA, "the persistent BPTT recurrence could not be launched");
+    LSTM_LAUNCHED(1);
   }
   for (int t = T; t >= 1 && !persistent; t--) {
     tc::BwdStepArgs a;
@@ -289,6 +304,10 @@ int tc_backward(lstm_ctx* ctx) {
   }
   if (!persistent) LSTM_LAUNCHED(T);
   PROF(5);
+  if (s->bnj5) {
+    rc = lstm_allreduce_bucket(ctx, 1);
+    if (rc) return rc;
+  }
   // K6a+b: [dW | dU | db](r, col) = sum_(s,b) dG^T[r][(s,b)] * [X^T ; H^T ; 1][col][(s,b)]  — the flat gradient
   // vector's first three tensors are exactly this column-major 4N x (M+N+1) matrix.
   {
@@ -297,9 +316,10 @@ int tc_backward(lstm_ctx* ctx) {
     const int bn = (M + N + 1 >= 1024) ? 256 : 128;   // wide tiles once there are enough of them to fill the SMs
     g.C = ctx->g(LSTM_W); g.ldc = (long)N4; g.tiles_m = (int)N4 / 128; g.tiles_n = (M + N + 1 + bn - 1) / bn;
     g.splits = 1; g.split_stride = 0;
-    // Data parallel: two column panels (6 + 4 tile columns of 256 at N = 2048: 2.6 + 1.7 waves, the same five tile times as one
-    // launch of 4.3 waves); the leading panel's allreduce then runs under the second panel's GEMM.
-    const int lead = g.tiles_n >= 10 ? (g.tiles_n * 6) / 10 : 0;
+    // Data parallel: two column panels (8 + 2 tile columns of 256 at N = 2048: 3.5 + 0.9 waves, the same five tile times as one
+    // launch of 4.3 waves).  The leading panel's allreduce (67 MB) runs under the trailing panel's GEMM — whose 128 tiles leave
+    // 20 SMs to NCCL — and only the trailing 8 MB are summed after the last GEMM has retired.
+    const int lead = g.tiles_n >= 6 ? g.tiles_n - 2 : 0;
     ctx->panel_split = 0;
     if (ctx->world > 1 && lead > 0) {
       tc::GemmArgs g1 = g, g2 = g;

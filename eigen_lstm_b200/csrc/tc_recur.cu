@@ -385,8 +385,9 @@ k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUt
   r_epilogue_end<BN, STAGES, PAIR>(c);
 }
 
+// dry = true: only answer whether every CTA of the launch would be co-resident on this device (asked once, at context creation)
 template <int BN, bool PAIR>
-bool launch_fwd_recur_t(const CUtensorMap& tmH, const CUtensorMap& tmWb, const FwdRecurArgs& a, cudaStream_t st) {
+bool launch_fwd_recur_t(const CUtensorMap& tmH, const CUtensorMap& tmWb, const FwdRecurArgs& a, cudaStream_t st, bool dry) {
   using F = FwdRecurCfg<BN, PAIR>;
   const int n_tiles = 4 * a.N / BN;
   auto kernel = k_fwd_recur<BN, PAIR>;
@@ -404,6 +405,7 @@ bool launch_fwd_recur_t(const CUtensorMap& tmH, const CUtensorMap& tmWb, const F
   int max_clusters = 0;
   if (cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return false; }
   if (max_clusters < n_tiles) return false;                  // every CTA must be resident: the grid barrier spins
+  if (dry) return true;
   if (cudaMemsetAsync(a.gbar, 0, 2 * R_SLOTS * sizeof(unsigned int), st) != cudaSuccess) { cudaGetLastError(); return false; }
   return cudaLaunchKernelEx(&cfg, kernel, tmH, tmWb, a) == cudaSuccess;
 }
@@ -721,7 +723,7 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
 
 template <int BNJ, int KS, bool PAIR>
 bool launch_bwd_recur_t(const CUtensorMap& tmdG, const CUtensorMap& tmWb, const CUtensorMap& tmdY, const BwdRecurArgs& a,
-                        cudaStream_t st) {
+                        cudaStream_t st, bool dry) {
   using F = BwdRecurCfg<BNJ, KS, PAIR>;
   const int JT = a.N / BNJ;
   auto kernel = k_bwd_recur<BNJ, KS, PAIR>;
@@ -740,6 +742,7 @@ bool launch_bwd_recur_t(const CUtensorMap& tmdG, const CUtensorMap& tmWb, const 
   int max_clusters = 0;
   if (cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return false; }
   if (max_clusters < JT * KS) return false;
+  if (dry) return true;
   if (cudaMemsetAsync(a.gbar, 0, 2 * R_SLOTS * sizeof(unsigned int), st) != cudaSuccess) { cudaGetLastError(); return false; }
   if (cudaMemsetAsync(a.xcnt, 0, (size_t)JT * 2 * sizeof(unsigned int), st) != cudaSuccess) { cudaGetLastError(); return false; }
   return cudaLaunchKernelEx(&cfg, kernel, tmdG, tmWb, tmdY, a) == cudaSuccess;
@@ -769,13 +772,13 @@ int fwd_recur_bn(int N, int Bp, int M) {
   }
   return 0;
 }
-bool launch_fwd_recur(int bn, const CUtensorMap& tmH, const CUtensorMap& tmWb, const FwdRecurArgs& a, cudaStream_t st) {
+bool launch_fwd_recur(int bn, const CUtensorMap& tmH, const CUtensorMap& tmWb, const FwdRecurArgs& a, cudaStream_t st, bool dry) {
   if (a.Bp == 256) {
-    if (bn == 128) return launch_fwd_recur_t<128, true>(tmH, tmWb, a, st);
-    if (bn == 64) return launch_fwd_recur_t<64, true>(tmH, tmWb, a, st);
+    if (bn == 128) return launch_fwd_recur_t<128, true>(tmH, tmWb, a, st, dry);
+    if (bn == 64) return launch_fwd_recur_t<64, true>(tmH, tmWb, a, st, dry);
   } else if (a.Bp == 128) {
-    if (bn == 64) return launch_fwd_recur_t<64, false>(tmH, tmWb, a, st);
-    if (bn == 32) return launch_fwd_recur_t<32, false>(tmH, tmWb, a, st);
+    if (bn == 64) return launch_fwd_recur_t<64, false>(tmH, tmWb, a, st, dry);
+    if (bn == 32) return launch_fwd_recur_t<32, false>(tmH, tmWb, a, st, dry);
   }
   return false;
 }
@@ -810,13 +813,13 @@ size_t bwd_recur_red_floats(int N, int bnj) {
 }
 int bwd_recur_box_rows(int bnj, int Bp) { return Bp == 256 ? bnj / 2 : bnj; }
 bool launch_bwd_recur(int bnj, const CUtensorMap& tmdG, const CUtensorMap& tmWb, const CUtensorMap& tmdY, const BwdRecurArgs& a,
-                      cudaStream_t st) {
+                      cudaStream_t st, bool dry) {
   if (a.Bp == 256) {
-    if (bnj == 256) return launch_bwd_recur_t<256, 8, true>(tmdG, tmWb, tmdY, a, st);
-    if (bnj == 128) return launch_bwd_recur_t<128, 4, true>(tmdG, tmWb, tmdY, a, st);
+    if (bnj == 256) return launch_bwd_recur_t<256, 8, true>(tmdG, tmWb, tmdY, a, st, dry);
+    if (bnj == 128) return launch_bwd_recur_t<128, 4, true>(tmdG, tmWb, tmdY, a, st, dry);
   } else if (a.Bp == 128) {
-    if (bnj == 64) return launch_bwd_recur_t<64, 4, false>(tmdG, tmWb, tmdY, a, st);
-    if (bnj == 32) return launch_bwd_recur_t<32, 4, false>(tmdG, tmWb, tmdY, a, st);
+    if (bnj == 64) return launch_bwd_recur_t<64, 4, false>(tmdG, tmWb, tmdY, a, st, dry);
+    if (bnj == 32) return launch_bwd_recur_t<32, 4, false>(tmdG, tmWb, tmdY, a, st, dry);
   }
   return false;
 }
