@@ -18,7 +18,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
           "--expt-extended-lambda", "-Xptxas", "-v"]
-CU = ["capi.cu", "kernels_f32.cu", "gradcheck.cu", "tc_path.cu", "tc_kernels.cu", "tc_steps.cu", "tc_recur.cu"]
+CU = ["capi.cu", "kernels_f32.cu", "train_small.cu", "gradcheck.cu", "tc_path.cu", "tc_kernels.cu", "tc_steps.cu", "tc_recur.cu"]
 
 
 def _newer(src_list, out):

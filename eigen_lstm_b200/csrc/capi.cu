@@ -62,6 +62,8 @@ static void free_iter_graph_keep_key(lstm_ctx::IterGraph& g) {
   g.exec = nullptr;
   g.segs.clear();
   g.seg_bucket.clear();
+  g.seg_wait.clear();
+  g.open_wait = 0;
 }
 static void free_iter_graph(lstm_ctx::IterGraph& g) {
   free_iter_graph_keep_key(g);
@@ -137,10 +139,16 @@ extern "C" int lstm_create(lstm_ctx** out, int M, int N, int S, int B, int devic
     }                                                                                        \
   } while (0)
   CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
-  CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->comm_st, cudaStreamNonBlocking));
+  {
+    // the communication stream outranks the compute stream: when an SM frees up while a weight-gradient panel still has tiles
+    // queued, NCCL's few CTAs are placed first, so an allreduce never waits for a whole GEMM wave
+    int prio_lo = 0, prio_hi = 0;
+    CREATE_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CREATE_CUDA(cudaStreamCreateWithPriority(&ctx->comm_st, cudaStreamNonBlocking, prio_hi));
+  }
   for (int i = 0; i < lstm_ctx::NBUCKET; i++) {
-    CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_bucket[i], cudaEventDisableTiming));
-    CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_comm[i], cudaEventDisableTiming));
+    CREATE_CUDA(cudaEventCreate(&ctx->ev_bucket[i]));   // timed: lstm_get_phase_ms reports when each bucket was handed over and summed
+    CREATE_CUDA(cudaEventCreate(&ctx->ev_comm[i]));
   }
   for (int i = 0; i < 16; i++) CREATE_CUDA(cudaEventCreate(&ctx->pev[i]));
   const size_t T = ctx->T, BN = (size_t)B * N;
@@ -178,8 +186,8 @@ extern "C" int lstm_create(lstm_ctx** out, int M, int N, int S, int B, int devic
     CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_win[k], cudaEventDisableTiming));
   }
   CREATE_CUDA(cudaMalloc(&ctx->pos0, (size_t)B * sizeof(unsigned long long)));
-  CREATE_CUDA(cudaMalloc(&ctx->vcount, sizeof(unsigned long long)));
-  CREATE_CUDA(cudaMemsetAsync(ctx->vcount, 0, sizeof(unsigned long long), ctx->st));
+  CREATE_CUDA(cudaMalloc(&ctx->vcount, 2 * sizeof(unsigned long long)));
+  CREATE_CUDA(cudaMemsetAsync(ctx->vcount, 0, 2 * sizeof(unsigned long long), ctx->st));
   ctx->h_pos0.assign(B, (uint64_t)S);
   CREATE_CUDA(cudaMemcpyAsync(ctx->pos0, ctx->h_pos0.data(), (size_t)B * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->st));
   if (dtype == LSTM_BF16) {
@@ -269,6 +277,7 @@ extern "C" int lstm_debug_variant(lstm_ctx* ctx, int out[8]) {
   if (!ctx || !out) return LSTM_ERR_ARG;
   for (int i = 0; i < 8; i++) out[i] = 0;
   if (ctx->tc) tc_variant(ctx, out);
+  out[7] = (ctx->dtype == LSTM_F32 && ctx->world == 1 && train_small_eligible(ctx->M, ctx->N, ctx->S, ctx->B)) ? 1 : 0;
   return LSTM_OK;
 }
 
@@ -434,23 +443,48 @@ static int cut_segment(lstm_ctx* ctx, int bucket) {
   if (ce != cudaSuccess) return lstm_fail(ctx, LSTM_ERR_CUDA, std::string("cudaGraphInstantiate (segment): ") + cudaGetErrorString(ce));
   g->segs.push_back(exec);
   g->seg_bucket.push_back(bucket);
+  g->seg_wait.push_back(g->open_wait);
+  g->open_wait = 0;
+  g->open_l0 = ctx->launches;
   LSTM_CUDA(cudaStreamBeginCapture(ctx->st, cudaStreamCaptureModeThreadLocal));
   return LSTM_OK;
 }
 
 int lstm_allreduce_bucket(lstm_ctx* ctx, int bucket) {
-  // bucket 0 = [W,U,b], bucket 1 = [Why,by]; both contiguous in the flat gradient vector.
+  // bucket 0 = [W,U,b] (or its last panel), bucket 1 = [Why,by]; each contiguous in the flat gradient vector.
   if (ctx->world <= 1) return LSTM_OK;
   if (ctx->seg_capture) return cut_segment(ctx, bucket);   // capture pass: the graph ends here, NCCL runs between replays
-  // K6a may be launched as two column panels of the column-major [W|U|b] matrix = two contiguous ranges of the flat gradient
-  // vector: the leading panel (bucket 2) is summed while the second one is still being computed
-  const size_t split = ctx->panel_split;
-  float* ptr = bucket == 1 ? ctx->g(LSTM_WHY) : (bucket == 2 ? ctx->g(LSTM_W) : ctx->g(LSTM_W) + split);
-  const size_t cnt = bucket == 1 ? ctx->P - ctx->off[LSTM_WHY] : (bucket == 2 ? split : ctx->off[LSTM_WHY] - split);
+  // K6a may be launched as up to three column panels of the column-major [W|U|b] matrix = contiguous ranges of the flat gradient
+  // vector: panel 0 (bucket 2) and panel 1 (bucket 3) are summed while the panels after them are still being computed
+  const size_t e0 = ctx->panel_end[0], e1 = ctx->panel_end[1] ? ctx->panel_end[1] : e0, end = ctx->off[LSTM_WHY];
+  float* ptr; size_t cnt;
+  switch (bucket) {
+    case 1: ptr = ctx->g(LSTM_WHY); cnt = ctx->P - end; break;
+    case 2: ptr = ctx->g(LSTM_W); cnt = e0; break;
+    case 3: ptr = ctx->g(LSTM_W) + e0; cnt = e1 - e0; break;
+    default: ptr = ctx->g(LSTM_W) + e1; cnt = end - e1; break;
+  }
+  if (cnt == 0) return LSTM_OK;
   LSTM_CUDA(cudaEventRecord(ctx->ev_bucket[bucket], ctx->st));
   LSTM_CUDA(cudaStreamWaitEvent(ctx->comm_st, ctx->ev_bucket[bucket], 0));
   LSTM_NCCL(g_nccl.AllReduce(ptr, ptr, cnt, ncclFloat, ncclSum, ctx->comm, ctx->comm_st));
   LSTM_CUDA(cudaEventRecord(ctx->ev_comm[bucket], ctx->comm_st));
+  return LSTM_OK;
+}
+
+int lstm_wait_buckets(lstm_ctx* ctx, unsigned mask) {
+  if (ctx->world <= 1 || mask == 0) return LSTM_OK;
+  if (ctx->seg_capture) {   // capture pass: the waits are issued between two segment launches, before the segment that needs them
+    lstm_ctx::IterGraph* g = ctx->seg_capture;
+    if (ctx->launches != g->open_l0) {   // the open segment already holds work that must not wait: close it
+      int rc = cut_segment(ctx, -1);
+      if (rc) return rc;
+    }
+    g->open_wait |= mask;
+    return LSTM_OK;
+  }
+  for (int b = 0; b < lstm_ctx::NBUCKET; b++)
+    if (mask & (1u << b)) LSTM_CUDA(cudaStreamWaitEvent(ctx->st, ctx->ev_comm[b], 0));
   return LSTM_OK;
 }
 
@@ -495,12 +529,28 @@ static int backward_device(lstm_ctx* ctx) {
 }
 
 static int adagrad_device(lstm_ctx* ctx, float lr, double eps, float clip) {
-  if (ctx->world > 1 && !ctx->seg_capture) {   // segmented replay issues these waits itself, before the last segment
-    for (int i = 0; i < lstm_ctx::NBUCKET; i++) LSTM_CUDA(cudaStreamWaitEvent(ctx->st, ctx->ev_comm[i], 0));
+  const unsigned all = (1u << lstm_ctx::NBUCKET) - 1u;
+  const size_t e1 = ctx->panel_end[1] ? ctx->panel_end[1] : ctx->panel_end[0], end = ctx->off[LSTM_WHY];
+  if (ctx->world > 1 && e1 > 0 && e1 < end) {
+    // Data parallel with K6a in column panels: the LAST panel's allreduce is the only one still in flight here.  Update
+    // everything that has already been summed — the leading panels of [W|U|b] and [Why|by] — under it, and its range afterwards.
+    int rc = lstm_wait_buckets(ctx, all & ~1u);
+    if (rc) return rc;
+    PROF(7);
+    launch_adagrad_f32(ctx->params, ctx->grads, ctx->mem, e1, lr, eps, clip, ctx->st);
+    launch_adagrad_f32(ctx->params + end, ctx->grads + end, ctx->mem + end, ctx->P - end, lr, eps, clip, ctx->st);
+    LSTM_LAUNCHED(2);
+    rc = lstm_wait_buckets(ctx, 1u);
+    if (rc) return rc;
+    launch_adagrad_f32(ctx->params + e1, ctx->grads + e1, ctx->mem + e1, end - e1, lr, eps, clip, ctx->st);
+    LSTM_LAUNCHED(1);
+  } else {
+    int rc = lstm_wait_buckets(ctx, all);
+    if (rc) return rc;
+    PROF(7);
+    launch_adagrad_f32(ctx->params, ctx->grads, ctx->mem, ctx->P, lr, eps, clip, ctx->st);
+    LSTM_LAUNCHED(1);
   }
-  PROF(7);
-  launch_adagrad_f32(ctx->params, ctx->grads, ctx->mem, ctx->P, lr, eps, clip, ctx->st);
-  LSTM_LAUNCHED(1);
   if (ctx->tc) {
     int rc = tc_params_changed(ctx);
     if (rc) return rc;
@@ -519,6 +569,23 @@ static int finish_profile(lstm_ctx* ctx) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ctx->pev[pairs[i][0]], ctx->pev[pairs[i][1]]) != cudaSuccess) { ms = -1.f; cudaGetLastError(); }
     ctx->phase_ms[i] = ms;
+  }
+  // data parallel: phase_ms[9 + b] = when bucket b's allreduce had finished, phase_ms[13..15] = when buckets 2, 3, 0 were handed
+  // to the communication stream — all in ms since the start of the iteration (0 = bucket not used)
+  for (int i = 9; i < 16; i++) ctx->phase_ms[i] = 0.f;
+  if (ctx->world > 1) {
+    LSTM_CUDA(cudaStreamSynchronize(ctx->comm_st));
+    const int handed[3] = {2, 3, 0};
+    for (int b = 0; b < lstm_ctx::NBUCKET; b++) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ctx->pev[0], ctx->ev_comm[b]) == cudaSuccess && ms > 0.f) ctx->phase_ms[9 + b] = ms;
+      else cudaGetLastError();
+    }
+    for (int i = 0; i < 3; i++) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ctx->pev[0], ctx->ev_bucket[handed[i]]) == cudaSuccess && ms > 0.f) ctx->phase_ms[13 + i] = ms;
+      else cudaGetLastError();
+    }
   }
   return LSTM_OK;
 }
@@ -605,7 +672,7 @@ static int run_iteration(lstm_ctx* ctx, int mode, int stride, float lr) {
     }
     const long l0 = ctx->launches;
     LSTM_CUDA(cudaStreamBeginCapture(ctx->st, cudaStreamCaptureModeThreadLocal));
-    if (dp) ctx->seg_capture = &g;
+    if (dp) { ctx->seg_capture = &g; g.open_wait = 0; g.open_l0 = ctx->launches; }
     int rc = iteration_body(ctx, mode, stride, lr);
     ctx->seg_capture = nullptr;
     cudaGraph_t graph = nullptr;
@@ -624,16 +691,15 @@ static int run_iteration(lstm_ctx* ctx, int mode, int stride, float lr) {
       free_iter_graph_keep_key(g);
       return lstm_fail(ctx, LSTM_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
     }
-    if (dp) { g.segs.push_back(exec); g.seg_bucket.push_back(-1); }
+    if (dp) { g.segs.push_back(exec); g.seg_bucket.push_back(-1); g.seg_wait.push_back(g.open_wait); g.open_wait = 0; }
     else g.exec = exec;
   }
   if (!dp) {
     LSTM_CUDA(cudaGraphLaunch(g.exec, ctx->st));
   } else {
     for (size_t i = 0; i < g.segs.size(); i++) {
-      if (i + 1 == g.segs.size() && i > 0) {                  // Adagrad reads the summed gradients
-        for (int b = 0; b < lstm_ctx::NBUCKET; b++) LSTM_CUDA(cudaStreamWaitEvent(ctx->st, ctx->ev_comm[b], 0));
-      }
+      for (int b = 0; b < lstm_ctx::NBUCKET; b++)             // Adagrad reads the summed gradients
+        if (g.seg_wait[i] & (1u << b)) LSTM_CUDA(cudaStreamWaitEvent(ctx->st, ctx->ev_comm[b], 0));
       LSTM_CUDA(cudaGraphLaunch(g.segs[i], ctx->st));
       if (g.seg_bucket[i] >= 0) {
         int rc = lstm_allreduce_bucket(ctx, g.seg_bucket[i]);
@@ -643,6 +709,33 @@ static int run_iteration(lstm_ctx* ctx, int mode, int stride, float lr) {
   }
   ctx->launches += g.launches;
   bump.ok = true;
+  return LSTM_OK;
+}
+
+// The reference's own default shape (batch 1, N = 64) trains inside ONE persistent kernel (train_small.cu): `iters` whole
+// iterations per launch, bit-identical to the launch-per-kernel path above.  Profiling (per-phase events) uses the general path.
+static bool small_path(const lstm_ctx* ctx) {
+  return ctx->dtype == LSTM_F32 && ctx->world == 1 && !ctx->profiling && train_small_eligible(ctx->M, ctx->N, ctx->S, ctx->B);
+}
+
+static int train_small_run(lstm_ctx* ctx, int iters, int stride, float lr, int mode) {
+  if (iters <= 0) return LSTM_OK;
+  TrainSmallArgs a;
+  a.W = ctx->p(LSTM_W); a.U = ctx->p(LSTM_U); a.b = ctx->p(LSTM_B); a.Why = ctx->p(LSTM_WHY); a.by = ctx->p(LSTM_BY);
+  a.mW = ctx->m(LSTM_W); a.mU = ctx->m(LSTM_U); a.mb = ctx->m(LSTM_B); a.mWhy = ctx->m(LSTM_WHY); a.mby = ctx->m(LSTM_BY);
+  a.gW = ctx->g(LSTM_W); a.gU = ctx->g(LSTM_U); a.gb = ctx->g(LSTM_B); a.gWhy = ctx->g(LSTM_WHY); a.gby = ctx->g(LSTM_BY);
+  a.Hs = ctx->Hs; a.Cs = ctx->Cs; a.Gs = ctx->Gs; a.dY = ctx->dY; a.dHy = ctx->dHy; a.dG = ctx->dG; a.surp = ctx->surp;
+  a.xs = ctx->xs; a.tg = ctx->tg;
+  a.text = ctx->text; a.len = ctx->text_len; a.pos0 = ctx->pos0; a.vcount = ctx->vcount;
+  a.ring = ctx->d_loss; a.cap = ctx->loss_cap; a.iter = ctx->d_iter;
+  a.S = ctx->S; a.T = ctx->T; a.iters = iters; a.stride = stride; a.mode = mode;
+  a.loss_mode = ctx->loss_mode; a.shift = ctx->softmax_shift;
+  a.lr = lr; a.clip = ctx->clip; a.eps = 1e-10;
+  LSTM_CUDA(launch_train_small(a, ctx->N, ctx->st));
+  ctx->launches += 1;
+  ctx->fwd_count += (uint64_t)iters;
+  ctx->iteration += iters;
+  ctx->fwd_done = true;
   return LSTM_OK;
 }
 
@@ -699,7 +792,7 @@ extern "C" int lstm_train_step(lstm_ctx* ctx, const int32_t* x_idx, const int32_
   LSTM_CUDA(cudaSetDevice(ctx->device));
   int rc = upload_window(ctx, x_idx, t_idx);
   if (rc) return rc;
-  rc = run_iteration(ctx, 1, stride, lr);
+  rc = small_path(ctx) ? train_small_run(ctx, 1, stride, lr, 1) : run_iteration(ctx, 1, stride, lr);
   if (rc) return rc;
   rc = finish_profile(ctx);
   if (rc) return rc;
@@ -734,7 +827,7 @@ extern "C" int lstm_set_positions(lstm_ctx* ctx, const uint64_t* pos) {
   ctx->h_pos0.assign(pos, pos + ctx->B);
   ctx->v_host = 0;
   LSTM_CUDA(cudaMemcpyAsync(ctx->pos0, ctx->h_pos0.data(), (size_t)ctx->B * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->st));
-  LSTM_CUDA(cudaMemsetAsync(ctx->vcount, 0, sizeof(unsigned long long), ctx->st));
+  LSTM_CUDA(cudaMemsetAsync(ctx->vcount, 0, 2 * sizeof(unsigned long long), ctx->st));
   LSTM_CUDA(cudaMemsetAsync(ctx->xs, 0xff, (size_t)ctx->S * ctx->B * sizeof(int), ctx->st));
   LSTM_CUDA(cudaMemsetAsync(ctx->tg, 0xff, (size_t)ctx->S * ctx->B * sizeof(int), ctx->st));
   LSTM_CUDA(cudaStreamSynchronize(ctx->st));
@@ -766,10 +859,16 @@ extern "C" int lstm_train_text(lstm_ctx* ctx, int iters, int stride, float lr, d
   int rc = ensure_loss_cap(ctx, (size_t)iters);
   if (rc) return rc;
   const uint64_t first = ctx->fwd_count;
-  for (int it = 0; it < iters; it++) {
-    rc = run_iteration(ctx, 0, stride, lr);
+  if (small_path(ctx)) {
+    rc = train_small_run(ctx, iters, stride, lr, 0);
     if (rc) return rc;
-    ctx->v_host += stride;   // host mirror of *vcount: moves only once the iteration is enqueued
+    ctx->v_host += (uint64_t)stride * (uint64_t)iters;
+  } else {
+    for (int it = 0; it < iters; it++) {
+      rc = run_iteration(ctx, 0, stride, lr);
+      if (rc) return rc;
+      ctx->v_host += stride;   // host mirror of *vcount: moves only once the iteration is enqueued
+    }
   }
   rc = finish_profile(ctx);
   if (rc) return rc;

@@ -15,9 +15,9 @@ struct Bf16State;  // bf16 tensor-core path state (tc_path.cu)
 struct lstm_ctx {
   int M = 0, N = 0, S = 0, B = 0, T = 0, device = 0, dtype = 0;
   cudaStream_t st = nullptr, comm_st = nullptr;
-  static constexpr int NBUCKET = 4;   // 0 = [W|U|b] (or its tail panel), 1 = [Why|by], 2 = leading column panel of [W|U|b]
+  static constexpr int NBUCKET = 4;   // 0 = [W|U|b] (or its last column panel), 1 = [Why|by], 2 / 3 = first / second column panel of [W|U|b]
   cudaEvent_t ev_bucket[NBUCKET] = {}, ev_comm[NBUCKET] = {};
-  size_t panel_split = 0;             // floats of [W|U|b] summed as bucket 2 (0 = none): set by the path that launches K6a in two panels
+  size_t panel_end[2] = {0, 0};       // end offsets (floats) of the panels summed as buckets 2 and 3 (0 = no such panel): set by the path that launches K6a in panels
   // flat parameter / gradient / Adagrad-memory vectors, tensor order W,U,b,Why,by (column-major each)
   size_t P = 0, off[5] = {0, 0, 0, 0, 0}, sz[5] = {0, 0, 0, 0, 0};
   float *params = nullptr, *grads = nullptr, *mem = nullptr;
@@ -42,6 +42,9 @@ struct lstm_ctx {
     cudaGraphExec_t exec = nullptr;
     std::vector<cudaGraphExec_t> segs;
     std::vector<int> seg_bucket;
+    std::vector<unsigned> seg_wait;      // buckets (bit mask) whose sums segment i waits for before it is launched
+    unsigned open_wait = 0;              // capture pass: the mask of the segment being captured
+    long open_l0 = 0;                    //               and the launch count when it was opened
     int stride = 0; float lr = 0.f; float clip = 0.f; long launches = 0; int warm = 0;
   } graph[2];
   IterGraph* seg_capture = nullptr;      // non-null while run_iteration captures a segmented graph
@@ -115,6 +118,8 @@ int tc_state_to_f32(lstm_ctx* ctx);    // bf16 h(0) -> Hs slot 0
 int tc_carry(lstm_ctx* ctx, int stride);
 int tc_debug_read(lstm_ctx* ctx, long long out[32]);
 void tc_variant(lstm_ctx* ctx, int out[8]);   // which kernel instantiations this context's shape selects
-// sum gradient bucket (0 = [W,U,b] from ctx->panel_split on, 1 = [Why,by], 2 = the first panel_split floats of [W,U,b]) over
+// sum gradient bucket (0 = [W,U,b] after the last panel end, 1 = [Why,by], 2 / 3 = the column panels ending at ctx->panel_end[0 / 1]) over
 // the data-parallel ranks on the communication stream
 int lstm_allreduce_bucket(lstm_ctx* ctx, int bucket);
+// make the compute stream wait until the buckets in `mask` (bit b = bucket b) have been summed
+int lstm_wait_buckets(lstm_ctx* ctx, unsigned mask);

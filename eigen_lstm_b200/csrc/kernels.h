@@ -64,4 +64,19 @@ cudaError_t launch_window_loss_f64(const float* params, const size_t off[5], con
                                    int n_probes, double delta, double* out, cudaStream_t st);
 void launch_eval_finish(const float* sum_part, const float* y_tgt, size_t steps, int G, double* bits_out, cudaStream_t st);
 
+// ---- the reference's default shape as one persistent kernel (train_small.cu): `iters` whole training iterations per launch ----
+struct TrainSmallArgs {
+  float *W, *U, *b, *Why, *by;         // parameters            (updated in place)
+  float *mW, *mU, *mb, *mWhy, *mby;    // Adagrad memory        (updated in place)
+  float *gW, *gU, *gb, *gWhy, *gby;    // gradients             (written for the LAST iteration of the call)
+  float *Hs, *Cs, *Gs, *dY, *dHy, *dG, *surp;   // activations  (slot 0 of Hs / Cs in and out; the rest written for the last iteration)
+  int *xs, *tg;                        // window: read when mode = 1, written (last iteration) when mode = 0
+  const uint8_t* text; unsigned long long len; const unsigned long long* pos0; unsigned long long* vcount;   // mode 0
+  double* ring; unsigned long long cap; unsigned long long* iter;                                             // loss ring
+  int S, T, iters, stride, mode, loss_mode, shift;
+  float lr, clip; double eps;
+};
+bool train_small_eligible(int M, int N, int S, int B);
+cudaError_t launch_train_small(const TrainSmallArgs& a, int N, cudaStream_t st);
+
 }  // namespace lstm

@@ -2,18 +2,11 @@
 // reference's Eigen CPU path) and the elementwise / data-pipeline kernels shared by both dtypes.
 // Every kernel cites the reference statement(s) it computes (R/ = reference root).
 #include "kernels.h"
+#include "scalar_f32.cuh"
 
 #include <math.h>
 
 namespace lstm {
-
-// ------------------------------------------------------------------------------------------------
-// scalar functions, written to round like the reference's scalar code (no FMA contraction where
-// the reference has separate multiply and add: g++ -O3 on x86-64 baseline does not fuse)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float logistic_f(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }  // R/lstm.cc:31-33
-__device__ __forceinline__ float tanh_prime_f(float x) { return __fsub_rn(1.0f, __fmul_rn(x, x)); }          // :36-38
-__device__ __forceinline__ float logistic_prime_f(float x) { return __fmul_rn(x, __fsub_rn(1.0f, x)); }      // :41-43
 
 // ------------------------------------------------------------------------------------------------
 // 64x64x16 SIMT tile engine: 256 threads, 4x4 register micro-tile per thread.
@@ -372,13 +365,6 @@ void launch_colsum_f32(const float* X, float* out, int I, int J, cudaStream_t st
 // :25,46-48).  HBM-bound: 20 B/param (read d, read+write m, read+write p); 128-bit accesses.
 // clip > 0 clamps d first (north-star addition; 0 = the reference's behaviour).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void adagrad_one(float& p, float d, float& m, float lr, double eps, float clip) {
-  if (clip > 0.f) d = fminf(fmaxf(d, -clip), clip);
-  m = __fadd_rn(m, __fmul_rn(d, d));
-  const float s = sqrtf((float)((double)m + eps));
-  p = __fsub_rn(p, __fmul_rn(lr, __fdiv_rn(d, s)));
-}
-
 __global__ void __launch_bounds__(256) k_adagrad_f32(float* __restrict__ p, const float* __restrict__ d,
                                                      float* __restrict__ m, size_t n, float lr, double eps,
                                                      float clip) {
@@ -424,21 +410,16 @@ void launch_fill_f32(float* p, float v, size_t n, cudaStream_t st) {
 // stream b has consumed v events; event q of stream b is E_b[q] = text[S + (pos0_b - S + q) mod (len - S)]
 // (positions wrap to S at the end of the text); target column s holds E_b[v-1-(S-1-s)], input column
 // s holds target column s-1; not-yet-filled columns are -1 (the all-zero one-hot).
-// Single CTA: it owns the event counter (so a captured CUDA graph can replay it).
+// The kernel owns the event counter (so a captured CUDA graph can replay it): every CTA reads v_counter[0]; the LAST CTA to
+// finish (ticket in v_counter[1]) advances it and re-arms the ticket.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_window_advance(const uint8_t* __restrict__ text, unsigned long long len,
-                                                         const unsigned long long* __restrict__ pos0,
-                                                         unsigned long long* __restrict__ v_counter, int stride,
-                                                         int S, int B, int* __restrict__ xs, int* __restrict__ tg) {
-  __shared__ unsigned long long v_new;
-  if (threadIdx.x == 0) {
-    v_new = v_counter[0] + (unsigned long long)stride;
-    v_counter[0] = v_new;
-  }
-  __syncthreads();
-  const long long v = (long long)v_new;
+__global__ void __launch_bounds__(256) k_window_advance(const uint8_t* __restrict__ text, unsigned long long len,
+                                                        const unsigned long long* __restrict__ pos0,
+                                                        unsigned long long* __restrict__ v_counter, int stride,
+                                                        int S, int B, int* __restrict__ xs, int* __restrict__ tg) {
+  const long long v = (long long)(v_counter[0] + (unsigned long long)stride);
   const unsigned long long span = len - (unsigned long long)S;
-  for (int e = threadIdx.x; e < S * B; e += blockDim.x) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < S * B; e += gridDim.x * blockDim.x) {
     const int s = e / B, b = e - s * B;
     const long long qt = v - 1 - (S - 1 - s);  // event index held by target column s
     const long long qx = qt - 1;               // input column s = target column s-1
@@ -446,12 +427,22 @@ __global__ void __launch_bounds__(1024) k_window_advance(const uint8_t* __restri
     tg[e] = (qt >= 0) ? (int)text[S + (off + (unsigned long long)qt) % span] : -1;
     xs[e] = (qx >= 0) ? (int)text[S + (off + (unsigned long long)qx) % span] : -1;
   }
+  __syncthreads();                             // every thread of this CTA has read the counter
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(v_counter + 1, 1ull) == (unsigned long long)gridDim.x - 1) {   // all CTAs have read it
+      v_counter[0] = (unsigned long long)v;
+      v_counter[1] = 0ull;
+    }
+  }
 }
 
 void launch_window_advance(const uint8_t* text, size_t len, const unsigned long long* pos0,
                            unsigned long long* v_counter, int stride, int S, int B, int* xs, int* tg,
                            cudaStream_t st) {
-  k_window_advance<<<1, 1024, 0, st>>>(text, (unsigned long long)len, pos0, v_counter, stride, S, B, xs, tg);
+  int grid = (S * B + 255) / 256;
+  if (grid > 148) grid = 148;
+  k_window_advance<<<grid, 256, 0, st>>>(text, (unsigned long long)len, pos0, v_counter, stride, S, B, xs, tg);
 }
 
 // ------------------------------------------------------------------------------------------------

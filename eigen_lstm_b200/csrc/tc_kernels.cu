@@ -321,16 +321,24 @@ __global__ void k_fill_bf16(__nv_bfloat16* p, float v, size_t n) {
 void launch_fill_bf16(__nv_bfloat16* p, float v, size_t n, cudaStream_t st) { k_fill_bf16<<<grid_for(n), 256, 0, st>>>(p, v, n); }
 
 // ZT rows [0,M): one-hot of the window's input bytes (W*x / dW += dg x^T as tensor-core contractions)
-__global__ void k_build_xt(const int* __restrict__ xs1, __nv_bfloat16* __restrict__ ZT, long ldz, int T, int B, int Bp) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_build_xt(const int* __restrict__ xs1, __nv_bfloat16* __restrict__ ZT, long ldz, int T,
+                                                  int B, int Bp) {
+  // one thread = 8 consecutive (timestep, stream) columns of symbol row m: one 16-byte store (Bp is a multiple of 8)
+  const int col = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (col >= T * Bp) return;
   const int m = blockIdx.y;
-  const int s = col / Bp, b = col - s * Bp;
-  const int x = (b < B) ? xs1[(size_t)s * B + b] : -1;
-  ZT[(size_t)m * ldz + col] = __float2bfloat16_rn(x == m ? 1.0f : 0.0f);
+  const int s = col / Bp, b0 = col - s * Bp;
+  const unsigned short one = 0x3F80;   // bf16 1.0
+  unsigned short v[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) v[i] = (b0 + i < B && xs1[(size_t)s * B + b0 + i] == m) ? one : (unsigned short)0;
+  uint4 o;
+  o.x = v[0] | ((unsigned)v[1] << 16); o.y = v[2] | ((unsigned)v[3] << 16);
+  o.z = v[4] | ((unsigned)v[5] << 16); o.w = v[6] | ((unsigned)v[7] << 16);
+  *reinterpret_cast<uint4*>(ZT + (size_t)m * ldz + col) = o;
 }
 void launch_build_xt(const int* xs1, __nv_bfloat16* ZT, long ldz, int M, int T, int B, int Bp, cudaStream_t st) {
-  k_build_xt<<<dim3((T * Bp + 255) / 256, M), 256, 0, st>>>(xs1, ZT, ldz, T, B, Bp);
+  k_build_xt<<<dim3((T * Bp / 8 + 255) / 256, M), 256, 0, st>>>(xs1, ZT, ldz, T, B, Bp);
 }
 
 __global__ void k_state_to_bf16(const float* __restrict__ h, __nv_bfloat16* __restrict__ Hbf, __nv_bfloat16* __restrict__ ZT_h,

@@ -316,25 +316,30 @@ int tc_backward(lstm_ctx* ctx) {
     const int bn = (M + N + 1 >= 1024) ? 256 : 128;   // wide tiles once there are enough of them to fill the SMs
     g.C = ctx->g(LSTM_W); g.ldc = (long)N4; g.tiles_m = (int)N4 / 128; g.tiles_n = (M + N + 1 + bn - 1) / bn;
     g.splits = 1; g.split_stride = 0;
-    // Data parallel: two column panels (8 + 2 tile columns of 256 at N = 2048: 3.5 + 0.9 waves, the same five tile times as one
-    // launch of 4.3 waves).  The leading panel's allreduce (67 MB) runs under the trailing panel's GEMM — whose 128 tiles leave
-    // 20 SMs to NCCL — and only the trailing 8 MB are summed after the last GEMM has retired.
-    const int lead = g.tiles_n >= 6 ? g.tiles_n - 2 : 0;
-    ctx->panel_split = 0;
-    if (ctx->world > 1 && lead > 0) {
-      tc::GemmArgs g1 = g, g2 = g;
-      g1.tiles_n = lead; g1.cols = lead * bn;
-      g2.tiles_n = g.tiles_n - lead; g2.cols = g.cols - lead * bn; g2.b_row0 = lead * bn; g2.C = g.C + (size_t)lead * bn * g.ldc;
-      ctx->panel_split = (size_t)lead * bn * (size_t)N4;
-      tc::launch_gemm_nt(bn, s->tmdGT, bn == 256 ? s->tmZT256 : s->tmZT, g1, ctx->st);
+    // Data parallel: two column panels (6 + 4 tile columns of 256 at N = 2048: 2.6 + 1.7 waves = the same five tile times as one
+    // launch of 4.3 waves).  Each panel is a contiguous range of the flat gradient vector; the leading panel's allreduce (50 MB)
+    // runs under the trailing panel's GEMM, the trailing 25 MB under the Adagrad update of everything else (adagrad_device).
+    // Measured on 2 GPUs (profiles/r02t_*): 4+4+2 panels and a cap on NCCL's CTAs (8 / 16 / 24 / 32) were all slower —
+    // every extra graph segment costs more than the shorter tail saves, and NCCL under a GEMM runs at ~110 GB/s whatever its CTA count.
+    int widths[3] = {g.tiles_n, 0, 0};
+    if (ctx->world > 1 && g.tiles_n >= 10) { widths[0] = (g.tiles_n * 6) / 10; widths[1] = g.tiles_n - widths[0]; }
+    ctx->panel_end[0] = ctx->panel_end[1] = 0;
+    int col0 = 0;
+    for (int i = 0; i < 3 && widths[i] > 0; i++) {
+      tc::GemmArgs gp = g;
+      const bool last = (i == 2 || widths[i + 1] == 0);
+      gp.tiles_n = widths[i];
+      gp.cols = last ? g.cols - col0 * bn : widths[i] * bn;
+      gp.b_row0 = col0 * bn;
+      gp.C = g.C + (size_t)col0 * bn * g.ldc;
+      tc::launch_gemm_nt(bn, s->tmdGT, bn == 256 ? s->tmZT256 : s->tmZT, gp, ctx->st);
       LSTM_LAUNCHED(1);
-      int rc2 = lstm_allreduce_bucket(ctx, 2);
-      if (rc2) return rc2;
-      tc::launch_gemm_nt(bn, s->tmdGT, bn == 256 ? s->tmZT256 : s->tmZT, g2, ctx->st);
-      LSTM_LAUNCHED(1);
-    } else {
-      tc::launch_gemm_nt(bn, s->tmdGT, bn == 256 ? s->tmZT256 : s->tmZT, g, ctx->st);
-      LSTM_LAUNCHED(1);
+      col0 += widths[i];
+      if (!last) {
+        ctx->panel_end[i] = (size_t)col0 * bn * (size_t)N4;
+        int rc2 = lstm_allreduce_bucket(ctx, 2 + i);
+        if (rc2) return rc2;
+      }
     }
   }
   PROF(6);

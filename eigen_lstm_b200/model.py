@@ -229,7 +229,11 @@ class LSTM:
         self._ck(self.lib.lstm_get_phase_ms(self.ctx, _ptr(a)))
         names = ["window", "fwd_recurrence", "logits_softmax", "dhy_dwhy_gemms", "bwd_recurrence", "weight_grads",
                  "allreduce_wait", "adagrad", "total"]
-        return dict(zip(names, a[:9].tolist()))
+        out = dict(zip(names, a[:9].tolist()))
+        if a[9:].any():   # data parallel: ms since the start of the iteration
+            out["comm_timeline"] = {"summed_at": dict(zip(["tail_panel", "why_by", "panel0", "panel1"], a[9:13].tolist())),
+                                    "handed_over_at": dict(zip(["panel0", "panel1", "tail_panel"], a[13:16].tolist()))}
+        return out
 
     # ---- options of the training path (include/lstm_b200.h LSTM_OPT_*) ----
     def set_clip(self, clip):
@@ -244,11 +248,11 @@ class LSTM:
         self._ck(self.lib.lstm_set_option(self.ctx, 2, float({"none": 0, "global": 1}[mode])))
 
     def variant(self):
-        """Kernel instantiations this context's shape selects (bf16 contexts), see lstm_debug_variant."""
+        """Kernel instantiations this context's shape selects, see lstm_debug_variant."""
         a = np.zeros(8, dtype=np.int32)
         self._ck(self.lib.lstm_debug_variant(self.ctx, _ptr(a)))
-        keys = ["fwd_bn", "fwd_pair", "bwd_bn", "bwd_variant", "wgrad_bn", "fwd_persistent", "bwd_persistent"]
-        return dict(zip(keys, a[:7].tolist()))
+        keys = ["fwd_bn", "fwd_pair", "bwd_bn", "bwd_variant", "wgrad_bn", "fwd_persistent", "bwd_persistent", "train_small"]
+        return dict(zip(keys, a.tolist()))
 
     def launch_count(self):
         return int(self.lib.lstm_launch_count(self.ctx))

@@ -183,10 +183,11 @@ int lstm_get_phase_ms(lstm_ctx* ctx, float ms[16]);
  * [2] first operand stage landed, [1] last TMA issued, [3] last MMA issued, [5] accumulator complete, [6] tile
  * re-mapped through shared memory / cluster reduce done, [7] LSTM math + stores done, [8] exit */
 int lstm_debug_kernel_clocks(lstm_ctx* ctx, long long out[32]);
-/* which kernel instantiations this context's shape selects (bf16 contexts; zeros otherwise), so that parity tests can assert
+/* which kernel instantiations this context's shape selects ([0..6]: bf16 contexts, zeros otherwise), so that parity tests can assert
  * that they cover the variants the benchmark runs: [0] K2 gate columns per CTA (BN), [1] K2 as cta_group::2 pairs,
  * [2] K5 hidden units per tile, [3] K5 variant (0 = split-K cluster of 4, 1 = pairs + 8-way split-K), [4] K6a tile width,
- * [5] K2 persistent, [6] K5 persistent, [7] reserved */
+ * [5] K2 persistent, [6] K5 persistent (tile width, 0 = per-timestep launches); [7] fp32 contexts: 1 = lstm_train_text /
+ * lstm_train_step run the whole iteration inside one persistent kernel (batch 1, N = 32 or 64: the reference's default shape) */
 int lstm_debug_variant(lstm_ctx* ctx, int out[8]);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 long lstm_launch_count(const lstm_ctx* ctx);
