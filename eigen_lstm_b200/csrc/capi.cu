@@ -186,6 +186,10 @@ extern "C" int lstm_create(lstm_ctx** out, int M, int N, int S, int B, int devic
     CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_win[k], cudaEventDisableTiming));
   }
   CREATE_CUDA(cudaMalloc(&ctx->pos0, (size_t)B * sizeof(unsigned long long)));
+  if (getenv("LSTM_TC_DEBUG") && dtype == LSTM_F32 && train_small_eligible(M, N, S, B)) {
+    CREATE_CUDA(cudaMalloc(&ctx->small_dbg, 32 * sizeof(long long)));
+    CREATE_CUDA(cudaMemsetAsync(ctx->small_dbg, 0, 32 * sizeof(long long), ctx->st));
+  }
   CREATE_CUDA(cudaMalloc(&ctx->vcount, 2 * sizeof(unsigned long long)));
   CREATE_CUDA(cudaMemsetAsync(ctx->vcount, 0, 2 * sizeof(unsigned long long), ctx->st));
   ctx->h_pos0.assign(B, (uint64_t)S);
@@ -212,7 +216,7 @@ extern "C" int lstm_destroy(lstm_ctx* ctx) {
   if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy(ctx->comm);
   if (ctx->tc) tc_destroy(ctx);
   void* bufs[] = {ctx->params, ctx->grads, ctx->mem, ctx->Hs, ctx->Cs, ctx->Gs, ctx->dY, ctx->dHy, ctx->dG,
-                  ctx->dcnext, ctx->surp, ctx->xs, ctx->tg, ctx->d_loss, ctx->text, ctx->pos0, ctx->vcount, ctx->logit_shift};
+                  ctx->dcnext, ctx->surp, ctx->xs, ctx->tg, ctx->d_loss, ctx->text, ctx->pos0, ctx->vcount, ctx->logit_shift, ctx->small_dbg};
   for (void* b : bufs) if (b) cudaFree(b);
   if (ctx->h_loss_ring) cudaFreeHost(ctx->h_loss_ring);
   for (int k = 0; k < 2; k++) {
@@ -731,6 +735,7 @@ static int train_small_run(lstm_ctx* ctx, int iters, int stride, float lr, int m
   a.S = ctx->S; a.T = ctx->T; a.iters = iters; a.stride = stride; a.mode = mode;
   a.loss_mode = ctx->loss_mode; a.shift = ctx->softmax_shift;
   a.lr = lr; a.clip = ctx->clip; a.eps = 1e-10;
+  a.dbg = ctx->small_dbg;
   LSTM_CUDA(launch_train_small(a, ctx->N, ctx->st));
   ctx->launches += 1;
   ctx->fwd_count += (uint64_t)iters;
@@ -1312,6 +1317,11 @@ extern "C" int lstm_dp_init(lstm_ctx* ctx, int rank, int world, const uint8_t id
 // ------------------------------------------------------------------------------------------------
 extern "C" int lstm_debug_kernel_clocks(lstm_ctx* ctx, long long out[32]) {
   if (!ctx || !out) return LSTM_ERR_ARG;
+  if (ctx->small_dbg) {
+    LSTM_CUDA(cudaStreamSynchronize(ctx->st));
+    LSTM_CUDA(cudaMemcpy(out, ctx->small_dbg, 32 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return LSTM_OK;
+  }
   return tc_debug_read(ctx, out);
 }
 

@@ -76,6 +76,7 @@ struct lstm_ctx {
   cudaEvent_t pev[16] = {};
   float phase_ms[16] = {};
   Bf16State* tc = nullptr;
+  long long* small_dbg = nullptr;   // LSTM_TC_DEBUG=1, fp32 one-kernel training: clock stamps (train_small.cu)
 
   float* p(int which) const { return params + off[which]; }
   float* g(int which) const { return grads + off[which]; }

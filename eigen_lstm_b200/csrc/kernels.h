@@ -75,6 +75,8 @@ struct TrainSmallArgs {
   double* ring; unsigned long long cap; unsigned long long* iter;                                             // loss ring
   int S, T, iters, stride, mode, loss_mode, shift;
   float lr, clip; double eps;
+  float m_exact;                       // set by the launcher: from this Adagrad memory value on, (float)(m + eps) == m
+  long long* dbg;                      // optional [32]: SM-clock stamps of the last iteration
 };
 bool train_small_eligible(int M, int N, int S, int B);
 cudaError_t launch_train_small(const TrainSmallArgs& a, int N, cudaStream_t st);
