@@ -480,6 +480,16 @@ def main():
                 "flops_per_launch": dom_flops * per_launch, "us_per_launch": dom_us * per_launch, "us_per_timestep": dom_us,
                 "note": "the recurrence is a serial chain per timestep (contraction -> exchange -> gate math -> publish): the tensor "
                         "pipe idles during the hand-offs, see DESIGN.md section 5 for the measured anatomy"}
+    if net_variant.get("train_small"):
+        # the timed region ran the one-kernel path (train_small.cu): every iteration inside one persistent launch on one SM;
+        # the phase times above come from the profiled iteration, which runs the launch-per-kernel path (same bits)
+        it_us = ms * 1e3 / args.steps
+        roofline = {"bound": "latency", "kernel": "k_train_small (whole training iterations in one persistent single-CTA launch, SIMT fp32)",
+                    "achieved": fl["dense"] * B * T / (it_us * 1e-6) / 1e12, "peak": None, "unit": "TFLOP/s", "frac": None,
+                    "traffic": None, "us_per_iteration": it_us,
+                    "note": "~250 K multiply-adds per iteration: bounded by the dependent chains of one iteration and by 33 K exact "
+                            "sqrt + divisions of the Adagrad update on ONE SM, not by any throughput roofline; "
+                            "profiles/r02w_small_clocks.txt has the in-kernel anatomy"}
     BT = B * T
     wg_flops = 2.0 * 4 * N * (M + N + 1) * BT               # dW|dU|db as one GEMM (bf16 path)
     pre_flops = 2.0 * M * (N + 1) * BT                      # dWhy|dby
@@ -508,7 +518,8 @@ def main():
                                   "frac_of_peak_alg": e2e_tf / (pk["tf_sustained"] * world)},
             "final_loss_bits_per_char": float(losses[-1] / T) if len(losses) else None, "learning_rate": LR,
             "kernel_variant": net_variant,
-            "launch_mode": "one CUDA graph per training iteration (timed region); plain stream launches for the profiled iteration"}
+            "launch_mode": ("all timed iterations in ONE persistent kernel launch (train_small.cu); " if net_variant.get("train_small") else
+                            "one CUDA graph per training iteration (timed region); ") + "plain stream launches for the profiled iteration"}
     if dpc is not None:
         dpc["replicas_identical_after_timed_region"] = same
         dpc["ok"] = bool(dpc["ok"] and same)

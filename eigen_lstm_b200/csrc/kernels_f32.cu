@@ -751,6 +751,7 @@ __global__ void __launch_bounds__(256, 1) k_recur_persist(const RecurArgs a) {
     // of the step — does not depend on the drawn byte: it is computed next to the logits, before the first barrier.
     for (size_t i = 0; i < a.n; i++) {
       const int buf = (int)(i & 1);
+      const float r_draw = (tid == 0 && a.mode == 1) ? a.uniforms[i] : 0.f;   // requested early, used after the softmax barrier
       load_h(buf);
       logits(se, nullptr);                                           // se[0..MPC) = owned exp(y)
       for (int mm = tid; mm < MPC; mm += blockDim.x)
@@ -781,7 +782,7 @@ __global__ void __launch_bounds__(256, 1) k_recur_persist(const RecurArgs a) {
         } else {
           // sequential cdf, first r < cdf (R/lstm.cc:321-338): the fp32 adds keep the reference's order; eight probabilities
           // are loaded per round so that the shared-memory latency is paid once per eight dependent adds instead of per add
-          const float r = a.uniforms[i];
+          const float r = r_draw;
           float cdf = 0.f;
           bool found = false;
           for (int q0 = 0; q0 < M && !found; q0 += 8) {
