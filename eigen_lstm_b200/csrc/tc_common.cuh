@@ -261,6 +261,21 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   return v;
 }
 
+// generic-proxy <-> async-proxy ordering for global memory
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+// whole warp: wait until the first `n` counters at `slots` have all reached `target` (bounded); backoff_ns > 0 sleeps between
+// polls (for waiters that are not on the critical path of the kernel that advances the counters)
+__device__ __forceinline__ void counters_wait(const unsigned int* slots, int n, unsigned int target, int lane, unsigned backoff_ns = 0) {
+  const long long t0 = clock64();
+  for (;;) {
+    const unsigned int v = lane < n ? ld_acquire_gpu(slots + lane) : target;
+    if (__all_sync(0xffffffffu, (int)(v - target) >= 0)) break;
+    if (backoff_ns) __nanosleep(backoff_ns);
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);

@@ -50,6 +50,11 @@ k_logits(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtens
     int g = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int row0 = tile * BM;                          // row in (slot s, padded b) space; h of slot s+1
+      if (a.progress) {                                    // beside a running forward recurrence: wait for h of that timestep
+        const int s = row0 / a.Bp, mb = (row0 - s * a.Bp) / BM;
+        counters_wait(a.progress + (size_t)mb * R_SLOTS, R_SLOTS, (unsigned int)(s + 1) * a.per_slot, lane, 500u);
+        fence_proxy_async_global();
+      }
       for (int kb = 0; kb < nkb; kb++, g++) {
         const int st = g % K3_STAGES;
         mbar_wait(&empty[st], ((uint32_t)(g / K3_STAGES) & 1u) ^ 1u);
@@ -212,23 +217,41 @@ k_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 // launchers
 // ------------------------------------------------------------------------------------------------
 
-void launch_logits(const CUtensorMap& tmH, const CUtensorMap& tmWmn, const LogitsArgs& a, cudaStream_t st) {
+// launch `kernel` as the programmatic dependent of the kernel before it in `st`: it may start as soon as every CTA of that kernel
+// has executed griddepcontrol.launch_dependents (it never calls griddepcontrol.wait: the two run side by side)
+template <typename K, typename... Args>
+static void launch_beside(K kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+void launch_logits(const CUtensorMap& tmH, const CUtensorMap& tmWmn, const LogitsArgs& a, cudaStream_t st, int max_ctas, bool beside) {
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   const int tiles = a.T * a.Bp / BM;
+  int grid = tiles < sms ? tiles : sms;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   set_smem(k_logits, Cfg<K3_BN, K3_STAGES>::SMEM_BYTES);
-  k_logits<<<tiles < sms ? tiles : sms, 192, Cfg<K3_BN, K3_STAGES>::SMEM_BYTES, st>>>(tmH, tmWmn, a);
+  if (beside) launch_beside(k_logits, dim3(grid), dim3(192), (size_t)Cfg<K3_BN, K3_STAGES>::SMEM_BYTES, st, tmH, tmWmn, a);
+  else k_logits<<<grid, 192, Cfg<K3_BN, K3_STAGES>::SMEM_BYTES, st>>>(tmH, tmWmn, a);
 }
 
 // bn = 128 or 256 = tile width; tmB must have a box of bn rows and a.tiles_n = ceil(cols / bn)
-void launch_gemm_nt(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st) {
+void launch_gemm_nt(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st, bool beside) {
   const dim3 grid(a.tiles_m * a.tiles_n, a.splits > 1 ? a.splits : 1);
   if (bn == 256) {
     set_smem(k_gemm_nt<256>, Cfg<256, 4>::SMEM_BYTES);
-    k_gemm_nt<256><<<grid, 192, Cfg<256, 4>::SMEM_BYTES, st>>>(tmA, tmB, a);
+    if (beside) launch_beside(k_gemm_nt<256>, grid, dim3(192), (size_t)Cfg<256, 4>::SMEM_BYTES, st, tmA, tmB, a);
+    else k_gemm_nt<256><<<grid, 192, Cfg<256, 4>::SMEM_BYTES, st>>>(tmA, tmB, a);
   } else {
     set_smem(k_gemm_nt<128>, Cfg<128, 6>::SMEM_BYTES);
-    k_gemm_nt<128><<<grid, 192, Cfg<128, 6>::SMEM_BYTES, st>>>(tmA, tmB, a);
+    if (beside) launch_beside(k_gemm_nt<128>, grid, dim3(192), (size_t)Cfg<128, 6>::SMEM_BYTES, st, tmA, tmB, a);
+    else k_gemm_nt<128><<<grid, 192, Cfg<128, 6>::SMEM_BYTES, st>>>(tmA, tmB, a);
   }
 }
 

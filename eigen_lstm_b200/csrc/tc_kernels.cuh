@@ -69,8 +69,14 @@ struct BwdRecurArgs {
   long long* dbg;              // optional clock64 stamps of CTA 0 around one timestep (NULL = off)
 };
 
+constexpr int R_SLOTS = 8;     // arrival counters per batch half of the persistent recurrences (spreads the same-address atomics)
+
 struct LogitsArgs {
   int B, Bp, N, M, T;
+  // optional: the arrival counters of a forward recurrence that is STILL RUNNING (k_fwd_recur, [Bp/128][R_SLOTS]): the tile of
+  // timestep t and batch half mb is contracted once all R_SLOTS counters of mb have reached t * per_slot
+  const unsigned int* progress = nullptr;
+  unsigned int per_slot = 0;
   const float* by;             // [M]
   const int* tg;               // [T][B] targets of timesteps 1..T
   __nv_bfloat16* dYbf;         // [T*Bp][M]
@@ -117,6 +123,8 @@ int fwd_recur_box_rows(int bn, int Bp);   // rows of the blocked-U TMA box: bn/2
 // with a box of bn/2 rows; tmH box = 128 rows
 // dry = true: launch nothing, only answer whether all CTAs would be co-resident on this device
 bool launch_fwd_recur(int bn, const CUtensorMap& tmH, const CUtensorMap& tmWb, const FwdRecurArgs& a, cudaStream_t st, bool dry = false);
+int bwd_recur_ctas(int bnj, int N, int Bp);
+int fwd_recur_ctas(int bn, int N, int Bp);                     // CTAs of that launch; arrivals per counter and timestep = tiles / R_SLOTS
 // tmWb = blocked BPTT weights, Wb5[(tile*NKBG + kbg)*bnj + row][c]: kbg < 4N/64: U(r' = kbg*64 + c, j = tile*bnj + row), else
 // Why(m = (kbg - 4N/64)*64 + c, j); NKBG = 4N/64 + M/64; box of bnj/2 rows
 int bwd_recur_bnj(int N, int Bp, int M);
@@ -125,12 +133,14 @@ int bwd_recur_box_rows(int bnj, int Bp);
 bool launch_bwd_recur(int bnj, const CUtensorMap& tmdG, const CUtensorMap& tmWb, const CUtensorMap& tmdY, const BwdRecurArgs& a,
                       cudaStream_t st, bool dry = false);
 // K3: logits + softmax + loss + dy for all timesteps
-void launch_logits(const CUtensorMap& tmH, const CUtensorMap& tmWmn, const LogitsArgs& a, cudaStream_t st);
+// beside = true: launched as the programmatic dependent of the forward recurrence that precedes it in the stream, on max_ctas CTAs
+void launch_logits(const CUtensorMap& tmH, const CUtensorMap& tmWmn, const LogitsArgs& a, cudaStream_t st, int max_ctas = 0, bool beside = false);
 // K5: one BPTT timestep.  BN in {32, 64, 128} hidden units per tile (4 split-K CTAs each).
 void launch_bwd_step(int BN, const CUtensorMap& tmdG, const CUtensorMap& tmUkr, const CUtensorMap& tmdY,
                      const CUtensorMap& tmWnm, const BwdStepArgs& a, cudaStream_t st);
 // K6: C = A * B^T, both K-major bf16, fp32 out, 128 x bn tiles (bn = 128 | 256; tmB box = bn rows)
-void launch_gemm_nt(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st);
+// beside = true: launched as the programmatic dependent of the kernel that precedes it in the stream (runs next to it)
+void launch_gemm_nt(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st, bool beside = false);
 
 // every bf16 operand copy of U from ONE pass over the fp32 master (null outputs skipped); N % 64 == 0
 void launch_refresh_u(const float* U, __nv_bfloat16* Urk, __nv_bfloat16* Ukr, __nv_bfloat16* Wb2, int bn2, __nv_bfloat16* Wb5,

@@ -29,6 +29,12 @@ struct Bf16State {
   unsigned int* xcnt = nullptr;   // per-tile arrival counters of the persistent BPTT recurrence's split-K exchange
   size_t xcnt_bytes = 0;
   long long* dbg = nullptr;   // [32] kernel-internal clock stamps (LSTM_TC_DEBUG=1)
+  // The persistent recurrences occupy 128 of the 148 SMs for 2.9 + 3.9 ms.  The small tensor-core kernels next to them are launched
+  // as their PROGRAMMATIC DEPENDENTS (same stream; the recurrence signals griddepcontrol.launch_dependents once all its CTAs are
+  // resident, the dependent never waits for its completion), so they run on the SMs the recurrence leaves free: K3 (logits,
+  // softmax, dy) follows the forward recurrence timestep by timestep, K6c (dWhy | dby) runs beside the BPTT recurrence.
+  // side_ctas = SMs the recurrences leave free (0 = no overlap).
+  int side_ctas = 0;
   size_t scratch_elems = 0;
   CUtensorMap tmH, tmUrk, tmUkr, tmWmn, tmWnm, tmdY, tmdYT, tmdG, tmdGT, tmZT, tmZT256;
 };
@@ -123,6 +129,15 @@ int tc_create(lstm_ctx* ctx) {
     if (s->bn2r && !tc::launch_fwd_recur(s->bn2r, none, none, fa, ctx->st, true)) s->bn2r = 0;
     if (s->bnj5 && !tc::launch_bwd_recur(s->bnj5, none, none, none, ba, ctx->st, true)) s->bnj5 = 0;
   }
+  if (s->bn2r || s->bnj5) {
+    // the SMs the persistent recurrences leave free run K3 / K6c beside them (tc_forward, tc_backward)
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device) != cudaSuccess) sms = 0;
+    int busy = 0;
+    if (s->bn2r) busy = tc::fwd_recur_ctas(s->bn2r, N, s->Bp);
+    if (s->bnj5 && tc::bwd_recur_ctas(s->bnj5, N, s->Bp) > busy) busy = tc::bwd_recur_ctas(s->bnj5, N, s->Bp);
+    s->side_ctas = sms - busy >= 8 ? sms - busy : 0;
+  }
   if (s->bn2r) TC_ALLOC(s->Wb2, N4 * N * sizeof(bf16));
   if (s->bnj5) {
     TC_ALLOC(s->Wb5, (size_t)N * (N4 + M) * sizeof(bf16));
@@ -210,6 +225,8 @@ int tc_forward(lstm_ctx* ctx) {
   tc::launch_build_xt(ctx->xs + B, s->ZT, s->LDZ, M, T, B, s->Bp, ctx->st);
   LSTM_LAUNCHED(1);
   bool persistent = false;
+  // per-phase profiling keeps the kernels one after the other on the compute stream
+  const bool overlap = s->bn2r && s->side_ctas > 0 && !ctx->profiling;
   if (s->bn2r) {                                         // the whole forward recurrence in one persistent launch (tc_recur.cu)
     tc::FwdRecurArgs pa;
     pa.B = B; pa.Bp = s->Bp; pa.N = N; pa.M = M; pa.T = T;
@@ -239,7 +256,29 @@ int tc_forward(lstm_ctx* ctx) {
   la.B = B; la.Bp = s->Bp; la.N = N; la.M = M; la.T = T;
   la.by = ctx->p(LSTM_BY); la.tg = ctx->tg + B;
   la.dYbf = s->dYbf; la.dYT = s->dYT; la.surp = ctx->surp;
-  tc::launch_logits(s->tmH, s->tmWmn, la, ctx->st);
+  if (overlap) {
+    // K3 beside the running recurrence: a programmatic dependent on the SMs the recurrence leaves free; it contracts the tile of
+    // timestep t as soon as the recurrence's arrival counters say that h(t) is complete.  The next launch in the stream (the
+    // loss reduction) waits for both kernels.
+    la.progress = s->gbar;
+    la.per_slot = (unsigned int)(4 * N / s->bn2r / tc::R_SLOTS);
+    tc::launch_logits(s->tmH, s->tmWmn, la, ctx->st, s->side_ctas, true);
+  } else {
+    tc::launch_logits(s->tmH, s->tmWmn, la, ctx->st);
+  }
+  LSTM_LAUNCHED(1);
+  return LSTM_OK;
+}
+
+// the whole BPTT recurrence in one persistent launch (tc_recur.cu)
+static int launch_bptt_persistent(lstm_ctx* ctx) {
+  Bf16State* s = ctx->tc;
+  tc::BwdRecurArgs pa;
+  pa.B = ctx->B; pa.Bp = s->Bp; pa.N = ctx->N; pa.M = ctx->M; pa.T = ctx->T;
+  pa.Gp = s->Gp; pa.Cs = ctx->Cs; pa.dGbf = s->dGbf; pa.dGT = s->dGT; pa.ldg = s->LDT; pa.red = s->red5;
+  pa.xcnt = s->xcnt; pa.gbar = s->gbar; pa.dbg = s->dbg ? s->dbg + 16 : nullptr;
+  if (!tc::launch_bwd_recur(s->bnj5, s->tmdG, s->tmWb5, s->tmdY, pa, ctx->st))
+    return lstm_fail(ctx, LSTM_ERR_CUDA, "the persistent BPTT recurrence could not be launched");
   LSTM_LAUNCHED(1);
   return LSTM_OK;
 }
@@ -248,8 +287,14 @@ int tc_backward(lstm_ctx* ctx) {
   Bf16State* s = ctx->tc;
   const int M = ctx->M, N = ctx->N, B = ctx->B, T = ctx->T;
   const size_t Bp = s->Bp, N4 = s->N4;
-  // K6c first (inputs complete after K3) so its allreduce bucket overlaps the BPTT recurrence:
-  // [dWhy | dby](m, n) = sum_(s,b) dY^T[m][(s,b)] * [H^T ; 1][n][(s+1,b)]
+  // K6c: [dWhy | dby](m, n) = sum_(s,b) dY^T[m][(s,b)] * [H^T ; 1][n][(s+1,b)] — inputs complete after K3.  With a persistent
+  // BPTT recurrence it is launched right AFTER it as its programmatic dependent: it runs beside the recurrence on the SMs that
+  // leaves free (it does not read anything the recurrence writes).
+  const bool overlap = s->bnj5 && s->side_ctas > 0 && !ctx->profiling;
+  if (overlap) {
+    int rc0 = launch_bptt_persistent(ctx);
+    if (rc0) return rc0;
+  }
   {
     tc::GemmArgs g;
     g.rows = M; g.cols = N + 1; g.nkb = (int)(s->LDT / 64); g.a_k0 = 0; g.b_k0 = s->Bp; g.b_row0 = M;
@@ -262,11 +307,11 @@ int tc_backward(lstm_ctx* ctx) {
     const size_t out_n = ctx->P - ctx->off[LSTM_WHY];        // [Why | by] incl. alignment padding: a multiple of 4 floats
     if (splits > 1 && s->kc_parts) {
       g.nkb /= splits; g.splits = splits; g.split_stride = out_n; g.C = s->kc_parts;
-      tc::launch_gemm_nt(128, s->tmdYT, s->tmZT, g, ctx->st);
-      tc::launch_sum_splits(s->kc_parts, ctx->g(LSTM_WHY), out_n, out_n, splits, ctx->st);
+      tc::launch_gemm_nt(128, s->tmdYT, s->tmZT, g, ctx->st, overlap);
+      tc::launch_sum_splits(s->kc_parts, ctx->g(LSTM_WHY), out_n, out_n, splits, ctx->st);   // plain launch: after both kernels
       LSTM_LAUNCHED(2);
     } else {
-      tc::launch_gemm_nt(128, s->tmdYT, s->tmZT, g, ctx->st);
+      tc::launch_gemm_nt(128, s->tmdYT, s->tmZT, g, ctx->st, overlap);
       LSTM_LAUNCHED(1);
     }
   }
@@ -276,15 +321,11 @@ int tc_backward(lstm_ctx* ctx) {
   // the recurrence and hides under the weight-gradient GEMM instead.
   int rc = s->bnj5 ? 0 : lstm_allreduce_bucket(ctx, 1);
   if (rc) return rc;
-  bool persistent = false;
-  if (s->bnj5) {                                         // the whole BPTT recurrence in one persistent launch (tc_recur.cu)
-    tc::BwdRecurArgs pa;
-    pa.B = B; pa.Bp = s->Bp; pa.N = N; pa.M = M; pa.T = T;
-    pa.Gp = s->Gp; pa.Cs = ctx->Cs; pa.dGbf = s->dGbf; pa.dGT = s->dGT; pa.ldg = s->LDT; pa.red = s->red5;
-    pa.xcnt = s->xcnt; pa.gbar = s->gbar; pa.dbg = s->dbg ? s->dbg + 16 : nullptr;
-    persistent = tc::launch_bwd_recur(s->bnj5, s->tmdG, s->tmWb5, s->tmdY, pa, ctx->st);
-    if (!persistent) return lstm_fail(ctx, LSTM_ERR_CUDA, "the persistent BPTT recurrence could not be launched");
-    LSTM_LAUNCHED(1);
+  bool persistent = overlap;
+  if (s->bnj5 && !overlap) {                             // the whole BPTT recurrence in one persistent launch (tc_recur.cu)
+    rc = launch_bptt_persistent(ctx);
+    if (rc) return rc;
+    persistent = true;
   }
   for (int t = T; t >= 1 && !persistent; t--) {
     tc::BwdStepArgs a;

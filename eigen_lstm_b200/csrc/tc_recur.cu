@@ -41,7 +41,6 @@ constexpr int R_EPI_WARPS = 16;
 constexpr int R_EPI_THREADS = R_EPI_WARPS * 32;
 constexpr int R_CTA_THREADS = 64 + R_EPI_THREADS;
 constexpr int R_HT_LD = 130;             // bf16 row pitch of the transposed staging tile: 65 words -> conflict-free
-constexpr int R_SLOTS = 8;               // arrival counters per batch half (spreads the same-address atomics)
 
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* local_bar, uint32_t cta_rank) {
   const uint32_t addr = mapa_u32(smem_u32(local_bar), cta_rank);
@@ -60,18 +59,6 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   if (mbar_try_wait_cluster(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait_cluster(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
-  }
-}
-// generic-proxy <-> async-proxy ordering for global memory
-__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
-
-// whole warp: wait until the first `n` counters at `slots` (stride words apart) have all reached `target` (bounded)
-__device__ __forceinline__ void counters_wait(const unsigned int* slots, int n, unsigned int target, int lane) {
-  const long long t0 = clock64();
-  for (;;) {
-    const unsigned int v = lane < n ? ld_acquire_gpu(slots + lane) : target;
-    if (__all_sync(0xffffffffu, (int)(v - target) >= 0)) break;
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
@@ -151,6 +138,9 @@ k_fwd_recur(const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUt
   constexpr int UC = F::CW / 4, RG = R_EPI_THREADS / UC, RPC = 128 / RG;   // per chunk: 16 units x 32 row groups, 4 rows per thread
   extern __shared__ uint8_t smem_raw[];
   TileCtx c = r_prologue<BN, STAGES, PAIR>(smem_raw);
+  // this CTA is resident: a kernel launched as our programmatic dependent (k_logits, following the arrival counters) may be
+  // scheduled on the SMs this grid leaves free once every CTA has said so
+  if (threadIdx.x == 0) pdl_launch_dependents();
   c.epi = c.tiles + STAGES * F::STAGE_BYTES + 256;
   uint64_t* tmem_free = c.accum_full + 2;
   uint64_t* res_full = c.accum_full + 3;                     // (leader) the CTAs' resident U k-blocks have landed
@@ -442,6 +432,7 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
   constexpr uint32_t NCTA = PAIR ? 2u : 1u;
   extern __shared__ uint8_t smem_raw[];
   TileCtx c = r_prologue<BNJ, STAGES, PAIR>(smem_raw);
+  if (threadIdx.x == 0) pdl_launch_dependents();   // see k_fwd_recur: the dWhy|dby GEMM runs beside this grid
   c.epi = c.tiles + STAGES * F::STAGE_BYTES + 256;
   uint64_t* tmem_free = c.accum_full + 2;                    // (leader) the CTAs have read the accumulator out of TMEM
   uint64_t* res_full = c.accum_full + 3;                     // (leader) the CTAs' resident weight k-blocks have landed
@@ -782,6 +773,7 @@ bool launch_fwd_recur(int bn, const CUtensorMap& tmH, const CUtensorMap& tmWb, c
   }
   return false;
 }
+int fwd_recur_ctas(int bn, int N, int Bp) { return (Bp == 256 ? 2 : 1) * (4 * N / bn); }
 int fwd_recur_box_rows(int bn, int Bp) { return Bp == 256 ? bn / 2 : bn; }
 
 // BPTT: tile = BNJ hidden units, KS split-K ranks, each rank finalises BNJ/KS units.
@@ -812,6 +804,7 @@ size_t bwd_recur_red_floats(int N, int bnj) {
   return (size_t)(N / bnj) * 2 * ks * ks * (bnj / ks / 4) * 128 * 4;
 }
 int bwd_recur_box_rows(int bnj, int Bp) { return Bp == 256 ? bnj / 2 : bnj; }
+int bwd_recur_ctas(int bnj, int N, int Bp) { return (Bp == 256 ? 2 : 1) * (N / bnj) * (bnj == 256 ? 8 : 4); }
 bool launch_bwd_recur(int bnj, const CUtensorMap& tmdG, const CUtensorMap& tmWb, const CUtensorMap& tmdY, const BwdRecurArgs& a,
                       cudaStream_t st, bool dry) {
   if (a.Bp == 256) {

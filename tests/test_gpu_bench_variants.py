@@ -140,3 +140,31 @@ np.savez(sys.argv[1], loss=loss, v=np.array([v["fwd_persistent"], v["bwd_persist
         assert int(c["v"][1]) == 256 and a["loss"] == c["loss"]   # same forward kernel
         for k in ("dg1", "dg7", "W", "U", "b", "Why", "by"):
             assert frob_rel(c[k], b[k]) < 3e-3, k
+
+
+@pytest.mark.parametrize("N,S,B", [(2048, 9, 256), (1024, 9, 128)])
+def test_kernels_beside_the_recurrences_change_nothing(N, S, B):
+    """K3 follows the running forward recurrence timestep by timestep and K6c runs beside the BPTT recurrence (programmatic
+    dependent launches on the SMs the persistent kernels leave free).  Per-phase profiling keeps the kernels one after the other:
+    both orders must give the same bits — losses, gradients, parameters — over several replayed iterations."""
+    import eigen_lstm_b200 as el
+    M = 256
+    rng = np.random.default_rng(5)
+    text = rng.integers(32, 127, 40000, dtype=np.uint8).tobytes()
+    pos = [S + 97 * b for b in range(B)]
+    out = []
+    for profiling in (False, True):
+        g = el.LSTM(M, N, S, B, dtype=el.BF16)
+        assert g.variant()["fwd_persistent"] and g.variant()["bwd_persistent"]
+        g.init_params(7, 0.01, 1.0)
+        g.load_text(text); g.set_positions(pos)
+        g.set_profiling(profiling)
+        losses = g.train_text(6, stride=S - 1, lr=0.01)
+        out.append((losses, g.params(), g.grads()))
+        g.close()
+    (la, pa, ga), (lb, pb, gb) = out
+    assert np.all(np.isfinite(la)) and np.array_equal(la, lb)
+    for name, a, b in zip(orc.NAMES, ga, gb):
+        assert np.array_equal(a, b), name
+    for name, a, b in zip(orc.NAMES, pa, pb):
+        assert np.array_equal(a, b), name
