@@ -601,7 +601,7 @@ struct RecurArgs {
 };
 
 __global__ void __launch_bounds__(256, 1) k_recur_persist(const RecurArgs a) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int N = a.N, M = a.M, N4 = 4 * N, G = gridDim.x, g = blockIdx.x, tid = threadIdx.x;
   const int UPC = a.UPC, R = 4 * UPC;                 // gate rows owned by this CTA (unit-major: r = 4*u + gate)
   const int MPC = (M + G - 1) / G;                    // logit rows owned by this CTA
@@ -662,7 +662,18 @@ __global__ void __launch_bounds__(256, 1) k_recur_persist(const RecurArgs a) {
       const bool ok = r < R && j < N;
       float acc = 0.f;
       if (ok) {
-        if (a.rows_resident) {
+        if (a.rows_resident && (N & 31) == 0) {
+          // 128-bit shared-memory loads: a quarter-warp (the 8 lanes of one row) reads 32 consecutive words = all 32 banks, and
+          // the four rows of a warp read the SAME h words (one broadcast wavefront): 5 wavefronts per 512 B of U instead of 8
+          const float4* ur4 = reinterpret_cast<const float4*>(sU + (size_t)r * UP);
+          const float4* sh4 = reinterpret_cast<const float4*>(sh);
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+          for (int k4 = lane8; k4 < (N >> 2); k4 += 8) {
+            const float4 u = ur4[k4], hv = sh4[k4];
+            a0 = fmaf(u.x, hv.x, a0); a1 = fmaf(u.y, hv.y, a1); a2 = fmaf(u.z, hv.z, a2); a3 = fmaf(u.w, hv.w, a3);
+          }
+          acc = (a0 + a1) + (a2 + a3);
+        } else if (a.rows_resident) {
           const float* ur = sU + (size_t)r * UP;
           for (int k = lane8; k < N; k += 8) acc = fmaf(ur[k], sh[k], acc);
         } else {
