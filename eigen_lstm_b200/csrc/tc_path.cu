@@ -360,7 +360,7 @@ int tc_backward(lstm_ctx* ctx) {
     // Data parallel: two column panels (6 + 4 tile columns of 256 at N = 2048: 2.6 + 1.7 waves = the same five tile times as one
     // launch of 4.3 waves).  Each panel is a contiguous range of the flat gradient vector; the leading panel's allreduce (50 MB)
     // runs under the trailing panel's GEMM, the trailing 25 MB under the Adagrad update of everything else (adagrad_device).
-    // Measured on 2 GPUs (profiles/r02t_*): 4+4+2 panels and a cap on NCCL's CTAs (8 / 16 / 24 / 32) were all slower —
+    // Measured on 2 GPUs (profiles/r02t_*): 4+4+2 panels (equal on 8 GPUs, profiles/r02ad_*) and a cap on NCCL's CTAs (8 / 16 / 24 / 32) were all slower —
     // every extra graph segment costs more than the shorter tail saves, and NCCL under a GEMM runs at ~110 GB/s whatever its CTA count.
     int widths[3] = {g.tiles_n, 0, 0};
     if (ctx->world > 1 && g.tiles_n >= 10) { widths[0] = (g.tiles_n * 6) / 10; widths[1] = g.tiles_n - widths[0]; }
