@@ -191,6 +191,10 @@ k_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   float* C = a.C + (size_t)split * a.split_stride;
   const KSeg s0{&tmA, &tmB, tm * BM, a.b_row0 + tn * K6_BN, a.a_k0 + split * a.nkb * BK, a.b_k0 + split * a.nkb * BK, a.nkb};
   const KSeg s1{&tmA, &tmB, 0, 0, 0, 0, 0};
+  if (a.wait_slots && c.warp == 0) {   // beside a running BPTT recurrence: this K range of dG is complete once the counters say so
+    counters_wait(a.wait_slots, a.wait_n, a.wait_target, c.lane, 1000u);
+    fence_proxy_async_global();
+  }
   tile_mainloop<K6_BN, K6_STAGES>(c, s0, s1);
   if (c.warp >= 2) {
     const int quarter = c.warp & 3;
@@ -202,10 +206,24 @@ k_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       float v[32];
       tmem_ld32(c.tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
       if (row < a.rows) {
+        if (a.addend) {
+          float ad[32];                                        // all 32 loads in flight before the first store (C may alias nothing,
+#pragma unroll                                                 // but the compiler cannot know: one load per store would serialise)
+          for (int i = 0; i < 32; i++) {
+            const int col = tn * K6_BN + c0 + i;
+            ad[i] = (col < a.cols) ? __ldg(a.addend + (size_t)col * a.ldc + row) : 0.f;
+          }
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
-          const int col = tn * K6_BN + c0 + i;
-          if (col < a.cols) C[(size_t)col * a.ldc + row] = v[i];
+          for (int i = 0; i < 32; i++) {
+            const int col = tn * K6_BN + c0 + i;
+            if (col < a.cols) C[(size_t)col * a.ldc + row] = v[i] + ad[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            const int col = tn * K6_BN + c0 + i;
+            if (col < a.cols) C[(size_t)col * a.ldc + row] = v[i];
+          }
         }
       }
     }

@@ -67,6 +67,7 @@ struct BwdRecurArgs {
   unsigned int* xcnt;          // [N/BNJ * 2] per-(tile, batch half) arrival counters of the exchange (zeroed by the launcher)
   unsigned int* gbar;          // [2][8] per-batch-half arrival counters of the dg barrier (zeroed by the launcher)
   long long* dbg;              // optional clock64 stamps of CTA 0 around one timestep (NULL = off)
+  int dbg_s = 0;               // which timestep is stamped (0-based from the end of the window; 0 = the fifth)
 };
 
 constexpr int R_SLOTS = 8;     // arrival counters per batch half of the persistent recurrences (spreads the same-address atomics)
@@ -110,6 +111,12 @@ struct GemmArgs {
   int tiles_m, tiles_n;
   int splits;                  // split-K: nkb is the k-blocks PER split; split s writes to C + s * split_stride (1 = off)
   size_t split_stride;
+  const float* addend = nullptr;   // optional: C = product + addend (same layout as C): the partial sum of another K range
+  // optional: contract only once the first wait_n arrival counters at wait_slots have reached wait_target — the kernel runs
+  // beside the persistent BPTT recurrence that is still producing the rest of dG (tc_backward)
+  const unsigned int* wait_slots = nullptr;
+  int wait_n = 0;
+  unsigned int wait_target = 0;
 };
 
 // K2 runs as cta_group::2 CTA pairs over the batch tiles when Bp/128 is even: each CTA then stages only half of the weight tile,
@@ -124,6 +131,7 @@ int fwd_recur_box_rows(int bn, int Bp);   // rows of the blocked-U TMA box: bn/2
 // dry = true: launch nothing, only answer whether all CTAs would be co-resident on this device
 bool launch_fwd_recur(int bn, const CUtensorMap& tmH, const CUtensorMap& tmWb, const FwdRecurArgs& a, cudaStream_t st, bool dry = false);
 int bwd_recur_ctas(int bnj, int N, int Bp);
+int bwd_recur_per_slot(int bnj, int N, int Bp);               // arrivals per counter and timestep of k_bwd_recur's dg barrier
 int fwd_recur_ctas(int bn, int N, int Bp);                     // CTAs of that launch; arrivals per counter and timestep = tiles / R_SLOTS
 // tmWb = blocked BPTT weights, Wb5[(tile*NKBG + kbg)*bnj + row][c]: kbg < 4N/64: U(r' = kbg*64 + c, j = tile*bnj + row), else
 // Why(m = (kbg - 4N/64)*64 + c, j); NKBG = 4N/64 + M/64; box of bnj/2 rows

@@ -20,6 +20,8 @@ struct Bf16State {
   bf16* Wb5 = nullptr;            // its blocked weight copy
   float* red5 = nullptr;
   float* kc_parts = nullptr;      // split-K partials of the dWhy|dby GEMM
+  float* k6_parts = nullptr;      // [dW|dU|db] summed over the LAST timesteps of the window (computed beside the BPTT recurrence)
+  int k6_late = 0;                // how many timesteps that is (0 = the weight-gradient GEMM is not split)
   CUtensorMap tmWb5;
   long LDZ = 0, LDT = 0;
   bf16 *Hbf = nullptr, *Urk = nullptr, *Ukr = nullptr, *Wmn = nullptr, *Wnm = nullptr;
@@ -137,6 +139,14 @@ int tc_create(lstm_ctx* ctx) {
     if (s->bn2r) busy = tc::fwd_recur_ctas(s->bn2r, N, s->Bp);
     if (s->bnj5 && tc::bwd_recur_ctas(s->bnj5, N, s->Bp) > busy) busy = tc::bwd_recur_ctas(s->bnj5, N, s->Bp);
     s->side_ctas = sms - busy >= 8 ? sms - busy : 0;
+    // The weight-gradient GEMM is split along time: BPTT runs from the last timestep to the first, so the last 3/16 of the window
+    // are final early; their share of the GEMM (2.7 ms on the 20 free SMs at config 4) fits beside the remaining 13/16 of the
+    // recurrence, and the GEMM that follows the recurrence is 3/16 shorter.
+    // (2/16 ... 5/16 measured, profiles/r02ag_*: 3/16 is the best; the GPU runs at its power cap, so work moved beside the
+    // recurrence lowers the clock of everything and only a part of the 3/16 shows up as time saved)
+    if (s->bnj5 && s->side_ctas) s->k6_late = (T * 3) / 16;
+    if (s->k6_late + 1 > T) s->k6_late = 0;
+    if (s->k6_late) TC_ALLOC(s->k6_parts, ctx->off[LSTM_WHY] * sizeof(float));
   }
   if (s->bn2r) TC_ALLOC(s->Wb2, N4 * N * sizeof(bf16));
   if (s->bnj5) {
@@ -168,7 +178,7 @@ void tc_destroy(lstm_ctx* ctx) {
   Bf16State* s = ctx->tc;
   if (!s) return;
   void* bufs[] = {s->Hbf, s->Urk, s->Ukr, s->Wmn, s->Wnm, s->dYbf, s->dYT, s->dGbf, s->dGT, s->ZT, s->Wp, s->bp, s->Gp,
-                  s->dcnext, s->scratch, s->red, s->dbg, s->gbar, s->xcnt, s->Wb5, s->red5, s->Wb2, s->kc_parts};
+                  s->dcnext, s->scratch, s->red, s->dbg, s->gbar, s->xcnt, s->Wb5, s->red5, s->Wb2, s->kc_parts, s->k6_parts};
   for (void* b : bufs) if (b) cudaFree(b);
   delete s;
   ctx->tc = nullptr;
@@ -277,8 +287,32 @@ static int launch_bptt_persistent(lstm_ctx* ctx) {
   pa.B = ctx->B; pa.Bp = s->Bp; pa.N = ctx->N; pa.M = ctx->M; pa.T = ctx->T;
   pa.Gp = s->Gp; pa.Cs = ctx->Cs; pa.dGbf = s->dGbf; pa.dGT = s->dGT; pa.ldg = s->LDT; pa.red = s->red5;
   pa.xcnt = s->xcnt; pa.gbar = s->gbar; pa.dbg = s->dbg ? s->dbg + 16 : nullptr;
+  if (const char* e = getenv("LSTM_TC_DEBUG_STEP")) pa.dbg_s = atoi(e);
   if (!tc::launch_bwd_recur(s->bnj5, s->tmdG, s->tmWb5, s->tmdY, pa, ctx->st))
     return lstm_fail(ctx, LSTM_ERR_CUDA, "the persistent BPTT recurrence could not be launched");
+  LSTM_LAUNCHED(1);
+  return LSTM_OK;
+}
+
+// [dW | dU | db] over the LAST k6_late timesteps of the window -> k6_parts.  beside = true: as a programmatic dependent right behind
+// K6c, next to the running BPTT recurrence; it starts contracting once the recurrence's arrival counters show that those timesteps
+// (and one more: a timestep's dG^T columns are stored after its arrival) are done.
+static int launch_k6a_late(lstm_ctx* ctx, bool beside) {
+  Bf16State* s = ctx->tc;
+  const int M = ctx->M, N = ctx->N, T = ctx->T;
+  const int N4 = 4 * N;
+  tc::GemmArgs g;
+  const int bn = (M + N + 1 >= 1024) ? 256 : 128;
+  g.rows = N4; g.cols = M + N + 1; g.nkb = s->k6_late * s->Bp / 64;
+  g.a_k0 = g.b_k0 = (T - s->k6_late) * s->Bp; g.b_row0 = 0;
+  g.C = s->k6_parts; g.ldc = (long)N4; g.tiles_m = N4 / 128; g.tiles_n = (M + N + 1 + bn - 1) / bn;
+  g.splits = 1; g.split_stride = 0;
+  if (beside) {
+    g.wait_slots = s->gbar;
+    g.wait_n = (s->Bp / 128) * tc::R_SLOTS;
+    g.wait_target = (unsigned int)(s->k6_late + 1) * (unsigned int)tc::bwd_recur_per_slot(s->bnj5, N, s->Bp);
+  }
+  tc::launch_gemm_nt(bn, s->tmdGT, bn == 256 ? s->tmZT256 : s->tmZT, g, ctx->st, beside);
   LSTM_LAUNCHED(1);
   return LSTM_OK;
 }
@@ -308,11 +342,14 @@ int tc_backward(lstm_ctx* ctx) {
     if (splits > 1 && s->kc_parts) {
       g.nkb /= splits; g.splits = splits; g.split_stride = out_n; g.C = s->kc_parts;
       tc::launch_gemm_nt(128, s->tmdYT, s->tmZT, g, ctx->st, overlap);
-      tc::launch_sum_splits(s->kc_parts, ctx->g(LSTM_WHY), out_n, out_n, splits, ctx->st);   // plain launch: after both kernels
-      LSTM_LAUNCHED(2);
+      LSTM_LAUNCHED(1);
+      if (overlap && s->k6_late) { int rc1 = launch_k6a_late(ctx, true); if (rc1) return rc1; }
+      tc::launch_sum_splits(s->kc_parts, ctx->g(LSTM_WHY), out_n, out_n, splits, ctx->st);   // plain launch: after all of the above
+      LSTM_LAUNCHED(1);
     } else {
       tc::launch_gemm_nt(128, s->tmdYT, s->tmZT, g, ctx->st, overlap);
       LSTM_LAUNCHED(1);
+      if (overlap && s->k6_late) { int rc1 = launch_k6a_late(ctx, true); if (rc1) return rc1; }
     }
   }
   PROF(4);
@@ -354,6 +391,11 @@ int tc_backward(lstm_ctx* ctx) {
   {
     tc::GemmArgs g;
     g.rows = (int)N4; g.cols = M + N + 1; g.nkb = (int)(s->LDT / 64); g.a_k0 = 0; g.b_k0 = 0; g.b_row0 = 0;
+    if (s->k6_late) {                                  // the last timesteps' share is already in k6_parts (or is computed now)
+      if (!overlap) { int rc1 = launch_k6a_late(ctx, false); if (rc1) return rc1; }
+      g.nkb = (T - s->k6_late) * (int)s->Bp / 64;
+      g.addend = s->k6_parts;
+    }
     const int bn = (M + N + 1 >= 1024) ? 256 : 128;   // wide tiles once there are enough of them to fill the SMs
     g.C = ctx->g(LSTM_W); g.ldc = (long)N4; g.tiles_m = (int)N4 / 128; g.tiles_n = (M + N + 1 + bn - 1) / bn;
     g.splits = 1; g.split_stride = 0;
@@ -373,6 +415,7 @@ int tc_backward(lstm_ctx* ctx) {
       gp.cols = last ? g.cols - col0 * bn : widths[i] * bn;
       gp.b_row0 = col0 * bn;
       gp.C = g.C + (size_t)col0 * bn * g.ldc;
+      if (g.addend) gp.addend = g.addend + (size_t)col0 * bn * g.ldc;
       tc::launch_gemm_nt(bn, s->tmdGT, bn == 256 ? s->tmZT256 : s->tmZT, gp, ctx->st);
       LSTM_LAUNCHED(1);
       col0 += widths[i];

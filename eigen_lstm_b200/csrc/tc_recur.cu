@@ -460,7 +460,7 @@ k_bwd_recur(const __grid_constant__ CUtensorMap tmdG, const __grid_constant__ CU
   const unsigned int per_slot = (unsigned int)(gridDim.x / NCTA / R_SLOTS);   // arrivals per counter and timestep
   float* red_tile = a.red + (size_t)tile * F::RED_TILE_FLOATS;             // [dst][src][u][row][4]
   long long* dbg = (a.dbg && blockIdx.x == 0) ? a.dbg : nullptr;
-  constexpr int DBG_S = 4;                                   // the timestep (0-based from the end of the window) that is stamped
+  const int DBG_S = a.dbg_s > 0 ? a.dbg_s : 4;               // the timestep (0-based from the end of the window) that is stamped
 
   if (c.warp == 0) {
     // ---------------- producer ----------------
@@ -805,6 +805,7 @@ size_t bwd_recur_red_floats(int N, int bnj) {
 }
 int bwd_recur_box_rows(int bnj, int Bp) { return Bp == 256 ? bnj / 2 : bnj; }
 int bwd_recur_ctas(int bnj, int N, int Bp) { return (Bp == 256 ? 2 : 1) * (N / bnj) * (bnj == 256 ? 8 : 4); }
+int bwd_recur_per_slot(int bnj, int N, int Bp) { return (N / bnj) * (bnj == 256 ? 8 : 4) / R_SLOTS; }
 bool launch_bwd_recur(int bnj, const CUtensorMap& tmdG, const CUtensorMap& tmWb, const CUtensorMap& tmdY, const BwdRecurArgs& a,
                       cudaStream_t st, bool dry) {
   if (a.Bp == 256) {
