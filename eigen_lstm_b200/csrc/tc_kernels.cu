@@ -231,6 +231,67 @@ k_gemm_nt(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   tile_epilogue_end<K6_BN, K6_STAGES>(c);
 }
 
+// The same GEMM as cta_group::2 PAIRS: a 256 x 256 output tile per pair of CTAs, every CTA stages its own 128 A rows and HALF of the
+// 256-row B tile — 32 KB of operands per k-block and SM instead of 48 KB for the same 512 tensor-core cycles.  The single-CTA
+// kernel above is bound by what one SM can take in (~61 B per clock measured: 790 cycles per k-block instead of 512).
+constexpr int K6P_BN = 256, K6P_STAGES = 6;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+k_gemm_nt_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  TileCtx c = pair_prologue<K6P_BN, K6P_STAGES>(smem_raw);
+  const uint32_t rank = cluster_ctarank();
+  constexpr int GROUP = 8;                                   // pair-rows per raster group (16 row tiles, like k_gemm_nt)
+  const int pid = blockIdx.x >> 1;
+  const int pair_rows = a.tiles_m >> 1;
+  const int per_group = GROUP * a.tiles_n;
+  const int group = pid / per_group;
+  const int first_m = group * GROUP;
+  const int gsize = min(pair_rows - first_m, GROUP);
+  const int tm = 2 * (first_m + (pid % per_group) % gsize) + (int)rank;   // this CTA's 128-row tile
+  const int tn = (pid % per_group) / gsize;
+  const KSeg s0{&tmA, &tmB, tm * BM, a.b_row0 + tn * K6P_BN, a.a_k0, a.b_k0, a.nkb};
+  const KSeg s1{&tmA, &tmB, 0, 0, 0, 0, 0};
+  if (a.wait_slots && c.warp == 0) {   // beside a running BPTT recurrence: this K range of dG is complete once the counters say so
+    counters_wait(a.wait_slots, a.wait_n, a.wait_target, c.lane, 1000u);
+    fence_proxy_async_global();
+  }
+  pair_mainloop<K6P_BN, K6P_STAGES>(c, s0, s1, rank, (uint16_t)0x3);
+  if (c.warp >= 2) {
+    const int quarter = c.warp & 3;
+    const int row = tm * BM + quarter * 32 + c.lane;
+    float* C = a.C;
+    mbar_wait(c.accum_full, 0);
+    tcgen05_after_sync();
+#pragma unroll 1
+    for (int c0 = 0; c0 < K6P_BN; c0 += 32) {
+      float v[32];
+      tmem_ld32(c.tmem_d + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+      if (row < a.rows) {
+        if (a.addend) {
+          float ad[32];
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            const int col = tn * K6P_BN + c0 + i;
+            ad[i] = (col < a.cols) ? __ldg(a.addend + (size_t)col * a.ldc + row) : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            const int col = tn * K6P_BN + c0 + i;
+            if (col < a.cols) C[(size_t)col * a.ldc + row] = v[i] + ad[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            const int col = tn * K6P_BN + c0 + i;
+            if (col < a.cols) C[(size_t)col * a.ldc + row] = v[i];
+          }
+        }
+      }
+    }
+  }
+  pair_epilogue_end<K6P_BN, K6P_STAGES>(c);
+}
+
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
@@ -260,9 +321,15 @@ void launch_logits(const CUtensorMap& tmH, const CUtensorMap& tmWmn, const Logit
 }
 
 // bn = 128 or 256 = tile width; tmB must have a box of bn rows and a.tiles_n = ceil(cols / bn)
-void launch_gemm_nt(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st, bool beside) {
+void launch_gemm_nt(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st, bool beside, bool pair) {
   const dim3 grid(a.tiles_m * a.tiles_n, a.splits > 1 ? a.splits : 1);
-  if (bn == 256) {
+  if (bn == 256 && pair) {
+    // tmB must have a box of 128 rows here: each CTA of a pair loads half of the 256-row B tile
+    constexpr int SMEM = PairCfg<K6P_BN, K6P_STAGES>::TILE_BYTES + 1024 + 256;
+    set_smem(k_gemm_nt_pair, SMEM);
+    if (beside) launch_beside(k_gemm_nt_pair, grid, dim3(192), (size_t)SMEM, st, tmA, tmB, a);
+    else k_gemm_nt_pair<<<grid, 192, SMEM, st>>>(tmA, tmB, a);
+  } else if (bn == 256) {
     set_smem(k_gemm_nt<256>, Cfg<256, 4>::SMEM_BYTES);
     if (beside) launch_beside(k_gemm_nt<256>, grid, dim3(192), (size_t)Cfg<256, 4>::SMEM_BYTES, st, tmA, tmB, a);
     else k_gemm_nt<256><<<grid, 192, Cfg<256, 4>::SMEM_BYTES, st>>>(tmA, tmB, a);

@@ -148,7 +148,9 @@ void launch_bwd_step(int BN, const CUtensorMap& tmdG, const CUtensorMap& tmUkr, 
                      const CUtensorMap& tmWnm, const BwdStepArgs& a, cudaStream_t st);
 // K6: C = A * B^T, both K-major bf16, fp32 out, 128 x bn tiles (bn = 128 | 256; tmB box = bn rows)
 // beside = true: launched as the programmatic dependent of the kernel that precedes it in the stream (runs next to it)
-void launch_gemm_nt(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st, bool beside = false);
+// pair = true (bn = 256, tiles_m even, no split-K): cta_group::2 pairs on 256 x 256 tiles; tmB must then have a box of 128 rows
+void launch_gemm_nt(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, cudaStream_t st, bool beside = false,
+                    bool pair = false);
 
 // every bf16 operand copy of U from ONE pass over the fp32 master (null outputs skipped); N % 64 == 0
 void launch_refresh_u(const float* U, __nv_bfloat16* Urk, __nv_bfloat16* Ukr, __nv_bfloat16* Wb2, int bn2, __nv_bfloat16* Wb5,

@@ -312,7 +312,8 @@ static int launch_k6a_late(lstm_ctx* ctx, bool beside) {
     g.wait_n = (s->Bp / 128) * tc::R_SLOTS;
     g.wait_target = (unsigned int)(s->k6_late + 1) * (unsigned int)tc::bwd_recur_per_slot(s->bnj5, N, s->Bp);
   }
-  tc::launch_gemm_nt(bn, s->tmdGT, bn == 256 ? s->tmZT256 : s->tmZT, g, ctx->st, beside);
+  const bool pair = bn == 256 && g.tiles_m % 2 == 0;   // cta_group::2 pairs on 256 x 256 tiles
+  tc::launch_gemm_nt(bn, s->tmdGT, pair ? s->tmZT : (bn == 256 ? s->tmZT256 : s->tmZT), g, ctx->st, beside, pair);
   LSTM_LAUNCHED(1);
   return LSTM_OK;
 }
@@ -416,7 +417,8 @@ int tc_backward(lstm_ctx* ctx) {
       gp.b_row0 = col0 * bn;
       gp.C = g.C + (size_t)col0 * bn * g.ldc;
       if (g.addend) gp.addend = g.addend + (size_t)col0 * bn * g.ldc;
-      tc::launch_gemm_nt(bn, s->tmdGT, bn == 256 ? s->tmZT256 : s->tmZT, gp, ctx->st);
+      const bool pair = bn == 256 && g.tiles_m % 2 == 0;   // cta_group::2 pairs on 256 x 256 tiles
+      tc::launch_gemm_nt(bn, s->tmdGT, pair ? s->tmZT : (bn == 256 ? s->tmZT256 : s->tmZT), gp, ctx->st, false, pair);
       LSTM_LAUNCHED(1);
       col0 += widths[i];
       if (!last) {
