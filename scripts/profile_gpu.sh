@@ -13,8 +13,8 @@ mkdir -p gpurun_out
 $CMD > gpurun_out/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_$TAG.log; exit 1; }
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c ${COUNT:-400} --csv \
     --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launch_$TAG.log 2>&1
-for K in ${KERNELS:-k_bwd_recur k_fwd_recur k_gemm_nt k_logits k_adagrad_f32}; do
-  case $K in k_gemm_nt) KS=7;; *) KS=3;; esac
+for K in ${KERNELS:-k_bwd_recur k_fwd_recur k_gemm_nt_pair k_logits k_adagrad_f32}; do
+  case $K in k_gemm_nt*) KS=7;; *) KS=3;; esac
   $CMD > gpurun_out/plain2_$TAG.log 2>&1 && \
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s $KS -c 1 \
       -o gpurun_out/prof_${K}_$TAG -f $CMD > gpurun_out/ncu_${K}_$TAG.log 2>&1
