@@ -175,7 +175,13 @@ int lstm_dp_init(lstm_ctx* ctx, int rank, int world, const uint8_t id[128]);
 /* ---- measurement ------------------------------------------------------------------------------ */
 /* CUDA-event time in ms of the phases of the LAST lstm_train_step / last iteration of
  * lstm_train_text when profiling is enabled: [0] window, [1] forward recurrence, [2] logits+softmax,
- * [3] dH_y (fp32 path) + dWhy|dby GEMM, [4] backward recurrence, [5] weight gradients, [6] allreduce wait, [7] adagrad, [8] total */
+ * [3] dH_y (fp32 path) + dWhy|dby GEMM, [4] backward recurrence, [5] weight gradients, [6] allreduce wait, [7] adagrad, [8] total.
+ * Profiling launches the kernels one after the other with plain stream launches: the kernels that normally run BESIDE the
+ * persistent recurrences (logits, dWhy|dby, the late share of the weight-gradient GEMM) and the one-kernel training path of
+ * the reference's default shape show up as separate phases (same results, bit for bit).
+ * Data parallel: [9 + b] = ms since the start of the iteration at which gradient bucket b (0 = last column panel of [W|U|b],
+ * 1 = [Why|by], 2 / 3 = leading panels) had been summed over the ranks, [13..15] = when buckets 2, 3, 0 were handed to the
+ * communication stream (0 = bucket not used). */
 int lstm_set_profiling(lstm_ctx* ctx, int on);
 int lstm_get_phase_ms(lstm_ctx* ctx, float ms[16]);
 /* diagnostics (LSTM_TC_DEBUG=1 in the environment at lstm_create, bf16 contexts): SM clock stamps taken inside the
