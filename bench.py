@@ -484,7 +484,7 @@ def main():
                 "kernel": f"{dom_kernel} ({'all ' + str(T) + ' timesteps of a window in one persistent launch' if persistent else 'one recurrent timestep'}, "
                           f"{'tcgen05 bf16' if dtype == 'bf16' else 'SIMT fp32'})",
                 "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
-                "traffic": traffic, "traffic_source": "ncu --set full dram__bytes_read+write per launch (profiles/r02_kernels.md)" if traffic else None,
+                "traffic": traffic, "traffic_source": "ncu --set full dram__bytes_read+write per launch (profiles/r02f_kernels.md)" if traffic else None,
                 "peak_source": f"{pk['src']} sustained bf16 (kernel timed inside a long step)",
                 "flops_per_launch": dom_flops * per_launch, "us_per_launch": dom_us * per_launch, "us_per_timestep": dom_us,
                 "note": "the recurrence is a serial chain per timestep (contraction -> exchange -> gate math -> publish): the tensor "

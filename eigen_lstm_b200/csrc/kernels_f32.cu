@@ -726,7 +726,6 @@ __global__ void __launch_bounds__(256, 1) k_recur_persist(const RecurArgs a) {
         if (y_out) y_out[mm] = y;
       }
     }
-    __syncthreads();
   };
 
   if (a.mode == 0) {
@@ -738,8 +737,12 @@ __global__ void __launch_bounds__(256, 1) k_recur_persist(const RecurArgs a) {
     for (size_t i = 0; i < a.n; i++) {
       const int buf = (int)(i & 1);
       load_h(buf);
+      // both products read h(i) only: the gate rows (all warps) and the owned logit rows (one more row for the first warps) run
+      // back to back, one barrier for both
+      if (i + 1 < a.n) matvec();
+      if (i > 0) logits(my_e, my_y);
+      __syncthreads();
       if (i > 0) {
-        logits(my_e, my_y);
         if (tid == 0) {
           float s = 0.f;
           const int tgt = (int)a.text[i];
@@ -751,8 +754,6 @@ __global__ void __launch_bounds__(256, 1) k_recur_persist(const RecurArgs a) {
         }
       }
       if (i + 1 < a.n) {
-        matvec();
-        __syncthreads();
         finish((int)a.text[i], buf ^ 1);
         grid_barrier(a.bar, ++epoch * G);
       }
@@ -765,6 +766,7 @@ __global__ void __launch_bounds__(256, 1) k_recur_persist(const RecurArgs a) {
       const float r_draw = (tid == 0 && a.mode == 1) ? a.uniforms[i] : 0.f;   // requested early, used after the softmax barrier
       load_h(buf);
       logits(se, nullptr);                                           // se[0..MPC) = owned exp(y)
+      __syncthreads();
       for (int mm = tid; mm < MPC; mm += blockDim.x)
         if (g * MPC + mm < M) a.ebuf[(size_t)buf * M + g * MPC + mm] = se[mm];
       grid_arrive(a.bar);                                            // split barrier: U h is computed while the other CTAs arrive
