@@ -448,6 +448,10 @@ def main():
            "d2h_bytes_per_step": 8, "ms_per_step": e2e_s * 1e3 / args.steps,
            "api": "lstm_train_step (host int32 windows -> pinned staging -> device, loss -> host, every step; steps are "
                   "asynchronous, the clock stops after lstm_sync has delivered all losses)"}
+    if net_variant.get("train_small"):
+        e2e["api"] = ("lstm_train_step on the one-kernel path: the host window travels as a kernel argument (its bytes are the "
+                      "h2d bytes), the kernel writes the step's loss into pinned host memory; one launch per step, asynchronous, "
+                      "the clock stops after lstm_sync has delivered all losses")
     same = replicas_identical(dist, net, local_rank) if world > 1 else None
 
     if rank != 0:

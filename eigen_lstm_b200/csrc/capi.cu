@@ -707,9 +707,20 @@ static bool small_path(const lstm_ctx* ctx) {
   return ctx->dtype == LSTM_F32 && ctx->world == 1 && !ctx->profiling && train_small_eligible(ctx->M, ctx->N, ctx->S, ctx->B);
 }
 
-static int train_small_run(lstm_ctx* ctx, int iters, int stride, float lr, int mode) {
+static int train_small_run(lstm_ctx* ctx, int iters, int stride, float lr, int mode, const int32_t* x_idx = nullptr,
+                           const int32_t* t_idx = nullptr, double* host_loss = nullptr) {
   if (iters <= 0) return LSTM_OK;
   TrainSmallArgs a;
+  a.host_loss = host_loss;
+  for (int i = 0; i < 8; i++) a.win_x[i] = a.win_t[i] = -1;
+  if (mode == 2) {                     // the window is a kernel argument: nothing is staged or copied
+    if (!x_idx || !t_idx) return lstm_fail(ctx, LSTM_ERR_ARG, "x_idx / t_idx is NULL");
+    for (int i = 0; i < ctx->S; i++) {
+      if (x_idx[i] < -1 || x_idx[i] >= ctx->M || t_idx[i] < -1 || t_idx[i] >= ctx->M)
+        return lstm_fail(ctx, LSTM_ERR_ARG, "window index outside [-1, M)");
+      a.win_x[i] = x_idx[i]; a.win_t[i] = t_idx[i];
+    }
+  }
   a.W = ctx->p(LSTM_W); a.U = ctx->p(LSTM_U); a.b = ctx->p(LSTM_B); a.Why = ctx->p(LSTM_WHY); a.by = ctx->p(LSTM_BY);
   a.mW = ctx->m(LSTM_W); a.mU = ctx->m(LSTM_U); a.mb = ctx->m(LSTM_B); a.mWhy = ctx->m(LSTM_WHY); a.mby = ctx->m(LSTM_BY);
   a.gW = ctx->g(LSTM_W); a.gU = ctx->g(LSTM_U); a.gb = ctx->g(LSTM_B); a.gWhy = ctx->g(LSTM_WHY); a.gby = ctx->g(LSTM_BY);
@@ -780,9 +791,23 @@ extern "C" int lstm_train_step(lstm_ctx* ctx, const int32_t* x_idx, const int32_
                                double* loss_out) {
   if (!ctx) return LSTM_ERR_ARG;
   LSTM_CUDA(cudaSetDevice(ctx->device));
+  if (small_path(ctx)) {
+    // one-kernel path: the window (S <= 5 bytes pairs) is a kernel argument and the loss lands in the pinned ring directly —
+    // the step is ONE kernel launch, no copies
+    double* slot = nullptr;
+    if (loss_out) {
+      if ((int)ctx->pending_loss.size() == lstm_ctx::LOSS_RING) { int rc0 = lstm_sync(ctx); if (rc0) return rc0; }
+      const int k = (int)ctx->pending_loss.size();
+      slot = ctx->h_loss_ring + k;
+      ctx->pending_loss.emplace_back(k, loss_out);
+    }
+    int rc = train_small_run(ctx, 1, stride, lr, 2, x_idx, t_idx, slot);
+    if (rc && loss_out) ctx->pending_loss.pop_back();
+    return rc;
+  }
   int rc = upload_window(ctx, x_idx, t_idx);
   if (rc) return rc;
-  rc = small_path(ctx) ? train_small_run(ctx, 1, stride, lr, 1) : run_iteration(ctx, 1, stride, lr);
+  rc = run_iteration(ctx, 1, stride, lr);
   if (rc) return rc;
   rc = finish_profile(ctx);
   if (rc) return rc;

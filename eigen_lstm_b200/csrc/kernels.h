@@ -73,7 +73,9 @@ struct TrainSmallArgs {
   int *xs, *tg;                        // window: read when mode = 1, written (last iteration) when mode = 0
   const uint8_t* text; unsigned long long len; const unsigned long long* pos0; unsigned long long* vcount;   // mode 0
   double* ring; unsigned long long cap; unsigned long long* iter;                                             // loss ring
-  int S, T, iters, stride, mode, loss_mode, shift;
+  int S, T, iters, stride, mode, loss_mode, shift;   // mode 0: window from the device text; 1: from xs / tg; 2: from win_x / win_t
+  int win_x[8], win_t[8];              // mode 2: the window itself travels as a kernel argument (S <= 5), no copy is enqueued
+  double* host_loss;                   // optional: pinned, device-accessible host double that also receives the last iteration's loss
   float lr, clip; double eps;
   float m_exact;                       // set by the launcher: from this Adagrad memory value on, (float)(m + eps) == m
   long long* dbg;                      // optional [32]: SM-clock stamps of the last iteration
