@@ -477,26 +477,34 @@ __global__ void __launch_bounds__(256) k_refresh_u(const float* __restrict__ U, 
   const int N4 = 4 * N;
   const int j0 = blockIdx.x * 16, kb = blockIdx.y, k0 = kb * 64;
   const int rp0 = 4 * j0;                                    // a multiple of 64: one k-block of the r' axis
-  for (int idx = threadIdx.x; idx < 64 * 64; idx += 256) {
-    const int u = idx & 15, g = (idx >> 4) & 3, k = idx >> 6;
-    tile[k][4 * u + g] = U[(size_t)(k0 + k) * N4 + (size_t)g * N + j0 + u];   // 16 consecutive floats per (k, gate)
+  // 128-bit loads: 4 consecutive hidden units of one (k, gate)
+  for (int idx = threadIdx.x; idx < 64 * 16; idx += 256) {
+    const int q = idx & 3, g = (idx >> 2) & 3, k = idx >> 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(U + (size_t)(k0 + k) * N4 + (size_t)g * N + j0 + 4 * q));
+    tile[k][4 * (4 * q + 0) + g] = v.x; tile[k][4 * (4 * q + 1) + g] = v.y;
+    tile[k][4 * (4 * q + 2) + g] = v.z; tile[k][4 * (4 * q + 3) + g] = v.w;
   }
   __syncthreads();
+  // every output row is 64 bf16 = 128 bytes; one thread writes 8 of them (16 bytes), 8 threads a whole row
   // rows = r', 64 consecutive k each (Urk / Wb2)
-  for (int idx = threadIdx.x; idx < 64 * 32; idx += 256) {
-    const int c2 = idx & 31, r = idx >> 5;
-    const __nv_bfloat162 v = __floats2bfloat162_rn(tile[2 * c2][r], tile[2 * c2 + 1][r]);
+  for (int idx = threadIdx.x; idx < 64 * 8; idx += 256) {
+    const int c8 = idx & 7, r = idx >> 3;
+    uint4 o;
+    o.x = pack_bf16x2(tile[8 * c8 + 0][r], tile[8 * c8 + 1][r]); o.y = pack_bf16x2(tile[8 * c8 + 2][r], tile[8 * c8 + 3][r]);
+    o.z = pack_bf16x2(tile[8 * c8 + 4][r], tile[8 * c8 + 5][r]); o.w = pack_bf16x2(tile[8 * c8 + 6][r], tile[8 * c8 + 7][r]);
     const int rp = rp0 + r;
-    if (Urk) *reinterpret_cast<__nv_bfloat162*>(Urk + (size_t)rp * N + k0 + 2 * c2) = v;
-    if (Wb2) *reinterpret_cast<__nv_bfloat162*>(Wb2 + (((size_t)(rp / bn2) * (N / 64) + kb) * bn2 + rp % bn2) * 64 + 2 * c2) = v;
+    if (Urk) *reinterpret_cast<uint4*>(Urk + (size_t)rp * N + k0 + 8 * c8) = o;
+    if (Wb2) *reinterpret_cast<uint4*>(Wb2 + (((size_t)(rp / bn2) * (N / 64) + kb) * bn2 + rp % bn2) * 64 + 8 * c8) = o;
   }
   // rows = k, 64 consecutive r' each (Ukr / Wb5)
-  for (int idx = threadIdx.x; idx < 64 * 32; idx += 256) {
-    const int c2 = idx & 31, kk = idx >> 5;
-    const __nv_bfloat162 v = __floats2bfloat162_rn(tile[kk][2 * c2], tile[kk][2 * c2 + 1]);
+  for (int idx = threadIdx.x; idx < 64 * 8; idx += 256) {
+    const int c8 = idx & 7, kk = idx >> 3;
+    const float* t = &tile[kk][8 * c8];
+    uint4 o;
+    o.x = pack_bf16x2(t[0], t[1]); o.y = pack_bf16x2(t[2], t[3]); o.z = pack_bf16x2(t[4], t[5]); o.w = pack_bf16x2(t[6], t[7]);
     const int k = k0 + kk;
-    if (Ukr) *reinterpret_cast<__nv_bfloat162*>(Ukr + (size_t)k * N4 + rp0 + 2 * c2) = v;
-    if (Wb5) *reinterpret_cast<__nv_bfloat162*>(Wb5 + (((size_t)(k / bn5) * nkbg + rp0 / 64) * bn5 + k % bn5) * 64 + 2 * c2) = v;
+    if (Ukr) *reinterpret_cast<uint4*>(Ukr + (size_t)k * N4 + rp0 + 8 * c8) = o;
+    if (Wb5) *reinterpret_cast<uint4*>(Wb5 + (((size_t)(k / bn5) * nkbg + rp0 / 64) * bn5 + k % bn5) * 64 + 8 * c8) = o;
   }
 }
 void launch_refresh_u(const float* U, __nv_bfloat16* Urk, __nv_bfloat16* Ukr, __nv_bfloat16* Wb2, int bn2, __nv_bfloat16* Wb5,
