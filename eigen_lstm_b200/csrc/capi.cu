@@ -449,7 +449,7 @@ static int cut_segment(lstm_ctx* ctx, int bucket) {
   g->seg_bucket.push_back(bucket);
   g->seg_wait.push_back(g->open_wait);
   g->open_wait = 0;
-  g->open_l0 = ctx->launches;
+  g->open_l0 = ctx->enqueued;
   LSTM_CUDA(cudaStreamBeginCapture(ctx->st, cudaStreamCaptureModeThreadLocal));
   return LSTM_OK;
 }
@@ -480,7 +480,7 @@ int lstm_wait_buckets(lstm_ctx* ctx, unsigned mask) {
   if (ctx->world <= 1 || mask == 0) return LSTM_OK;
   if (ctx->seg_capture) {   // capture pass: the waits are issued between two segment launches, before the segment that needs them
     lstm_ctx::IterGraph* g = ctx->seg_capture;
-    if (ctx->launches != g->open_l0) {   // the open segment already holds work that must not wait: close it
+    if (ctx->enqueued != g->open_l0) {   // the open segment already holds work that must not wait: close it
       int rc = cut_segment(ctx, -1);
       if (rc) return rc;
     }
@@ -627,9 +627,11 @@ static int iteration_body(lstm_ctx* ctx, int mode, int stride, float lr) {
   if (rc) return rc;
   rc = backward_device(ctx);
   if (rc) return rc;
-  rc = adagrad_device(ctx, lr, 1e-10, ctx->clip);
+  // slot 0 <- the state the next window starts from.  Independent of the update: issued before it, so that on several GPUs the
+  // copies run while the compute stream would otherwise wait for the last allreduce.
+  rc = lstm_carry_state(ctx, stride);
   if (rc) return rc;
-  return lstm_carry_state(ctx, stride);   // slot 0 now holds the state the next window starts from
+  return adagrad_device(ctx, lr, 1e-10, ctx->clip);
 }
 
 // Launch-bound inner loop (hundreds of short kernels per iteration): the iteration is captured once into a CUDA graph
@@ -661,7 +663,7 @@ static int run_iteration(lstm_ctx* ctx, int mode, int stride, float lr) {
     }
     const long l0 = ctx->launches;
     LSTM_CUDA(cudaStreamBeginCapture(ctx->st, cudaStreamCaptureModeThreadLocal));
-    if (dp) { ctx->seg_capture = &g; g.open_wait = 0; g.open_l0 = ctx->launches; }
+    if (dp) { ctx->seg_capture = &g; g.open_wait = 0; g.open_l0 = ctx->enqueued; }
     int rc = iteration_body(ctx, mode, stride, lr);
     ctx->seg_capture = nullptr;
     cudaGraph_t graph = nullptr;
@@ -784,6 +786,7 @@ extern "C" int lstm_carry_state(lstm_ctx* ctx, int stride) {
     LSTM_CUDA(cudaMemcpyAsync(ctx->Hslot(0), ctx->Hslot(stride), bytes, cudaMemcpyDeviceToDevice, ctx->st));
   }
   LSTM_CUDA(cudaMemcpyAsync(ctx->Cslot(0), ctx->Cslot(stride), bytes, cudaMemcpyDeviceToDevice, ctx->st));
+  ctx->enqueued += 1;
   return LSTM_OK;
 }
 

@@ -69,6 +69,7 @@ struct lstm_ctx {
   // bookkeeping
   bool fwd_done = false;
   long launches = 0;
+  long enqueued = 0;                     // kernels + copies put on the compute stream (tells an empty graph segment from a used one)
   long iteration = 0;
   std::string err;
   // profiling
@@ -102,6 +103,7 @@ int lstm_fail(lstm_ctx* c, int code, const std::string& msg);
 #define LSTM_LAUNCHED(n)                                                                              \
   do {                                                                                                \
     ctx->launches += (n);                                                                             \
+    ctx->enqueued += (n);                                                                             \
     cudaError_t e_ = cudaGetLastError();                                                              \
     if (e_ != cudaSuccess)                                                                            \
       return lstm_fail(ctx, LSTM_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_));  \

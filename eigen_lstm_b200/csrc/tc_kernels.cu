@@ -445,8 +445,10 @@ __global__ void __launch_bounds__(256) k_build_xt(const int* __restrict__ xs1, _
   o.z = v[4] | ((unsigned)v[5] << 16); o.w = v[6] | ((unsigned)v[7] << 16);
   *reinterpret_cast<uint4*>(ZT + (size_t)m * ldz + col) = o;
 }
-void launch_build_xt(const int* xs1, __nv_bfloat16* ZT, long ldz, int M, int T, int B, int Bp, cudaStream_t st) {
-  k_build_xt<<<dim3((T * Bp / 8 + 255) / 256, M), 256, 0, st>>>(xs1, ZT, ldz, T, B, Bp);
+void launch_build_xt(const int* xs1, __nv_bfloat16* ZT, long ldz, int M, int T, int B, int Bp, cudaStream_t st, bool beside) {
+  const dim3 grid((T * Bp / 8 + 255) / 256, M);
+  if (beside) launch_beside(k_build_xt, grid, dim3(256), (size_t)0, st, xs1, ZT, ldz, T, B, Bp);
+  else k_build_xt<<<grid, 256, 0, st>>>(xs1, ZT, ldz, T, B, Bp);
 }
 
 __global__ void k_state_to_bf16(const float* __restrict__ h, __nv_bfloat16* __restrict__ Hbf, __nv_bfloat16* __restrict__ ZT_h,

@@ -165,7 +165,7 @@ void launch_permute_rows_bf16(const float* in, __nv_bfloat16* out, int rows, int
 void launch_transpose_cast(const float* in, __nv_bfloat16* out, int R, int C, int permute, cudaStream_t st);
 void launch_cast_bf16(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t st);
 // ZT rows [0,M): one-hot of xs (slot s <- xs[(s+1)*B + b]); cols = T*Bp
-void launch_build_xt(const int* xs1, __nv_bfloat16* ZT, long ldz, int M, int T, int B, int Bp, cudaStream_t st);
+void launch_build_xt(const int* xs1, __nv_bfloat16* ZT, long ldz, int M, int T, int B, int Bp, cudaStream_t st, bool beside = false);
 void launch_fill_bf16(__nv_bfloat16* p, float v, size_t n, cudaStream_t st);
 // h state fp32 [B][N] <-> Hbf slot [Bp][N] + ZT h-rows of one slot
 void launch_state_to_bf16(const float* h, __nv_bfloat16* Hbf_slot, __nv_bfloat16* ZT_h, long ldz, int B, int N, cudaStream_t st);

@@ -232,11 +232,14 @@ int tc_forward(lstm_ctx* ctx) {
   Bf16State* s = ctx->tc;
   const int M = ctx->M, N = ctx->N, B = ctx->B, T = ctx->T;
   const size_t Bp = s->Bp, N4 = s->N4;
-  tc::launch_build_xt(ctx->xs + B, s->ZT, s->LDZ, M, T, B, s->Bp, ctx->st);
-  LSTM_LAUNCHED(1);
   bool persistent = false;
   // per-phase profiling keeps the kernels one after the other on the compute stream
   const bool overlap = s->bn2r && s->side_ctas > 0 && !ctx->profiling;
+  // the one-hot rows of ZT feed the weight-gradient GEMM only: next to a persistent forward recurrence they are built beside it
+  if (!overlap) {
+    tc::launch_build_xt(ctx->xs + B, s->ZT, s->LDZ, M, T, B, s->Bp, ctx->st);
+    LSTM_LAUNCHED(1);
+  }
   if (s->bn2r) {                                         // the whole forward recurrence in one persistent launch (tc_recur.cu)
     tc::FwdRecurArgs pa;
     pa.B = B; pa.Bp = s->Bp; pa.N = N; pa.M = M; pa.T = T;
@@ -272,6 +275,8 @@ int tc_forward(lstm_ctx* ctx) {
     // loss reduction) waits for both kernels.
     la.progress = s->gbar;
     la.per_slot = (unsigned int)(4 * N / s->bn2r / tc::R_SLOTS);
+    tc::launch_build_xt(ctx->xs + B, s->ZT, s->LDZ, M, T, B, s->Bp, ctx->st, true);
+    LSTM_LAUNCHED(1);
     tc::launch_logits(s->tmH, s->tmWmn, la, ctx->st, s->side_ctas, true);
   } else {
     tc::launch_logits(s->tmH, s->tmWmn, la, ctx->st);
