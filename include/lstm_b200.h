@@ -175,7 +175,7 @@ int lstm_dp_init(lstm_ctx* ctx, int rank, int world, const uint8_t id[128]);
 /* ---- measurement ------------------------------------------------------------------------------ */
 /* CUDA-event time in ms of the phases of the LAST lstm_train_step / last iteration of
  * lstm_train_text when profiling is enabled: [0] window, [1] forward recurrence, [2] logits+softmax,
- * [3] dH_y (fp32 path) + dWhy|dby GEMM, [4] backward recurrence, [5] weight gradients, [6] allreduce wait (and the state-carry copies, issued there), [7] adagrad, [8] total.
+ * [3] dH_y (fp32 path) + dWhy|dby GEMM, [4] backward recurrence, [5] weight gradients, [6] allreduce wait, [7] adagrad, [8] total.
  * Profiling launches the kernels one after the other with plain stream launches: the kernels that normally run BESIDE the
  * persistent recurrences (logits, dWhy|dby, the late share of the weight-gradient GEMM) and the one-kernel training path of
  * the reference's default shape show up as separate phases (same results, bit for bit).
