@@ -715,7 +715,7 @@ static int train_small_run(lstm_ctx* ctx, int iters, int stride, float lr, int m
   TrainSmallArgs a;
   a.host_loss = host_loss;
   for (int i = 0; i < 8; i++) a.win_x[i] = a.win_t[i] = -1;
-  if (mode == 2) {                     // the window is a kernel argument: nothing is staged or copied
+  if (mode == 1) {                     // the window is a kernel argument: nothing is staged or copied
     if (!x_idx || !t_idx) return lstm_fail(ctx, LSTM_ERR_ARG, "x_idx / t_idx is NULL");
     for (int i = 0; i < ctx->S; i++) {
       if (x_idx[i] < -1 || x_idx[i] >= ctx->M || t_idx[i] < -1 || t_idx[i] >= ctx->M)
@@ -804,7 +804,7 @@ extern "C" int lstm_train_step(lstm_ctx* ctx, const int32_t* x_idx, const int32_
       slot = ctx->h_loss_ring + k;
       ctx->pending_loss.emplace_back(k, loss_out);
     }
-    int rc = train_small_run(ctx, 1, stride, lr, 2, x_idx, t_idx, slot);
+    int rc = train_small_run(ctx, 1, stride, lr, 1, x_idx, t_idx, slot);
     if (rc && loss_out) ctx->pending_loss.pop_back();
     return rc;
   }

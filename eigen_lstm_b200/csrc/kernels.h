@@ -70,11 +70,11 @@ struct TrainSmallArgs {
   float *mW, *mU, *mb, *mWhy, *mby;    // Adagrad memory        (updated in place)
   float *gW, *gU, *gb, *gWhy, *gby;    // gradients             (written for the LAST iteration of the call)
   float *Hs, *Cs, *Gs, *dY, *dHy, *dG, *surp;   // activations  (slot 0 of Hs / Cs in and out; the rest written for the last iteration)
-  int *xs, *tg;                        // window: read when mode = 1, written (last iteration) when mode = 0
+  int *xs, *tg;                        // the last iteration's window is written here (lstm_get_window)
   const uint8_t* text; unsigned long long len; const unsigned long long* pos0; unsigned long long* vcount;   // mode 0
   double* ring; unsigned long long cap; unsigned long long* iter;                                             // loss ring
-  int S, T, iters, stride, mode, loss_mode, shift;   // mode 0: window from the device text; 1: from xs / tg; 2: from win_x / win_t
-  int win_x[8], win_t[8];              // mode 2: the window itself travels as a kernel argument (S <= 5), no copy is enqueued
+  int S, T, iters, stride, mode, loss_mode, shift;   // mode 0: windows from the device text; 1: ONE iteration on the window in win_x / win_t
+  int win_x[8], win_t[8];              // mode 1: the window itself travels as a kernel argument (S <= 5), no copy is enqueued
   double* host_loss;                   // optional: pinned, device-accessible host double that also receives the last iteration's loss
   float lr, clip; double eps;
   float m_exact;                       // set by the launcher: from this Adagrad memory value on, (float)(m + eps) == m
